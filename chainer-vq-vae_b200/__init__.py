@@ -1,0 +1,22 @@
+"""chainer-vq-vae_b200: the B200-native hot path of dhgrs/chainer-VQ-VAE.
+
+The directory name carries a hyphen, so import it through the `chainer_vq_vae_b200` shim at
+the repository root (or `importlib`); see DESIGN.md.  Importing this package loads
+csrc/libvqw.so and raises if it is missing -- there is no CPU or eager fallback."""
+from . import _lib
+from ._lib import MODES, VqwError, launch_count
+from .functions import conv, embed_gather, residual_stack, straight_through, vq_lookup
+from .links import Convolution2D, DilatedConvolution2D, EmbedID, namedparams
+from .losses import logistic_loss, softmax_cross_entropy
+from .net import VAE, ConditionEmbed, Encoder
+from .updaters import Adam, GradBucket, VQVAE_ParallelUpdater, VQVAE_StandardUpdater
+from .utils import VQ, ExponentialMovingAverage, MuLaw
+from .wavenet import ResidualBlock, ResidualNet, WaveNet
+
+__all__ = [
+    "Encoder", "ConditionEmbed", "VAE", "VQ", "straight_through", "ExponentialMovingAverage",
+    "MuLaw", "ResidualBlock", "ResidualNet", "WaveNet", "VQVAE_StandardUpdater",
+    "VQVAE_ParallelUpdater", "Adam", "GradBucket", "softmax_cross_entropy", "logistic_loss",
+    "conv", "embed_gather", "residual_stack", "vq_lookup", "Convolution2D",
+    "DilatedConvolution2D", "EmbedID", "namedparams", "MODES", "VqwError", "launch_count",
+]

@@ -1,0 +1,120 @@
+"""ctypes binding of libvqw.so (include/vqw.h).  The product path has NO fallback: if the
+shared library is missing or a symbol is absent, importing this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libvqw.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `./build.sh` (or __graft_entry__.build()); "
+        "this package has no CPU / eager fallback")
+
+lib = C.CDLL(LIB_PATH)
+
+VQW_MAX_SRC = 4
+MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+
+c_float_p = C.c_void_p   # device pointers are passed as integers
+c_int = C.c_int
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("w", C.c_void_p), ("in_mask", C.c_void_p),
+                ("K", c_int), ("Tin", c_int), ("wm", c_int), ("wk", c_int),
+                ("mul", c_int), ("shift", c_int), ("div", c_int), ("relu_in", c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("B", c_int), ("M", c_int), ("T", c_int), ("nsrc", c_int),
+                ("src", ConvSrc * VQW_MAX_SRC),
+                ("bias", C.c_void_p), ("addend", C.c_void_p), ("out_mask", C.c_void_p),
+                ("relu_out", c_int), ("accumulate", c_int),
+                ("gate_tanh", C.c_void_p), ("gate_sig", C.c_void_p)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("B", c_int), ("M", c_int), ("T", c_int),
+                ("a", C.c_void_p), ("a_mask", C.c_void_p), ("in_", C.c_void_p),
+                ("in_mul", C.c_void_p), ("K", c_int), ("Tin", c_int),
+                ("mul", c_int), ("shift", c_int), ("div", c_int), ("relu_in", c_int),
+                ("gm", c_int), ("gk", c_int)]
+
+
+class ResblockDesc(C.Structure):
+    _fields_ = [("B", c_int), ("T", c_int), ("Cr", c_int), ("Cd", c_int), ("Cs", c_int),
+                ("Cc", c_int), ("fs", c_int), ("dilation", c_int),
+                ("skip_accumulate", c_int), ("write_residual", c_int), ("mode", c_int)]
+
+
+class ResblockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv_w", "conv_b", "cond_w", "cond_b", "res_w",
+                                          "res_b", "skip_w", "skip_b")]
+
+
+_SIGNATURES = {
+    "vqw_version": (c_int, []),
+    "vqw_last_error": (C.c_char_p, []),
+    "vqw_vq_forward": (c_int, [C.c_void_p] * 7 + [c_int] * 4 + [C.c_void_p]),
+    "vqw_vq_backward_w": (c_int, [C.c_void_p] * 3 + [c_int] * 4 + [C.c_void_p]),
+    "vqw_conv_forward": (c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
+    "vqw_conv_wgrad": (c_int, [C.POINTER(WgradDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vqw_resblock_forward": (c_int, [C.POINTER(ResblockDesc), C.c_void_p, C.c_void_p,
+                                     C.POINTER(ResblockWeights)] + [C.c_void_p] * 5),
+    "vqw_resblock_backward_workspace": (C.c_int64, [C.POINTER(ResblockDesc)]),
+    "vqw_resblock_backward": (c_int, [C.POINTER(ResblockDesc)] + [C.c_void_p] * 6 +
+                              [C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p,
+                               C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p]),
+    "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
+    "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
+}
+
+
+def _bind():
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of C-ABI compute calls issued by this process (each is >= 1 kernel launch)."""
+    return _launches
+
+
+class VqwError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    global _launches
+    _launches += 1
+    if rc != 0:
+        msg = lib.vqw_last_error().decode("utf-8", "replace")
+        raise VqwError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VqwError("libvqw operates on CUDA tensors only (no CPU fallback); got a "
+                       f"{t.device} tensor")
+    if not t.is_contiguous():
+        raise VqwError("libvqw needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

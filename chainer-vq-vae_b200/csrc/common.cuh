@@ -1,0 +1,54 @@
+// Shared helpers for libvqw.so (sm_100a).  No torch types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/vqw.h"
+
+namespace vqw {
+
+// thread-local error text returned by vqw_last_error()
+char* error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define VQW_REQUIRE(cond, ...)                              \
+  do {                                                      \
+    if (!(cond)) return ::vqw::set_error(-1, __VA_ARGS__);  \
+  } while (0)
+
+#define VQW_CHECK_LAUNCH(name)                                                        \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess)                                                           \
+      return ::vqw::set_error((int)e__, "%s: %s", name, cudaGetErrorString(e__));     \
+  } while (0)
+
+#define VQW_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      return ::vqw::set_error((int)e__, "%s: %s", #expr, cudaGetErrorString(e__));    \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// tanh through one exp: accurate to a few ulp of fp32 over the whole range
+__device__ __forceinline__ float tanhf_(float v) {
+  float a = fabsf(v);
+  float e = __expf(-2.0f * a);
+  float r = (1.0f - e) / (1.0f + e);
+  return copysignf(r, v);
+}
+
+// conv.cu
+int launch_conv(const vqw_conv_desc& d, float* out, cudaStream_t stream);
+int launch_wgrad(const vqw_wgrad_desc& d, float* gw, float* gb, cudaStream_t stream);
+// resblock_tc.cu (tcgen05 path); returns -2 when the shape is not supported by that path
+int resblock_forward_tc(const vqw_resblock_desc& d, const float* x, const float* cond,
+                        const vqw_resblock_weights& w, float* residual, float* skip,
+                        float* gate_tanh, float* gate_sig, cudaStream_t stream);
+
+}  // namespace vqw

@@ -1,0 +1,344 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/vqw.h).
+
+Tensors keep the reference layout (B, C, T, 1) float32.  Every function launches on the
+current CUDA stream and raises on non-CUDA input: there is no eager/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _as3(x: torch.Tensor):
+    """(B,C,T,1) or (B,C,T) -> sizes; the memory is identical."""
+    if x.dim() == 4:
+        if x.shape[3] != 1:
+            raise ValueError("the last (width) axis must be 1, as in the reference's (k,1) convs")
+    elif x.dim() != 3:
+        raise ValueError(f"expected a (B,C,T,1) tensor, got shape {tuple(x.shape)}")
+    return x.shape[0], x.shape[1], x.shape[2]
+
+
+def _f32c(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        raise TypeError(f"float32 expected, got {x.dtype}")
+    return x.contiguous()
+
+
+# ---------------------------------------------------------------------------------------
+# generic strided / dilated convolution with (k,1) kernels
+# ---------------------------------------------------------------------------------------
+def conv_out_len(L_in: int, k: int, stride: int, pad: int, dilate: int) -> int:
+    """Chainer's get_conv_outsize: (L + 2p - dil*(k-1) - 1)//s + 1."""
+    return (L_in + 2 * pad - dilate * (k - 1) - 1) // stride + 1
+
+
+def _conv_launch(desc: L.ConvDesc, out: torch.Tensor, what: str) -> None:
+    L.check(L.lib.vqw_conv_forward(C.byref(desc), L.ptr(out), L.stream()), what)
+
+
+def _fill_src(s: L.ConvSrc, inp, w_ptr, K, Tin, wm, wk, mul, shift, div, relu_in=0, in_mask=None):
+    s.in_ = L.ptr(inp)
+    s.w = w_ptr
+    s.in_mask = L.ptr(in_mask)
+    s.K, s.Tin, s.wm, s.wk = K, Tin, wm, wk
+    s.mul, s.shift, s.div, s.relu_in = mul, shift, div, relu_in
+
+
+class _Conv(torch.autograd.Function):
+    """y = [relu](conv(x, W) + b) over the time axis; cross-correlation, symmetric zero pad."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, stride, pad, dilate, relu_out, out_len, relu_in=False):
+        x, W = _f32c(x), _f32c(W)
+        B, Cin, Tin = _as3(x)
+        Cout, Cin_w, kh = W.shape[0], W.shape[1], W.shape[2]
+        if Cin_w != Cin:
+            raise ValueError(f"conv: input has {Cin} channels, weight expects {Cin_w}")
+        Tout = conv_out_len(Tin, kh, stride, pad, dilate)
+        if out_len is not None:
+            Tout = min(Tout, out_len)        # the reference slices [:, :, :length]
+        out = torch.empty((B, Cout, max(Tout, 0), 1), device=x.device, dtype=torch.float32)
+        if b is not None:
+            b = _f32c(b)
+        wp = L.ptr(W)
+        for j0 in range(0, kh, L.VQW_MAX_SRC):
+            d = L.ConvDesc()
+            d.B, d.M, d.T = B, Cout, Tout
+            taps = range(j0, min(kh, j0 + L.VQW_MAX_SRC))
+            d.nsrc = len(taps)
+            for n, j in enumerate(taps):
+                _fill_src(d.src[n], x, wp + 4 * j, Cin, Tin, Cin * kh, kh, stride,
+                          j * dilate - pad, 1, int(relu_in))
+            last = j0 + L.VQW_MAX_SRC >= kh
+            d.bias = L.ptr(b) if (b is not None and j0 == 0) else None
+            d.accumulate = 1 if j0 > 0 else 0
+            d.relu_out = 1 if (relu_out and last) else 0
+            if relu_out and not last:
+                raise NotImplementedError("relu fusion needs filter_size <= 4")
+            _conv_launch(d, out, "vqw_conv_forward")
+        ctx.cfg = (stride, pad, dilate, relu_out, B, Cin, Tin, Cout, kh, Tout, b is not None,
+                   relu_in)
+        ctx.save_for_backward(x, W, out if relu_out else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        stride, pad, dilate, relu_out, B, Cin, Tin, Cout, kh, Tout, has_b, relu_in = ctx.cfg
+        x, W, y = ctx.saved_tensors
+        gy = _f32c(gy)
+        gx = gW = gb = None
+        wp = L.ptr(W)
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            for j0 in range(0, kh, L.VQW_MAX_SRC):
+                d = L.ConvDesc()
+                d.B, d.M, d.T = B, Cin, Tin
+                taps = range(j0, min(kh, j0 + L.VQW_MAX_SRC))
+                d.nsrc = len(taps)
+                for n, j in enumerate(taps):
+                    _fill_src(d.src[n], gy, wp + 4 * j, Cout, Tout, kh, Cin * kh, 1,
+                              pad - j * dilate, stride, 0, y if relu_out else None)
+                d.accumulate = 1 if j0 > 0 else 0
+                if relu_in:
+                    if j0 + L.VQW_MAX_SRC < kh:
+                        raise NotImplementedError("relu_in fusion needs filter_size <= 4")
+                    d.out_mask = L.ptr(x)        # relu'(x) = (x > 0)
+                _conv_launch(d, gx, "vqw_conv_forward(dgrad)")
+        if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
+            gW = torch.zeros_like(W)
+            gb = torch.zeros(Cout, device=x.device, dtype=torch.float32) if has_b else None
+            for j in range(kh):
+                g = L.WgradDesc()
+                g.B, g.M, g.T = B, Cout, Tout
+                g.a, g.a_mask = L.ptr(gy), (L.ptr(y) if relu_out else None)
+                g.in_, g.in_mul = L.ptr(x), None
+                g.K, g.Tin = Cin, Tin
+                g.mul, g.shift, g.div, g.relu_in = stride, j * dilate - pad, 1, int(relu_in)
+                g.gm, g.gk = Cin * kh, kh
+                L.check(L.lib.vqw_conv_wgrad(C.byref(g), L.ptr(gW) + 4 * j,
+                                             L.ptr(gb) if (j == 0 and has_b) else None,
+                                             L.stream()), "vqw_conv_wgrad")
+        return gx, gW, gb, None, None, None, None, None, None
+
+
+def conv(x, W, b=None, stride=1, pad=0, dilate=1, relu=False, out_len=None, relu_in=False):
+    """Chainer `L.Convolution2D` / `L.DilatedConvolution2D` arithmetic for (k,1) kernels;
+    `relu_in` / `relu` fuse an F.relu before / after the convolution."""
+    return _Conv.apply(x, W, b, stride, pad, dilate, relu, out_len, relu_in)
+
+
+# ---------------------------------------------------------------------------------------
+# VQ straight-through (utils.py:161-236)
+# ---------------------------------------------------------------------------------------
+def check_type_forward(x: torch.Tensor, W: torch.Tensor) -> None:
+    """StraightThrough.check_type_forward, utils.py:162-174 (InvalidType -> TypeError/ValueError)."""
+    if not (x.is_floating_point() and W.is_floating_point()):
+        raise TypeError("straight_through: x and W must be floating point (utils.py:168-169)")
+    if not (3 <= x.dim() <= 4):
+        raise ValueError("straight_through: x.ndim must be 3 or 4 (utils.py:170-171)")
+    if W.dim() != 2:
+        raise ValueError("straight_through: W.ndim must be 2 (utils.py:172)")
+    if x.shape[1] != W.shape[1]:
+        raise ValueError("straight_through: x.shape[1] != W.shape[1] (utils.py:173)")
+    if x.device != W.device:
+        raise ValueError("straight_through: x and W must live on the same device "
+                         "(numpy and cupy must not be used together, utils.py:183-186)")
+
+
+def vq_lookup(x: torch.Tensor, W: torch.Tensor, stats: bool = False):
+    """One launch of the fused distance + argmin + gather kernel.
+    Returns (e, indexes int32 shaped like x without the channel axis, count, zsum, sqerr)."""
+    check_type_forward(x, W)
+    x, W = _f32c(x), _f32c(W)
+    B, d = x.shape[0], x.shape[1]
+    T = x.shape[2] if x.dim() == 3 else x.shape[2] * x.shape[3]
+    k = W.shape[0]
+    idx = torch.empty((B,) + tuple(x.shape[2:]), device=x.device, dtype=torch.int32)
+    e = torch.empty_like(x)
+    count = zsum = sqerr = None
+    if stats:
+        count = torch.zeros(k, device=x.device, dtype=torch.float32)
+        zsum = torch.zeros(k, d, device=x.device, dtype=torch.float32)
+        sqerr = torch.zeros(1, device=x.device, dtype=torch.float64)
+    L.check(L.lib.vqw_vq_forward(L.ptr(x), L.ptr(W), L.ptr(idx), L.ptr(e), L.ptr(count),
+                                 L.ptr(zsum), L.ptr(sqerr), B, d, T, k, L.stream()),
+            "vqw_vq_forward")
+    return e, idx, count, zsum, sqerr
+
+
+class _StraightThrough(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, cached):
+        if cached is None:
+            e, idx, _, _, _ = vq_lookup(x, W)
+        else:
+            e, idx = cached
+        ctx.save_for_backward(idx)
+        ctx.wshape = tuple(W.shape)
+        ctx.mark_non_differentiable(idx)
+        return e, idx
+
+    @staticmethod
+    def backward(ctx, gy, _gidx):
+        (idx,) = ctx.saved_tensors
+        gx = gy if ctx.needs_input_grad[0] else None          # utils.py:218-219
+        gW = None
+        if ctx.needs_input_grad[1]:                            # utils.py:220-230
+            gyc = _f32c(gy)
+            k, d = ctx.wshape
+            B = gyc.shape[0]
+            T = gyc.numel() // (B * d)
+            gW = torch.empty(k, d, device=gy.device, dtype=torch.float32)
+            L.check(L.lib.vqw_vq_backward_w(L.ptr(gyc), L.ptr(idx), L.ptr(gW), B, d, T, k,
+                                            L.stream()), "vqw_vq_backward_w")
+        return gx, gW, None
+
+
+def straight_through(x, W, cached=None, return_indexes=False):
+    """utils.py:234-236.  `cached=(e, idx)` reuses a previous lookup of the same (x, W) values
+    (VAE.__call__ quantises z twice, net.py:82-83; the kernel runs once)."""
+    e, idx = _StraightThrough.apply(x, W, cached)
+    return (e, idx) if return_indexes else e
+
+
+# ---------------------------------------------------------------------------------------
+# fused residual block stack (modules.py:30-56, 89-96)
+# ---------------------------------------------------------------------------------------
+def _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dil, accumulate, write_res, mode) -> L.ResblockDesc:
+    d = L.ResblockDesc()
+    d.B, d.T, d.Cr, d.Cd, d.Cs, d.Cc = B, T, Cr, Cd, Cs, Cc
+    d.fs, d.dilation = fs, dil
+    d.skip_accumulate, d.write_residual, d.mode = int(accumulate), int(write_res), mode
+    return d
+
+
+def _rb_weights(ws: Sequence[Optional[torch.Tensor]]) -> L.ResblockWeights:
+    w = L.ResblockWeights()
+    for name, t in zip(("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b", "skip_w",
+                        "skip_b"), ws):
+        setattr(w, name, L.ptr(t))
+    return w
+
+
+class _ResidualStack(torch.autograd.Function):
+    """All blocks of a ResidualNet in one autograd node: forward launches one fused kernel
+    per block (skip accumulated in place, modules.py:92-95); backward walks the blocks in
+    reverse with the shared g_skip and the accumulated g_condition."""
+
+    @staticmethod
+    def forward(ctx, x, cond, dilations, fs, mode, keep_last_residual, *weights):
+        x, cond = _f32c(x), _f32c(cond)
+        B, Cr, T = _as3(x)
+        Bc, Cc, Tc = _as3(cond)
+        if (Bc, Tc) != (B, T):
+            raise ValueError(f"condition shape {tuple(cond.shape)} does not match x {tuple(x.shape)}")
+        n = len(dilations)
+        assert len(weights) == 8 * n
+        weights = [_f32c(w) for w in weights]
+        Cd = weights[0].shape[0]
+        Cs = weights[6].shape[0]
+        skip = torch.empty((B, Cs, T, 1), device=x.device, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad)
+        xs: List[torch.Tensor] = [x]
+        gates: List[torch.Tensor] = []
+        residual = None
+        for i, dil in enumerate(dilations):
+            last = i == n - 1
+            write_res = (not last) or keep_last_residual
+            residual = (torch.empty((B, Cr, T, 1), device=x.device, dtype=torch.float32)
+                        if write_res else None)
+            gt = gs = None
+            if need_grad:
+                gt = torch.empty((B, Cd // 2, T, 1), device=x.device, dtype=torch.float32)
+                gs = torch.empty_like(gt)
+            d = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dil, i > 0, write_res, mode)
+            w = _rb_weights(weights[8 * i:8 * i + 8])
+            L.check(L.lib.vqw_resblock_forward(C.byref(d), L.ptr(xs[-1]), L.ptr(cond), C.byref(w),
+                                               L.ptr(residual), L.ptr(skip), L.ptr(gt), L.ptr(gs),
+                                               L.stream()), "vqw_resblock_forward")
+            if need_grad:
+                gates += [gt, gs]
+            if not last:
+                xs.append(residual)
+        ctx.cfg = (tuple(dilations), fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last_residual)
+        ctx.save_for_backward(cond, *xs, *gates, *weights)
+        if keep_last_residual:
+            return skip, residual
+        return skip
+
+    @staticmethod
+    def backward(ctx, g_skip, g_last_res=None):
+        dilations, fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last = ctx.cfg
+        n = len(dilations)
+        saved = ctx.saved_tensors
+        cond = saved[0]
+        xs = saved[1:1 + n]
+        gates = saved[1 + n:1 + 3 * n]
+        weights = saved[1 + 3 * n:]
+        g_skip = _f32c(g_skip)
+        dev = g_skip.device
+        gcond = torch.zeros((B, Cc, T, 1), device=dev, dtype=torch.float32)
+        gws = [torch.zeros_like(w) for w in weights]
+        d0 = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, 1, 0, 1, L.MODE_FP32)
+        ws_bytes = L.lib.vqw_resblock_backward_workspace(C.byref(d0))
+        workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        g_res = _f32c(g_last_res) if (keep_last and g_last_res is not None) else None
+        for i in reversed(range(n)):
+            d = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dilations[i], i > 0, 1, L.MODE_FP32)
+            w = _rb_weights(weights[8 * i:8 * i + 8])
+            gw = _rb_weights(gws[8 * i:8 * i + 8])
+            gx = torch.empty((B, Cr, T, 1), device=dev, dtype=torch.float32)
+            L.check(L.lib.vqw_resblock_backward(
+                C.byref(d), L.ptr(g_res), L.ptr(g_skip), L.ptr(xs[i]), L.ptr(cond),
+                L.ptr(gates[2 * i]), L.ptr(gates[2 * i + 1]), C.byref(w), L.ptr(gx),
+                L.ptr(gcond), C.byref(gw), L.ptr(workspace), L.stream()),
+                "vqw_resblock_backward")
+            g_res = gx
+        return (g_res, gcond, None, None, None, None, *gws)
+
+
+def residual_stack(x, cond, dilations, fs, weights, mode=L.MODE_FP32, keep_last_residual=False):
+    return _ResidualStack.apply(x, cond, tuple(dilations), fs, mode, keep_last_residual, *weights)
+
+
+# ---------------------------------------------------------------------------------------
+# causal embedding of mu-law indices (modules.py:151-152 on a one-hot input)
+# ---------------------------------------------------------------------------------------
+class _EmbedGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, W, b):
+        W = _f32c(W)
+        if q.dtype != torch.int32:
+            raise TypeError("embed indices must be int32")
+        q = q.contiguous()
+        B, T = q.shape[0], q.shape[1]
+        Cr, Q = W.shape[0], W.shape[1]
+        out = torch.empty((B, Cr, T, 1), device=W.device, dtype=torch.float32)
+        L.check(L.lib.vqw_embed_gather_forward(L.ptr(q), L.ptr(W), L.ptr(b), L.ptr(out), B, T, Cr,
+                                               Q, L.stream()), "vqw_embed_gather_forward")
+        ctx.save_for_backward(q)
+        ctx.cfg = (tuple(W.shape), b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (q,) = ctx.saved_tensors
+        wshape, has_b = ctx.cfg
+        g = _f32c(g)
+        Cr, Q = wshape[0], wshape[1]
+        gW = torch.zeros(wshape, device=g.device, dtype=torch.float32)
+        gb = torch.zeros(Cr, device=g.device, dtype=torch.float32) if has_b else None
+        L.check(L.lib.vqw_embed_gather_backward(L.ptr(q), L.ptr(g), L.ptr(gW), L.ptr(gb),
+                                                q.shape[0], q.shape[1], Cr, Q, L.stream()),
+                "vqw_embed_gather_backward")
+        return None, gW, gb
+
+
+def embed_gather(q, W, b):
+    """q (B,T) int32 -> (B,Cr,T,1); W is the embed conv's weight (Cr, Q, 2, 1)."""
+    return _EmbedGather.apply(q, W, b)

@@ -1,0 +1,40 @@
+"""Output losses of the path: softmax cross entropy (train.py:95) and the discretised
+mixture-of-logistics NLL (WaveNet.calculate_logistic_loss, modules.py:169-230)."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def softmax_cross_entropy(y, t):
+    """chainer.functions.softmax_cross_entropy: log-softmax over axis 1, mean over all labels.
+    y (B,Q,T,1) f32, t (B,T,1) int."""
+    logp = F.log_softmax(y, dim=1)
+    picked = torch.gather(logp, 1, t.long().unsqueeze(1))
+    return -picked.sum() / t.numel()
+
+
+def logistic_loss(y, t, quantize, log_scale_min):
+    """modules.py:169-230, term by term."""
+    nr_mix = y.shape[1] // 3
+    logit_probs = y[:, :nr_mix]
+    means = y[:, nr_mix:2 * nr_mix]
+    log_scales = torch.clamp_min(y[:, 2 * nr_mix:3 * nr_mix], log_scale_min)      # :178-179
+    t = (127.5 * t).expand_as(means)                                              # :181
+    centered_t = t - means
+    inv_std = torch.exp(-log_scales)
+    half = 127.5 / (quantize - 1)
+    plus_in = inv_std * (centered_t + half)
+    cdf_plus = torch.sigmoid(plus_in)
+    min_in = inv_std * (centered_t - half)
+    cdf_min = torch.sigmoid(min_in)
+    log_cdf_plus = plus_in - F.softplus(plus_in)
+    log_one_minus_cdf_min = -F.softplus(min_in)
+    cdf_delta = cdf_plus - cdf_min
+    inner = torch.log(torch.clamp_min(cdf_delta, 1e-12))                          # :214-215
+    lo = torch.tensor(127.5 * -0.999, dtype=torch.float32, device=y.device)
+    hi = torch.tensor(127.5 * 0.999, dtype=torch.float32, device=y.device)
+    log_probs = torch.where(t < lo, log_cdf_plus,
+                            torch.where(t > hi, log_one_minus_cdf_min, inner))    # :198-226
+    log_probs = log_probs + F.log_softmax(logit_probs, dim=1)                     # :228
+    return -torch.mean(torch.logsumexp(log_probs, dim=1))                         # :229

@@ -1,0 +1,130 @@
+"""Encoder / ConditionEmbed / VAE behind the reference's callable surface (net.py:8-96)."""
+from __future__ import annotations
+
+import numpy
+import torch
+from torch import nn
+
+from . import functions as Fn
+from .links import Convolution2D, DilatedConvolution2D, EmbedID
+from .utils import VQ, ExponentialMovingAverage  # noqa: F401
+
+
+class Encoder(nn.Module):
+    """net.py:8-26: six Convolution2D(k=(4,1), stride=(2,1), pad=(1,0)); ReLU after the first
+    five (fused into the conv kernel's epilogue)."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.conv1 = Convolution2D(1, d, (4, 1), (2, 1), (1, 0))
+        self.conv2 = Convolution2D(d, d, (4, 1), (2, 1), (1, 0))
+        self.conv3 = Convolution2D(d, d, (4, 1), (2, 1), (1, 0))
+        self.conv4 = Convolution2D(d, d, (4, 1), (2, 1), (1, 0))
+        self.conv5 = Convolution2D(d, d, (4, 1), (2, 1), (1, 0))
+        self.conv6 = Convolution2D(d, d, (4, 1), (2, 1), (1, 0))
+
+    def forward(self, x):
+        h = self.conv1(x, relu=True)
+        h = self.conv2(h, relu=True)
+        h = self.conv3(h, relu=True)
+        h = self.conv4(h, relu=True)
+        h = self.conv5(h, relu=True)
+        return self.conv6(h)
+
+
+_RESIZE_CACHE = {}
+
+
+def _resize_plan(H, out_h, device):
+    """F.resize_images coordinates for a (H,1) -> (out_h,1) resize [dep], in exact integer
+    form: v = i*(H-1)/(out_h-1), v0 = min(floor v, H-2), frac = v - v0 (SURVEY.md appendix B;
+    fp32 coordinates would drift by 9e-5 at T=24000)."""
+    key = (H, out_h, str(device))
+    if key not in _RESIZE_CACHE:
+        i = numpy.arange(out_h, dtype=numpy.int64)
+        num = i * (H - 1)
+        den = max(out_h - 1, 1)
+        v0 = numpy.minimum(num // den, H - 2)
+        frac = (num - v0 * den).astype(numpy.float64) / den
+        w1 = torch.from_numpy(frac.astype(numpy.float32)).to(device).reshape(1, 1, out_h, 1)
+        w0 = torch.from_numpy((1.0 - frac).astype(numpy.float32)).to(device).reshape(1, 1, out_h, 1)
+        i0 = torch.from_numpy(v0).to(device)
+        _RESIZE_CACHE[key] = (i0, i0 + 1, w0, w1)
+    return _RESIZE_CACHE[key]
+
+
+def resize_images_h(x, out_h):
+    """F.resize_images(x, (out_h, 1)) for width-1 images: 1-D align-corners linear
+    interpolation; H == 1 degenerates to a broadcast (net.py:60-61)."""
+    B, Cn, H, _ = x.shape
+    if H == 1:
+        return x.expand(B, Cn, out_h, 1)
+    i0, i1, w0, w1 = _resize_plan(H, out_h, x.device)
+    return w0 * x.index_select(2, i0) + w1 * x.index_select(2, i1)
+
+
+class ConditionEmbed(nn.Module):
+    """net.py:29-64: five non-causal dilated convs (dil 1,2,4,8,16; ReLU fused) on the VQ
+    output, x upscale_factor linear upsampling, speaker EmbedID broadcast, channel concat
+    (local first)."""
+
+    def __init__(self, n_global_cond, global_embed_dim, local_embed_dim, upscale_factor=64,
+                 local_in_channels=None):
+        super().__init__()
+        # the reference passes in_channels=None (lazy); the input is the VQ output, so its
+        # channel count is d.  local_in_channels=None defers to local_embed_dim == d
+        # (the BASELINE configs), otherwise give d explicitly.
+        cin = local_embed_dim if local_in_channels is None else local_in_channels
+        self.local_embed1 = DilatedConvolution2D(cin, local_embed_dim, (3, 1), pad=(1, 0), dilate=(1, 1))
+        self.local_embed2 = DilatedConvolution2D(local_embed_dim, local_embed_dim, (3, 1), pad=(2, 0), dilate=(2, 1))
+        self.local_embed3 = DilatedConvolution2D(local_embed_dim, local_embed_dim, (3, 1), pad=(4, 0), dilate=(4, 1))
+        self.local_embed4 = DilatedConvolution2D(local_embed_dim, local_embed_dim, (3, 1), pad=(8, 0), dilate=(8, 1))
+        self.local_embed5 = DilatedConvolution2D(local_embed_dim, local_embed_dim, (3, 1), pad=(16, 0), dilate=(16, 1))
+        self.global_embed = EmbedID(n_global_cond, global_embed_dim)
+        self.upscale_factor = upscale_factor
+
+    def forward(self, local_condition, global_condition):
+        h = self.local_embed1(local_condition, relu=True)
+        h = self.local_embed2(h, relu=True)
+        h = self.local_embed3(h, relu=True)
+        h = self.local_embed4(h, relu=True)
+        h = self.local_embed5(h, relu=True)
+        h = resize_images_h(h, self.upscale_factor * h.shape[2])
+        g = self.global_embed(global_condition)
+        g = g.reshape(g.shape + (1, 1))
+        g = resize_images_h(g, h.shape[2])
+        return torch.cat((h, g), dim=1).contiguous()
+
+
+class VAE(nn.Module):
+    """net.py:67-96.  `__call__(x_enc, x_dec, global_condition, t)` returns
+    (loss1, loss2, loss3); `.encoder .vq .condition_embed .decoder` as in the reference
+    (updaters.py:16,65 reach into `.vq`).  The VQ kernel runs once: the second quantisation of
+    net.py:83 reuses its indices (identical by construction)."""
+
+    def __init__(self, encoder, decoder, condition_embed, d, k, beta, loss_func):
+        super().__init__()
+        self.beta = beta
+        self.loss_func = loss_func
+        self.encoder = encoder
+        self.vq = VQ(k, d)
+        self.condition_embed = condition_embed
+        self.decoder = decoder
+        self.observation = {}
+
+    def forward(self, x_enc, x_dec, global_condition, t):
+        z = self.encoder(x_enc)                                        # :81
+        e = self.vq(z)                                                 # :82
+        idx = self.vq.indexes
+        zd = z.detach()
+        e_ = self.vq(zd, cached=(e.detach(), idx))                     # :83
+        condition = self.condition_embed(e, global_condition)          # :85
+        y = self.decoder(x_dec, condition)                             # :86
+        loss1 = self.loss_func(y, t)                                   # :89
+        loss2 = torch.mean((zd - e_) ** 2)                             # :90
+        loss3 = self.beta * torch.mean((z - e.detach()) ** 2)          # :91
+        loss = loss1 + loss2 + loss3
+        self.observation = {"loss1": loss1.detach(), "loss2": loss2.detach(),
+                            "loss3": loss3.detach(), "loss": loss.detach()}   # reporter, :93-95
+        self.y = y
+        return loss1, loss2, loss3

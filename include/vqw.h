@@ -1,0 +1,172 @@
+/*
+ * vqw.h -- C-ABI of libvqw.so: the B200 (sm_100a) hot path of dhgrs/chainer-VQ-VAE.
+ *
+ * The reference has no FFI/plugin layer (it is pure Python on Chainer); its hot path is the
+ * set of Chain.__call__ methods in net.py, utils.py and WaveNet/modules.py.  Each entry point
+ * below replaces the library calls one of those methods makes; the reference lines are cited
+ * per function (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * stub that binds them from the reference's side.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is CALLER-OWNED DEVICE memory (the library never allocates or frees);
+ *   - tensors use the reference layout (B, C, T, 1) float32, contiguous, T fastest;
+ *   - the call is ASYNCHRONOUS on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 = ok, <0 = argument error detected before launch (see vqw_last_error()),
+ *     >0 = cudaError_t of the failed launch;
+ *   - no global mutable state other than a thread-local error string.
+ */
+#ifndef VQW_H_
+#define VQW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vqw_stream_t; /* cudaStream_t */
+
+#define VQW_VERSION 100
+
+int vqw_version(void);
+const char* vqw_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * VQ nearest-codebook lookup.  Replaces StraightThrough.forward, utils.py:176-211
+ * (expand/broadcast/sub/square/sum(axis=2)/argmin(axis=1)/take/transpose).
+ *   z (B,d,T) f32, W (k,d) f32  ->  idx (B,T) i32, e (B,d,T) f32 = W[idx] channel-first.
+ * Distances are accumulated sequentially over d in fp32 without FMA contraction and ties
+ * go to the lowest k, i.e. NumPy's semantics: indices are bit-exact.
+ * Optional outputs (NULL to skip; each must be zeroed by the caller, they are accumulated):
+ *   count (k) f32        per-code usage n_k
+ *   zsum  (k,d) f32      per-code sum of assigned z
+ *   sqerr (1) f64        sum over all elements of (z - e)^2  (loss2/loss3 numerator, net.py:90-91)
+ */
+int vqw_vq_forward(const float* z, const float* W, int32_t* idx, float* e, float* count,
+                   float* zsum, double* sqerr, int B, int d, int T, int k, vqw_stream_t stream);
+
+/* StraightThrough.backward for W, utils.py:222-230: gW[k,:] = sum_{idx==k} gy[b,:,t]
+ * (float64 accumulation then cast to f32 like the reference's eye(k) dot).  gW is overwritten. */
+int vqw_vq_backward_w(const float* gy, const int32_t* idx, float* gW, int B, int d, int T, int k,
+                      vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generic strided/dilated 1-D convolution family (fp32 SIMT).  Replaces the cuDNN/NumPy
+ * convolution calls made by L.Convolution2D / L.DilatedConvolution2D in
+ * net.py:12-17,34-43 (Encoder, ConditionEmbed), modules.py:127-141,151-159 (embed, proj1,
+ * proj2) and the unfused pieces of the ResidualBlock backward.
+ *
+ *   out[b,m,t] = post( bias[m] + sum_s sum_k  w_s[m*wm_s + k*wk_s] * pre_s(in_s[b,k,ti]) )
+ *   ti = (t*mul_s + shift_s) / div_s  (term dropped unless divisible and 0 <= ti < Tin_s)
+ *   pre_s(v)  = v, relu(v), or v * (in_mask_s[b,k,ti] > 0)
+ *   post(v)   = v (+ addend[b,m,t]) (relu) (* (out_mask[b,m,t] > 0)) (+ previous out if accumulate)
+ */
+#define VQW_MAX_SRC 4
+typedef struct {
+  const float* in;      /* (B, K, Tin) */
+  const float* w;       /* weight base pointer (already offset to the tap) */
+  const float* in_mask; /* optional (B, K, Tin): in is multiplied by (mask > 0) */
+  int K;                /* input channels */
+  int Tin;              /* input length */
+  int wm, wk;           /* weight strides (in floats) along output channel m / input channel k */
+  int mul, shift, div;  /* time index map */
+  int relu_in;          /* apply relu to the input */
+} vqw_conv_src;
+
+typedef struct {
+  int B, M, T;          /* batch, output channels, output length */
+  int nsrc;
+  vqw_conv_src src[VQW_MAX_SRC];
+  const float* bias;    /* (M) or NULL */
+  const float* addend;  /* (B, M, T) or NULL */
+  const float* out_mask;/* (B, M, T) or NULL */
+  int relu_out;
+  int accumulate;       /* out += result instead of out = result */
+  /* gate backward epilogue (modules.py:47-48 differentiated): when gate_tanh != NULL the GEMM
+   * result is gz (M = Cd/2 rows) and TWO rows are written into out (B, 2M, T):
+   *   out[b,m,t]   = gz * sig * (1 - tanh^2),  out[b,m+M,t] = gz * tanh * sig * (1 - sig) */
+  const float* gate_tanh; /* (B, M, T) or NULL */
+  const float* gate_sig;  /* (B, M, T) or NULL */
+} vqw_conv_desc;
+
+int vqw_conv_forward(const vqw_conv_desc* desc, float* out, vqw_stream_t stream);
+
+/* Weight/bias gradient of the same family:
+ *   gw[m*gm + k*gk] (+)= sum_{b,t} A(b,m,t) * Bv(b,k,ti),   gb[m] (+)= sum_{b,t} A(b,m,t)
+ *   A  = a (* (a_mask > 0));  Bv = pre(in) (* in_mul);  ti as above.
+ * gw/gb are ACCUMULATED with atomics (zero them first). */
+typedef struct {
+  int B, M, T;          /* a is (B, M, T) */
+  const float* a;
+  const float* a_mask;  /* optional (B, M, T) */
+  const float* in;      /* (B, K, Tin) */
+  const float* in_mul;  /* optional (B, K, Tin): in is multiplied elementwise (z = tanh*sig) */
+  int K, Tin;
+  int mul, shift, div;
+  int relu_in;
+  int gm, gk;           /* gw strides */
+} vqw_wgrad_desc;
+
+int vqw_conv_wgrad(const vqw_wgrad_desc* desc, float* gw, float* gb /* or NULL */,
+                   vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused WaveNet residual block.  Replaces ResidualBlock.__call__, modules.py:30-56
+ * (dilated causal conv :40-41, condition_proj :44, split/tanh/sigmoid/mul :47-48,
+ * res 1x1 + residual add :51-54, skip 1x1 :55) and ResidualNet's skip accumulation
+ * (modules.py:92-95) in ONE kernel.
+ *
+ * Weights are in the reference's layout: conv_w (Cd,Cr,fs), cond_w (Cd,Cc), res_w (Cr,Cd/2),
+ * skip_w (Cs,Cd/2), biases (Cd),(Cd),(Cr),(Cs).
+ */
+#define VQW_MODE_FP32 0      /* fp32 CUDA-core path, any channel count with Cd/2 <= 256 */
+#define VQW_MODE_BF16X3 1    /* tcgen05, bf16 hi/lo split operands, 3 MMAs per product (~fp32) */
+#define VQW_MODE_BF16 2      /* tcgen05, single bf16 pass (throughput mode, not parity) */
+
+typedef struct {
+  int B, T;
+  int Cr, Cd, Cs, Cc;
+  int fs, dilation;
+  int skip_accumulate;   /* 0: skip = value (first block), 1: skip += value (modules.py:92-95) */
+  int write_residual;    /* 0: the last block's residual is unused (modules.py:52,91) */
+  int mode;
+} vqw_resblock_desc;
+
+typedef struct {
+  const float *conv_w, *conv_b, *cond_w, *cond_b, *res_w, *res_b, *skip_w, *skip_b;
+} vqw_resblock_weights;
+
+/* x (B,Cr,T), cond (B,Cc,T) -> residual (B,Cr,T) [may alias nothing], skip (B,Cs,T) in/out,
+ * gate_tanh / gate_sig (B,Cd/2,T) saved for backward (both NULL for inference). */
+int vqw_resblock_forward(const vqw_resblock_desc* desc, const float* x, const float* cond,
+                         const vqw_resblock_weights* w, float* residual, float* skip,
+                         float* gate_tanh, float* gate_sig, vqw_stream_t stream);
+
+typedef struct {
+  float *conv_w, *conv_b, *cond_w, *cond_b, *res_w, *res_b, *skip_w, *skip_b;
+} vqw_resblock_wgrads;
+
+/* Backward of the block.  g_res (B,Cr,T) may be NULL (last block),
+ * g_skip (B,Cs,T).  gx (B,Cr,T) overwritten; gcond (B,Cc,T) accumulated; weight grads
+ * accumulated.  workspace: vqw_resblock_backward_workspace() bytes, 256-byte aligned. */
+int64_t vqw_resblock_backward_workspace(const vqw_resblock_desc* desc);
+int vqw_resblock_backward(const vqw_resblock_desc* desc, const float* g_res, const float* g_skip,
+                          const float* x, const float* cond, const float* gate_tanh,
+                          const float* gate_sig, const vqw_resblock_weights* w, float* gx,
+                          float* gcond, const vqw_resblock_wgrads* gw, void* workspace,
+                          vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot
+ * tensor, modules.py:151-152: out[b,c,t] = b[c] + W[c,q[t-1],0] + W[c,q[t],1] (t-1<0 dropped).
+ *   q (B,T) i32 in [0,Q), W (Cr,Q,2), bias (Cr) -> out (B,Cr,T). */
+int vqw_embed_gather_forward(const int32_t* q, const float* W, const float* bias, float* out,
+                             int B, int T, int Cr, int Q, vqw_stream_t stream);
+/* gW (Cr,Q,2) and gb (Cr) accumulated. */
+int vqw_embed_gather_backward(const int32_t* q, const float* gout, float* gW, float* gb, int B,
+                              int T, int Cr, int Q, vqw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQW_H_ */

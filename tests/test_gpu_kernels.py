@@ -1,0 +1,194 @@
+"""GPU parity tests of the individual C-ABI kernels against the oracle (run on the B200)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import chainer_vq_vae_b200 as V
+from oracle import vqvae_oracle as O
+from helpers import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ---------------------------------------------------------------- VQ -----------------
+@pytest.mark.parametrize("B,d,T,k", [(2, 64, 16, 128), (16, 64, 120, 512), (1, 64, 375, 512),
+                                      (3, 7, 5, 33), (2, 512, 9, 128)])
+def test_vq_forward_bit_exact(B, d, T, k):
+    rng = np.random.default_rng(B * 1000 + T)
+    z = rng.normal(size=(B, d, T, 1)).astype(np.float32)
+    W = rng.normal(0, 1 / np.sqrt(d), size=(k, d)).astype(np.float32)
+    # planted ties: duplicated codebook rows (first occurrence must win) and exact hits
+    W[k // 2] = W[3]
+    W[k - 1] = W[0]
+    z[0, :, 0, 0] = W[3]
+    z[-1, :, T - 1, 0] = W[0]
+    ref = O.vq_indexes(z, W)
+    e, idx, count, zsum, sqerr = V.vq_lookup(torch.from_numpy(z).to(DEV), torch.from_numpy(W).to(DEV),
+                                             stats=True)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (B, T, 1)
+    assert np.array_equal(idx.cpu().numpy(), ref), "VQ indices must be bit-identical"
+    assert idx[0, 0, 0] == 3 and idx[-1, T - 1, 0] == 0
+    e_ref = np.transpose(W[ref], (0, 3, 1, 2))
+    assert np.array_equal(e.cpu().numpy(), e_ref)
+    assert np.array_equal(count.cpu().numpy(), np.bincount(ref.ravel(), minlength=k).astype(np.float32))
+    zs = np.zeros((k, d), np.float64)
+    np.add.at(zs, ref.ravel(), np.transpose(z[..., 0], (0, 2, 1)).reshape(-1, d))
+    assert rel_err(zsum, zs) < 1e-5
+    assert abs(float(sqerr) - float(((z.astype(np.float64) - e_ref) ** 2).sum())) < 1e-6 * z.size
+
+
+def test_vq_small_literal_numpy_and_3d():
+    rng = np.random.default_rng(5)
+    z = rng.normal(size=(2, 8, 6)).astype(np.float32)          # 3-D input (utils.py:170-171)
+    W = rng.normal(size=(16, 8)).astype(np.float32)
+    ref = O.vq_indexes_numpy(z, W)
+    e, idx, *_ = V.vq_lookup(torch.from_numpy(z).to(DEV), torch.from_numpy(W).to(DEV))
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(e.cpu().numpy(), np.transpose(W[ref], (0, 2, 1)))
+
+
+def test_vq_empty_and_errors():
+    W = torch.zeros(4, 8, device=DEV)
+    e, idx, *_ = V.vq_lookup(torch.zeros(0, 8, 5, 1, device=DEV), W)
+    assert e.shape == (0, 8, 5, 1) and idx.shape == (0, 5, 1)
+    with pytest.raises(ValueError):
+        V.straight_through(torch.zeros(2, 7, 5, 1, device=DEV), W)       # channel mismatch
+    with pytest.raises(ValueError):
+        V.straight_through(torch.zeros(2, 8, device=DEV), W)             # ndim 2
+    with pytest.raises(TypeError):
+        V.straight_through(torch.zeros(2, 8, 5, 1, device=DEV, dtype=torch.int32), W)
+
+
+def test_vq_straight_through_gradients():
+    rng = np.random.default_rng(11)
+    B, d, T, k = 4, 64, 30, 128
+    z = torch.from_numpy(rng.normal(size=(B, d, T, 1)).astype(np.float32))
+    W = torch.from_numpy(rng.normal(0, 0.125, size=(k, d)).astype(np.float32))
+    gy = torch.from_numpy(rng.normal(size=(B, d, T, 1)).astype(np.float32))
+    zo = z.clone().requires_grad_(True)
+    Wo = W.clone().requires_grad_(True)
+    O.straight_through(zo, Wo).backward(gy)
+    zg = z.to(DEV).requires_grad_(True)
+    Wg = W.to(DEV).requires_grad_(True)
+    V.straight_through(zg, Wg).backward(gy.to(DEV))
+    assert torch.equal(zg.grad.cpu(), gy), "gx must equal gy bitwise (utils.py:218-219)"
+    assert torch.equal(Wg.grad.cpu(), Wo.grad), "float64-accumulated gW must match exactly"
+
+
+# ---------------------------------------------------------------- generic conv -------
+@pytest.mark.parametrize("cin,cout,k,stride,pad,dil,T,relu,relu_in", [
+    (1, 64, 4, 2, 1, 1, 1025, True, False),     # Encoder conv1 (net.py:12)
+    (64, 64, 4, 2, 1, 1, 512, False, False),    # Encoder conv6
+    (64, 64, 3, 1, 4, 4, 16, True, False),      # ConditionEmbed local_embed3 (net.py:38-39)
+    (64, 64, 3, 1, 16, 16, 16, True, False),    # dilation wider than the signal
+    (32, 256, 1, 1, 0, 1, 300, False, True),    # proj (modules.py:158-159)
+    (256, 32, 2, 1, 1, 1, 77, False, False),    # embed (modules.py:127-128)
+    (5, 3, 3, 2, 2, 3, 41, True, True),         # ragged everything
+])
+def test_conv_forward_backward(cin, cout, k, stride, pad, dil, T, relu, relu_in):
+    rng = np.random.default_rng(cin * 7 + T)
+    B = 3
+    x = torch.from_numpy(rng.normal(size=(B, cin, T, 1)).astype(np.float32))
+    W = torch.from_numpy(rng.normal(0, 1 / np.sqrt(cin * k), size=(cout, cin, k, 1)).astype(np.float32))
+    b = torch.from_numpy(rng.normal(0, 0.1, size=(cout,)).astype(np.float32))
+    xo, Wo, bo = (t.double().clone().requires_grad_(True) for t in (x, W, b))
+    yo = O.conv2d(F.relu(xo) if relu_in else xo, Wo, bo, stride=stride, pad=pad, dilate=dil)
+    if relu:
+        yo = F.relu(yo)
+    gy = torch.from_numpy(rng.normal(size=tuple(yo.shape)).astype(np.float32))
+    yo.backward(gy.double())
+    xg, Wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, W, b))
+    yg = V.conv(xg, Wg, bg, stride, pad, dil, relu, None, relu_in)
+    assert tuple(yg.shape) == tuple(yo.shape)
+    yg.backward(gy.to(DEV))
+    assert rel_err(yg, yo) < 1e-5
+    assert rel_err(xg.grad, xo.grad) < 1e-5
+    assert rel_err(Wg.grad, Wo.grad) < 1e-4
+    assert rel_err(bg.grad, bo.grad) < 1e-4
+
+
+# ---------------------------------------------------------------- embed --------------
+def test_embed_gather_matches_one_hot_conv():
+    rng = np.random.default_rng(3)
+    B, T, Cr, Q = 3, 301, 32, 256
+    q = rng.integers(0, Q, size=(B, T)).astype(np.int32)
+    W = torch.from_numpy(rng.normal(0, 0.05, size=(Cr, Q, 2, 1)).astype(np.float32))
+    b = torch.from_numpy(rng.normal(0, 0.01, size=(Cr,)).astype(np.float32))
+    onehot = torch.from_numpy(np.identity(Q, dtype=np.float32)[q].transpose(0, 2, 1)[..., None].copy())
+    Wo, bo = W.double().clone().requires_grad_(True), b.double().clone().requires_grad_(True)
+    yo = O.conv2d(onehot.double(), Wo, bo, pad=1)[:, :, :T]                 # modules.py:151-152
+    gy = torch.from_numpy(rng.normal(size=tuple(yo.shape)).astype(np.float32))
+    yo.backward(gy.double())
+    Wg, bg = W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    yg = V.embed_gather(torch.from_numpy(q).to(DEV), Wg, bg)
+    yg.backward(gy.to(DEV))
+    assert rel_err(yg, yo) < 1e-6
+    assert rel_err(Wg.grad, Wo.grad) < 1e-5
+    assert rel_err(bg.grad, bo.grad) < 1e-5
+
+
+# ---------------------------------------------------------------- residual block -----
+def _block_params(rng, Cr, Cd, Cs, Cc, fs):
+    def w(*shape):
+        fan = int(np.prod(shape[1:]))
+        return torch.from_numpy(rng.normal(0, 1 / np.sqrt(fan), size=shape).astype(np.float32))
+
+    def bias(n):
+        return torch.from_numpy(rng.normal(0, 0.05, size=(n,)).astype(np.float32))
+    return {"conv/W": w(Cd, Cr, fs, 1), "conv/b": bias(Cd), "condition_proj/W": w(Cd, Cc, 1, 1),
+            "condition_proj/b": bias(Cd), "res/W": w(Cr, Cd // 2, 1, 1), "res/b": bias(Cr),
+            "skip/W": w(Cs, Cd // 2, 1, 1), "skip/b": bias(Cs)}
+
+
+ORDER = ["conv/W", "conv/b", "condition_proj/W", "condition_proj/b", "res/W", "res/b", "skip/W",
+         "skip/b"]
+
+
+@pytest.mark.parametrize("Cr,Cd,Cs,Cc,fs,dil,T", [
+    (32, 32, 32, 192, 3, 1, 1024),     # CPU config block (BASELINE.json configs[0])
+    (32, 32, 32, 192, 3, 8, 100),      # ragged T, dilation reaching past the start
+    (32, 32, 32, 192, 2, 4, 64),       # reference default filter_size (params.py:31)
+    (24, 40, 12, 10, 3, 2, 50),        # nothing a multiple of anything
+    (64, 128, 48, 192, 3, 16, 96),     # PPW=8
+    (128, 256, 64, 192, 3, 2, 64),     # PPW=16
+    (512, 512, 256, 192, 3, 4, 64),    # the B200 config's channel counts (fp32 mode)
+])
+def test_resblock_forward_backward_fp32(Cr, Cd, Cs, Cc, fs, dil, T):
+    rng = np.random.default_rng(Cr + T)
+    B = 2
+    p = _block_params(rng, Cr, Cd, Cs, Cc, fs)
+    x = torch.from_numpy(rng.normal(size=(B, Cr, T, 1)).astype(np.float32))
+    c = torch.from_numpy(rng.normal(size=(B, Cc, T, 1)).astype(np.float32))
+    po = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    xo, co = x.double().clone().requires_grad_(True), c.double().clone().requires_grad_(True)
+    ro, so = O.residual_block_forward(po, xo, co, fs, dil)
+    gr = torch.from_numpy(rng.normal(size=tuple(ro.shape)).astype(np.float32))
+    gs = torch.from_numpy(rng.normal(size=tuple(so.shape)).astype(np.float32))
+    (ro * gr.double()).sum().backward(retain_graph=True)
+    (so * gs.double()).sum().backward()
+
+    blk = V.ResidualBlock(fs, dil, Cr, Cd, Cs, Cc, 0).to(DEV)
+    with torch.no_grad():
+        for name, t in zip(ORDER, blk.weights()):
+            t.copy_(p[name])
+    xg, cg = x.to(DEV).requires_grad_(True), c.to(DEV).requires_grad_(True)
+    rg, sg = blk(xg, cg)
+    assert rel_err(rg, ro) < 1e-5 and rel_err(sg, so) < 1e-5
+    ((rg * gr.to(DEV)).sum() + (sg * gs.to(DEV)).sum()).backward()
+    assert rel_err(xg.grad, xo.grad) < 1e-4
+    assert rel_err(cg.grad, co.grad) < 1e-4
+    for name, t in zip(ORDER, blk.weights()):
+        assert rel_err(t.grad, po[name].grad) < 2e-4, name
+
+
+def test_resblock_rejects_bad_arguments():
+    blk = V.ResidualBlock(3, 1, 32, 32, 32, 16, 0).to(DEV)
+    x = torch.zeros(2, 32, 64, 1, device=DEV)
+    with pytest.raises(ValueError):
+        blk(x, torch.zeros(2, 16, 63, 1, device=DEV))           # length mismatch
+    with pytest.raises(V.VqwError):
+        blk(x.cpu(), torch.zeros(2, 16, 64, 1))                  # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        V.ResidualBlock(3, 1, 32, 32, 32, 16, 0.05)

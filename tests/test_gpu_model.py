@@ -1,0 +1,113 @@
+"""GPU parity of the whole path at the CPU-reference config (BASELINE.json configs[0]):
+VAE forward, the three-loss backward ordering, one optimiser step, the weight-EMA quirk."""
+import numpy as np
+import pytest
+import torch
+
+import chainer_vq_vae_b200 as V
+from oracle import vqvae_oracle as O
+from helpers import TOL, build_model, grads_by_name, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cpu_case():
+    cfg = O.config_cpu()
+    params = O.make_params(cfg)
+    inp = O.make_inputs(cfg)
+    args = [torch.from_numpy(inp[k]) for k in ("x_enc", "x_dec", "speaker", "t")]
+    losses, grads, inter = O.three_loss_grads(params, cfg, *args)
+    return cfg, params, inp, losses, grads, inter
+
+
+@pytest.mark.parametrize("indices", [False, True])
+def test_vae_forward_matches_oracle(cpu_case, indices):
+    cfg, params, inp, losses, grads, inter = cpu_case
+    model = build_model(cfg, params)
+    l1, l2, l3 = model(*to_dev(inp, cfg, indices=indices))
+    assert np.array_equal(model.vq.indexes.cpu().numpy(), inter["indexes"]), \
+        "VQ indices must be bit-identical to the reference formulation"
+    assert rel_err(model.y, inter["y"]) < TOL
+    for got, want in zip((l1, l2, l3), losses):
+        assert abs(float(got) - float(want)) <= TOL * abs(float(want))
+
+
+def test_three_loss_backward_ordering(cpu_case):
+    cfg, params, inp, losses, grads, inter = cpu_case
+    model = build_model(cfg, params)
+    opt = V.Adam(2e-4).setup(model)
+    upd = V.VQVAE_StandardUpdater(None, opt)
+    l1, l2, l3 = model(*to_dev(inp, cfg, indices=True))
+    upd.backward_three(model, l1, l2, l3)
+    got = grads_by_name(model)
+    assert set(got) == set(grads)
+    for name, g in grads.items():
+        assert rel_err(got[name], g) < TOL, name
+    # vq.W carries loss2's gradient only (updaters.py:16): (2/M)(n_k W_k - sum z)
+    z, idx, W = inter["z"].detach().numpy(), inter["indexes"], params["vq/W"].numpy()
+    M = z.size
+    want = np.zeros_like(W, dtype=np.float64)
+    cnt = np.bincount(idx.ravel(), minlength=cfg.k)
+    zs = np.zeros_like(want)
+    np.add.at(zs, idx.ravel(), np.transpose(z[..., 0], (0, 2, 1)).reshape(-1, cfg.d))
+    want = (2.0 / M) * (cnt[:, None] * W - zs)
+    assert rel_err(got["vq/W"], want) < 1e-4
+
+
+def test_adam_step_and_weight_ema(cpu_case):
+    cfg, params, inp, losses, grads, inter = cpu_case
+    decay = 0.9999
+    model = build_model(cfg, params, ema_decay=decay)
+    opt = V.Adam(2e-4).setup(model)
+
+    class It:
+        def next(self_inner):
+            return None
+    upd = V.VQVAE_StandardUpdater(It(), opt, converter=lambda b, d: to_dev(inp, cfg, indices=True))
+    model.train()
+    upd.update()
+    # oracle: EMA refresh happens inside the forward, BEFORE the optimiser step (utils.py:142-155)
+    dec = O.sub(params, "decoder/")
+    ema = {k: v.clone() for k, v in dec.items()}
+    O.weight_ema_update(dec, ema, decay)
+    new = {k: v.clone() for k, v in params.items()}
+    for k in new:
+        m, v = torch.zeros_like(new[k]), torch.zeros_like(new[k])
+        O.adam_step(new[k], grads[k], m, v, 1, 2e-4)
+    own = dict(model.named_parameters())
+    for k in new:
+        key = k.replace("/", ".")
+        if key.startswith("decoder."):
+            tkey = "decoder.target" + key[len("decoder"):]
+            ekey = "decoder.ema" + key[len("decoder"):]
+            assert rel_err(own[ekey], ema[k[len("decoder/"):]]) < 1e-6, ekey
+        else:
+            tkey = key
+        # Adam's first step moves every weight by ~alpha*sign(g): compare the step itself
+        step_got = own[tkey].detach().cpu() - params[k]
+        step_want = new[k] - params[k]
+        big = grads[k].abs() > 1e-3 * grads[k].abs().max()
+        assert (step_got[big] - step_want[big]).abs().max() <= 0.05 * 2e-4 + 1e-9, k
+    model.eval()
+    with torch.no_grad():
+        model(*to_dev(inp, cfg, indices=True))       # evaluation runs the EMA copy (utils.py:156-157)
+
+
+def test_causality(cpu_case):
+    cfg, params, inp, *_ = cpu_case
+    model = build_model(cfg, params)
+    dec = model.decoder
+    rng = np.random.default_rng(0)
+    B, T = 2, 256
+    q = torch.from_numpy(rng.integers(0, 256, size=(B, T)).astype(np.int32)).cuda()
+    c = torch.from_numpy(rng.normal(size=(B, cfg.condition_dim, T, 1)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        y0 = dec(q, c)
+        t0 = 100
+        q2, c2 = q.clone(), c.clone()
+        q2[:, t0:] = (q2[:, t0:] + 17) % 256
+        c2[:, :, t0:] += 1.0
+        y1 = dec(q2, c2)
+    assert torch.equal(y0[:, :, :t0], y1[:, :, :t0]), "outputs before t0 must be bit-unchanged"
+    assert not torch.equal(y0[:, :, t0:], y1[:, :, t0:])
