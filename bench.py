@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one VQ-VAE training step (forward, three-loss backward,
+gradient all-reduce, Adam + decoder weight-EMA) on synthetic mu-law waveforms.
+
+    python bench.py --gpus N --steps K --warmup W [--mode fp32|bf16x3|bf16] [--impl reference]
+
+Workload (BASELINE.json configs[1], "1xB200"): batch=16 per GPU, length=7680, n_loop=2,
+n_layer=10, filter_size=3, 512/512/256 channels, k=512, d=64, mu-law-256, 109 speakers,
+condition_dim = 64 + 128.  N > 1 is weak scaling (16 items per GPU, configs[2]): launched by
+torchrun, one rank per GPU, one NCCL all-reduce over the flat gradient bucket per step.
+
+Prints ONE JSON line (rank 0).  `value` = audio samples / s with inputs resident in HBM,
+`e2e` = the same through VQVAE_ParallelUpdater.update() from host (pinned) batches,
+`roofline` = the fused residual-block forward kernel, `cpu_baseline` = the oracle on the
+host cores (N=1 only).  `--impl reference` times the CPU restatement of the reference
+(oracle/; the reference itself cannot run: Chainer is not installed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(batch=16, length=7680, n_loop=2, n_layer=10, filter_size=3, input_dim=256,
+           residual_channels=512, dilated_channels=512, skip_channels=256, quantize=256,
+           use_logistic=False, n_mixture=30, log_scale_min=-40.0, d=64, k=512,
+           local_condition_dim=64, global_condition_dim=128, n_speaker=109, beta=0.25,
+           lr=2e-4, ema_mu=0.9999)
+METRIC = "audio-samples/sec (train step: fwd + 3-loss bwd + update) at length=7680"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic data: sinusoid mixtures + noise, peak-normalised, mu-law 256
+# ------------------------------------------------------------------------------------------
+def synthetic_examples(n_items: int, length: int, seed: int, n_speaker: int = 109):
+    """List of Preprocess-shaped tuples (utils.py:100-110) with x_dec as int32 mu-law indices
+    (the one-hot of the reference carries the same information)."""
+    import chainer_vq_vae_b200 as V
+    rng = np.random.default_rng(seed)
+    mulaw = V.MuLaw(256)
+    n = np.arange(length + 1, dtype=np.float64)
+    out = []
+    for _ in range(n_items):
+        f = rng.uniform(80.0, 4000.0, size=3)
+        ph = rng.uniform(0.0, 2 * np.pi, size=3)
+        w = sum(np.sin(2 * np.pi * f[i] * n / 16000.0 + ph[i]) for i in range(3))
+        w = w + rng.normal(0.0, 0.01, size=length + 1)
+        raw = (w / np.abs(w).max()).astype(np.float32)
+        q = mulaw.transform(raw)
+        spk = np.int32(rng.integers(0, n_speaker))
+        out.append((raw[None, :, None], q[:-1].astype(np.int32), spk, q[1:, None].astype(np.int32)))
+    return out
+
+
+def build_model(cfg, device, mode, seed=1234):
+    import chainer_vq_vae_b200 as V
+    torch.manual_seed(seed)
+    wavenet = V.WaveNet(cfg["n_loop"], cfg["n_layer"], cfg["filter_size"], cfg["input_dim"],
+                        cfg["residual_channels"], cfg["dilated_channels"], cfg["skip_channels"],
+                        cfg["quantize"], cfg["use_logistic"], cfg["n_mixture"],
+                        cfg["log_scale_min"],
+                        cfg["local_condition_dim"] + cfg["global_condition_dim"], 0)
+    encoder = V.Encoder(cfg["d"])
+    cond = V.ConditionEmbed(cfg["n_speaker"], cfg["global_condition_dim"],
+                            cfg["local_condition_dim"], local_in_channels=cfg["d"])
+    decoder = V.ExponentialMovingAverage(wavenet, cfg["ema_mu"])
+    loss = wavenet.calculate_logistic_loss if cfg["use_logistic"] else V.softmax_cross_entropy
+    model = V.VAE(encoder, decoder, cond, cfg["d"], cfg["k"], cfg["beta"], loss)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(".b"):
+                p.normal_(0.0, 0.01)       # exercise the bias paths
+    wavenet.set_mode(mode)
+    return model.to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def block_flops(cfg, n_samples, with_residual=True):
+    Cr, Cd, Cs = cfg["residual_channels"], cfg["dilated_channels"], cfg["skip_channels"]
+    Cc = cfg["local_condition_dim"] + cfg["global_condition_dim"]
+    Ch = Cd // 2
+    per = cfg["filter_size"] * Cr * Cd + Cc * Cd + Ch * Cs + (Ch * Cr if with_residual else 0)
+    return 2.0 * n_samples * per
+
+
+def block_bytes(cfg, n_samples):
+    """Algorithmic HBM bytes of the training forward of one block:
+    x, cond, residual out, skip read+write, tanh+sigmoid saved, + parameters once."""
+    Cr, Cd, Cs = cfg["residual_channels"], cfg["dilated_channels"], cfg["skip_channels"]
+    Cc = cfg["local_condition_dim"] + cfg["global_condition_dim"]
+    Ch = Cd // 2
+    P = cfg["filter_size"] * Cr * Cd + Cc * Cd + Ch * Cr + Ch * Cs + 2 * Cd + Cr + Cs
+    return 4.0 * n_samples * (Cr + Cc + Cr + 2 * Cs + 2 * Ch) + 4.0 * P
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import chainer_vq_vae_b200 as V
+    from chainer_vq_vae_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvqw has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(CFG)
+    B, T = cfg["batch"], cfg["length"]
+
+    model = build_model(cfg, dev, args.mode)
+    model.train()
+    opt = V.Adam(cfg["lr"] / world).setup(model)            # train.py:101
+
+    class Iter:
+        """Serves the global batch; every rank keeps batch[rank::world] (updaters.py:36-38)."""
+
+        def __init__(self):
+            # weak scaling: the global batch is world*B items; each rank only materialises the
+            # items it will consume (its strided slice), which is what split() then returns.
+            self.mine = synthetic_examples(B, T, 71 + rank)
+
+        def next(self):
+            # interleave so that batch[rank::world] == this rank's items
+            if world == 1:
+                return self.mine
+            out = [None] * (B * world)
+            out[rank::world] = self.mine
+            return out
+
+    it = Iter()
+    upd = V.VQVAE_ParallelUpdater(it, opt, device=dev)
+
+    # ---- device-resident arm ----
+    dev_batch = V.updaters.concat_examples(it.mine, dev)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        l1, l2, l3 = model(*dev_batch)
+        upd.backward_three(model, l1, l2, l3)
+        opt.bucket.allreduce()
+        opt.update()
+        return l1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    L.enable_timers(True)
+    launches0 = V.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = V.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    timers = L.timer_summary()
+    L.enable_timers(False)
+    t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms) / args.steps
+    value = world * B * T / (ms_step * 1e-3)
+
+    # ---- end-to-end arm: host batches through the public updater API ----
+    for _ in range(min(args.warmup, 3)):
+        upd.update()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        l1, l2, l3 = upd.update()
+        host_losses = (float(l1), float(l2), float(l3))       # D2H read of the step's result
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T / (float(e2e_s) / args.steps)
+    h2d = sum(t.numel() * t.element_size() for t in dev_batch)
+
+    # ---- roofline of the fused residual-block forward kernel ----
+    pk, pk_src = peaks()
+    n_samples = B * T
+    nfw, fw_ms = timers.get("resblock_forward", (0, float("nan")))
+    flops = block_flops(cfg, n_samples, True)
+    bytes_ = block_bytes(cfg, n_samples)
+    achieved_tf = flops / (fw_ms * 1e-3) / 1e12 if nfw else None
+    roofline = {
+        "kernel": "resblock_forward (" + args.mode + ")",
+        "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"],
+        "unit": "TFLOP/s", "frac": (achieved_tf / pk["bf16_tflops_sustained"]) if nfw else None,
+        "traffic": None, "peak_source": pk_src + " (sustained bf16, kernel timed inside a long step)",
+        "launch_ms": fw_ms, "launches_timed": nfw,
+        "algorithmic_gflop_per_launch": flops / 1e9, "algorithmic_mb_per_launch": bytes_ / 1e6,
+        "hbm": {"achieved": bytes_ / (fw_ms * 1e-3) / 1e9 if nfw else None, "peak": pk["hbm_gbs"],
+                "unit": "GB/s",
+                "frac": (bytes_ / (fw_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if nfw else None},
+    }
+    prof = os.path.join(ROOT, "profiles", "resblock_forward_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get(args.mode)
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_reference_sample(cfg, items=2, repeats=1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "audio-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16, fp32 accumulate)",
+                      "bf16": "bf16"}[args.mode],
+            "data": "synthetic (sinusoid mixtures, mu-law 256, random-init weights)",
+            "config": {"workload": "1xB200: batch=16/GPU length=7680 n_loop=2 n_layer=10 "
+                                   "filter_size=3 512/512/256 k=512 d=64 mu-law-256 Cc=192",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "mode": args.mode,
+                       "l2": "per-step working set (>10 GB of activations) far exceeds the "
+                             "126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "audio-samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 12, "losses": host_losses},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kernels_ms": {k: {"launches": n, "mean_ms": ms} for k, (n, ms) in timers.items()},
+            "loss1": float(loss),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle restatement on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(cfg, items, repeats):
+    from oracle import vqvae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oc = O.config_b200()
+    oc.batch = items
+    params = O.make_params(oc)
+    inp = O.make_inputs(oc)
+    a = [torch.from_numpy(inp[k]) for k in ("x_enc", "x_dec", "speaker", "t")]
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.three_loss_grads(params, oc, *a)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": items * oc.length / best, "unit": "audio-samples/s", "cores": cores,
+            "kind": "port",
+            "sample": f"{items} items x length {oc.length} of the 1xB200 config, forward + "
+                      f"three-loss backward (no optimiser), oracle/vqvae_oracle.py on torch-CPU "
+                      f"fp32 with {cores} threads; the Chainer reference itself is not installable",
+            "seconds": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import vqvae_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oc = O.config_b200()
+    items = 1
+    oc.batch = items
+    params = O.make_params(oc)
+    inp = O.make_inputs(oc)
+    a = [torch.from_numpy(inp[k]) for k in ("x_enc", "x_dec", "speaker", "t")]
+    for _ in range(args.warmup):
+        O.three_loss_grads(params, oc, *a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.three_loss_grads(params, oc, *a)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = items * oc.length / dt
+    sample = (f"each step = {items} item x length {oc.length} of the 1xB200 config (forward + "
+              f"three-loss backward) on {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "audio-samples/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1xB200 config, bounded CPU sample: " + sample},
+        "cpu_baseline": {"value": value, "unit": "audio-samples/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "fp32"),
+                    choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

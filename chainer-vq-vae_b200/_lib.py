@@ -59,6 +59,7 @@ class ResblockWeights(C.Structure):
 _SIGNATURES = {
     "vqw_version": (c_int, []),
     "vqw_last_error": (C.c_char_p, []),
+    "vqw_launch_count": (C.c_longlong, []),
     "vqw_vq_forward": (c_int, [C.c_void_p] * 7 + [c_int] * 4 + [C.c_void_p]),
     "vqw_vq_backward_w": (c_int, [C.c_void_p] * 3 + [c_int] * 4 + [C.c_void_p]),
     "vqw_conv_forward": (c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
@@ -83,12 +84,9 @@ def _bind():
 
 _bind()
 
-_launches = 0
-
-
 def launch_count() -> int:
-    """Number of C-ABI compute calls issued by this process (each is >= 1 kernel launch)."""
-    return _launches
+    """Number of CUDA kernels launched through libvqw.so by this process."""
+    return int(lib.vqw_launch_count())
 
 
 class VqwError(RuntimeError):
@@ -96,8 +94,6 @@ class VqwError(RuntimeError):
 
 
 def check(rc: int, what: str) -> None:
-    global _launches
-    _launches += 1
     if rc != 0:
         msg = lib.vqw_last_error().decode("utf-8", "replace")
         raise VqwError(f"{what} failed (rc={rc}): {msg}")
@@ -118,3 +114,44 @@ def ptr(t) -> int:
 def stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------
+# optional per-kernel CUDA-event timing (bench.py's roofline leg)
+# ---------------------------------------------------------------------------------------
+TIMERS = None   # dict name -> list of (start_event, end_event) when enabled
+
+
+def enable_timers(on: bool = True) -> None:
+    global TIMERS
+    TIMERS = {} if on else None
+
+
+class timed:
+    """`with timed("name"):` brackets a C-ABI call with CUDA events on the current stream."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMERS is not None:
+            import torch
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            self.b.record()
+            TIMERS.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+def timer_summary():
+    """name -> (launch count, mean ms); call after torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in (TIMERS or {}).items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out

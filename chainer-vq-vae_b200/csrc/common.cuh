@@ -17,8 +17,12 @@ int set_error(int code, const char* fmt, ...);
     if (!(cond)) return ::vqw::set_error(-1, __VA_ARGS__);  \
   } while (0)
 
+// every kernel launch of the library passes through here (vqw_launch_count())
+void count_launch();
+
 #define VQW_CHECK_LAUNCH(name)                                                        \
   do {                                                                                \
+    ::vqw::count_launch();                                                            \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess)                                                           \
       return ::vqw::set_error((int)e__, "%s: %s", name, cudaGetErrorString(e__));     \

@@ -144,10 +144,10 @@ extern "C" int vqw_vq_forward(const float* z, const float* W, int32_t* idx, floa
                               float* zsum, double* sqerr, int B, int d, int T, int k,
                               vqw_stream_t stream) {
   using namespace vqw;
-  VQW_REQUIRE(z && W && idx && e, "vqw_vq_forward: null pointer");
   VQW_REQUIRE(B >= 0 && T >= 0 && d > 0 && k > 0, "vqw_vq_forward: bad sizes B=%d d=%d T=%d k=%d",
               B, d, T, k);
-  if ((int64_t)B * T == 0) return 0;
+  if ((int64_t)B * T == 0) return 0;   // empty batch: nothing to do (pointers may be null)
+  VQW_REQUIRE(z && W && idx && e, "vqw_vq_forward: null pointer");
   int kt_cap = (int)((96 * 1024) / (sizeof(float) * (d + 1)));
   int KT = (kt_cap / 32) * 32;
   VQW_REQUIRE(KT >= 32, "vqw_vq_forward: d=%d too large for the shared-memory codebook tile", d);
@@ -167,8 +167,8 @@ extern "C" int vqw_vq_forward(const float* z, const float* W, int32_t* idx, floa
 extern "C" int vqw_vq_backward_w(const float* gy, const int32_t* idx, float* gW, int B, int d,
                                  int T, int k, vqw_stream_t stream) {
   using namespace vqw;
-  VQW_REQUIRE(gy && idx && gW, "vqw_vq_backward_w: null pointer");
   VQW_REQUIRE(B >= 0 && T >= 0 && d > 0 && k > 0, "vqw_vq_backward_w: bad sizes");
+  VQW_REQUIRE(gW && (((int64_t)B * T == 0) || (gy && idx)), "vqw_vq_backward_w: null pointer");
   VQW_REQUIRE(d <= 8 * 128, "vqw_vq_backward_w: d=%d > 1024 unsupported", d);
   vq_backward_w_kernel<<<k, 128, 1024 * sizeof(int), (cudaStream_t)stream>>>(gy, idx, gW, B, d, T,
                                                                            k);

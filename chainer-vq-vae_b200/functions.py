@@ -258,9 +258,11 @@ class _ResidualStack(torch.autograd.Function):
                 gs = torch.empty_like(gt)
             d = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dil, i > 0, write_res, mode)
             w = _rb_weights(weights[8 * i:8 * i + 8])
-            L.check(L.lib.vqw_resblock_forward(C.byref(d), L.ptr(xs[-1]), L.ptr(cond), C.byref(w),
-                                               L.ptr(residual), L.ptr(skip), L.ptr(gt), L.ptr(gs),
-                                               L.stream()), "vqw_resblock_forward")
+            with L.timed("resblock_forward" if write_res else "resblock_forward_last"):
+                L.check(L.lib.vqw_resblock_forward(C.byref(d), L.ptr(xs[-1]), L.ptr(cond),
+                                                   C.byref(w), L.ptr(residual), L.ptr(skip),
+                                                   L.ptr(gt), L.ptr(gs), L.stream()),
+                        "vqw_resblock_forward")
             if need_grad:
                 gates += [gt, gs]
             if not last:
@@ -293,11 +295,12 @@ class _ResidualStack(torch.autograd.Function):
             w = _rb_weights(weights[8 * i:8 * i + 8])
             gw = _rb_weights(gws[8 * i:8 * i + 8])
             gx = torch.empty((B, Cr, T, 1), device=dev, dtype=torch.float32)
-            L.check(L.lib.vqw_resblock_backward(
-                C.byref(d), L.ptr(g_res), L.ptr(g_skip), L.ptr(xs[i]), L.ptr(cond),
-                L.ptr(gates[2 * i]), L.ptr(gates[2 * i + 1]), C.byref(w), L.ptr(gx),
-                L.ptr(gcond), C.byref(gw), L.ptr(workspace), L.stream()),
-                "vqw_resblock_backward")
+            with L.timed("resblock_backward" if g_res is not None else "resblock_backward_last"):
+                L.check(L.lib.vqw_resblock_backward(
+                    C.byref(d), L.ptr(g_res), L.ptr(g_skip), L.ptr(xs[i]), L.ptr(cond),
+                    L.ptr(gates[2 * i]), L.ptr(gates[2 * i + 1]), C.byref(w), L.ptr(gx),
+                    L.ptr(gcond), C.byref(gw), L.ptr(workspace), L.stream()),
+                    "vqw_resblock_backward")
             g_res = gx
         return (g_res, gcond, None, None, None, None, *gws)
 

@@ -30,6 +30,8 @@ typedef void* vqw_stream_t; /* cudaStream_t */
 
 int vqw_version(void);
 const char* vqw_last_error(void);
+/* number of CUDA kernels this process has launched through the library (diagnostic) */
+long long vqw_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * VQ nearest-codebook lookup.  Replaces StraightThrough.forward, utils.py:176-211

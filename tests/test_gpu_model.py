@@ -88,6 +88,8 @@ def test_adam_step_and_weight_ema(cpu_case):
         step_got = own[tkey].detach().cpu() - params[k]
         step_want = new[k] - params[k]
         big = grads[k].abs() > 1e-3 * grads[k].abs().max()
+        if not bool(big.any()):
+            continue
         assert (step_got[big] - step_want[big]).abs().max() <= 0.05 * 2e-4 + 1e-9, k
     model.eval()
     with torch.no_grad():
