@@ -267,7 +267,11 @@ def run_ours(args):
     # ---- roofline of the fused residual-block forward kernel ----
     pk, pk_src = peaks()
     n_samples = B * T
-    nfw, fw_ms = timers.get("resblock_forward", (0, float("nan")))
+    # one vqw_resnet_forward call = n_blocks fused block kernels (+ operand packing in the
+    # tensor-core modes); the per-launch figure is its duration / n_blocks (conservative).
+    n_blocks = cfg["n_loop"] * cfg["n_layer"]
+    ncalls, call_ms = timers.get("resnet_forward", (0, float("nan")))
+    nfw, fw_ms = ncalls * n_blocks, call_ms / n_blocks
     flops = block_flops(cfg, n_samples, True)
     bytes_ = block_bytes(cfg, n_samples)
     achieved_tf = flops / (fw_ms * 1e-3) / 1e12 if nfw else None

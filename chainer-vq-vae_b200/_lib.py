@@ -56,6 +56,12 @@ class ResblockWeights(C.Structure):
                                           "res_b", "skip_w", "skip_b")]
 
 
+class ResnetDesc(C.Structure):
+    _fields_ = [("B", c_int), ("T", c_int), ("Cr", c_int), ("Cd", c_int), ("Cs", c_int),
+                ("Cc", c_int), ("fs", c_int), ("n_blocks", c_int),
+                ("dilations", C.POINTER(c_int)), ("mode", c_int), ("keep_last_residual", c_int)]
+
+
 _SIGNATURES = {
     "vqw_version": (c_int, []),
     "vqw_last_error": (C.c_char_p, []),
@@ -70,6 +76,11 @@ _SIGNATURES = {
     "vqw_resblock_backward": (c_int, [C.POINTER(ResblockDesc)] + [C.c_void_p] * 6 +
                               [C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p,
                                C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p]),
+    "vqw_resnet_forward_workspace": (C.c_int64, [C.POINTER(ResnetDesc)]),
+    "vqw_resnet_forward": (c_int, [C.POINTER(ResnetDesc), C.c_void_p, C.c_void_p,
+                                   C.POINTER(ResblockWeights), C.POINTER(C.c_void_p), C.c_void_p,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                   C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
 }

@@ -50,9 +50,12 @@ __device__ __forceinline__ float tanhf_(float v) {
 // conv.cu
 int launch_conv(const vqw_conv_desc& d, float* out, cudaStream_t stream);
 int launch_wgrad(const vqw_wgrad_desc& d, float* gw, float* gb, cudaStream_t stream);
-// resblock_tc.cu (tcgen05 path); returns -2 when the shape is not supported by that path
-int resblock_forward_tc(const vqw_resblock_desc& d, const float* x, const float* cond,
-                        const vqw_resblock_weights& w, float* residual, float* skip,
-                        float* gate_tanh, float* gate_sig, cudaStream_t stream);
+// resblock_tc.cu (tcgen05 path)
+bool resnet_tc_supported(const vqw_resnet_desc& d);
+int64_t resnet_tc_workspace(const vqw_resnet_desc& d);
+int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* cond,
+                      const vqw_resblock_weights* weights, float* const* residuals, float* skip,
+                      float* const* gate_tanh, float* const* gate_sig, void* workspace,
+                      cudaStream_t stream);
 
 }  // namespace vqw

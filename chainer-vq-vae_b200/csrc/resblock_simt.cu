@@ -218,9 +218,9 @@ extern "C" int vqw_resblock_forward(const vqw_resblock_desc* desc, const float* 
                   w->skip_w && w->skip_b, "vqw_resblock_forward: null weight");
   if (d.B == 0 || d.T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16)
-    return resblock_forward_tc(d, x, cond, *w, residual, skip, gate_tanh, gate_sig, st);
-  VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resblock_forward: unknown mode %d", d.mode);
+  VQW_REQUIRE(d.mode == VQW_MODE_FP32,
+              "vqw_resblock_forward: only VQW_MODE_FP32 here; the tensor-core modes run through "
+              "vqw_resnet_forward (mode %d)", d.mode);
   int Ch = d.Cd / 2;
   VQW_REQUIRE(Ch <= 256, "vqw_resblock_forward: fp32 path supports dilated_channels <= 512");
   if (Ch <= 32) return launch_fwd<4>(d, x, cond, *w, residual, skip, gate_tanh, gate_sig, st);
@@ -320,5 +320,65 @@ extern "C" int vqw_resblock_backward(const vqw_resblock_desc* desc, const float*
       if (int rc = launch_wgrad(g, gw->skip_w, gw->skip_b, st)) return rc;
     }
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// whole stack (modules.py:89-96)
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc) {
+  if (!desc) return -1;
+  if (desc->mode == VQW_MODE_FP32)
+    return 2 * (int64_t)sizeof(float) * desc->B * desc->Cr * desc->T + 512;
+  return vqw::resnet_tc_workspace(*desc);
+}
+
+extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, const float* cond,
+                                  const vqw_resblock_weights* weights, float* const* residuals,
+                                  float* skip, float* const* gate_tanh, float* const* gate_sig,
+                                  void* workspace, vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(desc && weights, "vqw_resnet_forward: null descriptor");
+  const vqw_resnet_desc& d = *desc;
+  VQW_REQUIRE(d.n_blocks >= 1 && d.dilations, "vqw_resnet_forward: n_blocks/dilations");
+  VQW_REQUIRE(d.B >= 0 && d.T >= 0, "vqw_resnet_forward: bad B/T");
+  if (d.B == 0 || d.T == 0) return 0;
+  VQW_REQUIRE(x && cond && skip, "vqw_resnet_forward: null tensor");
+  VQW_REQUIRE((gate_tanh == nullptr) == (gate_sig == nullptr),
+              "vqw_resnet_forward: gate_tanh and gate_sig must be given together");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16)
+    return resnet_forward_tc(d, x, cond, weights, residuals, skip, gate_tanh, gate_sig, workspace,
+                             st);
+  VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_forward: unknown mode %d", d.mode);
+  float* pp[2] = {nullptr, nullptr};
+  if (workspace) {
+    uintptr_t a = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+    pp[0] = reinterpret_cast<float*>(a);
+    pp[1] = pp[0] + (int64_t)d.B * d.Cr * d.T;
+  }
+  const float* cur = x;
+  for (int i = 0; i < d.n_blocks; ++i) {
+    const bool last = i == d.n_blocks - 1;
+    vqw_resblock_desc b = {};
+    b.B = d.B; b.T = d.T; b.Cr = d.Cr; b.Cd = d.Cd; b.Cs = d.Cs; b.Cc = d.Cc; b.fs = d.fs;
+    b.dilation = d.dilations[i];
+    b.skip_accumulate = i > 0;
+    b.write_residual = (!last || d.keep_last_residual) ? 1 : 0;
+    b.mode = VQW_MODE_FP32;
+    float* out = nullptr;
+    if (b.write_residual) {
+      out = residuals ? residuals[i] : nullptr;
+      if (!out) out = pp[i & 1];
+      VQW_REQUIRE(out != nullptr, "vqw_resnet_forward: no buffer for the residual of block %d "
+                                  "(pass residuals[] or a workspace)", i);
+    }
+    if (int rc = vqw_resblock_forward(&b, cur, cond, &weights[i], out, skip,
+                                      gate_tanh ? gate_tanh[i] : nullptr,
+                                      gate_sig ? gate_sig[i] : nullptr, stream))
+      return rc;
+    cur = out;
+  }
+  (void)st;
   return 0;
 }

@@ -244,31 +244,51 @@ class _ResidualStack(torch.autograd.Function):
         Cs = weights[6].shape[0]
         skip = torch.empty((B, Cs, T, 1), device=x.device, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad)
-        xs: List[torch.Tensor] = [x]
+        tc_mode = mode != L.MODE_FP32
+
+        def new(ch):
+            return torch.empty((B, ch, T, 1), device=x.device, dtype=torch.float32)
+
+        # residual[i] = output of block i = saved input of block i+1.  Training keeps all of
+        # them; inference only needs two ping-pong buffers (the tensor-core modes read the
+        # previous one as the exact fp32 residual-add operand).
+        if need_grad:
+            res = [new(Cr) for _ in range(n - 1)] + [new(Cr) if keep_last_residual else None]
+        else:
+            pp = [new(Cr), new(Cr)] if (tc_mode and n > 1) else [None, None]
+            res = [pp[i & 1] for i in range(n - 1)] + [new(Cr) if keep_last_residual else None]
         gates: List[torch.Tensor] = []
-        residual = None
-        for i, dil in enumerate(dilations):
-            last = i == n - 1
-            write_res = (not last) or keep_last_residual
-            residual = (torch.empty((B, Cr, T, 1), device=x.device, dtype=torch.float32)
-                        if write_res else None)
-            gt = gs = None
-            if need_grad:
-                gt = torch.empty((B, Cd // 2, T, 1), device=x.device, dtype=torch.float32)
-                gs = torch.empty_like(gt)
-            d = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dil, i > 0, write_res, mode)
-            w = _rb_weights(weights[8 * i:8 * i + 8])
-            with L.timed("resblock_forward" if write_res else "resblock_forward_last"):
-                L.check(L.lib.vqw_resblock_forward(C.byref(d), L.ptr(xs[-1]), L.ptr(cond),
-                                                   C.byref(w), L.ptr(residual), L.ptr(skip),
-                                                   L.ptr(gt), L.ptr(gs), L.stream()),
-                        "vqw_resblock_forward")
-            if need_grad:
-                gates += [gt, gs]
-            if not last:
-                xs.append(residual)
+        if need_grad:
+            for _ in range(n):
+                gates += [new(Cd // 2), new(Cd // 2)]
+
+        d = L.ResnetDesc()
+        d.B, d.T, d.Cr, d.Cd, d.Cs, d.Cc, d.fs = B, T, Cr, Cd, Cs, Cc, fs
+        d.n_blocks = n
+        dil_arr = (C.c_int * n)(*dilations)
+        d.dilations = C.cast(dil_arr, C.POINTER(C.c_int))
+        d.mode, d.keep_last_residual = mode, int(keep_last_residual)
+        warr = (L.ResblockWeights * n)()
+        for i in range(n):
+            for name, t in zip(("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b",
+                                "skip_w", "skip_b"), weights[8 * i:8 * i + 8]):
+                setattr(warr[i], name, L.ptr(t))
+        rarr = (C.c_void_p * n)(*[L.ptr(r) for r in res])
+        garr_t = garr_s = None
+        if need_grad:
+            garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
+            garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
+        ws_bytes = L.lib.vqw_resnet_forward_workspace(C.byref(d))
+        workspace = torch.empty(max(int(ws_bytes), 1), device=x.device, dtype=torch.uint8)
+        with L.timed("resnet_forward"):
+            L.check(L.lib.vqw_resnet_forward(C.byref(d), L.ptr(x), L.ptr(cond), warr, rarr,
+                                             L.ptr(skip), garr_t, garr_s, L.ptr(workspace),
+                                             L.stream()), "vqw_resnet_forward")
+        xs: List[torch.Tensor] = [x] + [r for r in res[:n - 1]]
+        residual = res[n - 1]
         ctx.cfg = (tuple(dilations), fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last_residual)
-        ctx.save_for_backward(cond, *xs, *gates, *weights)
+        if need_grad:
+            ctx.save_for_backward(cond, *xs, *gates, *weights)
         if keep_last_residual:
             return skip, residual
         return skip

@@ -159,6 +159,32 @@ int vqw_resblock_backward(const vqw_resblock_desc* desc, const float* g_res, con
                           vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * The whole residual stack.  Replaces ResidualNet.__call__, modules.py:89-96: n_blocks fused
+ * block kernels chained on the device, skip summed in place.  This is the entry point the
+ * tensor-core modes need: between blocks the activations stay in the packed bf16 hi/lo
+ * (B,T,C) layout the MMA consumes, and each block's weights are packed once per call.
+ *
+ * Host arrays (length n_blocks): dilations, weights (structs of device pointers),
+ * residuals[i] = (B,Cr,T) fp32 output of block i (the saved input of block i+1; required in
+ * the tensor-core modes for i < n_blocks-1, optional -- ping-pong in the workspace -- in fp32
+ * mode; the last entry is only written when keep_last_residual), gate_tanh[i] / gate_sig[i] =
+ * (B,Cd/2,T) fp32 saved gate factors (arrays may be NULL for inference).
+ */
+typedef struct {
+  int B, T, Cr, Cd, Cs, Cc, fs;
+  int n_blocks;
+  const int* dilations;
+  int mode;
+  int keep_last_residual;
+} vqw_resnet_desc;
+
+int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc);
+int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, const float* cond,
+                       const vqw_resblock_weights* weights, float* const* residuals, float* skip,
+                       float* const* gate_tanh, float* const* gate_sig, void* workspace,
+                       vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot
  * tensor, modules.py:151-152: out[b,c,t] = b[c] + W[c,q[t-1],0] + W[c,q[t],1] (t-1<0 dropped).
  *   q (B,T) i32 in [0,Q), W (Cr,Q,2), bias (Cr) -> out (B,Cr,T). */

@@ -1,0 +1,99 @@
+"""tcgen05 residual stack (VQW_MODE_BF16X3 / BF16) against the oracle at the B200 config's
+channel counts (512/512/256, Cc=192, filter_size=3)."""
+import numpy as np
+import pytest
+import torch
+
+import chainer_vq_vae_b200 as V
+from chainer_vq_vae_b200 import _lib as L
+from oracle import vqvae_oracle as O
+from helpers import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+ORDER = ["conv/W", "conv/b", "condition_proj/W", "condition_proj/b", "res/W", "res/b", "skip/W",
+         "skip/b"]
+
+
+def _stack_case(dilations, B, T, fs=3, Cr=512, Cd=512, Cs=256, Cc=192, seed=0):
+    cfg = O.Config(batch=B, length=T, n_loop=1, n_layer=len(dilations), filter_size=fs,
+                   residual_channels=Cr, dilated_channels=Cd, skip_channels=Cs,
+                   local_condition_dim=Cc - 128, global_condition_dim=128)
+    rng = np.random.default_rng(seed)
+    p = {}
+    for i in range(len(dilations)):
+        for name, shape in (("conv/W", (Cd, Cr, fs, 1)), ("condition_proj/W", (Cd, Cc, 1, 1)),
+                            ("res/W", (Cr, Cd // 2, 1, 1)), ("skip/W", (Cs, Cd // 2, 1, 1))):
+            fan = int(np.prod(shape[1:]))
+            p[f"resnet/{i}/{name}"] = torch.from_numpy(
+                rng.normal(0, 1 / np.sqrt(fan), size=shape).astype(np.float32))
+        for name, n in (("conv/b", Cd), ("condition_proj/b", Cd), ("res/b", Cr), ("skip/b", Cs)):
+            p[f"resnet/{i}/{name}"] = torch.from_numpy(rng.normal(0, 0.05, size=(n,)).astype(np.float32))
+    x = torch.from_numpy(rng.normal(size=(B, Cr, T, 1)).astype(np.float32))
+    c = torch.from_numpy(rng.normal(size=(B, Cc, T, 1)).astype(np.float32))
+    return cfg, p, x, c
+
+
+def _oracle_stack(cfg, p, x, c, dilations):
+    p64 = {k: v.double() for k, v in p.items()}
+    cfg.n_loop, cfg.n_layer = 1, len(dilations)
+    coll = []
+    xx, skip = x.double(), None
+    for i, dil in enumerate(dilations):
+        xx, s = O.residual_block_forward(O.sub(p64, f"resnet/{i}/"), xx, c.double(),
+                                         cfg.filter_size, dil)
+        coll.append(xx)
+        skip = s if skip is None else skip + s
+    return skip, coll
+
+
+def _run(mode, dilations, B, T, keep_last=False):
+    cfg, p, x, c = _stack_case(dilations, B, T)
+    skip_o, coll = _oracle_stack(cfg, p, x, c, dilations)
+    weights = []
+    for i in range(len(dilations)):
+        weights += [p[f"resnet/{i}/{n}"].to(DEV) for n in ORDER]
+    with torch.no_grad():
+        out = V.residual_stack(x.to(DEV), c.to(DEV), dilations, cfg.filter_size, weights,
+                               L.MODES[mode], keep_last_residual=keep_last)
+    torch.cuda.synchronize()
+    return out, skip_o, coll
+
+
+@pytest.mark.parametrize("dilations,B,T", [([1], 1, 128), ([1, 2, 4], 2, 256), ([64, 128, 512], 1, 384),
+                                           ([2, 1], 2, 200)])
+def test_tc_bf16x3_matches_oracle(dilations, B, T):
+    (skip, res), skip_o, coll = _run("bf16x3", dilations, B, T, keep_last=True)
+    e_skip, e_res = rel_err(skip, skip_o), rel_err(res, coll[-1])
+    print(f"bf16x3 dil={dilations} skip err {e_skip:.2e} residual err {e_res:.2e}")
+    assert e_skip < 1e-4 and e_res < 1e-4          # well inside the 1e-3 parity bar
+
+
+def test_tc_bf16_throughput_mode_is_close():
+    skip, skip_o, coll = _run("bf16", [1, 2, 4], 2, 256)
+    e = rel_err(skip, skip_o)
+    print(f"bf16 skip err {e:.2e}")
+    assert e < 3e-2                                   # single bf16 pass: not a parity mode
+
+
+def test_tc_matches_fp32_path_with_saved_gates():
+    dil = [1, 2]
+    cfg, p, x, c = _stack_case(dil, 2, 256, seed=3)
+    outs = {}
+    for mode in ("fp32", "bf16x3"):
+        weights = []
+        for i in range(len(dil)):
+            weights += [p[f"resnet/{i}/{n}"].to(DEV).requires_grad_(True) for n in ORDER]
+        xg = x.to(DEV).requires_grad_(True)
+        skip = V.residual_stack(xg, c.to(DEV), dil, cfg.filter_size, weights, L.MODES[mode])
+        skip.sum().backward()
+        outs[mode] = (skip.detach(), xg.grad.detach(), weights[0].grad.detach())
+    for a, b in zip(outs["bf16x3"], outs["fp32"]):
+        assert rel_err(a, b) < 1e-4
+
+
+def test_tc_rejects_unsupported_shapes():
+    cfg, p, x, c = _stack_case([1], 1, 128, Cr=32, Cd=32, Cs=32, Cc=192)
+    weights = [p[f"resnet/0/{n}"].to(DEV) for n in ORDER]
+    with pytest.raises(V.VqwError):
+        V.residual_stack(x.to(DEV), c.to(DEV), [1], 3, weights, L.MODES["bf16x3"])
