@@ -81,6 +81,11 @@ _SIGNATURES = {
                                    C.POINTER(ResblockWeights), C.POINTER(C.c_void_p), C.c_void_p,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
                                    C.c_void_p]),
+    "vqw_resnet_backward_workspace": (C.c_int64, [C.POINTER(ResnetDesc)]),
+    "vqw_resnet_backward": (c_int, [C.POINTER(ResnetDesc)] + [C.c_void_p] * 4 +
+                            [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(ResblockWeights), C.c_void_p,
+                                                           C.c_void_p, C.POINTER(ResblockWeights),
+                                                           C.c_void_p, C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
 }

@@ -1,5 +1,6 @@
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace vqw {
@@ -7,6 +8,11 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQW_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 char* error_buffer() { return g_err; }
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

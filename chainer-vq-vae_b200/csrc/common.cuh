@@ -19,11 +19,15 @@ int set_error(int code, const char* fmt, ...);
 
 // every kernel launch of the library passes through here (vqw_launch_count())
 void count_launch();
+// VQW_DEBUG_SYNC=1 in the environment: synchronise after every launch so a device fault is
+// attributed to the kernel that raised it
+bool debug_sync();
 
 #define VQW_CHECK_LAUNCH(name)                                                        \
   do {                                                                                \
     ::vqw::count_launch();                                                            \
     cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ == cudaSuccess && ::vqw::debug_sync()) e__ = cudaDeviceSynchronize();     \
     if (e__ != cudaSuccess)                                                           \
       return ::vqw::set_error((int)e__, "%s: %s", name, cudaGetErrorString(e__));     \
   } while (0)
@@ -57,5 +61,13 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
                       const vqw_resblock_weights* weights, float* const* residuals, float* skip,
                       float* const* gate_tanh, float* const* gate_sig, void* workspace,
                       cudaStream_t stream);
+
+// tc_gemm.cu (tcgen05 backward)
+int64_t resnet_backward_tc_workspace(const vqw_resnet_desc& d);
+int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const float* g_last_res,
+                       const float* x0, const float* cond, float* const* residuals,
+                       float* const* gate_tanh, float* const* gate_sig,
+                       const vqw_resblock_weights* weights, float* gx0, float* gcond,
+                       const vqw_resblock_wgrads* wgrads, void* workspace, cudaStream_t stream);
 
 }  // namespace vqw

@@ -382,3 +382,49 @@ extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, c
   (void)st;
   return 0;
 }
+
+extern "C" int64_t vqw_resnet_backward_workspace(const vqw_resnet_desc* desc) {
+  if (!desc) return -1;
+  if (desc->mode == VQW_MODE_FP32)
+    return (int64_t)sizeof(float) * desc->B * desc->T * ((int64_t)desc->Cd + 2 * desc->Cr) + 1024;
+  return vqw::resnet_backward_tc_workspace(*desc);
+}
+
+extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_skip,
+                                   const float* g_last_res, const float* x, const float* cond,
+                                   float* const* residuals, float* const* gate_tanh,
+                                   float* const* gate_sig, const vqw_resblock_weights* weights,
+                                   float* gx, float* gcond, const vqw_resblock_wgrads* wgrads,
+                                   void* workspace, vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(desc && weights && wgrads, "vqw_resnet_backward: null descriptor");
+  const vqw_resnet_desc& d = *desc;
+  VQW_REQUIRE(d.n_blocks >= 1 && d.dilations, "vqw_resnet_backward: n_blocks/dilations");
+  if (d.B == 0 || d.T == 0) return 0;
+  VQW_REQUIRE(g_skip && x && cond && gate_tanh && gate_sig && workspace && gcond,
+              "vqw_resnet_backward: null tensor");
+  VQW_REQUIRE(d.n_blocks == 1 || residuals, "vqw_resnet_backward: residuals[] is required");
+  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16)
+    return resnet_backward_tc(d, g_skip, g_last_res, x, cond, residuals, gate_tanh, gate_sig,
+                              weights, gx, gcond, wgrads, workspace, (cudaStream_t)stream);
+  VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_backward: unknown mode %d", d.mode);
+  uintptr_t a = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  float* gh = reinterpret_cast<float*>(a);
+  float* pp[2] = {gh + (int64_t)d.B * d.Cd * d.T, gh + (int64_t)d.B * (d.Cd + d.Cr) * d.T};
+  const float* g_res = g_last_res;
+  for (int i = d.n_blocks - 1; i >= 0; --i) {
+    vqw_resblock_desc b = {};
+    b.B = d.B; b.T = d.T; b.Cr = d.Cr; b.Cd = d.Cd; b.Cs = d.Cs; b.Cc = d.Cc; b.fs = d.fs;
+    b.dilation = d.dilations[i];
+    b.mode = VQW_MODE_FP32;
+    const float* xin = (i == 0) ? x : residuals[i - 1];
+    VQW_REQUIRE(xin && gate_tanh[i] && gate_sig[i], "vqw_resnet_backward: block %d saved tensors", i);
+    float* out = (i == 0) ? gx : pp[i & 1];
+    if (int rc = vqw_resblock_backward(&b, g_res, g_skip, xin, cond, gate_tanh[i], gate_sig[i],
+                                       &weights[i], out, gcond, &wgrads[i], gh, stream))
+      return rc;
+    g_res = out;
+    if (i == 0) break;
+  }
+  return 0;
+}

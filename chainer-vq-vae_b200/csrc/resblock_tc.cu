@@ -27,22 +27,12 @@
 //                    O_0, O_1 = Wr z (A operand read straight from TMEM) -> + bias + x -> residual
 //                    O_2 = Ws z -> skip (+)=
 // so the gated activation never leaves the SM and the block is one kernel.
-#include "common.cuh"
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace vqw {
 namespace tc {
 
-constexpr int TM = 128;     // time rows per CTA = UMMA M
-constexpr int TN = 256;     // UMMA N
-constexpr int BK = 32;      // K elements per pipeline stage (one 64-byte swizzle row)
-constexpr int UK = 16;      // UMMA K for 16-bit operands
 constexpr int STAGES = 4;
-constexpr int A_PLANE = TM * BK * 2;                      // 8 KB
-constexpr int B_PLANE = TN * BK * 2;                      // 16 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 48 KB
-constexpr int NTHREADS = 192;
 constexpr int ACC_COL = 0, ZHI_COL = 256, ZLO_COL = 384;
 constexpr int CD = 512, CH = 256, HALF = 128;             // dilated channels handled by this kernel
 
@@ -60,129 +50,6 @@ struct Params {
   float* gate_tanh;     // (B,Ch,T) fp32 or null
   float* gate_sig;
 };
-
-// ------------------------------------------------------------------ PTX wrappers ----------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded spin: a protocol bug must surface as a launch error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// K-major, 64-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bits):
-// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 8 rows * 64 B,
-// [46,48) version = 1, [61,64) layout = 4 (SWIZZLE_64B).
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both,
-// N>>3 at [17,23), M>>4 at [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
-                           ((uint32_t)(TM >> 4) << 24);
-
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
 
 // ------------------------------------------------------------------ the kernel -------------
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -392,16 +259,39 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_arrive(acc_empty);
     }
     // ---- output phases: residual chunks then skip chunks ----
+    // The fp32 operands added in the epilogue (x for the residual, the running skip sum) are
+    // prefetched PF chunks ahead into registers -- before the accumulator is even ready -- so
+    // the 4 epilogue warps keep PF*16 independent 128-byte requests in flight each instead
+    // of one dependent load per channel.
+    constexpr int PF = 3;
     for (int oc = o_begin; oc < o_end; ++oc, ++nphase) {
+      const bool is_res = oc < P.Cr / TN;
+      const int cbase = is_res ? oc * TN : (oc - P.Cr / TN) * TN;
+      const int C = is_res ? P.Cr : P.Cs;
+      const float* addsrc = is_res ? P.x : (P.skip_accumulate ? P.skip : nullptr);
+      const float* addp = addsrc ? addsrc + ((int64_t)b * C + cbase) * P.T + t : nullptr;
+      float pre[PF][16];
+#pragma unroll
+      for (int f = 0; f < PF; ++f)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pre[f][i] = (addp && t_ok) ? __ldcs(addp + (int64_t)(16 * f + i) * P.T) : 0.0f;
       mbar_wait(acc_full, nphase & 1);
       tc_fence_after();
-      const bool is_res = oc < P.Cr / TN;
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < TN / 16; ++q) {
-        float o[16];
+        float o[16], add[16];
         tmem_ld16(lane_base + ACC_COL + 16 * q, o);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) add[i] = pre[q % PF][i];
+        if (q + PF < TN / 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pre[q % PF][i] =
+                (addp && t_ok) ? __ldcs(addp + (int64_t)(16 * (q + PF) + i) * P.T) : 0.0f;
+        }
+        const int ch0 = cbase + 16 * q;
         if (is_res) {
-          const int ch0 = oc * TN + 16 * q;
           uint32_t rh[8], rl[8];
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
@@ -409,12 +299,9 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int ch = ch0 + i + u;
-              float v = o[i + u] + brs[ch];
-              if (t_ok) {
-                const int64_t off = ((int64_t)b * P.Cr + ch) * P.T + t;
-                v += __ldg(P.x + off);
-                if (P.res_f32 != nullptr) P.res_f32[off] = v;
-              }
+              const float v = o[i + u] + brs[ch] + add[i + u];
+              if (t_ok && P.res_f32 != nullptr)
+                P.res_f32[((int64_t)b * P.Cr + ch) * P.T + t] = v;
               v2[u] = v;
             }
             __nv_bfloat16 h0, l0, h1, l1;
@@ -434,17 +321,11 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               dl[1] = make_uint4(rl[4], rl[5], rl[6], rl[7]);
             }
           }
-        } else {
-          const int ch0 = (oc - P.Cr / TN) * TN + 16 * q;
-          if (t_ok) {
+        } else if (t_ok) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int ch = ch0 + i;
-              const int64_t off = ((int64_t)b * P.Cs + ch) * P.T + t;
-              float v = o[i] + bss[ch];
-              if (P.skip_accumulate) v += P.skip[off];
-              P.skip[off] = v;
-            }
+          for (int i = 0; i < 16; ++i) {
+            const int ch = ch0 + i;
+            P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
           }
         }
       }
@@ -486,6 +367,14 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
       if (lo) lo[off] = l;
     }
   }
+}
+
+int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
+                    cudaStream_t stream) {
+  dim3 g(ceil_div(T, 32), ceil_div(C, 32), B);
+  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T);
+  VQW_CHECK_LAUNCH("pack_act_kernel");
+  return 0;
 }
 
 // W1 packed [512 rows in phase order][K1 = fs*Cr + Cc]: row r -> original row
@@ -550,7 +439,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor (rank 2 or 3), innermost extent `inner` contiguous; box = {BK, box_rows, 1}
-static int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t rows,
+int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t rows,
                     uint64_t batch, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   VQW_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -576,7 +465,8 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 
 bool resnet_tc_supported(const vqw_resnet_desc& d) {
   return d.Cd == tc::CD && d.Cr % tc::TN == 0 && d.Cs % tc::TN == 0 && d.Cc % tc::BK == 0 &&
-         d.Cr >= tc::TN && d.Cs >= tc::TN && d.fs >= 1;
+         d.Cr >= tc::TN && d.Cs >= tc::TN && d.fs >= 1 && d.T >= tc::TM && d.T % 8 == 0 &&
+         d.Cc % 16 == 0;
 }
 
 // workspace: [cond hi|lo] [x ping hi|lo] [x pong hi|lo] [per block: w1 hi|lo, w2 hi|lo]
@@ -608,9 +498,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
                       cudaStream_t stream) {
   using namespace tc;
   VQW_REQUIRE(resnet_tc_supported(d),
-              "tcgen05 path needs dilated_channels=512, residual/skip channels multiples of 256 "
-              "and condition channels a multiple of 32 (got Cr=%d Cd=%d Cs=%d Cc=%d)",
-              d.Cr, d.Cd, d.Cs, d.Cc);
+              "tcgen05 path needs dilated_channels=512, residual/skip channels multiples of 256, "
+              "condition channels a multiple of 32, T >= 128 and T %% 8 == 0 "
+              "(got Cr=%d Cd=%d Cs=%d Cc=%d T=%d)", d.Cr, d.Cd, d.Cs, d.Cc, d.T);
   VQW_REQUIRE(workspace != nullptr, "vqw_resnet_forward: workspace is null");
   VQW_REQUIRE(d.B <= 65535, "vqw_resnet_forward: B > 65535");
   const bool x3 = d.mode == VQW_MODE_BF16X3;

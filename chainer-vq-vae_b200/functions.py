@@ -306,22 +306,32 @@ class _ResidualStack(torch.autograd.Function):
         dev = g_skip.device
         gcond = torch.zeros((B, Cc, T, 1), device=dev, dtype=torch.float32)
         gws = [torch.zeros_like(w) for w in weights]
-        d0 = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, 1, 0, 1, L.MODE_FP32)
-        ws_bytes = L.lib.vqw_resblock_backward_workspace(C.byref(d0))
-        workspace = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        g_res = _f32c(g_last_res) if (keep_last and g_last_res is not None) else None
-        for i in reversed(range(n)):
-            d = _rb_desc(B, T, Cr, Cd, Cs, Cc, fs, dilations[i], i > 0, 1, L.MODE_FP32)
-            w = _rb_weights(weights[8 * i:8 * i + 8])
-            gw = _rb_weights(gws[8 * i:8 * i + 8])
-            gx = torch.empty((B, Cr, T, 1), device=dev, dtype=torch.float32)
-            with L.timed("resblock_backward" if g_res is not None else "resblock_backward_last"):
-                L.check(L.lib.vqw_resblock_backward(
-                    C.byref(d), L.ptr(g_res), L.ptr(g_skip), L.ptr(xs[i]), L.ptr(cond),
-                    L.ptr(gates[2 * i]), L.ptr(gates[2 * i + 1]), C.byref(w), L.ptr(gx),
-                    L.ptr(gcond), C.byref(gw), L.ptr(workspace), L.stream()),
-                    "vqw_resblock_backward")
-            g_res = gx
+        d = L.ResnetDesc()
+        d.B, d.T, d.Cr, d.Cd, d.Cs, d.Cc, d.fs = B, T, Cr, Cd, Cs, Cc, fs
+        d.n_blocks = n
+        dil_arr = (C.c_int * n)(*dilations)
+        d.dilations = C.cast(dil_arr, C.POINTER(C.c_int))
+        d.mode, d.keep_last_residual = mode, int(keep_last)
+        warr = (L.ResblockWeights * n)()
+        gwarr = (L.ResblockWeights * n)()
+        names = ("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b", "skip_w", "skip_b")
+        for i in range(n):
+            for j, name in enumerate(names):
+                setattr(warr[i], name, L.ptr(weights[8 * i + j]))
+                setattr(gwarr[i], name, L.ptr(gws[8 * i + j]))
+        rarr = (C.c_void_p * n)(*([L.ptr(xs[i + 1]) for i in range(n - 1)] + [None]))
+        garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
+        garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
+        ws_bytes = L.lib.vqw_resnet_backward_workspace(C.byref(d))
+        workspace = torch.empty(int(ws_bytes), device=dev, dtype=torch.uint8)
+        g_last = _f32c(g_last_res) if (keep_last and g_last_res is not None) else None
+        g_res = torch.empty((B, Cr, T, 1), device=dev, dtype=torch.float32) \
+            if ctx.needs_input_grad[0] else None
+        with L.timed("resnet_backward"):
+            L.check(L.lib.vqw_resnet_backward(
+                C.byref(d), L.ptr(g_skip), L.ptr(g_last), L.ptr(xs[0]), L.ptr(cond), rarr, garr_t,
+                garr_s, warr, L.ptr(g_res), L.ptr(gcond), gwarr, L.ptr(workspace), L.stream()),
+                "vqw_resnet_backward")
         return (g_res, gcond, None, None, None, None, *gws)
 
 

@@ -184,6 +184,19 @@ int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, const float*
                        float* const* gate_tanh, float* const* gate_sig, void* workspace,
                        vqw_stream_t stream);
 
+/* Backward of the whole stack, blocks walked in reverse with the shared
+ * g_skip (B,Cs,T) and the accumulated g_condition.  x = the stack input, residuals[i] /
+ * gate_tanh[i] / gate_sig[i] = what vqw_resnet_forward saved.  g_last_res (B,Cr,T) or NULL.
+ * gx (B,Cr,T) overwritten (may be NULL); gcond (B,Cc,T) and every weight gradient ACCUMULATED.
+ * fp32 mode composes the CUDA-core conv family; the tensor-core modes run tcgen05 GEMMs for
+ * the gate-gradient, data-gradient and weight-gradient contractions. */
+int64_t vqw_resnet_backward_workspace(const vqw_resnet_desc* desc);
+int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_skip, const float* g_last_res,
+                        const float* x, const float* cond, float* const* residuals,
+                        float* const* gate_tanh, float* const* gate_sig,
+                        const vqw_resblock_weights* weights, float* gx, float* gcond,
+                        const vqw_resblock_wgrads* wgrads, void* workspace, vqw_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot
  * tensor, modules.py:151-152: out[b,c,t] = b[c] + W[c,q[t-1],0] + W[c,q[t],1] (t-1<0 dropped).

@@ -76,20 +76,36 @@ def test_tc_bf16_throughput_mode_is_close():
     assert e < 3e-2                                   # single bf16 pass: not a parity mode
 
 
-def test_tc_matches_fp32_path_with_saved_gates():
-    dil = [1, 2]
-    cfg, p, x, c = _stack_case(dil, 2, 256, seed=3)
+@pytest.mark.parametrize("dil,B,T,keep_last", [([1, 2], 2, 256, False), ([4, 1, 2], 1, 384, False),
+                                               ([8], 2, 200, True)])
+def test_tc_backward_matches_fp32_path(dil, B, T, keep_last):
+    """bf16x3 forward + backward (tcgen05 GEMMs for gz / gx / gcond / all weight grads) against
+    the fp32 CUDA-core path, which test_gpu_kernels.py pins to the oracle."""
+    cfg, p, x, c = _stack_case(dil, B, T, seed=3)
+    rng = np.random.default_rng(9)
+    g_skip = torch.from_numpy(rng.normal(size=(B, 256, T, 1)).astype(np.float32)).to(DEV)
+    g_res = torch.from_numpy(rng.normal(size=(B, 512, T, 1)).astype(np.float32)).to(DEV)
     outs = {}
     for mode in ("fp32", "bf16x3"):
         weights = []
         for i in range(len(dil)):
             weights += [p[f"resnet/{i}/{n}"].to(DEV).requires_grad_(True) for n in ORDER]
         xg = x.to(DEV).requires_grad_(True)
-        skip = V.residual_stack(xg, c.to(DEV), dil, cfg.filter_size, weights, L.MODES[mode])
-        skip.sum().backward()
-        outs[mode] = (skip.detach(), xg.grad.detach(), weights[0].grad.detach())
-    for a, b in zip(outs["bf16x3"], outs["fp32"]):
-        assert rel_err(a, b) < 1e-4
+        cg = c.to(DEV).requires_grad_(True)
+        out = V.residual_stack(xg, cg, dil, cfg.filter_size, weights, L.MODES[mode],
+                               keep_last_residual=keep_last)
+        if keep_last:
+            skip, res = out
+            ((skip * g_skip).sum() + (res * g_res).sum()).backward()
+        else:
+            skip = out
+            (skip * g_skip).sum().backward()
+        outs[mode] = [skip.detach(), xg.grad.detach(), cg.grad.detach()] + \
+                     [w.grad.detach() for w in weights]
+    names = ["skip", "gx", "gcond"] + [f"{i}/{n}" for i in range(len(dil)) for n in ORDER]
+    for name, a, b in zip(names, outs["bf16x3"], outs["fp32"]):
+        e = rel_err(a, b)
+        assert e < 2e-4, (name, e)
 
 
 def test_tc_rejects_unsupported_shapes():
