@@ -237,6 +237,14 @@ def resize_images_h(x, out_h):
     return w0 * x[:, :, i0] + w1 * x[:, :, i1]
 
 
+def sigmoid(x):
+    """chainer.functions.sigmoid on CPU [dep]: tanh(x * 0.5) * 0.5 + 0.5.  The formulation
+    matters for calculate_logistic_loss, where cdf_plus - cdf_min cancels catastrophically in
+    float32 (pinned by tests/golden/ref_mol_T256.npz)."""
+    half = 0.5
+    return torch.tanh(x * half) * half + half
+
+
 def softmax_cross_entropy(y, t):
     """chainer.functions.softmax_cross_entropy (train.py:95) [dep]: log-softmax over axis 1,
     mean over all labels (normalize=True, ignore_label=-1 never hit)."""
@@ -355,7 +363,7 @@ def residual_block_forward(p: Params, x, condition, filter_size, dilation, pad=N
     h = h[:, :, :length]                                                   # :41
     h = h + conv2d(condition, p["condition_proj/W"], p["condition_proj/b"])  # :44
     tanh_z, sig_z = torch.split(h, h.shape[1] // 2, dim=1)                 # :47
-    z = torch.tanh(tanh_z) * torch.sigmoid(sig_z)                          # :48
+    z = torch.tanh(tanh_z) * sigmoid(sig_z)                                # :48
     if x.shape[2] == z.shape[2]:                                           # :51-54
         residual = conv2d(z, p["res/W"], p["res/b"]) + x
     else:
@@ -400,9 +408,9 @@ def calculate_logistic_loss(cfg: Config, y, t):
     inv_std = torch.exp(-log_scales)
     half = 127.5 / (cfg.quantize - 1)
     plus_in = inv_std * (centered_t + half)                                # :185
-    cdf_plus = torch.sigmoid(plus_in)
+    cdf_plus = sigmoid(plus_in)
     min_in = inv_std * (centered_t - half)                                 # :187
-    cdf_min = torch.sigmoid(min_in)
+    cdf_min = sigmoid(min_in)
     log_cdf_plus = plus_in - F.softplus(plus_in)                           # :190
     log_one_minus_cdf_min = -F.softplus(min_in)                            # :191
     cdf_delta = cdf_plus - cdf_min                                         # :193
@@ -413,6 +421,45 @@ def calculate_logistic_loss(cfg: Config, y, t):
                             torch.where(t > hi, log_one_minus_cdf_min, inner))      # :198-226
     log_probs = log_probs + F.log_softmax(logit_probs, dim=1)              # :228
     return -torch.mean(torch.logsumexp(log_probs, dim=1))                  # :229
+
+
+def calculate_logistic_loss_numpy(cfg: Config, y: np.ndarray, t: np.ndarray) -> float:
+    """modules.py:169-230 evaluated with NumPy in y.dtype exactly as Chainer's CPU functions do
+    (sigmoid = tanh(x/2)/2 + 1/2, softplus = max(x,0) + log1p(exp(-|x|)), log_softmax and
+    logsumexp with max subtraction) [dep].  In float32 `cdf_plus - cdf_min` cancels
+    catastrophically wherever the logistic is narrow, so the loss is only reproducible to
+    ~1e-2 rel by an implementation with different elementary-function rounding (torch, CUDA);
+    this literal form is what pins the formula to the golden vector."""
+    dt = y.dtype
+    nr_mix = y.shape[1] // 3
+    logit_probs, means = y[:, :nr_mix], y[:, nr_mix:2 * nr_mix]
+    log_scales = np.maximum(y[:, 2 * nr_mix:3 * nr_mix], np.full_like(means, cfg.log_scale_min))
+    tt = np.broadcast_to(dt.type(127.5) * t, means.shape)
+    centered = tt - means
+    inv_std = np.exp(-log_scales)
+    half_bin = 127.5 / (cfg.quantize - 1)
+
+    def sig(v):
+        h = dt.type(0.5)
+        return np.tanh(v * h) * h + h
+
+    def softplus(v):
+        return np.maximum(v, 0) + np.log1p(np.exp(-np.fabs(v)))
+    plus_in = inv_std * (centered + dt.type(half_bin))
+    min_in = inv_std * (centered - dt.type(half_bin))
+    cdf_delta = sig(plus_in) - sig(min_in)
+    log_cdf_plus = plus_in - softplus(plus_in)
+    log_one_minus_cdf_min = -softplus(min_in)
+    lo = np.full(tt.shape, 127.5 * -0.999, dtype=np.float32)
+    hi = np.full(tt.shape, 127.5 * 0.999, dtype=np.float32)
+    inner = np.log(np.maximum(cdf_delta, np.full(cdf_delta.shape, 1e-12, dtype=np.float32)))
+    log_probs = np.where(tt < lo, log_cdf_plus, np.where(tt > hi, log_one_minus_cdf_min, inner))
+    m = logit_probs.max(axis=1, keepdims=True)
+    ls = (logit_probs - m) - np.log(np.exp(logit_probs - m).sum(axis=1, keepdims=True))
+    log_probs = log_probs + ls
+    mm = log_probs.max(axis=1, keepdims=True)
+    lse = np.log(np.exp(log_probs - mm).sum(axis=1)) + np.squeeze(mm, axis=1)
+    return float(-lse.mean())
 
 
 class WaveNetGenerator:

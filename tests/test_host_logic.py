@@ -1,0 +1,102 @@
+"""Host-side logic that needs no GPU: shapes, error behaviour, naming, optimiser arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+import chainer_vq_vae_b200 as V
+from chainer_vq_vae_b200 import functions as Fn
+from chainer_vq_vae_b200.net import resize_images_h
+from oracle import vqvae_oracle as O
+
+
+def test_conv_out_len_matches_chainer_formula():
+    assert [Fn.conv_out_len(n, 4, 2, 1, 1) for n in (7681, 3840, 1920, 960, 480, 240)] == \
+        [3840, 1920, 960, 480, 240, 120]                       # net.py:12-17 at T+1 = 7681
+    assert Fn.conv_out_len(1024, 3, 1, 8, 4) == 1024 + 8      # modules.py:13-16 before the slice
+
+
+def test_parameter_tree_names_match_the_reference():
+    cfg = O.config_cpu()
+    from helpers import build_model
+    model = build_model(cfg, O.make_params(cfg), device="cpu")
+    got = {n.lstrip("/") for n, _ in V.namedparams(model)}
+    assert got == set(O.param_shapes(cfg))
+    for name, p in V.namedparams(model):
+        assert tuple(p.shape) == O.param_shapes(cfg)[name.lstrip("/")]
+
+
+def test_cpu_tensors_fail_loudly():
+    blk = V.ResidualBlock(3, 1, 32, 32, 32, 16, 0)
+    with pytest.raises(V.VqwError):
+        blk(torch.zeros(1, 32, 8, 1), torch.zeros(1, 16, 8, 1))
+    with pytest.raises(V.VqwError):
+        V.Encoder(8)(torch.zeros(1, 1, 65, 1))
+
+
+def test_straight_through_type_checks():
+    W = torch.zeros(4, 8)
+    with pytest.raises(ValueError):
+        V.straight_through(torch.zeros(2, 7, 5, 1), W)
+    with pytest.raises(ValueError):
+        V.straight_through(torch.zeros(2, 8), W)
+    with pytest.raises(ValueError):
+        V.straight_through(torch.zeros(2, 8, 5, 1), torch.zeros(4, 8, 1))
+    with pytest.raises(TypeError):
+        V.straight_through(torch.zeros(2, 8, 5, 1, dtype=torch.int64), W)
+
+
+def test_resize_images_matches_chainer_coordinates():
+    rng = np.random.default_rng(0)
+    for H, f in ((16, 64), (120, 64), (375, 64), (5, 3)):
+        x = torch.from_numpy(rng.normal(size=(2, 3, H, 1)).astype(np.float32))
+        assert torch.allclose(resize_images_h(x, H * f), O.resize_images_h(x, H * f), atol=2e-6)
+    g = torch.randn(2, 4, 1, 1)
+    assert torch.equal(resize_images_h(g, 7), g.expand(2, 4, 7, 1))
+
+
+def test_adam_matches_chainer_rule_and_bucket_views():
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    opt = V.Adam(1e-3).setup(lin)
+    assert opt.bucket.flat.numel() == 18
+    p0 = [p.detach().clone() for p in lin.parameters()]
+    ms = [torch.zeros_like(p) for p in p0]
+    vs = [torch.zeros_like(p) for p in p0]
+    for step in range(1, 4):
+        opt.bucket.zero()
+        lin(torch.randn(7, 5)).pow(2).sum().backward()
+        grads = [p.grad.clone() for p in lin.parameters()]
+        assert all(p.grad.data_ptr() >= opt.bucket.flat.data_ptr() for p in lin.parameters())
+        opt.update()
+        for p, g, m, v in zip(p0, grads, ms, vs):
+            O.adam_step(p, g, m, v, step, 1e-3)
+        for p, q in zip(lin.parameters(), p0):
+            assert torch.allclose(p, q, atol=1e-7)
+
+
+def test_weight_ema_quirk_on_module():
+    lin = torch.nn.Linear(2, 2)
+    ema = V.ExponentialMovingAverage(lin, 0.9)
+    with torch.no_grad():
+        for p in ema.ema.parameters():
+            p.zero_()
+        w = lin.weight.clone()
+    ema.update_average()
+    assert torch.allclose(ema.ema.weight, 0.9 * w)            # decay multiplies the TARGET
+    assert not any(p.requires_grad for p in ema.ema.parameters())
+
+
+def test_concat_examples_and_split():
+    ex = [(np.full((1, 9, 1), i, np.float32), np.arange(8, dtype=np.int32), np.int32(i),
+           np.zeros((8, 1), np.int32)) for i in range(6)]
+    a, b, c, d = V.updaters.concat_examples(ex, None)
+    assert a.shape == (6, 1, 9, 1) and b.shape == (6, 8) and c.shape == (6,) and d.shape == (6, 8, 1)
+    assert [int(e[2]) for e in V.VQVAE_ParallelUpdater.split(ex, 1, 2)] == [1, 3, 5]   # batch[i::n]
+
+
+def test_mulaw_roundtrip():
+    m = V.MuLaw(256)
+    q = m.transform(np.linspace(-1, 1, 1001).astype(np.float32))
+    assert q.min() == 0 and q.max() == 255 and q.dtype == np.int32
+    x = m.itransform(q)
+    assert np.all(np.diff(x) >= 0) and abs(x[500]) < 0.01
