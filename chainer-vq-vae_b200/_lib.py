@@ -62,6 +62,13 @@ class ResnetDesc(C.Structure):
                 ("dilations", C.POINTER(c_int)), ("mode", c_int), ("keep_last_residual", c_int)]
 
 
+class GenerateDesc(C.Structure):
+    _fields_ = [("n_blocks", c_int), ("dilations", C.POINTER(c_int)), ("fs", c_int),
+                ("Cr", c_int), ("Cd", c_int), ("Cs", c_int), ("Cc", c_int), ("Q", c_int),
+                ("T_total", c_int), ("n_steps", c_int), ("t_start", c_int),
+                ("set_state", c_int), ("s1", c_int), ("s2", c_int), ("cond_t0", c_int)]
+
+
 _SIGNATURES = {
     "vqw_version": (c_int, []),
     "vqw_last_error": (C.c_char_p, []),
@@ -86,6 +93,9 @@ _SIGNATURES = {
                             [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(ResblockWeights), C.c_void_p,
                                                            C.c_void_p, C.POINTER(ResblockWeights),
                                                            C.c_void_p, C.c_void_p]),
+    "vqw_generate_workspace": (C.c_int64, [C.POINTER(GenerateDesc)]),
+    "vqw_generate": (c_int, [C.POINTER(GenerateDesc), C.POINTER(ResblockWeights)] +
+                     [C.c_void_p] * 13),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
 }

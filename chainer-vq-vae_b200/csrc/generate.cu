@@ -1,0 +1,377 @@
+// Persistent autoregressive generation kernel (sm_100a).
+//
+// Replaces the reference's per-sample Python loop, generate.py:109-145, together with the
+// queue-based incremental WaveNet it drives (WaveNet.initialize / generate, modules.py:232-255;
+// ResidualNet.generate :102-110; ResidualBlock.push / pop :58-74): ~500 Chainer calls, 16.8 MB
+// of concat-shift queue copies and a device->host sync per generated sample become ONE
+// cooperative kernel launch for the whole utterance.
+//
+//   * The kernel stays resident on every SM and walks the samples; phases that depend on each
+//     other are separated by grid-wide barriers (the layer chain of one sample is strictly
+//     sequential; only utterances are independent -- "replicas only").
+//   * The dilation queues are ring buffers in global memory (L2 resident): a push is one
+//     512-float row write, a tap read is an index computation -- nothing is shifted.
+//   * Sampling happens on the device from a host-supplied uniform stream with
+//     numpy.random.choice's rule (float64 cumsum of the float32 softmax, normalise,
+//     searchsorted(side='right')), so a run is comparable with generate.py:139-141 given the
+//     same draws.  The first input is all-zeros, not a one-hot (generate.py:51).
+//
+// Per block two phases:
+//   A  h = conv_b + cond_b + Wp cond[t] + sum_j Wc[:,:,j] x_l[t - dil*(fs-1-j)]   (K split in 4:
+//      one (gate pair, K chunk) item per warp, partial sums to global -- deterministic)
+//   B  every CTA rebuilds z = tanh(h_t) * sigmoid(h_s) from the partials, then one output row
+//      per warp: x_{l+1} = Wr z + br + x_l (pushed into the next block's ring), skip += Ws z + bs
+// then the head (relu, proj1, relu, proj2), softmax and the draw.
+#include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace vqw {
+
+constexpr int GEN_THREADS = 256;
+constexpr int GEN_WARPS = GEN_THREADS / 32;
+constexpr int KCH = 4;   // K chunks per gate pair in phase A
+
+struct GenBlock {
+  const float *conv_w, *conv_b, *cond_w, *cond_b, *res_w, *res_b, *skip_w, *skip_b;
+  int dilation;
+  int qlen;        // dil*(fs-1)+1 ring slots
+  long long qoff;  // offset (floats) of this block's ring in the queue area
+};
+
+struct GenParams {
+  int n_blocks, fs, Cr, Cd, Cs, Cc, Q;
+  int T_total, n_steps, t_start, cond_t0;
+  const GenBlock* blocks;      // device array
+  const float *embed_w, *embed_b, *proj1_w, *proj1_b, *proj2_w, *proj2_b;
+  const float* cond;           // (Cc, T_total)
+  const double* uniforms;      // n_steps
+  const int32_t* forced;       // n_steps or null: teacher forcing (sample still recorded)
+  int32_t* samples;            // n_steps
+  float* logits;               // n_steps * Q or null
+  float* queues;               // rings
+  float* partial;              // [Cd/2][KCH][2]
+  float* xbuf;                 // [2][Cr] current block input / output (ping-pong)
+  float* skipacc;              // [Cs]
+  float* h1;                   // [Cs] relu(proj1(relu(skip)))
+  float* logit_buf;            // [Q]
+  int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// dot product of a contiguous weight row segment (global) with a shared-memory vector
+__device__ __forceinline__ float dot_row(const float* __restrict__ w, const float* v, int n, int lane) {
+  float acc = 0.0f;
+  int i = lane * 4;
+  if ((((uintptr_t)w) & 15) == 0) {
+    for (; i + 3 < n; i += 128) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(w + i));
+      acc = fmaf(a.x, v[i], acc);
+      acc = fmaf(a.y, v[i + 1], acc);
+      acc = fmaf(a.z, v[i + 2], acc);
+      acc = fmaf(a.w, v[i + 3], acc);
+    }
+    // tail (n not a multiple of 4)
+    for (int j = (n & ~3) + lane; j < n; j += 32) acc = fmaf(__ldg(w + j), v[j], acc);
+  } else {
+    for (int j = lane; j < n; j += 32) acc = fmaf(__ldg(w + j), v[j], acc);
+  }
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(GEN_THREADS)
+generate_kernel(const GenParams P) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float sm[];
+  const int Ch = P.Cd / 2;
+  const int KX = P.fs * P.Cr;           // interleaved tap vector length
+  float* vx = sm;                       // [KX]  v[c*fs + j] = x_l[t - s_j][c]
+  float* vc = vx + ((KX + 3) & ~3);     // [Cc]  cond[:, t]
+  float* zs = vc + ((P.Cc + 3) & ~3);   // [Ch]
+  float* xs = zs + ((Ch + 3) & ~3);     // [max(Cr, Cs, Q)] scratch vector
+  __shared__ int s_sample;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gwarp = blockIdx.x * GEN_WARPS + warp;
+  const int nwarps = gridDim.x * GEN_WARPS;
+
+  for (int step = 0; step < P.n_steps; ++step) {
+    const int t = P.t_start + step;
+    // ---- embed: x_0 = b + W[:, s(t-2), 0] + W[:, s(t-1), 1]   (modules.py:246-247; zeros at start)
+    {
+      const int s1 = P.state[0], s2 = P.state[1];
+      float* x0 = P.xbuf;   // slot 0
+      for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cr; c += gridDim.x * GEN_THREADS) {
+        float v = __ldg(P.embed_b + c);
+        const float* wr = P.embed_w + (long long)c * P.Q * 2;
+        if (s2 >= 0) v += __ldg(wr + 2 * s2);
+        if (s1 >= 0) v += __ldg(wr + 2 * s1 + 1);
+        x0[c] = v;
+      }
+      for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cs; c += gridDim.x * GEN_THREADS)
+        P.skipacc[c] = 0.0f;
+    }
+    grid.sync();
+
+    for (int l = 0; l < P.n_blocks; ++l) {
+      const GenBlock& blk = P.blocks[l];
+      const float* xin = P.xbuf + (l & 1) * P.Cr;
+      float* xout = P.xbuf + ((l + 1) & 1) * P.Cr;
+      float* ring = P.queues + blk.qoff;
+      // ---- phase A ----
+      // push x_l into the ring (one CTA writes; everyone reads the value from xin directly)
+      if (blockIdx.x == 0)
+        for (int c = tid; c < P.Cr; c += GEN_THREADS)
+          ring[(long long)(t % blk.qlen) * P.Cr + c] = xin[c];
+      for (int i = tid; i < KX; i += GEN_THREADS) {
+        const int c = i / P.fs, j = i - c * P.fs;
+        const int s = blk.dilation * (P.fs - 1 - j);
+        float v = 0.0f;
+        if (s == 0) v = xin[c];
+        else if (t - s >= 0) v = ring[(long long)((t - s) % blk.qlen) * P.Cr + c];
+        vx[i] = v;
+      }
+      for (int i = tid; i < P.Cc; i += GEN_THREADS) vc[i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
+      __syncthreads();
+      {
+        const int chunk = (KX + KCH - 1) / KCH;
+        const int clen4 = (chunk + 3) & ~3;           // keep chunks float4 aligned
+        for (int item = gwarp; item < Ch * KCH; item += nwarps) {
+          const int p = item / KCH, kc = item - p * KCH;
+          const int k0 = kc * clen4;
+          const int n = max(0, min(clen4, KX - k0));
+          float at = 0.0f, ag = 0.0f;
+          if (n > 0) {
+            at = dot_row(blk.conv_w + (long long)p * KX + k0, vx + k0, n, lane);
+            ag = dot_row(blk.conv_w + (long long)(Ch + p) * KX + k0, vx + k0, n, lane);
+          }
+          if (kc == 0) {
+            at += dot_row(blk.cond_w + (long long)p * P.Cc, vc, P.Cc, lane);
+            ag += dot_row(blk.cond_w + (long long)(Ch + p) * P.Cc, vc, P.Cc, lane);
+          }
+          if (lane == 0) {
+            P.partial[(p * KCH + kc) * 2 + 0] = at;
+            P.partial[(p * KCH + kc) * 2 + 1] = ag;
+          }
+        }
+      }
+      grid.sync();
+      // ---- phase B ----
+      for (int p = tid; p < Ch; p += GEN_THREADS) {
+        float ht = __ldg(blk.conv_b + p) + __ldg(blk.cond_b + p);
+        float hg = __ldg(blk.conv_b + Ch + p) + __ldg(blk.cond_b + Ch + p);
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc) {
+          ht += P.partial[(p * KCH + kc) * 2 + 0];
+          hg += P.partial[(p * KCH + kc) * 2 + 1];
+        }
+        zs[p] = tanhf(ht) * (1.0f / (1.0f + expf(-hg)));
+      }
+      __syncthreads();
+      {
+        const int R = P.Cr + P.Cs;
+        for (int r = gwarp; r < R; r += nwarps) {
+          if (r < P.Cr) {
+            float v = dot_row(blk.res_w + (long long)r * Ch, zs, Ch, lane);
+            if (lane == 0) xout[r] = v + __ldg(blk.res_b + r) + xin[r];
+          } else {
+            const int s = r - P.Cr;
+            float v = dot_row(blk.skip_w + (long long)s * Ch, zs, Ch, lane);
+            if (lane == 0) P.skipacc[s] += v + __ldg(blk.skip_b + s);
+          }
+        }
+      }
+      grid.sync();
+    }
+
+    // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
+    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = fmaxf(P.skipacc[i], 0.0f);
+    __syncthreads();
+    for (int r = gwarp; r < P.Cs; r += nwarps) {
+      float v = dot_row(P.proj1_w + (long long)r * P.Cs, xs, P.Cs, lane);
+      if (lane == 0) P.h1[r] = fmaxf(v + __ldg(P.proj1_b + r), 0.0f);
+    }
+    grid.sync();
+    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = P.h1[i];
+    __syncthreads();
+    for (int r = gwarp; r < P.Q; r += nwarps) {
+      float v = dot_row(P.proj2_w + (long long)r * P.Cs, xs, P.Cs, lane);
+      if (lane == 0) P.logit_buf[r] = v + __ldg(P.proj2_b + r);
+    }
+    grid.sync();
+
+    // ---- softmax + draw: every CTA does it redundantly (identical inputs -> identical result)
+    __syncthreads();
+    for (int i = tid; i < P.Q; i += GEN_THREADS) xs[i] = P.logit_buf[i];
+    __syncthreads();
+    if (warp == 0) {
+      float m = -INFINITY;
+      for (int i = lane; i < P.Q; i += 32) m = fmaxf(m, xs[i]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      float s = 0.0f;
+      for (int i = lane; i < P.Q; i += 32) {
+        float e = expf(xs[i] - m);
+        vx[i] = e;              // reuse vx as the probability buffer (Q <= KX checked on host)
+        s += e;
+      }
+      s = warp_sum(s);
+      __syncwarp();
+      if (lane == 0) {
+        // numpy.random.choice: cdf = cumsum(p as float64); cdf /= cdf[-1]; searchsorted(u, 'right')
+        double tot = 0.0;
+        for (int i = 0; i < P.Q; ++i) tot += (double)(vx[i] / s);
+        const double u = P.uniforms[step];
+        double run = 0.0;
+        int pick = P.Q - 1;
+        for (int i = 0; i < P.Q; ++i) {
+          run += (double)(vx[i] / s);
+          if (run / tot > u) { pick = i; break; }
+        }
+        s_sample = pick;
+      }
+    }
+    __syncthreads();
+    const int pick = s_sample;
+    const int fed = P.forced ? P.forced[step] : pick;
+    if (blockIdx.x == 0) {
+      if (P.logits)
+        for (int i = tid; i < P.Q; i += GEN_THREADS) P.logits[(long long)step * P.Q + i] = xs[i];
+      if (tid == 0) P.samples[step] = pick;
+    }
+    grid.sync();   // everyone has read state/logit_buf before they change
+    if (blockIdx.x == 0 && tid == 0) {
+      P.state[1] = P.state[0];
+      P.state[0] = fed;
+    }
+    grid.sync();
+  }
+}
+
+}  // namespace vqw
+
+static inline int64_t gen_align(int64_t v) { return (v + 255) / 256 * 256; }
+
+struct GenLayout {
+  int64_t blocks, queues, partial, xbuf, skipacc, h1, logit, state, total;
+};
+
+static GenLayout gen_layout(const vqw_generate_desc& d) {
+  GenLayout L;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += gen_align(bytes); return o; };
+  L.blocks = take((int64_t)d.n_blocks * sizeof(vqw::GenBlock));
+  int64_t q = 0;
+  for (int i = 0; i < d.n_blocks; ++i) q += (int64_t)(d.dilations[i] * (d.fs - 1) + 1) * d.Cr;
+  L.queues = take(q * 4);
+  L.partial = take((int64_t)(d.Cd / 2) * vqw::KCH * 2 * 4);
+  L.xbuf = take((int64_t)2 * d.Cr * 4);
+  L.skipacc = take((int64_t)d.Cs * 4);
+  L.h1 = take((int64_t)d.Cs * 4);
+  L.logit = take((int64_t)d.Q * 4);
+  L.state = take(16);
+  L.total = off + 256;
+  return L;
+}
+
+extern "C" int64_t vqw_generate_workspace(const vqw_generate_desc* desc) {
+  if (!desc || !desc->dilations || desc->n_blocks < 1) return -1;
+  return gen_layout(*desc).total;
+}
+
+extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_weights* blocks,
+                            const float* embed_w, const float* embed_b, const float* proj1_w,
+                            const float* proj1_b, const float* proj2_w, const float* proj2_b,
+                            const float* cond, const double* uniforms, const int32_t* forced,
+                            int32_t* samples, float* logits, void* workspace,
+                            vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(desc && blocks, "vqw_generate: null descriptor");
+  const vqw_generate_desc& d = *desc;
+  VQW_REQUIRE(d.n_blocks >= 1 && d.dilations, "vqw_generate: n_blocks/dilations");
+  VQW_REQUIRE(d.fs >= 1 && d.Cr > 0 && d.Cd > 0 && d.Cd % 2 == 0 && d.Cs > 0 && d.Cc > 0 && d.Q > 0,
+              "vqw_generate: bad channel counts");
+  VQW_REQUIRE(d.n_steps >= 0 && d.t_start >= 0 && d.t_start - d.cond_t0 >= 0 &&
+                  d.t_start - d.cond_t0 + d.n_steps <= d.T_total,
+              "vqw_generate: steps [%d, %d) are outside the condition columns [%d, %d)", d.t_start,
+              d.t_start + d.n_steps, d.cond_t0, d.cond_t0 + d.T_total);
+  VQW_REQUIRE(d.Q <= d.fs * d.Cr, "vqw_generate: quantize larger than fs*Cr is unsupported");
+  if (d.n_steps == 0) return 0;
+  VQW_REQUIRE(embed_w && embed_b && proj1_w && proj1_b && proj2_w && proj2_b && cond && uniforms &&
+                  samples && workspace, "vqw_generate: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const GenLayout L = gen_layout(d);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(gen_align((int64_t)(uintptr_t)workspace));
+
+  // block table (device copy in the workspace)
+  static thread_local GenBlock host_blocks[256];
+  VQW_REQUIRE(d.n_blocks <= 256, "vqw_generate: more than 256 blocks");
+  long long qoff = 0;
+  for (int i = 0; i < d.n_blocks; ++i) {
+    const vqw_resblock_weights& w = blocks[i];
+    VQW_REQUIRE(w.conv_w && w.conv_b && w.cond_w && w.cond_b && w.res_w && w.res_b && w.skip_w &&
+                    w.skip_b, "vqw_generate: block %d has a null weight", i);
+    GenBlock& g = host_blocks[i];
+    g.conv_w = w.conv_w; g.conv_b = w.conv_b; g.cond_w = w.cond_w; g.cond_b = w.cond_b;
+    g.res_w = w.res_w; g.res_b = w.res_b; g.skip_w = w.skip_w; g.skip_b = w.skip_b;
+    g.dilation = d.dilations[i];
+    g.qlen = d.dilations[i] * (d.fs - 1) + 1;
+    g.qoff = qoff;
+    qoff += (long long)g.qlen * d.Cr;
+  }
+  VQW_CHECK_CUDA(cudaMemcpyAsync(ws + L.blocks, host_blocks, sizeof(GenBlock) * d.n_blocks,
+                                 cudaMemcpyHostToDevice, st));
+  if (d.t_start == 0) {
+    // WaveNet.initialize(): zero queues (modules.py:59-66,236-243); no previous samples
+    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.queues, 0, (size_t)qoff * 4, st));
+    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.state, 0xff, 16, st));
+  }
+  if (d.set_state) {
+    static thread_local int32_t hs[4];
+    hs[0] = d.s1; hs[1] = d.s2; hs[2] = hs[3] = -1;
+    VQW_CHECK_CUDA(cudaMemcpyAsync(ws + L.state, hs, 16, cudaMemcpyHostToDevice, st));
+  }
+
+  GenParams P;
+  P.n_blocks = d.n_blocks; P.fs = d.fs; P.Cr = d.Cr; P.Cd = d.Cd; P.Cs = d.Cs; P.Cc = d.Cc; P.Q = d.Q;
+  P.T_total = d.T_total; P.n_steps = d.n_steps; P.t_start = d.t_start; P.cond_t0 = d.cond_t0;
+  P.blocks = reinterpret_cast<const GenBlock*>(ws + L.blocks);
+  P.embed_w = embed_w; P.embed_b = embed_b; P.proj1_w = proj1_w; P.proj1_b = proj1_b;
+  P.proj2_w = proj2_w; P.proj2_b = proj2_b;
+  P.cond = cond; P.uniforms = uniforms; P.forced = forced; P.samples = samples; P.logits = logits;
+  P.queues = reinterpret_cast<float*>(ws + L.queues);
+  P.partial = reinterpret_cast<float*>(ws + L.partial);
+  P.xbuf = reinterpret_cast<float*>(ws + L.xbuf);
+  P.skipacc = reinterpret_cast<float*>(ws + L.skipacc);
+  P.h1 = reinterpret_cast<float*>(ws + L.h1);
+  P.logit_buf = reinterpret_cast<float*>(ws + L.logit);
+  P.state = reinterpret_cast<int32_t*>(ws + L.state);
+
+  const int KX = d.fs * d.Cr, Ch = d.Cd / 2;
+  int mx = d.Cr > d.Cs ? d.Cr : d.Cs;
+  if (d.Q > mx) mx = d.Q;
+  size_t smem = sizeof(float) * (((KX + 3) & ~3) + ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) + mx + 8);
+  VQW_REQUIRE(smem <= 200 * 1024, "vqw_generate: channel counts too large for shared memory");
+  VQW_CHECK_CUDA(cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  int dev = 0, sms = 0, per_sm = 0, coop = 0;
+  VQW_CHECK_CUDA(cudaGetDevice(&dev));
+  VQW_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  VQW_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  VQW_REQUIRE(coop, "vqw_generate: device does not support cooperative launch");
+  VQW_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generate_kernel, GEN_THREADS,
+                                                              smem));
+  VQW_REQUIRE(per_sm >= 1, "vqw_generate: kernel does not fit on an SM");
+  int grid = sms;   // one CTA per SM
+  void* args[] = {(void*)&P};
+  VQW_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)generate_kernel, dim3(grid), dim3(GEN_THREADS),
+                                             args, smem, st));
+  VQW_CHECK_LAUNCH("generate_kernel");
+  return 0;
+}

@@ -1,0 +1,108 @@
+"""Autoregressive generation (generate.py:104-145 of the reference) on the persistent kernel.
+
+`generate_utterance` is the whole sample loop in one cooperative launch; `WaveNetState` gives
+the reference's step-wise `WaveNet.initialize(n)` / `WaveNet.generate(x, condition)` pair
+(modules.py:232-255) on the same kernel, one step per call, with the dilation queues living in
+the kernel's workspace (ring buffers) instead of concat-shifted Variables."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy
+import torch
+
+from . import _lib as L
+
+
+def _desc(wavenet, T_total, n_steps, t_start):
+    blocks = list(wavenet.resnet)
+    n = len(blocks)
+    d = L.GenerateDesc()
+    d.n_blocks = n
+    dil = (C.c_int * n)(*[b.dilation for b in blocks])
+    d.dilations = C.cast(dil, C.POINTER(C.c_int))
+    d.fs, d.Cr, d.Cd = wavenet.filter_size, wavenet.residual_channels, wavenet.dilated_channels
+    d.Cs, d.Cc, d.Q = wavenet.skip_channels, wavenet.condition_dim, wavenet.proj2.W.shape[0]
+    d.T_total, d.n_steps, d.t_start = T_total, n_steps, t_start
+    warr = (L.ResblockWeights * n)()
+    for i, b in enumerate(blocks):
+        for name, t in zip(("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b", "skip_w",
+                            "skip_b"), b.weights()):
+            setattr(warr[i], name, L.ptr(t.detach()))
+    return d, dil, warr
+
+
+class WaveNetState:
+    """initialize(n) state: queues are zeroed on the first step (modules.py:59-66,236-243)."""
+
+    def __init__(self, wavenet, n):
+        if n != 1:
+            raise NotImplementedError("generation supports n = 1, like generate.py:42")
+        if wavenet.input_dim == 1:
+            raise NotImplementedError("persistent generation covers the categorical decoder; "
+                                      "the mixture-of-logistics sampler is not implemented")
+        self.w = wavenet
+        self.t = 0
+        self.prev = -1                      # input of the previous step (-1 = all zeros)
+        self.workspace = None
+
+    def _launch(self, cond2d, t_start, n_steps, uniforms, forced, want_logits, state=None,
+                cond_t0=0):
+        w = self.w
+        dev = cond2d.device
+        d, _dil, warr = _desc(w, cond2d.shape[1], n_steps, t_start)
+        d.cond_t0 = cond_t0
+        if state is not None:
+            d.set_state, d.s1, d.s2 = 1, state[0], state[1]
+        if self.workspace is None:
+            nbytes = L.lib.vqw_generate_workspace(C.byref(d))
+            self.workspace = torch.empty(int(nbytes), device=dev, dtype=torch.uint8)
+        samples = torch.empty(n_steps, device=dev, dtype=torch.int32)
+        logits = torch.empty(n_steps, d.Q, device=dev, dtype=torch.float32) if want_logits else None
+        L.check(L.lib.vqw_generate(
+            C.byref(d), warr, L.ptr(w.embed.W.detach()), L.ptr(w.embed.b.detach()),
+            L.ptr(w.proj1.W.detach()), L.ptr(w.proj1.b.detach()), L.ptr(w.proj2.W.detach()),
+            L.ptr(w.proj2.b.detach()), L.ptr(cond2d), L.ptr(uniforms), L.ptr(forced),
+            L.ptr(samples), L.ptr(logits), L.ptr(self.workspace), L.stream()), "vqw_generate")
+        return samples, logits
+
+    def step(self, x, condition):
+        """One `WaveNet.generate(x, condition)` call (modules.py:245-255): x (1, Q, 1, 1) one-hot
+        or all-zero float (generate.py:51,142-144), condition (1, Cc, 1, 1).  Returns the decoder
+        output (1, Q, 1, 1).  The embed queue (modules.py:246) is the pair (previous x, x)."""
+        if x.shape[0] != 1 or x.shape[2] != 1:
+            raise ValueError("generate() takes one time step of one utterance")
+        xv = x.reshape(-1)
+        cur = int(torch.argmax(xv)) if bool((xv != 0).any()) else -1
+        cond2d = condition.reshape(condition.shape[1], 1).contiguous().float()
+        u = torch.zeros(1, device=cond2d.device, dtype=torch.float64)
+        _, logits = self._launch(cond2d, self.t, 1, u, None, True, state=(cur, self.prev),
+                                 cond_t0=self.t)
+        self.prev = cur
+        self.t += 1
+        return logits.reshape(1, -1, 1, 1)
+
+
+def generate_utterance(wavenet, condition: torch.Tensor, uniforms, n_steps: Optional[int] = None,
+                       forced=None, return_logits: bool = False):
+    """The loop of generate.py:109-145 for one utterance in one kernel launch.
+
+    condition (1, Cc, T, 1) from ConditionEmbed; uniforms: the draws numpy.random.choice would
+    make, one per step.  Returns `output` as generate.py builds it -- length T, the last entry
+    left 0 (generate.py:110-112) -- and optionally the per-step decoder outputs (steps, Q)."""
+    if condition.shape[0] != 1:
+        raise NotImplementedError("generation supports n = 1, like generate.py:42")
+    T = condition.shape[2]
+    steps = T - 1 if n_steps is None else min(n_steps, T - 1)
+    dev = condition.device
+    cond2d = condition.reshape(condition.shape[1], T).contiguous().float()
+    u = torch.as_tensor(numpy.asarray(uniforms, dtype=numpy.float64)[:steps]).to(dev)
+    f = None
+    if forced is not None:
+        f = torch.as_tensor(numpy.asarray(forced, dtype=numpy.int32)[:steps]).to(dev)
+    st = WaveNetState(wavenet, 1)
+    samples, logits = st._launch(cond2d, 0, steps, u, f, return_logits)
+    out = torch.zeros(T, device=dev, dtype=torch.float64)
+    out[:steps] = samples.double()
+    return (out, logits) if return_logits else out

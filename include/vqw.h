@@ -207,6 +207,38 @@ int vqw_embed_gather_forward(const int32_t* q, const float* W, const float* bias
 int vqw_embed_gather_backward(const int32_t* q, const float* gout, float* gW, float* gb, int B,
                               int T, int Cr, int Q, vqw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Persistent autoregressive generation.  Replaces the sample loop of generate.py:109-145 and
+ * the queue-based incremental decoder it drives (WaveNet.initialize / generate,
+ * modules.py:232-255; ResidualNet.generate :102-110; ResidualBlock.push / pop :58-74) with ONE
+ * cooperative kernel launch for `n_steps` samples of one utterance (n = 1, generate.py:42).
+ *
+ *   cond      (Cc, T_total) f32   full-rate condition (ConditionEmbed output, net.py:48-64)
+ *   uniforms  (n_steps) f64       the draws numpy.random.choice would make (generate.py:139)
+ *   forced    (n_steps) i32/NULL  teacher forcing: value fed back instead of the drawn sample
+ *   samples   (n_steps) i32       drawn indices (generate.py:145)
+ *   logits    (n_steps, Q) f32    decoder outputs per step, or NULL
+ * t_start = 0 zero-initialises the dilation queues (initialize()); a later call with
+ * t_start = previous t_start + n_steps continues the same utterance from the workspace.
+ * set_state != 0 overrides the two most recent inputs (s1 = input of step t_start, s2 = the
+ * one before; -1 = the all-zero vector of generate.py:51) before the first step.
+ */
+typedef struct {
+  int n_blocks;
+  const int* dilations;
+  int fs, Cr, Cd, Cs, Cc, Q;
+  int T_total, n_steps, t_start;
+  int set_state, s1, s2;
+  int cond_t0;   /* time index of cond's first column (0 for a whole-utterance condition) */
+} vqw_generate_desc;
+
+int64_t vqw_generate_workspace(const vqw_generate_desc* desc);
+int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_weights* blocks,
+                 const float* embed_w, const float* embed_b, const float* proj1_w,
+                 const float* proj1_b, const float* proj2_w, const float* proj2_b,
+                 const float* cond, const double* uniforms, const int32_t* forced,
+                 int32_t* samples, float* logits, void* workspace, vqw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

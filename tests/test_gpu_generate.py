@@ -1,0 +1,100 @@
+"""Persistent generation kernel against the oracle's restatement of generate.py:104-145 with
+the reference's concat-shift queues."""
+import numpy as np
+import pytest
+import torch
+
+import chainer_vq_vae_b200 as V
+from chainer_vq_vae_b200.generate import generate_utterance
+from oracle import vqvae_oracle as O
+from helpers import TOL, build_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(cfg, length):
+    cfg.length = length
+    cfg.batch = 1
+    params = O.make_params(cfg)
+    inp = O.make_inputs(cfg)
+    return params, inp
+
+
+@pytest.mark.parametrize("fs,n_loop", [(3, 1), (2, 2)])
+def test_generate_matches_oracle(fs, n_loop):
+    cfg = O.config_cpu()
+    cfg.filter_size, cfg.n_loop = fs, n_loop
+    params, inp = _case(cfg, 256)
+    steps = 120
+    u = np.random.default_rng(0).uniform(size=steps)
+    out_o, logits_o = O.generate_loop(params, cfg, inp["x_enc"], inp["speaker"], u, n_steps=steps,
+                                      return_logits=True)
+    model = build_model(cfg, params).eval()
+    with torch.no_grad():
+        x_enc = torch.from_numpy(inp["x_enc"]).cuda()
+        z = model.encoder(x_enc)
+        e = model.vq(z)
+        cond = model.condition_embed(e, torch.from_numpy(inp["speaker"]).cuda())
+        out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps,
+                                             return_logits=True)
+    out_g = out_g.cpu().numpy()
+    assert out_g.shape == out_o.shape and out_g[-1] == 0          # generate.py:110-112
+    assert np.array_equal(out_g[:steps], out_o[:steps]), "sampled indices must be identical"
+    assert rel_err(logits_g, logits_o) < TOL
+
+
+def test_generate_teacher_forced_and_stepwise_api():
+    cfg = O.config_cpu()
+    params, inp = _case(cfg, 192)
+    model = build_model(cfg, params).eval()
+    dec = model.decoder
+    steps = 40
+    with torch.no_grad():
+        x_enc = torch.from_numpy(inp["x_enc"]).cuda()
+        cond = model.condition_embed(model.vq(model.encoder(x_enc)),
+                                     torch.from_numpy(inp["speaker"]).cuda())
+        q = inp["quantized"][0]
+        # teacher forcing: feed the ground-truth sample after every step
+        forced = q[1:steps + 1].astype(np.int32)
+        u = np.full(steps, 0.5)
+        _, logits = generate_utterance(dec, cond, u, n_steps=steps, forced=forced, return_logits=True)
+        # full-sequence forward on the same inputs: column i sees x[i-1], x[i] with x[0]=zeros...
+        # the stepwise API reproduces WaveNet.generate (modules.py:245-255) exactly:
+        dec.initialize(1)
+        x = torch.zeros(1, cfg.input_dim, 1, 1, device="cuda")
+        outs = []
+        for i in range(steps):
+            o = dec.generate(x, cond[:, :, i:i + 1])
+            outs.append(o[0, :, 0, 0])
+            x = torch.zeros(1, cfg.input_dim, 1, 1, device="cuda")
+            x[0, int(forced[i])] = 1
+        outs = torch.stack(outs)
+    assert rel_err(outs, logits) < 1e-6
+    # and both equal the oracle's queue-based generator
+    gen = O.WaveNetGenerator(O.sub(params, "decoder/"), cfg, 1)
+    xo = torch.zeros(1, cfg.input_dim, 1, 1)
+    ref = []
+    with torch.no_grad():
+        for i in range(steps):
+            o = gen.generate(xo, cond[:, :, i:i + 1].cpu())
+            ref.append(o[0, :, 0, 0])
+            xo = torch.zeros(1, cfg.input_dim, 1, 1)
+            xo[0, int(forced[i])] = 1
+    assert rel_err(logits, torch.stack(ref)) < TOL
+
+
+def test_generate_b200_channels_smoke():
+    """512/512/256 channels, n_loop=2 x n_layer=10: a few steps against the oracle."""
+    cfg = O.config_b200()
+    params, inp = _case(cfg, 128)
+    steps = 6
+    u = np.random.default_rng(1).uniform(size=steps)
+    out_o, logits_o = O.generate_loop(params, cfg, inp["x_enc"], inp["speaker"], u, n_steps=steps,
+                                      return_logits=True)
+    model = build_model(cfg, params).eval()
+    with torch.no_grad():
+        cond = model.condition_embed(model.vq(model.encoder(torch.from_numpy(inp["x_enc"]).cuda())),
+                                     torch.from_numpy(inp["speaker"]).cuda())
+        out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps, return_logits=True)
+    assert rel_err(logits_g, logits_o) < TOL
+    assert np.array_equal(out_g.cpu().numpy()[:steps], out_o[:steps])
