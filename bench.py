@@ -387,6 +387,84 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------------------------------
+# generation workload (BASELINE.json configs[4]): 24000-sample utterance, n_loop=4 n_layer=10
+# ------------------------------------------------------------------------------------------
+def run_generate(args):
+    import chainer_vq_vae_b200 as V
+    from chainer_vq_vae_b200.generate import generate_utterance
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cfg = dict(CFG)
+    cfg["n_loop"] = 4
+    T = args.gen_length
+    model = build_model(cfg, dev, "fp32").eval()
+    ex = synthetic_examples(1, T, 71)[0]
+    x_enc = torch.from_numpy(ex[0][None]).to(dev)
+    spk = torch.tensor([int(ex[2])], device=dev, dtype=torch.int32)
+    steps = min(args.gen_steps or (T - 1), T - 1)
+    u = np.random.default_rng(0).uniform(size=steps)
+    with torch.no_grad():
+        cond = model.condition_embed(model.vq(model.encoder(x_enc)), spk)
+        dec = model.decoder.ema
+        generate_utterance(dec, cond, u, n_steps=min(steps, 200))          # warm-up
+        torch.cuda.synchronize()
+        sampler = ClockSampler(0)
+        sampler.start()
+        launches0 = V.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = generate_utterance(dec, cond, u, n_steps=steps)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        # end to end: host condition -> device, kernel, samples back to the host
+        cond_h = cond.cpu().pin_memory()
+        t0 = time.perf_counter()
+        out2 = generate_utterance(dec, cond_h.to(dev, non_blocking=True), u, n_steps=steps).cpu()
+        e2e_s = time.perf_counter() - t0
+    pk, pk_src = peaks()
+    n_blocks = cfg["n_loop"] * cfg["n_layer"]
+    Cr, Cd, Cs, Cc = 512, 512, 256, 192
+    wbytes = 4.0 * (n_blocks * (3 * Cr * Cd + Cc * Cd + (Cd // 2) * (Cr + Cs)) + 2 * 256 * 256)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import vqvae_oracle as O
+        oc = O.config_gen()
+        oc.length = 1024
+        params = O.make_params(oc)
+        inp = O.make_inputs(oc)
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_cpu = 60
+        t0 = time.perf_counter()
+        O.generate_loop(params, oc, inp["x_enc"], inp["speaker"], u[:n_cpu], n_steps=n_cpu)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{n_cpu} steps of the same decoder (n_loop=4, n_layer=10, 512/512/256) "
+                         "with the reference's concat-shift queues, oracle on torch-CPU"}
+    per_step_s = ms * 1e-3 / steps
+    print(json.dumps({
+        "metric": "generate samples/sec (one utterance, persistent kernel)",
+        "value": steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": steps,
+        "warmup": 200, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "replicas only",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic condition, random-init weights",
+        "config": {"workload": f"generate: {steps} samples, n_loop=4 n_layer=10 filter_size=3 "
+                               "512/512/256 Cc=192 mu-law-256, batch 1"},
+        "e2e": {"value": steps / e2e_s, "unit": "samples/s",
+                "h2d_bytes_per_step": cond_h.numel() * 4 / steps, "d2h_bytes_per_step": 8},
+        "gpu_launches": V.launch_count() - launches0, "clocks": clocks,
+        "roofline": {"kernel": "generate_kernel", "bound": "hbm",
+                     "achieved": wbytes / per_step_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": wbytes / per_step_s / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "peak_source": pk_src,
+                     "note": "algorithmic bytes = every weight read once per sample (174.9 MB "
+                             "fp32); the weights fit the 126 MB L2 only partly, the kernel is "
+                             "grid-barrier latency bound (82 barriers per sample)"},
+        "cpu_baseline": cpu, "first_samples": [int(v) for v in out[:8].tolist()],
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,8 +474,13 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "fp32"),
                     choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "generate"])
+    ap.add_argument("--gen-length", type=int, default=24000)
+    ap.add_argument("--gen-steps", type=int, default=0)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "generate":
+        run_generate(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -95,6 +95,7 @@ generate_kernel(const GenParams P) {
   float* vc = vx + ((KX + 3) & ~3);     // [Cc]  cond[:, t]
   float* zs = vc + ((P.Cc + 3) & ~3);   // [Ch]
   float* xs = zs + ((Ch + 3) & ~3);     // [max(Cr, Cs, Q)] scratch vector
+  float* ps = xs + ((max(max(P.Cr, P.Cs), P.Q) + 3) & ~3);   // [Q] softmax numerators
   __shared__ int s_sample;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -218,7 +219,7 @@ generate_kernel(const GenParams P) {
       float s = 0.0f;
       for (int i = lane; i < P.Q; i += 32) {
         float e = expf(xs[i] - m);
-        vx[i] = e;              // reuse vx as the probability buffer (Q <= KX checked on host)
+        ps[i] = e;
         s += e;
       }
       s = warp_sum(s);
@@ -226,12 +227,12 @@ generate_kernel(const GenParams P) {
       if (lane == 0) {
         // numpy.random.choice: cdf = cumsum(p as float64); cdf /= cdf[-1]; searchsorted(u, 'right')
         double tot = 0.0;
-        for (int i = 0; i < P.Q; ++i) tot += (double)(vx[i] / s);
+        for (int i = 0; i < P.Q; ++i) tot += (double)(ps[i] / s);
         const double u = P.uniforms[step];
         double run = 0.0;
         int pick = P.Q - 1;
         for (int i = 0; i < P.Q; ++i) {
-          run += (double)(vx[i] / s);
+          run += (double)(ps[i] / s);
           if (run / tot > u) { pick = i; break; }
         }
         s_sample = pick;
@@ -301,7 +302,6 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
                   d.t_start - d.cond_t0 + d.n_steps <= d.T_total,
               "vqw_generate: steps [%d, %d) are outside the condition columns [%d, %d)", d.t_start,
               d.t_start + d.n_steps, d.cond_t0, d.cond_t0 + d.T_total);
-  VQW_REQUIRE(d.Q <= d.fs * d.Cr, "vqw_generate: quantize larger than fs*Cr is unsupported");
   if (d.n_steps == 0) return 0;
   VQW_REQUIRE(embed_w && embed_b && proj1_w && proj1_b && proj2_w && proj2_b && cond && uniforms &&
                   samples && workspace, "vqw_generate: null tensor");
@@ -356,7 +356,8 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   const int KX = d.fs * d.Cr, Ch = d.Cd / 2;
   int mx = d.Cr > d.Cs ? d.Cr : d.Cs;
   if (d.Q > mx) mx = d.Q;
-  size_t smem = sizeof(float) * (((KX + 3) & ~3) + ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) + mx + 8);
+  size_t smem = sizeof(float) * (((KX + 3) & ~3) + ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) +
+                                 ((mx + 3) & ~3) + d.Q + 8);
   VQW_REQUIRE(smem <= 200 * 1024, "vqw_generate: channel counts too large for shared memory");
   VQW_CHECK_CUDA(cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
