@@ -28,11 +28,15 @@
 //                    O_2 = Ws z -> skip (+)=
 // so the gated activation never leaves the SM and the block is one kernel.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace vqw {
 namespace tc {
 
 constexpr int STAGES = 4;
+constexpr int FWD_EPI_WARPS = 16;                       // 4 warps per TMEM lane quadrant
+constexpr int FWD_THREADS = (FWD_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
+constexpr int W_TMA = FWD_EPI_WARPS, W_MMA = FWD_EPI_WARPS + 1;
 constexpr int ACC_COL = 0, ZHI_COL = 256, ZLO_COL = 384;
 constexpr int CD = 512, CH = 256, HALF = 128;             // dilated channels handled by this kernel
 
@@ -41,7 +45,8 @@ struct Params {
   int x3;               // 1: bf16x3, 0: single bf16 pass
   int skip_accumulate;
   int write_residual;   // 0 for the last block: O_0/O_1 are skipped entirely
-  const float* x;       // (B,Cr,T) fp32: the residual-add operand (exact fp32 value)
+  const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
+  const __nv_bfloat16* xp_lo;
   const float* conv_b;  const float* cond_b;  const float* res_b;  const float* skip_b;
   float* res_f32;       // (B,Cr,T) fp32 or null (saved block input of the next block / API output)
   __nv_bfloat16* res_hi;  // packed (B,T,Cr) planes for the next block (null for the last block)
@@ -49,10 +54,11 @@ struct Params {
   float* skip;          // (B,Cs,T) fp32 in/out
   float* gate_tanh;     // (B,Ch,T) fp32 or null
   float* gate_sig;
+  long long* dbg;       // optional phase timestamps of CTA (0,0) (VQW_TC_TIMELINE=1)
 };
 
 // ------------------------------------------------------------------ the kernel -------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                    const __grid_constant__ CUtensorMap map_x_lo,
                    const __grid_constant__ CUtensorMap map_c_hi,
@@ -82,7 +88,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   const int o_begin = P.write_residual ? 0 : P.Cr / TN;  // first N chunk of [Wr ; Ws]
   const int o_end = P.Cr / TN + P.Cs / TN;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
     prefetch_tmap(&map_w2_hi);
     if (P.x3) {
@@ -94,27 +100,27 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, FWD_EPI_WARPS * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp < 4) {
-    for (int i = threadIdx.x; i < CD; i += 128) b1s[i] = P.conv_b[i] + P.cond_b[i];
-    for (int i = threadIdx.x; i < P.Cr; i += 128) brs[i] = P.res_b[i];
-    for (int i = threadIdx.x; i < P.Cs; i += 128) bss[i] = P.skip_b[i];
+  if (warp < FWD_EPI_WARPS) {
+    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.conv_b[i] + P.cond_b[i];
+    for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
+    for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == W_TMA) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0;
@@ -153,18 +159,20 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // =============================== MMA issuer =================================
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
       int nphase = 0;
       const uint32_t acc = tmem_base + ACC_COL;
+      const bool rec = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;
       for (int gp = 0; gp < 2; ++gp, ++nphase) {
         if (nphase > 0) {
           mbar_wait(acc_empty, (nphase - 1) & 1);
           tc_fence_after();
         }
+        if (rec) P.dbg[2 * nphase] = clock64();
         for (int i = 0; i < nk1; ++i) {
           mbar_wait(full0 + 8 * stage, ph);
           tc_fence_after();
@@ -185,10 +193,12 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
         tc_commit(acc_full);
+        if (rec) P.dbg[2 * nphase + 1] = clock64();
       }
       for (int oc = o_begin; oc < o_end; ++oc, ++nphase) {
         mbar_wait(acc_empty, (nphase - 1) & 1);   // accumulator drained AND z complete in TMEM
         tc_fence_after();
+        if (rec) P.dbg[2 * nphase] = clock64();
         for (int i = 0; i < nk2; ++i) {
           mbar_wait(full0 + 8 * stage, ph);
           tc_fence_after();
@@ -210,21 +220,29 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
         tc_commit(acc_full);
+        if (rec) P.dbg[2 * nphase + 1] = clock64();
       }
     }
   } else {
-    // =============================== epilogue (warps 0-3) =======================
-    const int row = warp * 32 + lane;
+    // =============================== epilogue (warps 0-15) ======================
+    // warp e: TMEM lane quadrant e%4 (hardware rule: a warp reaches lanes 32*(warp%4)..+31),
+    // column group e/4 -- the 16-column chunks of a phase are dealt round-robin to the 4 groups,
+    // so every SM sub-partition has 4 resident epilogue warps to hide latencies with.
+    const int quad = warp & 3, grp = warp >> 2;
+    constexpr int NG = FWD_EPI_WARPS / 4;
+    const int row = quad * 32 + lane;
     const int t = t0 + row;
     const bool t_ok = t < P.T;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     int nphase = 0;
+    const bool rec = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0;
     // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), kept in TMEM as bf16 hi/lo planes ----
     for (int gp = 0; gp < 2; ++gp, ++nphase) {
       mbar_wait(acc_full, nphase & 1);
       tc_fence_after();
+      if (rec) P.dbg[16 + 2 * nphase] = clock64();
 #pragma unroll 1
-      for (int q = 0; q < HALF / 16; ++q) {
+      for (int q = grp; q < HALF / 16; q += NG) {
         float a[16], g[16];
         tmem_ld16(lane_base + ACC_COL + 16 * q, a);
         tmem_ld16(lane_base + ACC_COL + HALF + 16 * q, g);
@@ -236,13 +254,13 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int ch = ch0 + i + u;
-            const float th = tanhf_(a[i + u] + b1s[ch]);
-            const float sg = sigmoidf_(g[i + u] + b1s[CH + ch]);
+            const float th = tanh_fast(a[i + u] + b1s[ch]);
+            const float sg = sigmoid_fast(g[i + u] + b1s[CH + ch]);
             z2[u] = th * sg;
             if (P.gate_tanh != nullptr && t_ok) {
               const int64_t off = ((int64_t)b * CH + ch) * P.T + t;
-              P.gate_tanh[off] = th;
-              P.gate_sig[off] = sg;
+              __stcs(P.gate_tanh + off, th);
+              __stcs(P.gate_sig + off, sg);
             }
           }
           __nv_bfloat16 h0, l0, h1, l1;
@@ -257,39 +275,63 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(acc_empty);
+      if (rec) P.dbg[16 + 2 * nphase + 1] = clock64();
     }
     // ---- output phases: residual chunks then skip chunks ----
-    // The fp32 operands added in the epilogue (x for the residual, the running skip sum) are
-    // prefetched PF chunks ahead into registers -- before the accumulator is even ready -- so
-    // the 4 epilogue warps keep PF*16 independent 128-byte requests in flight each instead
-    // of one dependent load per channel.
-    constexpr int PF = 3;
+    // residual = Wr z + br + x with x read back from the packed hi/lo planes (x = hi + lo to
+    // 2^-17: two 16-byte loads per plane per 16 channels instead of 16 strided fp32 loads);
+    // the running skip sum is fp32 (B,Cs,T): lanes are consecutive t, so every access is a
+    // coalesced 128-byte row segment.  Operands of the NEXT chunk are fetched before the
+    // current one is processed.
     for (int oc = o_begin; oc < o_end; ++oc, ++nphase) {
       const bool is_res = oc < P.Cr / TN;
       const int cbase = is_res ? oc * TN : (oc - P.Cr / TN) * TN;
-      const int C = is_res ? P.Cr : P.Cs;
-      const float* addsrc = is_res ? P.x : (P.skip_accumulate ? P.skip : nullptr);
-      const float* addp = addsrc ? addsrc + ((int64_t)b * C + cbase) * P.T + t : nullptr;
-      float pre[PF][16];
+      float addf[16];
+      uint4 xh[2], xl[2];
+      auto fetch = [&](int q) {
+        const int ch0 = cbase + 16 * q;
+        if (is_res) {
+          const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
+          if (t_ok) {
+            const uint4* ph = reinterpret_cast<const uint4*>(P.xp_hi + poff);
+            xh[0] = __ldg(ph); xh[1] = __ldg(ph + 1);
+            if (P.x3) {
+              const uint4* pl = reinterpret_cast<const uint4*>(P.xp_lo + poff);
+              xl[0] = __ldg(pl); xl[1] = __ldg(pl + 1);
+            }
+          }
+        } else if (P.skip_accumulate && t_ok) {
+          const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
 #pragma unroll
-      for (int f = 0; f < PF; ++f)
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pre[f][i] = (addp && t_ok) ? __ldcs(addp + (int64_t)(16 * f + i) * P.T) : 0.0f;
+          for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
+        }
+      };
+      fetch(grp);
       mbar_wait(acc_full, nphase & 1);
       tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < TN / 16; ++q) {
+      if (rec) P.dbg[16 + 2 * nphase] = clock64();
+#pragma unroll 1
+      for (int q = grp; q < TN / 16; q += NG) {
         float o[16], add[16];
         tmem_ld16(lane_base + ACC_COL + 16 * q, o);
+        if (is_res) {
+          const uint32_t hw[8] = {xh[0].x, xh[0].y, xh[0].z, xh[0].w, xh[1].x, xh[1].y, xh[1].z, xh[1].w};
+          const uint32_t lw[8] = {xl[0].x, xl[0].y, xl[0].z, xl[0].w, xl[1].x, xl[1].y, xl[1].z, xl[1].w};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) add[i] = pre[q % PF][i];
-        if (q + PF < TN / 16) {
+          for (int i = 0; i < 8; ++i) {
+            float v0 = __uint_as_float(hw[i] << 16), v1 = __uint_as_float(hw[i] & 0xffff0000u);
+            if (P.x3) {
+              v0 += __uint_as_float(lw[i] << 16);
+              v1 += __uint_as_float(lw[i] & 0xffff0000u);
+            }
+            add[2 * i] = t_ok ? v0 : 0.0f;
+            add[2 * i + 1] = t_ok ? v1 : 0.0f;
+          }
+        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pre[q % PF][i] =
-                (addp && t_ok) ? __ldcs(addp + (int64_t)(16 * (q + PF) + i) * P.T) : 0.0f;
+          for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
         }
+        if (q + NG < TN / 16) fetch(q + NG);
         const int ch0 = cbase + 16 * q;
         if (is_res) {
           uint32_t rh[8], rl[8];
@@ -301,7 +343,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               const int ch = ch0 + i + u;
               const float v = o[i + u] + brs[ch] + add[i + u];
               if (t_ok && P.res_f32 != nullptr)
-                P.res_f32[((int64_t)b * P.Cr + ch) * P.T + t] = v;
+                __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
             __nv_bfloat16 h0, l0, h1, l1;
@@ -331,12 +373,13 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       }
       tc_fence_before();
       mbar_arrive(acc_empty);
+      if (rec) P.dbg[16 + 2 * nphase + 1] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == W_MMA) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
@@ -565,11 +608,10 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.x3 = x3 ? 1 : 0;
     P.skip_accumulate = i > 0;
     P.write_residual = write_res ? 1 : 0;
-    P.x = (i == 0) ? x : residuals[i - 1];
-    VQW_REQUIRE(P.x != nullptr, "vqw_resnet_forward: residuals[%d] is needed as the fp32 "
-                                "residual-add operand of block %d", i - 1, i);
+    P.xp_hi = x_hi[cur];
+    P.xp_lo = x_lo[cur];
     P.conv_b = w.conv_b; P.cond_b = w.cond_b; P.res_b = w.res_b; P.skip_b = w.skip_b;
-    P.res_f32 = write_res ? residuals[i] : nullptr;
+    P.res_f32 = (write_res && residuals) ? residuals[i] : nullptr;
     P.res_hi = last ? nullptr : x_hi[nxt];
     P.res_lo = last ? nullptr : x_lo[nxt];
     P.skip = skip;
@@ -577,10 +619,27 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.gate_sig = gate_sig ? gate_sig[i] : nullptr;
     VQW_REQUIRE((P.gate_tanh == nullptr) == (P.gate_sig == nullptr),
                 "vqw_resnet_forward: gate_tanh/gate_sig of block %d must be given together", i);
+    static long long* dbg_buf = nullptr;
+    static const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
+    P.dbg = nullptr;
+    if (timeline) {
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+      P.dbg = dbg_buf;
+    }
     dim3 grid(ceil_div(d.T, TM), d.B);
-    resblock_tc_kernel<<<grid, NTHREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
+    resblock_tc_kernel<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
                                                         m_w1_lo, m_w2_hi, m_w2_lo, P);
     VQW_CHECK_LAUNCH("resblock_tc_kernel");
+    if (timeline) {
+      long long h[64];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[vqw timeline] block %d (cycles rel. to first MMA phase start)\n", i);
+      for (int n = 0; n < 5; ++n)
+        fprintf(stderr, "  phase %d: mma [%lld, %lld]  epilogue [%lld, %lld]\n", n, h[2 * n] - h[0],
+                h[2 * n + 1] - h[0], h[16 + 2 * n] - h[0], h[16 + 2 * n + 1] - h[0]);
+    }
   }
   return 0;
 }

@@ -132,6 +132,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
                            ((uint32_t)(TM >> 4) << 24);
 
+// gate non-linearities on the special-function unit (ex2 + fast division), ~1e-6 relative
+__device__ __forceinline__ float sigmoid_fast(float v) {
+  return __fdividef(1.0f, 1.0f + __expf(-v));
+}
+__device__ __forceinline__ float tanh_fast(float v) {
+  const float e = __expf(-2.0f * fabsf(v));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), v);
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));

@@ -250,13 +250,11 @@ class _ResidualStack(torch.autograd.Function):
             return torch.empty((B, ch, T, 1), device=x.device, dtype=torch.float32)
 
         # residual[i] = output of block i = saved input of block i+1.  Training keeps all of
-        # them; inference only needs two ping-pong buffers (the tensor-core modes read the
-        # previous one as the exact fp32 residual-add operand).
+        # them; inference chains the blocks through the library's workspace.
         if need_grad:
             res = [new(Cr) for _ in range(n - 1)] + [new(Cr) if keep_last_residual else None]
         else:
-            pp = [new(Cr), new(Cr)] if (tc_mode and n > 1) else [None, None]
-            res = [pp[i & 1] for i in range(n - 1)] + [new(Cr) if keep_last_residual else None]
+            res = [None] * (n - 1) + [new(Cr) if keep_last_residual else None]
         gates: List[torch.Tensor] = []
         if need_grad:
             for _ in range(n):
