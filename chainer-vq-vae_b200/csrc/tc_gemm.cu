@@ -24,6 +24,9 @@ namespace vqw {
 namespace tc {
 
 constexpr int G_STAGES = 2;
+constexpr int G_EPI_WARPS = 8;                         // 2 warps per TMEM lane quadrant
+constexpr int G_THREADS = (G_EPI_WARPS + 2) * 32;
+constexpr int GW_TMA = G_EPI_WARPS, GW_MMA = G_EPI_WARPS + 1;
 constexpr int MAX_SEG = 4;
 enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3 };
 
@@ -62,7 +65,7 @@ struct Maps {
 };
 
 template <int EPI>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(G_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -87,7 +90,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     for (int s = 0; s < P.nseg; ++s) total_slabs += P.seg[s].nslabs;
   }
 
-  if (warp == 4 && lane == 0) {
+  if (warp == GW_TMA && lane == 0) {
     for (int i = 0; i < 8; ++i) prefetch_tmap(&maps.m[i]);
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -96,7 +99,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == GW_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(256)
@@ -108,7 +111,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == GW_TMA) {
     // =============================== TMA producer ===============================
     if (lane == 0 && total_slabs > 0) {
       int stage = 0;
@@ -146,7 +149,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == GW_MMA) {
     // =============================== MMA issuer =================================
     if (lane == 0 && total_slabs > 0) {
       int stage = 0;
@@ -173,10 +176,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       tc_commit(acc_full);
     }
   } else if (total_slabs > 0) {
-    // =============================== epilogue (warps 0-3) =======================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    constexpr int PF = 2;
+    // =============================== epilogue (warps 0-7) =======================
+    // warp e: TMEM lane quadrant e%4, column group e/4; 16-column chunks dealt round-robin.
+    const int quad = warp & 3, grp = warp >> 2;
+    constexpr int NG = G_EPI_WARPS / 4;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     if (EPI == EPI_WGRAD) {
       const int m = blockIdx.x * TM + row;
@@ -184,7 +189,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       mbar_wait(acc_full, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int q = 0; q < TN / 16; ++q) {
+      for (int q = grp; q < TN / 16; q += NG) {
         float o[16];
         tmem_ld16(lane_base + 16 * q, o);
         if (m < P.M) {
@@ -209,29 +214,24 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         const int CHh = TN;   // 256 gate pairs
         const float* tp = P.f0 + ((int64_t)b * CHh) * P.T + t;
         const float* sp = P.f1 + ((int64_t)b * CHh) * P.T + t;
-        float pt[PF][16], ps[PF][16];
-#pragma unroll
-        for (int f = 0; f < PF; ++f)
+        float pt[16], ps[16];
+        auto fetch = [&](int q) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            pt[f][i] = t_ok ? __ldcs(tp + (int64_t)(16 * f + i) * P.T) : 0.0f;
-            ps[f][i] = t_ok ? __ldcs(sp + (int64_t)(16 * f + i) * P.T) : 0.0f;
+            pt[i] = t_ok ? __ldcs(tp + (int64_t)(16 * q + i) * P.T) : 0.0f;
+            ps[i] = t_ok ? __ldcs(sp + (int64_t)(16 * q + i) * P.T) : 0.0f;
           }
+        };
+        fetch(grp);
         mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < TN / 16; ++q) {
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
           float gz[16], th[16], sg[16];
           tmem_ld16(lane_base + 16 * q, gz);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { th[i] = pt[q % PF][i]; sg[i] = ps[q % PF][i]; }
-          if (q + PF < TN / 16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              pt[q % PF][i] = t_ok ? __ldcs(tp + (int64_t)(16 * (q + PF) + i) * P.T) : 0.0f;
-              ps[q % PF][i] = t_ok ? __ldcs(sp + (int64_t)(16 * (q + PF) + i) * P.T) : 0.0f;
-            }
-          }
+          for (int i = 0; i < 16; ++i) { th[i] = pt[i]; sg[i] = ps[i]; }
+          if (q + NG < TN / 16) fetch(q + NG);
           uint32_t th_hi[8], th_lo[8], sg_hi[8], sg_lo[8];
           const int zc0 = 16 * q;
 #pragma unroll
@@ -280,27 +280,23 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         const int cbase = TN * blockIdx.y;
         const float* addsrc = (EPI == EPI_GX) ? P.f0 : P.o0;
         const float* addp = addsrc ? addsrc + ((int64_t)b * P.Cout + cbase) * P.T + t : nullptr;
-        float pre[PF][16];
-#pragma unroll
-        for (int f = 0; f < PF; ++f)
+        float pre[16];
+        auto fetch = [&](int q) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            pre[f][i] = (addp && t_ok && cbase + 16 * f + i < P.Cout)
-                            ? __ldcs(addp + (int64_t)(16 * f + i) * P.T) : 0.0f;
+            pre[i] = (addp && t_ok && cbase + 16 * q + i < P.Cout)
+                         ? __ldcs(addp + (int64_t)(16 * q + i) * P.T) : 0.0f;
+        };
+        fetch(grp);
         mbar_wait(acc_full, 0);
         tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < TN / 16; ++q) {
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
           float o[16], add[16];
           tmem_ld16(lane_base + 16 * q, o);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) add[i] = pre[q % PF][i];
-          if (q + PF < TN / 16) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              pre[q % PF][i] = (addp && t_ok && cbase + 16 * (q + PF) + i < P.Cout)
-                                   ? __ldcs(addp + (int64_t)(16 * (q + PF) + i) * P.T) : 0.0f;
-          }
+          for (int i = 0; i < 16; ++i) add[i] = pre[i];
+          if (q + NG < TN / 16) fetch(q + NG);
           const int ch0 = cbase + 16 * q;
           if (ch0 >= P.Cout) continue;      // Cout is a multiple of 16
           uint32_t vh[8], vl[8];
@@ -340,7 +336,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == GW_MMA) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
@@ -355,7 +351,7 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
   auto kern = tc_gemm_kernel<EPI>;
   const size_t smem = gemm_smem();
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, NTHREADS, smem, stream>>>(maps, P);
+  kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
   static const char* names[4] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
                                  "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>"};
   VQW_CHECK_LAUNCH(names[EPI]);
@@ -370,26 +366,58 @@ __global__ void __launch_bounds__(256)
 cvt_planes_kernel(const float* __restrict__ in, const float* __restrict__ mul,
                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int rows,
                   int T, int B, int shift) {
-  const int64_t n = (int64_t)B * rows * T;
+  // one thread = 8 consecutive time steps of one (b, row): 2 x float4 in, 16-byte stores out
+  const int T8 = T >> 3;
+  const int64_t n = (int64_t)B * rows * T8;
+  const bool vec = (shift & 3) == 0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const int t = (int)(e % T);
-    const int64_t r = e / T;
+    const int t0 = (int)(e % T8) * 8;
+    const int64_t r = e / T8;
     const int c = (int)(r % rows), b = (int)(r / rows);
-    float v = (c == C) ? 1.0f : 0.0f;
-    if (c < C) {
-      const int ts = t - shift;          // out[t] = in[t - shift] (zero before the start)
-      v = 0.0f;
-      if (ts >= 0 && ts < T) {
-        const int64_t off = ((int64_t)b * C + c) * T + ts;
-        v = in[off];
-        if (mul) v *= mul[off];
+    float v[8];
+    if (c >= C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (c == C) ? 1.0f : 0.0f;
+    } else {
+      const int64_t rowoff = ((int64_t)b * C + c) * T;
+      const int ts0 = t0 - shift;          // out[t] = in[t - shift] (zero before the start)
+      if (vec && ts0 >= 0 && ts0 + 7 < T) {
+        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(in + rowoff + ts0));
+        const float4 a1 = __ldcs(reinterpret_cast<const float4*>(in + rowoff + ts0 + 4));
+        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+        v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        if (mul) {
+          const float4 m0 = __ldcs(reinterpret_cast<const float4*>(mul + rowoff + ts0));
+          const float4 m1 = __ldcs(reinterpret_cast<const float4*>(mul + rowoff + ts0 + 4));
+          v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w;
+          v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ts = ts0 + i;
+          float x = 0.0f;
+          if (ts >= 0 && ts < T) {
+            x = in[rowoff + ts];
+            if (mul) x *= mul[rowoff + ts];
+          }
+          v[i] = x;
+        }
       }
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[e] = h;
-    if (lo) lo[e] = l;
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * i], h0, l0);
+      split_bf16(v[2 * i + 1], h1, l1);
+      ph[i] = pack2(h0, h1);
+      pl[i] = pack2(l0, l1);
+    }
+    const int64_t o = (r * T + t0);
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
@@ -453,7 +481,7 @@ struct BwdLayout {
   int64_t total;
   int64_t gs_p[2], gs_c[2];          // g_skip: time-major / channel-major planes
   int64_t cond_c[2];                 // cond channel-major planes with the ones row (Cc+1 rows)
-  int64_t x_c[2], z_c[2];            // per-block: x and z = tanh*sig channel-major planes
+  int64_t x_c[2], x_s[2], z_c[2];    // per-block: x, x delayed by an unaligned tap shift, z = tanh*sig
   int64_t gh_p[2], gh_c[2];          // per-block: gh both layouts
   int64_t gr_f[2], gr_p[2][2], gr_c[2][2];   // g_res ping-pong: fp32, time-major, channel-major
   int64_t w2t[2], wct[2], wpt[2];    // per-block transposed weight planes (base; + i*wstride)
@@ -469,6 +497,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   for (int p = 0; p < 2; ++p) L.gs_c[p] = take(N * d.Cs * 2);
   for (int p = 0; p < 2; ++p) L.cond_c[p] = take(N * pad256(d.Cc + 1) * 2);
   for (int p = 0; p < 2; ++p) L.x_c[p] = take(N * d.Cr * 2);
+  for (int p = 0; p < 2; ++p) L.x_s[p] = take(N * d.Cr * 2);
   for (int p = 0; p < 2; ++p) L.z_c[p] = take(N * (d.Cd / 2) * 2);
   for (int p = 0; p < 2; ++p) L.gh_p[p] = take(N * d.Cd * 2);
   for (int p = 0; p < 2; ++p) L.gh_c[p] = take(N * d.Cd * 2);
@@ -642,14 +671,25 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         dim3 grid(ceil_div(M, TM), ceil_div(Nrows, TN), B);
         return launch_gemm<EPI_WGRAD>(maps, P, grid, stream);
       };
+      // x as channel-major planes; a tap delay that is a multiple of 8 samples (16 bytes) is a
+      // TMA box coordinate, any other delay needs its own shifted copy (TMA alignment rule)
+      cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_c[0]), LO(L.x_c[1]), Cr, Cr,
+                                                    T, B, 0);
+      VQW_CHECK_LAUNCH("cvt_planes_kernel(x)");
       for (int j = 0; j < fs; ++j) {
-        // x delayed by the tap's causal shift, channel-major planes
-        cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_c[0]), LO(L.x_c[1]), Cr,
-                                                      Cr, T, B, dil * (fs - 1 - j));
-        VQW_CHECK_LAUNCH("cvt_planes_kernel(x)");
-        if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.x_c[0], L.x_c[1], Cr, Cr, 0, gw.conv_w + j,
-                           (long long)Cr * fs, fs, nullptr, nullptr, -1))
-          return rc;
+        const int sh = dil * (fs - 1 - j);
+        if (sh % 8 == 0) {
+          if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.x_c[0], L.x_c[1], Cr, Cr, -sh,
+                             gw.conv_w + j, (long long)Cr * fs, fs, nullptr, nullptr, -1))
+            return rc;
+        } else {
+          cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_s[0]), LO(L.x_s[1]), Cr,
+                                                        Cr, T, B, sh);
+          VQW_CHECK_LAUNCH("cvt_planes_kernel(x shifted)");
+          if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.x_s[0], L.x_s[1], Cr, Cr, 0, gw.conv_w + j,
+                             (long long)Cr * fs, fs, nullptr, nullptr, -1))
+            return rc;
+        }
       }
       // cond projection; the appended row of ones gives sum_t gh = gb_conv = gb_cond
       if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.cond_c[0], L.cond_c[1], CcP, Cc, 0,
