@@ -498,6 +498,21 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t
   return 0;
 }
 
+int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
+                uint64_t B) {
+  EncodeTiledFn enc = get_encode();
+  VQW_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[3] = {C, T, B};
+  cuuint64_t strides[2] = {pitch * 2, pitch * T * 2};
+  cuuint32_t box[3] = {64, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VQW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(mn) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 size_t smem_bytes(int Cr, int Cs) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * (2 * STAGES + 2) + 16;
 }

@@ -127,10 +127,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// MN-major, 128-byte swizzle descriptor for an operand whose M/N axis is contiguous in shared
+// memory: canonical layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in bf16 elements, i.e. rows of
+// 64 contiguous M/N elements (128 B), 8 K-rows per 1024-byte swizzle atom.  LBO = byte distance
+// between successive 64-element M/N groups, SBO = byte distance between successive 8-row K
+// groups.  Tiles are written by TMA boxes {64 elements, 32 rows} with CU_TENSOR_MAP_SWIZZLE_128B,
+// one 4096-byte box per 64-element group: LBO = 4096, SBO = 1024.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
                            ((uint32_t)(TM >> 4) << 24);
+// same, both operands MN-major (bit 15 = A, bit 16 = B)
+constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
 
 // gate non-linearities on the special-function unit (ex2 + fast division), ~1e-6 relative
 __device__ __forceinline__ float sigmoid_fast(float v) {
@@ -154,6 +171,11 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 // 64-byte swizzle, out-of-bounds elements read as zero.
 int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t rows,
              uint64_t batch, uint32_t box_rows);
+// time-major plane (C channels contiguous with row pitch `pitch` elements, T rows, B items):
+// box = {64 channels, 32 rows, 1}, 128-byte swizzle (MN-major operand tiles of the weight-
+// gradient GEMMs)
+int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
+                uint64_t B);
 
 }  // namespace tc
 }  // namespace vqw

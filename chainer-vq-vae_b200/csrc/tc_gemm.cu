@@ -19,6 +19,7 @@
 // epilogue, one thread per TMEM lane) but with a 2-stage ring and a 256-column accumulator so
 // that TWO CTAs are resident per SM: one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace vqw {
 namespace tc {
@@ -28,7 +29,7 @@ constexpr int G_EPI_WARPS = 8;                         // 2 warps per TMEM lane 
 constexpr int G_THREADS = (G_EPI_WARPS + 2) * 32;
 constexpr int GW_TMA = G_EPI_WARPS, GW_MMA = G_EPI_WARPS + 1;
 constexpr int MAX_SEG = 4;
-enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3 };
+enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3, EPI_WGRAD_MN = 4 };
 
 struct Seg {
   int a_map, b_map;   // tensor-map pair index: hi plane = maps[2*i], lo plane = maps[2*i+1]
@@ -76,7 +77,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool WG = (EPI == EPI_WGRAD);
+  constexpr bool WG = (EPI == EPI_WGRAD || EPI == EPI_WGRAD_MN);
+  constexpr bool MN = (EPI == EPI_WGRAD_MN);   // operands read from time-major planes (MN-major tiles)
   const int nplanes = P.x3 ? 2 : 1;
 
   // total number of K slabs this CTA contracts over
@@ -129,7 +131,37 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         }
         if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
       };
-      if (WG) {
+      if (MN) {
+        // K = time is the ROW axis of the time-major planes: a stage is 2 (A) + 4 (B) boxes of
+        // {64 channels, 32 time steps}; the tap delay is a row coordinate (no alignment rule)
+        const Seg& sg = P.seg[0];
+        const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+        const int items = P.B * P.chunks_per_b;
+        for (int c = blockIdx.z; c < items; c += gridDim.z) {
+          const int bb = c / P.chunks_per_b;
+          const int tk = (c % P.chunks_per_b) * P.slabs_per_item * BK;
+          for (int i = 0; i < P.slabs_per_item; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = base + stage * STAGE_BYTES;
+            mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
+            const int ta = tk + sg.a_c0 + i * BK, tb = tk + sg.b_c0 + i * BK;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_3d(sa + h * 4096, &maps.m[2 * sg.a_map], fb, m0 + 64 * h, ta, bb);
+              if (P.x3) tma_load_3d(sa + A_PLANE + h * 4096, &maps.m[2 * sg.a_map + 1], fb, m0 + 64 * h, ta, bb);
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              tma_load_3d(sa + 2 * A_PLANE + h * 4096, &maps.m[2 * sg.b_map], fb, n0 + 64 * h, tb, bb);
+              if (P.x3)
+                tma_load_3d(sa + 2 * A_PLANE + B_PLANE + h * 4096, &maps.m[2 * sg.b_map + 1], fb,
+                            n0 + 64 * h, tb, bb);
+            }
+            if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+      } else if (WG) {
         const Seg& sg = P.seg[0];
         const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
         const int items = P.B * P.chunks_per_b;
@@ -160,14 +192,27 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         const uint32_t sa = base + stage * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / UK; ++ks) {
-          const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-          const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-          mma_ss(tmem_base, a_hi, b_hi, IDESC, (i | ks) ? 1u : 0u);
-          if (P.x3) {
-            const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-            const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
-            mma_ss(tmem_base, a_lo, b_hi, IDESC, 1u);
-            mma_ss(tmem_base, a_hi, b_lo, IDESC, 1u);
+          if (MN) {
+            // 16 K-rows = two 1024-byte swizzle atoms per step
+            const uint64_t a_hi = smem_desc_sw128_mn(sa + ks * 2048);
+            const uint64_t b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
+            mma_ss(tmem_base, a_hi, b_hi, IDESC_MN, (i | ks) ? 1u : 0u);
+            if (P.x3) {
+              const uint64_t a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
+              const uint64_t b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE + ks * 2048);
+              mma_ss(tmem_base, a_lo, b_hi, IDESC_MN, 1u);
+              mma_ss(tmem_base, a_hi, b_lo, IDESC_MN, 1u);
+            }
+          } else {
+            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
+            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            mma_ss(tmem_base, a_hi, b_hi, IDESC, (i | ks) ? 1u : 0u);
+            if (P.x3) {
+              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
+              mma_ss(tmem_base, a_lo, b_hi, IDESC, 1u);
+              mma_ss(tmem_base, a_hi, b_lo, IDESC, 1u);
+            }
           }
         }
         tc_commit(empty0 + 8 * stage);
@@ -183,7 +228,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
-    if (EPI == EPI_WGRAD) {
+    if (WG) {
       const int m = blockIdx.x * TM + row;
       const int n0 = blockIdx.y * TN;
       mbar_wait(acc_full, 0);
@@ -352,8 +397,9 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
   const size_t smem = gemm_smem();
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
-  static const char* names[4] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
-                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>"};
+  static const char* names[5] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
+                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>",
+                                 "tc_gemm_kernel<WGRAD_MN>"};
   VQW_CHECK_LAUNCH(names[EPI]);
   return 0;
 }
@@ -676,6 +722,28 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_c[0]), LO(L.x_c[1]), Cr, Cr,
                                                     T, B, 0);
       VQW_CHECK_LAUNCH("cvt_planes_kernel(x)");
+      static const bool use_mn = getenv("VQW_WGRAD_MN") && getenv("VQW_WGRAD_MN")[0] == '1';
+      if (use_mn) {
+        // MN-major validation path: gh and x as TIME-major planes, tap delay = row coordinate
+        if (int rc = pack_act_launch(xin, P16(L.x_s[0]), LO(L.x_s[1]), B, Cr, T, stream)) return rc;
+        for (int j = 0; j < fs; ++j) {
+          Maps maps;
+          if (int rc = make_map_mn(&maps.m[0], ws + L.gh_p[0], Cd, Cd, T, B)) return rc;
+          if (int rc = make_map_mn(&maps.m[1], ws + (x3 ? L.gh_p[1] : L.gh_p[0]), Cd, Cd, T, B)) return rc;
+          if (int rc = make_map_mn(&maps.m[2], ws + L.x_s[0], Cr, Cr, T, B)) return rc;
+          if (int rc = make_map_mn(&maps.m[3], ws + (x3 ? L.x_s[1] : L.x_s[0]), Cr, Cr, T, B)) return rc;
+          for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
+          GemmParams P = {};
+          P.nseg = 1;
+          P.seg[0] = Seg{0, 1, 0, 0, -dil * (fs - 1 - j), 0, 0};
+          P.x3 = x3; P.B = B; P.T = T;
+          P.M = Cd; P.N = Cr;
+          P.slabs_per_item = slabs; P.chunks_per_b = 1;
+          P.o0 = gw.conv_w + j; P.gm = (long long)Cr * fs; P.gk = fs; P.ones_col = -1;
+          dim3 grid(ceil_div(Cd, TM), ceil_div(Cr, TN), B);
+          if (int rc = launch_gemm<EPI_WGRAD_MN>(maps, P, grid, stream)) return rc;
+        }
+      } else
       for (int j = 0; j < fs; ++j) {
         const int sh = dil * (fs - 1 - j);
         if (sh % 8 == 0) {
