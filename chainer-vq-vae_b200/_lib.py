@@ -84,15 +84,16 @@ _SIGNATURES = {
                               [C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p,
                                C.POINTER(ResblockWeights), C.c_void_p, C.c_void_p]),
     "vqw_resnet_forward_workspace": (C.c_int64, [C.POINTER(ResnetDesc)]),
+    "vqw_resnet_saved_bytes": (C.c_int64, [C.POINTER(ResnetDesc)]),
     "vqw_resnet_forward": (c_int, [C.POINTER(ResnetDesc), C.c_void_p, C.c_void_p,
                                    C.POINTER(ResblockWeights), C.POINTER(C.c_void_p), C.c_void_p,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
-                                   C.c_void_p]),
+                                   C.c_void_p, C.c_void_p]),
     "vqw_resnet_backward_workspace": (C.c_int64, [C.POINTER(ResnetDesc)]),
     "vqw_resnet_backward": (c_int, [C.POINTER(ResnetDesc)] + [C.c_void_p] * 4 +
                             [C.POINTER(C.c_void_p)] * 3 + [C.POINTER(ResblockWeights), C.c_void_p,
                                                            C.c_void_p, C.POINTER(ResblockWeights),
-                                                           C.c_void_p, C.c_void_p]),
+                                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "vqw_generate_workspace": (C.c_int64, [C.POINTER(GenerateDesc)]),
     "vqw_generate": (c_int, [C.POINTER(GenerateDesc), C.POINTER(ResblockWeights)] +
                      [C.c_void_p] * 13),

@@ -60,14 +60,15 @@ int64_t resnet_tc_workspace(const vqw_resnet_desc& d);
 int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* cond,
                       const vqw_resblock_weights* weights, float* const* residuals, float* skip,
                       float* const* gate_tanh, float* const* gate_sig, void* workspace,
-                      cudaStream_t stream);
+                      void* saved, cudaStream_t stream);
+int64_t resnet_tc_saved_bytes(const vqw_resnet_desc& d);
 
 // tc_gemm.cu (tcgen05 backward)
 int64_t resnet_backward_tc_workspace(const vqw_resnet_desc& d);
 int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const float* g_last_res,
-                       const float* x0, const float* cond, float* const* residuals,
                        float* const* gate_tanh, float* const* gate_sig,
                        const vqw_resblock_weights* weights, float* gx0, float* gcond,
-                       const vqw_resblock_wgrads* wgrads, void* workspace, cudaStream_t stream);
+                       const vqw_resblock_wgrads* wgrads, void* workspace, const void* saved,
+                       cudaStream_t stream);
 
 }  // namespace vqw

@@ -336,7 +336,7 @@ extern "C" int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc) {
 extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, const float* cond,
                                   const vqw_resblock_weights* weights, float* const* residuals,
                                   float* skip, float* const* gate_tanh, float* const* gate_sig,
-                                  void* workspace, vqw_stream_t stream) {
+                                  void* workspace, void* saved, vqw_stream_t stream) {
   using namespace vqw;
   VQW_REQUIRE(desc && weights, "vqw_resnet_forward: null descriptor");
   const vqw_resnet_desc& d = *desc;
@@ -349,7 +349,7 @@ extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, c
   cudaStream_t st = (cudaStream_t)stream;
   if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16)
     return resnet_forward_tc(d, x, cond, weights, residuals, skip, gate_tanh, gate_sig, workspace,
-                             st);
+                             saved, st);
   VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_forward: unknown mode %d", d.mode);
   float* pp[2] = {nullptr, nullptr};
   if (workspace) {
@@ -383,6 +383,12 @@ extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, c
   return 0;
 }
 
+extern "C" int64_t vqw_resnet_saved_bytes(const vqw_resnet_desc* desc) {
+  if (!desc) return -1;
+  if (desc->mode == VQW_MODE_FP32) return 0;
+  return vqw::resnet_tc_saved_bytes(*desc);
+}
+
 extern "C" int64_t vqw_resnet_backward_workspace(const vqw_resnet_desc* desc) {
   if (!desc) return -1;
   if (desc->mode == VQW_MODE_FP32)
@@ -395,19 +401,23 @@ extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_s
                                    float* const* residuals, float* const* gate_tanh,
                                    float* const* gate_sig, const vqw_resblock_weights* weights,
                                    float* gx, float* gcond, const vqw_resblock_wgrads* wgrads,
-                                   void* workspace, vqw_stream_t stream) {
+                                   void* workspace, const void* saved, vqw_stream_t stream) {
   using namespace vqw;
   VQW_REQUIRE(desc && weights && wgrads, "vqw_resnet_backward: null descriptor");
   const vqw_resnet_desc& d = *desc;
   VQW_REQUIRE(d.n_blocks >= 1 && d.dilations, "vqw_resnet_backward: n_blocks/dilations");
   if (d.B == 0 || d.T == 0) return 0;
-  VQW_REQUIRE(g_skip && x && cond && gate_tanh && gate_sig && workspace && gcond,
+  VQW_REQUIRE(g_skip && gate_tanh && gate_sig && workspace && gcond,
               "vqw_resnet_backward: null tensor");
-  VQW_REQUIRE(d.n_blocks == 1 || residuals, "vqw_resnet_backward: residuals[] is required");
-  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16)
-    return resnet_backward_tc(d, g_skip, g_last_res, x, cond, residuals, gate_tanh, gate_sig,
-                              weights, gx, gcond, wgrads, workspace, (cudaStream_t)stream);
+  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16) {
+    VQW_REQUIRE(saved, "vqw_resnet_backward: the tensor-core modes need the `saved` buffer that "
+                       "vqw_resnet_forward filled");
+    return resnet_backward_tc(d, g_skip, g_last_res, gate_tanh, gate_sig, weights, gx, gcond,
+                              wgrads, workspace, saved, (cudaStream_t)stream);
+  }
   VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_backward: unknown mode %d", d.mode);
+  VQW_REQUIRE(x && cond, "vqw_resnet_backward: null tensor");
+  VQW_REQUIRE(d.n_blocks == 1 || residuals, "vqw_resnet_backward: residuals[] is required");
   uintptr_t a = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   float* gh = reinterpret_cast<float*>(a);
   float* pp[2] = {gh + (int64_t)d.B * d.Cd * d.T, gh + (int64_t)d.B * (d.Cd + d.Cr) * d.T};

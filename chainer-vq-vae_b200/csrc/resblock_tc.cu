@@ -54,6 +54,8 @@ struct Params {
   float* skip;          // (B,Cs,T) fp32 in/out
   float* gate_tanh;     // (B,Ch,T) fp32 or null
   float* gate_sig;
+  __nv_bfloat16* zp_hi; // packed (B,T,Ch) planes of z = tanh*sigmoid, saved for the backward (or null)
+  __nv_bfloat16* zp_lo;
   long long* dbg;       // optional phase timestamps of CTA (0,0) (VQW_TC_TIMELINE=1)
 };
 
@@ -271,6 +273,17 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         }
         tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
         if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
+        if (P.zp_hi != nullptr && t_ok) {
+          const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
+          uint4* dh = reinterpret_cast<uint4*>(P.zp_hi + zoff);
+          dh[0] = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+          dh[1] = make_uint4(zh[4], zh[5], zh[6], zh[7]);
+          if (P.x3) {
+            uint4* dl = reinterpret_cast<uint4*>(P.zp_lo + zoff);
+            dl[0] = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+            dl[1] = make_uint4(zl[4], zl[5], zl[6], zl[7]);
+          }
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -549,11 +562,12 @@ static TcWorkspace tc_layout(const vqw_resnet_desc& d) {
 }
 
 int64_t resnet_tc_workspace(const vqw_resnet_desc& d) { return tc_layout(d).total + 1024; }
+int64_t resnet_tc_saved_bytes(const vqw_resnet_desc& d) { return tc_saved_layout(d).total; }
 
 int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* cond,
                       const vqw_resblock_weights* weights, float* const* residuals, float* skip,
                       float* const* gate_tanh, float* const* gate_sig, void* workspace,
-                      cudaStream_t stream) {
+                      void* saved, cudaStream_t stream) {
   using namespace tc;
   VQW_REQUIRE(resnet_tc_supported(d),
               "tcgen05 path needs dilated_channels=512, residual/skip channels multiples of 256, "
@@ -565,10 +579,19 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   const TcWorkspace L = tc_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
   auto plane = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
-  __nv_bfloat16* c_hi = plane(L.off_cond);
-  __nv_bfloat16* c_lo = plane(L.off_cond + L.cond_plane);
-  __nv_bfloat16* x_hi[2] = {plane(L.off_x[0]), plane(L.off_x[1])};
-  __nv_bfloat16* x_lo[2] = {plane(L.off_x[0] + L.x_plane), plane(L.off_x[1] + L.x_plane)};
+  // activation planes: in the caller's `saved` buffer when training (every block's input and
+  // z are kept for the backward), else ping-pong in the workspace
+  const TcSaved S = tc_saved_layout(d);
+  uint8_t* sv = saved ? reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)saved, 1024)) : nullptr;
+  auto splane = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(sv + off); };
+  __nv_bfloat16* c_hi = sv ? splane(S.cond[0]) : plane(L.off_cond);
+  __nv_bfloat16* c_lo = sv ? splane(S.cond[1]) : plane(L.off_cond + L.cond_plane);
+  auto xin_hi = [&](int i) { return sv ? splane(S.x0 + i * S.x_stride) : plane(L.off_x[i & 1]); };
+  auto xin_lo = [&](int i) {
+    return sv ? splane(S.x0 + i * S.x_stride + S.x_plane) : plane(L.off_x[i & 1] + L.x_plane);
+  };
+  __nv_bfloat16* x_hi[2] = {xin_hi(0), nullptr};
+  __nv_bfloat16* x_lo[2] = {xin_lo(0), nullptr};
   const int K1 = d.fs * d.Cr + d.Cc;
 
   // pack the two inputs and every block's weights
@@ -604,7 +627,10 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   for (int i = 0; i < d.n_blocks; ++i) {
     const bool last = (i == d.n_blocks - 1);
     const bool write_res = !last || d.keep_last_residual;
-    const int cur = i & 1, nxt = cur ^ 1;
+    const int cur = 0, nxt = 1;
+    x_hi[0] = xin_hi(i); x_lo[0] = xin_lo(i);
+    x_hi[1] = last ? nullptr : xin_hi(i + 1);
+    x_lo[1] = last ? nullptr : xin_lo(i + 1);
     const vqw_resblock_weights& w = weights[i];
     __nv_bfloat16* w1h = plane(L.off_w + i * L.block_stride);
     __nv_bfloat16* w1l = plane(L.off_w + i * L.block_stride + L.w1_plane);
@@ -632,6 +658,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.skip = skip;
     P.gate_tanh = gate_tanh ? gate_tanh[i] : nullptr;
     P.gate_sig = gate_sig ? gate_sig[i] : nullptr;
+    P.zp_hi = sv ? splane(S.z0 + i * S.z_stride) : nullptr;
+    P.zp_lo = sv ? splane(S.z0 + i * S.z_stride + S.z_plane) : nullptr;
     VQW_REQUIRE((P.gate_tanh == nullptr) == (P.gate_sig == nullptr),
                 "vqw_resnet_forward: gate_tanh/gate_sig of block %d must be given together", i);
     static long long* dbg_buf = nullptr;

@@ -178,4 +178,30 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
                 uint64_t B);
 
 }  // namespace tc
+
+// Layout of the caller-owned `saved` buffer the tensor-core forward fills for the backward:
+// time-major (B,T,C) bf16 hi/lo planes of the condition, of every block's input x_i and of
+// every block's gated activation z_i (all offsets 1024-byte aligned).
+struct TcSaved {
+  int64_t cond[2];
+  int64_t x0, x_plane, x_stride;   // block i: hi at x0 + i*x_stride, lo at + x_plane
+  int64_t z0, z_plane, z_stride;
+  int64_t total;
+};
+inline TcSaved tc_saved_layout(const vqw_resnet_desc& d) {
+  auto al = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
+  TcSaved L;
+  const int64_t N = (int64_t)d.B * d.T;
+  const int64_t cplane = al(N * d.Cc * 2);
+  L.cond[0] = 0;
+  L.cond[1] = cplane;
+  L.x_plane = al(N * d.Cr * 2);
+  L.x_stride = 2 * L.x_plane;
+  L.x0 = 2 * cplane;
+  L.z_plane = al(N * (d.Cd / 2) * 2);
+  L.z_stride = 2 * L.z_plane;
+  L.z0 = L.x0 + (int64_t)d.n_blocks * L.x_stride;
+  L.total = L.z0 + (int64_t)d.n_blocks * L.z_stride + 1024;
+  return L;
+}
 }  // namespace vqw

@@ -1,22 +1,26 @@
 // Tensor-core (tcgen05 / TMEM / TMA) GEMM kernels of the residual-block BACKWARD pass
 // (the reference leaves this to Chainer autograd over modules.py:30-56).
 //
-// One kernel template, four epilogues.  Operands are K-major bf16 hi/lo planes (see
-// resblock_tc.cu for the split-precision scheme); every product is 3 MMAs in bf16x3 mode.
+// One kernel template, four epilogues.  Every operand is a TIME-major (B, T, C) bf16 hi/lo plane
+// (the layout the forward writes, see resblock_tc.cu); every product is 3 MMAs in bf16x3 mode.
 //
-//   "time" flavour (rows of the tile = 128 time steps of one batch item, like the forward):
+//   "time" flavour -- tile rows = 128 time steps of one batch item, K = channels (K-major tiles,
+//   64-byte swizzle, exactly like the forward):
 //     EPI_GATE_BWD  gz = Wr^T g_res + Ws^T g_skip (K = Cr + Cs), then the gate derivative with
-//                   the saved tanh/sigmoid -> gh, written both time-major (B,T,Cd) for the
-//                   data-gradient GEMMs and channel-major (B,Cd,T) for the weight-gradient GEMMs
+//                   the saved tanh/sigmoid -> gh planes
 //     EPI_GX        gx[t] = g_res[t] + sum_j Wc_j^T gh[t + dil*(fs-1-j)]  (anti-causal taps are
-//                   row shifts of the TMA box; rows past T are out of bounds = zero)
-//     EPI_ACCUM     gcond += Wp^T gh
-//   "wgrad" flavour (rows = 128 output channels, K = time, split over batch items):
-//     EPI_WGRAD     gW[m,n] += sum_t A[m,t] * B[n,t - shift]   (atomic accumulation; a row of
-//                   ones appended to B yields the bias gradient in the same MMA)
+//                   row shifts of the TMA box; rows past T are out of bounds = zero) -> planes of
+//                   the next g_res (and fp32 (B,Cr,T) for the gradient handed back to autograd)
+//     EPI_ACCUM     gcond += Wp^T gh   (fp32 (B,Cc,T), read-modify-write)
+//   "wgrad" flavour -- tile rows = 128 output channels, K = time.  Time is the ROW axis of the
+//   planes, so both operands are MN-major tiles (128-byte swizzle, TMA boxes {64 channels, 32
+//   steps}); the per-tap delay is a row coordinate.  All weight gradients of a block -- fs conv
+//   taps, condition projection, res and skip 1x1 -- are ONE grouped launch: a job table maps
+//   blockIdx.x to (operand planes, tile origin, delay, destination), blockIdx.z splits K over
+//   batch items; fp32 atomics accumulate into the gradient tensors.
 //
-// CTA layout as in the forward kernel (warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 =
-// epilogue, one thread per TMEM lane) but with a 2-stage ring and a 256-column accumulator so
+// CTA layout as in the forward kernel (warp 8 = TMA producer, warp 9 = MMA issuer, warps 0-7 =
+// epilogue, two per TMEM lane quadrant) with a 2-stage ring and a 256-column accumulator so
 // that TWO CTAs are resident per SM: one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
 #include <stdlib.h>
@@ -25,18 +29,29 @@ namespace vqw {
 namespace tc {
 
 constexpr int G_STAGES = 2;
-constexpr int G_EPI_WARPS = 8;                         // 2 warps per TMEM lane quadrant
+constexpr int G_EPI_WARPS = 8;
 constexpr int G_THREADS = (G_EPI_WARPS + 2) * 32;
 constexpr int GW_TMA = G_EPI_WARPS, GW_MMA = G_EPI_WARPS + 1;
 constexpr int MAX_SEG = 4;
-enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3, EPI_WGRAD_MN = 4 };
+constexpr int MAX_JOBS = 48;
+constexpr int NMAPS = 12;
+enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3 };
 
 struct Seg {
   int a_map, b_map;   // tensor-map pair index: hi plane = maps[2*i], lo plane = maps[2*i+1]
-  int nslabs;         // K / 32 (time flavour)
+  int nslabs;         // K / 32
   int a_c0, b_c0;     // coordinate along the contiguous (K) axis of slab 0
-  int a_shift;        // time flavour: added to the time-row coordinate of A
-  int b_row0;         // time flavour: first B row; + 256 * blockIdx.y
+  int a_shift;        // added to the time-row coordinate of A
+  int b_row0;         // first B row; + 256 * blockIdx.y
+};
+
+struct Job {          // one 128 x 256 tile of one weight-gradient GEMM
+  int a_map, b_map;   // plane pairs: A rows = output channels of the gradient, B rows = its inputs
+  int m0, n0;         // tile origin (channels)
+  int shift;          // B is read at time t + shift (shift = -delay of the tap)
+  int M, N;           // valid extent of the gradient matrix
+  float* out;         // gW base (already offset to the tap)
+  long long gm, gk;   // strides along m / n
 };
 
 struct GemmParams {
@@ -44,25 +59,22 @@ struct GemmParams {
   Seg seg[MAX_SEG];
   int x3;
   int B, T;
-  int M, N;              // wgrad: valid rows / cols of the whole output
-  int slabs_per_item;    // wgrad: K slabs per (batch item, time chunk) work item
-  int chunks_per_b;      // wgrad: work items per batch item
-  const float* f0;       // GATE_BWD: tanh (B,256,T);  GX: g_res addend (B,Cout,T) or null
-  const float* f1;       // GATE_BWD: sigmoid
-  float* o0;             // GX: gx fp32 (B,Cout,T) | ACCUM: gcond (B,Cout,T) | WGRAD: gW
-  __nv_bfloat16* p_hi;   // time-major (B,T,C) output planes (or null)
+  int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
+  int chunks_per_b;            // wgrad: work items per batch item
+  const float* f0;             // GATE_BWD: tanh (B,256,T)
+  const float* f1;             // GATE_BWD: sigmoid
+  const __nv_bfloat16* a_hi;   // GX: addend planes (B,T,Cout) (g_res) or null
+  const __nv_bfloat16* a_lo;
+  float* o0;                   // GX: fp32 (B,Cout,T) output or null | ACCUM: gcond (B,Cout,T)
+  __nv_bfloat16* p_hi;         // GATE_BWD / GX: output planes (B,T,C) or null
   __nv_bfloat16* p_lo;
-  __nv_bfloat16* c_hi;   // channel-major (B,C,T) output planes (or null)
-  __nv_bfloat16* c_lo;
-  int Cout;              // channels of the output tensor
-  long long gm, gk;      // WGRAD: strides of gW along m / n
-  float* gb;             // WGRAD: bias gradient (or null)
-  float* gb2;            // WGRAD: second bias receiving the same gradient (conv_b and cond_b)
-  int ones_col;          // WGRAD: column of B that is the appended row of ones (-1: none)
+  int Cout;
+  int njobs;
+  Job jobs[MAX_JOBS];
 };
 
 struct Maps {
-  CUtensorMap m[8];
+  CUtensorMap m[NMAPS];
 };
 
 template <int EPI>
@@ -77,15 +89,13 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool WG = (EPI == EPI_WGRAD || EPI == EPI_WGRAD_MN);
-  constexpr bool MN = (EPI == EPI_WGRAD_MN);   // operands read from time-major planes (MN-major tiles)
+  constexpr bool WG = (EPI == EPI_WGRAD);
   const int nplanes = P.x3 ? 2 : 1;
 
-  // total number of K slabs this CTA contracts over
   int total_slabs = 0;
-  int n_items = 0;
   if (WG) {
     const int items = P.B * P.chunks_per_b;
+    int n_items = 0;
     for (int c = blockIdx.z; c < items; c += gridDim.z) ++n_items;
     total_slabs = n_items * P.slabs_per_item;
   } else {
@@ -93,7 +103,6 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   }
 
   if (warp == GW_TMA && lane == 0) {
-    for (int i = 0; i < 8; ++i) prefetch_tmap(&maps.m[i]);
     for (int s = 0; s < G_STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -118,24 +127,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     if (lane == 0 && total_slabs > 0) {
       int stage = 0;
       uint32_t ph = 0;
-      auto issue = [&](const Seg& sg, int a0, int a1, int a2, int b0, int b1, int b2) {
-        mbar_wait(empty0 + 8 * stage, ph ^ 1);
-        const uint32_t fb = full0 + 8 * stage;
-        const uint32_t sa = base + stage * STAGE_BYTES;
-        mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
-        tma_load_3d(sa, &maps.m[2 * sg.a_map], fb, a0, a1, a2);
-        tma_load_3d(sa + 2 * A_PLANE, &maps.m[2 * sg.b_map], fb, b0, b1, b2);
-        if (P.x3) {
-          tma_load_3d(sa + A_PLANE, &maps.m[2 * sg.a_map + 1], fb, a0, a1, a2);
-          tma_load_3d(sa + 2 * A_PLANE + B_PLANE, &maps.m[2 * sg.b_map + 1], fb, b0, b1, b2);
-        }
-        if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
-      };
-      if (MN) {
-        // K = time is the ROW axis of the time-major planes: a stage is 2 (A) + 4 (B) boxes of
-        // {64 channels, 32 time steps}; the tap delay is a row coordinate (no alignment rule)
-        const Seg& sg = P.seg[0];
-        const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+      if (WG) {
+        // a stage = 2 (A) + 4 (B) boxes of {64 channels, 32 time steps} per plane
+        const Job& jb = P.jobs[blockIdx.x];
+        const CUtensorMap* ma = &maps.m[2 * jb.a_map];
+        const CUtensorMap* mb = &maps.m[2 * jb.b_map];
+        prefetch_tmap(ma); prefetch_tmap(mb);
         const int items = P.B * P.chunks_per_b;
         for (int c = blockIdx.z; c < items; c += gridDim.z) {
           const int bb = c / P.chunks_per_b;
@@ -145,39 +142,42 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             const uint32_t fb = full0 + 8 * stage;
             const uint32_t sa = base + stage * STAGE_BYTES;
             mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
-            const int ta = tk + sg.a_c0 + i * BK, tb = tk + sg.b_c0 + i * BK;
+            const int ta = tk + i * BK, tb = ta + jb.shift;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              tma_load_3d(sa + h * 4096, &maps.m[2 * sg.a_map], fb, m0 + 64 * h, ta, bb);
-              if (P.x3) tma_load_3d(sa + A_PLANE + h * 4096, &maps.m[2 * sg.a_map + 1], fb, m0 + 64 * h, ta, bb);
+              tma_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
+              if (P.x3) tma_load_3d(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
             }
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              tma_load_3d(sa + 2 * A_PLANE + h * 4096, &maps.m[2 * sg.b_map], fb, n0 + 64 * h, tb, bb);
+              tma_load_3d(sa + 2 * A_PLANE + h * 4096, mb, fb, jb.n0 + 64 * h, tb, bb);
               if (P.x3)
-                tma_load_3d(sa + 2 * A_PLANE + B_PLANE + h * 4096, &maps.m[2 * sg.b_map + 1], fb,
-                            n0 + 64 * h, tb, bb);
+                tma_load_3d(sa + 2 * A_PLANE + B_PLANE + h * 4096, mb + 1, fb, jb.n0 + 64 * h, tb, bb);
             }
             if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
           }
-        }
-      } else if (WG) {
-        const Seg& sg = P.seg[0];
-        const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
-        const int items = P.B * P.chunks_per_b;
-        for (int c = blockIdx.z; c < items; c += gridDim.z) {
-          const int bb = c / P.chunks_per_b;
-          const int tk = (c % P.chunks_per_b) * P.slabs_per_item * BK;
-          for (int i = 0; i < P.slabs_per_item; ++i)
-            issue(sg, tk + sg.a_c0 + i * BK, m0, bb, tk + sg.b_c0 + i * BK, n0, bb);
         }
       } else {
         const int t0 = blockIdx.x * TM, bb = blockIdx.z;
         for (int s = 0; s < P.nseg; ++s) {
           const Seg& sg = P.seg[s];
-          for (int i = 0; i < sg.nslabs; ++i)
-            issue(sg, sg.a_c0 + i * BK, t0 + sg.a_shift, bb, sg.b_c0 + i * BK,
-                  sg.b_row0 + TN * blockIdx.y, 0);
+          const CUtensorMap* ma = &maps.m[2 * sg.a_map];
+          const CUtensorMap* mb = &maps.m[2 * sg.b_map];
+          if (s == 0) { prefetch_tmap(ma); prefetch_tmap(mb); }
+          for (int i = 0; i < sg.nslabs; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = base + stage * STAGE_BYTES;
+            mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
+            tma_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+            tma_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, sg.b_row0 + TN * blockIdx.y, 0);
+            if (P.x3) {
+              tma_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+              tma_load_3d(sa + 2 * A_PLANE + B_PLANE, mb + 1, fb, sg.b_c0 + i * BK,
+                          sg.b_row0 + TN * blockIdx.y, 0);
+            }
+            if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -192,27 +192,23 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         const uint32_t sa = base + stage * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < BK / UK; ++ks) {
-          if (MN) {
-            // 16 K-rows = two 1024-byte swizzle atoms per step
-            const uint64_t a_hi = smem_desc_sw128_mn(sa + ks * 2048);
-            const uint64_t b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
-            mma_ss(tmem_base, a_hi, b_hi, IDESC_MN, (i | ks) ? 1u : 0u);
-            if (P.x3) {
-              const uint64_t a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
-              const uint64_t b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE + ks * 2048);
-              mma_ss(tmem_base, a_lo, b_hi, IDESC_MN, 1u);
-              mma_ss(tmem_base, a_hi, b_lo, IDESC_MN, 1u);
-            }
+          uint64_t a_hi, b_hi, a_lo, b_lo;
+          if (WG) {   // 16 K-rows = two 1024-byte swizzle atoms per step
+            a_hi = smem_desc_sw128_mn(sa + ks * 2048);
+            b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
+            a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
+            b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE + ks * 2048);
           } else {
-            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma_ss(tmem_base, a_hi, b_hi, IDESC, (i | ks) ? 1u : 0u);
-            if (P.x3) {
-              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
-              mma_ss(tmem_base, a_lo, b_hi, IDESC, 1u);
-              mma_ss(tmem_base, a_hi, b_lo, IDESC, 1u);
-            }
+            a_hi = smem_desc_sw64(sa + ks * UK * 2);
+            b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+            b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
+          }
+          constexpr uint32_t ID = WG ? IDESC_MN : IDESC;
+          mma_ss(tmem_base, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
+          if (P.x3) {
+            mma_ss(tmem_base, a_lo, b_hi, ID, 1u);
+            mma_ss(tmem_base, a_hi, b_lo, ID, 1u);
           }
         }
         tc_commit(empty0 + 8 * stage);
@@ -229,24 +225,19 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
 
     if (WG) {
-      const int m = blockIdx.x * TM + row;
-      const int n0 = blockIdx.y * TN;
+      const Job& jb = P.jobs[blockIdx.x];
+      const int m = jb.m0 + row;
       mbar_wait(acc_full, 0);
       tc_fence_after();
 #pragma unroll 1
       for (int q = grp; q < TN / 16; q += NG) {
         float o[16];
         tmem_ld16(lane_base + 16 * q, o);
-        if (m < P.M) {
+        if (m < jb.M) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int n = n0 + 16 * q + i;
-            if (n < P.N)
-              atomicAdd(P.o0 + (long long)m * P.gm + (long long)n * P.gk, o[i]);
-            else if (n == P.ones_col && P.gb != nullptr) {
-              atomicAdd(P.gb + m, o[i]);
-              if (P.gb2 != nullptr) atomicAdd(P.gb2 + m, o[i]);
-            }
+            const int n = jb.n0 + 16 * q + i;
+            if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i]);
           }
         }
       }
@@ -278,32 +269,22 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           for (int i = 0; i < 16; ++i) { th[i] = pt[i]; sg[i] = ps[i]; }
           if (q + NG < TN / 16) fetch(q + NG);
           uint32_t th_hi[8], th_lo[8], sg_hi[8], sg_lo[8];
-          const int zc0 = 16 * q;
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             __nv_bfloat16 h[2][2], l[2][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const float g = gz[i + u], a = th[i + u], s = sg[i + u];
-              const float ght = g * s * (1.0f - a * a);
-              const float ghs = g * a * s * (1.0f - s);
-              split_bf16(ght, h[0][u], l[0][u]);
-              split_bf16(ghs, h[1][u], l[1][u]);
-              if (t_ok && P.c_hi != nullptr) {
-                const int64_t o1 = ((int64_t)b * 2 * CHh + zc0 + i + u) * P.T + t;
-                const int64_t o2 = o1 + (int64_t)CHh * P.T;
-                P.c_hi[o1] = h[0][u];
-                P.c_hi[o2] = h[1][u];
-                if (P.x3) { P.c_lo[o1] = l[0][u]; P.c_lo[o2] = l[1][u]; }
-              }
+              split_bf16(g * s * (1.0f - a * a), h[0][u], l[0][u]);
+              split_bf16(g * a * s * (1.0f - s), h[1][u], l[1][u]);
             }
             th_hi[i >> 1] = pack2(h[0][0], h[0][1]);
             th_lo[i >> 1] = pack2(l[0][0], l[0][1]);
             sg_hi[i >> 1] = pack2(h[1][0], h[1][1]);
             sg_lo[i >> 1] = pack2(l[1][0], l[1][1]);
           }
-          if (t_ok && P.p_hi != nullptr) {
-            const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + zc0;
+          if (t_ok) {
+            const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + 16 * q;
             uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
             uint4* d1 = reinterpret_cast<uint4*>(P.p_hi + poff + CHh);
             d0[0] = make_uint4(th_hi[0], th_hi[1], th_hi[2], th_hi[3]);
@@ -320,17 +301,79 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             }
           }
         }
-      } else {
-        // EPI_GX / EPI_ACCUM: out[b, ch, t] = acc (+ addend) for ch = 256*blockIdx.y + col < Cout
+      } else if (EPI == EPI_GX) {
+        // gx = acc + g_res: the addend and the result are time-major planes (16-byte accesses);
+        // the fp32 (B,Cout,T) copy is only written for the gradient handed back to autograd
         const int cbase = TN * blockIdx.y;
-        const float* addsrc = (EPI == EPI_GX) ? P.f0 : P.o0;
-        const float* addp = addsrc ? addsrc + ((int64_t)b * P.Cout + cbase) * P.T + t : nullptr;
+        uint4 ah[2], al[2];
+        auto fetch = [&](int q) {
+          if (P.a_hi != nullptr && t_ok) {
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + cbase + 16 * q;
+            const uint4* ph = reinterpret_cast<const uint4*>(P.a_hi + poff);
+            ah[0] = __ldg(ph); ah[1] = __ldg(ph + 1);
+            if (P.x3) {
+              const uint4* pl = reinterpret_cast<const uint4*>(P.a_lo + poff);
+              al[0] = __ldg(pl); al[1] = __ldg(pl + 1);
+            }
+          }
+        };
+        fetch(grp);
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
+          float o[16];
+          tmem_ld16(lane_base + 16 * q, o);
+          if (P.a_hi != nullptr && t_ok) {
+            const uint32_t hw[8] = {ah[0].x, ah[0].y, ah[0].z, ah[0].w, ah[1].x, ah[1].y, ah[1].z, ah[1].w};
+            const uint32_t lw[8] = {al[0].x, al[0].y, al[0].z, al[0].w, al[1].x, al[1].y, al[1].z, al[1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[2 * i] += __uint_as_float(hw[i] << 16);
+              o[2 * i + 1] += __uint_as_float(hw[i] & 0xffff0000u);
+              if (P.x3) {
+                o[2 * i] += __uint_as_float(lw[i] << 16);
+                o[2 * i + 1] += __uint_as_float(lw[i] & 0xffff0000u);
+              }
+            }
+          }
+          if (q + NG < TN / 16) fetch(q + NG);
+          const int ch0 = cbase + 16 * q;
+          if (!t_ok) continue;
+          if (P.o0 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i];
+          }
+          if (P.p_hi != nullptr) {
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(o[2 * i], h0, l0);
+              split_bf16(o[2 * i + 1], h1, l1);
+              vh[i] = pack2(h0, h1);
+              vl[i] = pack2(l0, l1);
+            }
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
+            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
+            d0[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+            d0[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+            if (P.x3) {
+              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
+              e0[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+              e0[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+            }
+          }
+        }
+      } else {
+        // EPI_ACCUM: gcond[b, ch, t] += acc for ch = 256*blockIdx.y + col < Cout (fp32, lanes = t)
+        const int cbase = TN * blockIdx.y;
+        float* op = P.o0 + ((int64_t)b * P.Cout + cbase) * P.T + t;
         float pre[16];
         auto fetch = [&](int q) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            pre[i] = (addp && t_ok && cbase + 16 * q + i < P.Cout)
-                         ? __ldcs(addp + (int64_t)(16 * q + i) * P.T) : 0.0f;
+            pre[i] = (t_ok && cbase + 16 * q + i < P.Cout) ? __ldcs(op + (int64_t)(16 * q + i) * P.T) : 0.0f;
         };
         fetch(grp);
         mbar_wait(acc_full, 0);
@@ -342,37 +385,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 #pragma unroll
           for (int i = 0; i < 16; ++i) add[i] = pre[i];
           if (q + NG < TN / 16) fetch(q + NG);
-          const int ch0 = cbase + 16 * q;
-          if (ch0 >= P.Cout) continue;      // Cout is a multiple of 16
-          uint32_t vh[8], vl[8];
+          if (!t_ok) continue;
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            __nv_bfloat16 h[2], l[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float v = o[i + u] + add[i + u];
-              const int64_t off = ((int64_t)b * P.Cout + ch0 + i + u) * P.T + t;
-              if (t_ok) P.o0[off] = v;
-              split_bf16(v, h[u], l[u]);
-              if (EPI == EPI_GX && t_ok && P.c_hi != nullptr) {
-                P.c_hi[off] = h[u];
-                if (P.x3) P.c_lo[off] = l[u];
-              }
-            }
-            vh[i >> 1] = pack2(h[0], h[1]);
-            vl[i >> 1] = pack2(l[0], l[1]);
-          }
-          if (EPI == EPI_GX && t_ok && P.p_hi != nullptr) {
-            const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
-            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
-            d0[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-            d0[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-            if (P.x3) {
-              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
-              e0[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]);
-              e0[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
-            }
-          }
+          for (int i = 0; i < 16; ++i)
+            if (cbase + 16 * q + i < P.Cout) op[(int64_t)(16 * q + i) * P.T] = o[i] + add[i];
         }
       }
     }
@@ -397,80 +413,17 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
   const size_t smem = gemm_smem();
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
-  static const char* names[5] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
-                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>",
-                                 "tc_gemm_kernel<WGRAD_MN>"};
+  static const char* names[4] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
+                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>"};
   VQW_CHECK_LAUNCH(names[EPI]);
   return 0;
 }
 
 // ------------------------------------------------------------------ operand preparation ----
-// (B,C,T) fp32 [* mul], delayed by `shift` steps -> (B,rows,T) bf16 hi/lo planes; row C (if any)
-// is ones, rows > C zero.  (TMA wants 16-byte aligned starts along the contiguous axis, so the
-// per-tap time shift of the weight-gradient operand is applied here, not as a box coordinate.)
-__global__ void __launch_bounds__(256)
-cvt_planes_kernel(const float* __restrict__ in, const float* __restrict__ mul,
-                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int rows,
-                  int T, int B, int shift) {
-  // one thread = 8 consecutive time steps of one (b, row): 2 x float4 in, 16-byte stores out
-  const int T8 = T >> 3;
-  const int64_t n = (int64_t)B * rows * T8;
-  const bool vec = (shift & 3) == 0;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int t0 = (int)(e % T8) * 8;
-    const int64_t r = e / T8;
-    const int c = (int)(r % rows), b = (int)(r / rows);
-    float v[8];
-    if (c >= C) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (c == C) ? 1.0f : 0.0f;
-    } else {
-      const int64_t rowoff = ((int64_t)b * C + c) * T;
-      const int ts0 = t0 - shift;          // out[t] = in[t - shift] (zero before the start)
-      if (vec && ts0 >= 0 && ts0 + 7 < T) {
-        const float4 a0 = __ldcs(reinterpret_cast<const float4*>(in + rowoff + ts0));
-        const float4 a1 = __ldcs(reinterpret_cast<const float4*>(in + rowoff + ts0 + 4));
-        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
-        v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-        if (mul) {
-          const float4 m0 = __ldcs(reinterpret_cast<const float4*>(mul + rowoff + ts0));
-          const float4 m1 = __ldcs(reinterpret_cast<const float4*>(mul + rowoff + ts0 + 4));
-          v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w;
-          v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ts = ts0 + i;
-          float x = 0.0f;
-          if (ts >= 0 && ts < T) {
-            x = in[rowoff + ts];
-            if (mul) x *= mul[rowoff + ts];
-          }
-          v[i] = x;
-        }
-      }
-    }
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * i], h0, l0);
-      split_bf16(v[2 * i + 1], h1, l1);
-      ph[i] = pack2(h0, h1);
-      pl[i] = pack2(l0, l1);
-    }
-    const int64_t o = (r * T + t0);
-    *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-  }
-}
-
 // out[r][k] (rows x K, K contiguous) = src(r, k) for the three transposed weight operands
 //   kind 0: W2T [Ch rows][Cr + Cs]   = [Wr ; Ws]^T
 //   kind 1: WcT [Cr rows][fs * Cd]   : WcT[cr][j*Cd + cd] = conv_w[cd][cr][j]
-//   kind 2: WpT [Cc rows][Cd]        : WpT[cc][cd] = cond_w[cd][cc]
+//   kind 2: WpT [rows >= Cc][Cd]     : WpT[cc][cd] = cond_w[cd][cc], zero rows beyond Cc
 __global__ void __launch_bounds__(256)
 pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__ w1,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int K,
@@ -496,22 +449,31 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
   }
 }
 
-// gb[c] += sum_{b,t} in[b,c,t]
+// bias gradients: g0[c] (and g1[c]) += sum over all (b,t) rows of a time-major plane pair
 __global__ void __launch_bounds__(256)
-rowsum_kernel(const float* __restrict__ in, float* __restrict__ gb, int C, int T) {
-  const int c = blockIdx.x, b = blockIdx.y;
-  const float* p = in + ((int64_t)b * C + c) * T;
-  float s = 0.0f;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) s += p[t];
-  __shared__ float red[8];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot = 0.0f;
-    for (int i = 0; i < 8; ++i) tot += red[i];
-    atomicAdd(gb + c, tot);
+colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                     float* __restrict__ g0, float* __restrict__ g1, int C, int64_t rows,
+                     int rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + r * C + 2 * c2);
+      s0 += __uint_as_float(h << 16);
+      s1 += __uint_as_float(h & 0xffff0000u);
+      if (lo) {
+        const uint32_t l = *reinterpret_cast<const uint32_t*>(lo + r * C + 2 * c2);
+        s0 += __uint_as_float(l << 16);
+        s1 += __uint_as_float(l & 0xffff0000u);
+      }
+    }
+    atomicAdd(g0 + 2 * c2, s0);
+    atomicAdd(g0 + 2 * c2 + 1, s1);
+    if (g1) {
+      atomicAdd(g1 + 2 * c2, s0);
+      atomicAdd(g1 + 2 * c2 + 1, s1);
+    }
   }
 }
 
@@ -523,14 +485,11 @@ int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B
 static inline int64_t al(int64_t v) { return (v + 1023) / 1024 * 1024; }
 static inline int pad256(int v) { return (v + 255) / 256 * 256; }   // TMA boxes never exceed the tensor
 
+// workspace: g_skip planes, gh planes, g_res planes (ping-pong), transposed weight planes per block
 struct BwdLayout {
   int64_t total;
-  int64_t gs_p[2], gs_c[2];          // g_skip: time-major / channel-major planes
-  int64_t cond_c[2];                 // cond channel-major planes with the ones row (Cc+1 rows)
-  int64_t x_c[2], x_s[2], z_c[2];    // per-block: x, x delayed by an unaligned tap shift, z = tanh*sig
-  int64_t gh_p[2], gh_c[2];          // per-block: gh both layouts
-  int64_t gr_f[2], gr_p[2][2], gr_c[2][2];   // g_res ping-pong: fp32, time-major, channel-major
-  int64_t w2t[2], wct[2], wpt[2];    // per-block transposed weight planes (base; + i*wstride)
+  int64_t gs_p[2], gh_p[2], gr_p[2][2];
+  int64_t w2t[2], wct[2], wpt[2];
   int64_t wstride;
 };
 
@@ -540,18 +499,9 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   const int64_t N = (int64_t)d.B * d.T;
   auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
   for (int p = 0; p < 2; ++p) L.gs_p[p] = take(N * d.Cs * 2);
-  for (int p = 0; p < 2; ++p) L.gs_c[p] = take(N * d.Cs * 2);
-  for (int p = 0; p < 2; ++p) L.cond_c[p] = take(N * pad256(d.Cc + 1) * 2);
-  for (int p = 0; p < 2; ++p) L.x_c[p] = take(N * d.Cr * 2);
-  for (int p = 0; p < 2; ++p) L.x_s[p] = take(N * d.Cr * 2);
-  for (int p = 0; p < 2; ++p) L.z_c[p] = take(N * (d.Cd / 2) * 2);
   for (int p = 0; p < 2; ++p) L.gh_p[p] = take(N * d.Cd * 2);
-  for (int p = 0; p < 2; ++p) L.gh_c[p] = take(N * d.Cd * 2);
-  for (int q = 0; q < 2; ++q) {
-    L.gr_f[q] = take(N * d.Cr * 4);
+  for (int q = 0; q < 2; ++q)
     for (int p = 0; p < 2; ++p) L.gr_p[q][p] = take(N * d.Cr * 2);
-    for (int p = 0; p < 2; ++p) L.gr_c[q][p] = take(N * d.Cr * 2);
-  }
   const int64_t wbase = off;
   for (int p = 0; p < 2; ++p) L.w2t[p] = take((int64_t)(d.Cd / 2) * (d.Cr + d.Cs) * 2);
   for (int p = 0; p < 2; ++p) L.wct[p] = take((int64_t)d.Cr * d.fs * d.Cd * 2);
@@ -565,32 +515,29 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
 int64_t resnet_backward_tc_workspace(const vqw_resnet_desc& d) { return bwd_layout(d).total; }
 
 int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const float* g_last_res,
-                       const float* x0, const float* cond, float* const* residuals,
                        float* const* gate_tanh, float* const* gate_sig,
                        const vqw_resblock_weights* weights, float* gx0, float* gcond,
-                       const vqw_resblock_wgrads* wgrads, void* workspace, cudaStream_t stream) {
+                       const vqw_resblock_wgrads* wgrads, void* workspace, const void* saved,
+                       cudaStream_t stream) {
   using namespace tc;
   VQW_REQUIRE(resnet_tc_supported(d), "tcgen05 backward: unsupported channel counts");
-  VQW_REQUIRE(d.Cc % 16 == 0 && d.Cr % 16 == 0, "tcgen05 backward: channels must be multiples of 16");
-  VQW_REQUIRE(workspace && g_skip && x0 && cond && gate_tanh && gate_sig && weights && wgrads && gcond,
+  VQW_REQUIRE(workspace && saved && g_skip && gate_tanh && gate_sig && weights && wgrads && gcond,
               "vqw_resnet_backward: null argument");
+  VQW_REQUIRE(d.fs <= MAX_SEG, "tcgen05 backward: filter_size > %d unsupported", MAX_SEG);
   const bool x3 = d.mode == VQW_MODE_BF16X3;
   const BwdLayout L = bwd_layout(d);
+  const TcSaved S = tc_saved_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(al((int64_t)(uintptr_t)saved));
   auto P16 = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto LO = [&](int64_t off) { return x3 ? P16(off) : nullptr; };
   const int B = d.B, T = d.T, Cr = d.Cr, Cd = d.Cd, Cs = d.Cs, Cc = d.Cc, Ch = d.Cd / 2, fs = d.fs;
-  const int GRID1D = 148 * 8;
+  const int64_t NROWS = (int64_t)B * T;
+  const int RPB = 256;   // rows per block of the bias column sums
+  const int CS_GRID = (int)((NROWS + RPB - 1) / RPB);
 
-  // ---- once per call: g_skip in both layouts, cond channel-major with the ones row ----
+  // ---- once per call: g_skip planes, transposed weight planes of every block ----
   if (int rc = pack_act_launch(g_skip, P16(L.gs_p[0]), LO(L.gs_p[1]), B, Cs, T, stream)) return rc;
-  cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(g_skip, nullptr, P16(L.gs_c[0]), LO(L.gs_c[1]), Cs,
-                                                Cs, T, B, 0);
-  VQW_CHECK_LAUNCH("cvt_planes_kernel(g_skip)");
-  const int CcP = pad256(Cc + 1);   // rows: Cc condition channels, one row of ones, zero padding
-  cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(cond, nullptr, P16(L.cond_c[0]), LO(L.cond_c[1]),
-                                                Cc, CcP, T, B, 0);
-  VQW_CHECK_LAUNCH("cvt_planes_kernel(cond)");
   for (int i = 0; i < d.n_blocks; ++i) {
     const vqw_resblock_weights& w = weights[i];
     const int64_t wo = i * L.wstride;
@@ -604,50 +551,46 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
                                             LO(L.wpt[1] + wo), pad256(Cc), Cd, Cr, Cs, Cd, Cc, fs);
     VQW_CHECK_LAUNCH("pack_wt_kernel(2)");
   }
-  // gb_skip is the same for every block (g_skip is shared): computed per block below.
 
-  auto map3 = [&](CUtensorMap* m, int64_t off_hi, int64_t off_lo, uint64_t inner, uint64_t rows,
+  // K-major (64-byte swizzle) map pair of a time-major plane / weight plane
+  auto mapk = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t inner, uint64_t rows,
                   uint64_t batch, uint32_t box_rows) -> int {
-    if (int rc = make_map(&m[0], ws + off_hi, 3, inner, rows, batch, box_rows)) return rc;
-    return make_map(&m[1], ws + (x3 ? off_lo : off_hi), 3, inner, rows, batch, box_rows);
+    if (int rc = make_map(&m[0], hi, 3, inner, rows, batch, box_rows)) return rc;
+    return make_map(&m[1], x3 ? lo : hi, 3, inner, rows, batch, box_rows);
+  };
+  // MN-major (128-byte swizzle) map pair of a time-major plane
+  auto mapmn = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t C) -> int {
+    if (int rc = make_map_mn(&m[0], hi, C, C, T, B)) return rc;
+    return make_map_mn(&m[1], x3 ? lo : hi, C, C, T, B);
   };
 
-  // g_res of the last block: zero unless the caller kept the last residual
   int cur = 0;
   bool have_gres = false;
   if (g_last_res != nullptr) {
-    VQW_CHECK_CUDA(cudaMemcpyAsync(ws + L.gr_f[0], g_last_res, (size_t)B * Cr * T * 4,
-                                   cudaMemcpyDeviceToDevice, stream));
-    if (int rc = pack_act_launch(g_last_res, P16(L.gr_p[0][0]), LO(L.gr_p[0][1]), B, Cr, T, stream)) return rc;
-    cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(g_last_res, nullptr, P16(L.gr_c[0][0]),
-                                                  LO(L.gr_c[0][1]), Cr, Cr, T, B, 0);
-    VQW_CHECK_LAUNCH("cvt_planes_kernel(g_last_res)");
+    if (int rc = pack_act_launch(g_last_res, P16(L.gr_p[0][0]), LO(L.gr_p[0][1]), B, Cr, T, stream))
+      return rc;
     have_gres = true;
   }
 
   for (int i = d.n_blocks - 1; i >= 0; --i) {
-    const vqw_resblock_weights& w = weights[i];
     const vqw_resblock_wgrads& gw = wgrads[i];
     const int64_t wo = i * L.wstride;
-    const float* xin = (i == 0) ? x0 : residuals[i - 1];
-    VQW_REQUIRE(xin && gate_tanh[i] && gate_sig[i], "vqw_resnet_backward: block %d saved tensors", i);
+    VQW_REQUIRE(gate_tanh[i] && gate_sig[i], "vqw_resnet_backward: block %d saved gates", i);
     const int nxt = cur ^ 1;
     const int dil = d.dilations[i];
-    const float* gres_f = have_gres ? reinterpret_cast<const float*>(ws + L.gr_f[cur]) : nullptr;
+    const uint8_t* xp_hi = sv + S.x0 + i * S.x_stride;
+    const uint8_t* xp_lo = xp_hi + S.x_plane;
+    const uint8_t* zp_hi = sv + S.z0 + i * S.z_stride;
+    const uint8_t* zp_lo = zp_hi + S.z_plane;
 
-    // operands of the weight gradients: x and z = tanh*sig, channel-major planes
-    cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(gate_tanh[i], gate_sig[i], P16(L.z_c[0]),
-                                                  LO(L.z_c[1]), Ch, Ch, T, B, 0);
-    VQW_CHECK_LAUNCH("cvt_planes_kernel(z)");
-
-    // ---- A1: gz GEMM + gate derivative -> gh (both layouts) ----
+    // ---- A1: gz GEMM + gate derivative -> gh planes ----
     {
       Maps maps;
       GemmParams P = {};
-      if (int rc = map3(&maps.m[0], L.gr_p[cur][0], L.gr_p[cur][1], Cr, T, B, TM)) return rc;
-      if (int rc = map3(&maps.m[2], L.gs_p[0], L.gs_p[1], Cs, T, B, TM)) return rc;
-      if (int rc = map3(&maps.m[4], L.w2t[0] + wo, L.w2t[1] + wo, Cr + Cs, Ch, 1, TN)) return rc;
-      maps.m[6] = maps.m[4]; maps.m[7] = maps.m[5];
+      if (int rc = mapk(&maps.m[0], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr, T, B, TM)) return rc;
+      if (int rc = mapk(&maps.m[2], ws + L.gs_p[0], ws + L.gs_p[1], Cs, T, B, TM)) return rc;
+      if (int rc = mapk(&maps.m[4], ws + L.w2t[0] + wo, ws + L.w2t[1] + wo, Cr + Cs, Ch, 1, TN)) return rc;
+      for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
       int n = 0;
       if (have_gres) P.seg[n++] = Seg{0, 2, Cr / BK, 0, 0, 0, 0};
       P.seg[n++] = Seg{1, 2, Cs / BK, 0, Cr, 0, 0};
@@ -655,36 +598,27 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       P.x3 = x3; P.B = B; P.T = T;
       P.f0 = gate_tanh[i]; P.f1 = gate_sig[i];
       P.p_hi = P16(L.gh_p[0]); P.p_lo = LO(L.gh_p[1]);
-      P.c_hi = P16(L.gh_c[0]); P.c_lo = LO(L.gh_c[1]);
       P.Cout = Cd;
       if (int rc = launch_gemm<EPI_GATE_BWD>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;
     }
     // ---- A2: gx = g_res + sum_j Wc_j^T gh[t + s_j] ; gcond += Wp^T gh ----
     {
       Maps maps;
-      if (int rc = map3(&maps.m[0], L.gh_p[0], L.gh_p[1], Cd, T, B, TM)) return rc;
-      if (int rc = map3(&maps.m[2], L.wct[0] + wo, L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, TN)) return rc;
-      if (int rc = map3(&maps.m[4], L.wpt[0] + wo, L.wpt[1] + wo, Cd, pad256(Cc), 1, TN)) return rc;
-      maps.m[6] = maps.m[4]; maps.m[7] = maps.m[5];
-      float* gx_out = (i == 0) ? gx0 : reinterpret_cast<float*>(ws + L.gr_f[nxt]);
-      if (gx_out != nullptr) {
-        for (int j0 = 0; j0 < fs; j0 += MAX_SEG) {
-          GemmParams P = {};
-          int n = 0;
-          for (int j = j0; j < fs && n < MAX_SEG; ++j)
-            P.seg[n++] = Seg{0, 1, Cd / BK, 0, j * Cd, dil * (fs - 1 - j), 0};
-          P.nseg = n;
-          P.x3 = x3; P.B = B; P.T = T;
-          P.f0 = (j0 == 0) ? gres_f : gx_out;     // later tap groups accumulate onto the output
-          P.o0 = gx_out;
-          const bool lastgrp = j0 + MAX_SEG >= fs;
-          if (i > 0 && lastgrp) {
-            P.p_hi = P16(L.gr_p[nxt][0]); P.p_lo = LO(L.gr_p[nxt][1]);
-            P.c_hi = P16(L.gr_c[nxt][0]); P.c_lo = LO(L.gr_c[nxt][1]);
-          }
-          P.Cout = Cr;
-          if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN, B), stream)) return rc;
-        }
+      if (int rc = mapk(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd, T, B, TM)) return rc;
+      if (int rc = mapk(&maps.m[2], ws + L.wct[0] + wo, ws + L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, TN)) return rc;
+      if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cc), 1, TN)) return rc;
+      for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
+      if (i > 0 || gx0 != nullptr) {
+        GemmParams P = {};
+        int n = 0;
+        for (int j = 0; j < fs; ++j) P.seg[n++] = Seg{0, 1, Cd / BK, 0, j * Cd, dil * (fs - 1 - j), 0};
+        P.nseg = n;
+        P.x3 = x3; P.B = B; P.T = T;
+        if (have_gres) { P.a_hi = P16(L.gr_p[cur][0]); P.a_lo = LO(L.gr_p[cur][1]); }
+        if (i > 0) { P.p_hi = P16(L.gr_p[nxt][0]); P.p_lo = LO(L.gr_p[nxt][1]); }
+        else P.o0 = gx0;
+        P.Cout = Cr;
+        if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN, B), stream)) return rc;
       }
       {
         GemmParams P = {};
@@ -697,85 +631,52 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
           return rc;
       }
     }
-    // ---- weight gradients: K = time, split over batch items ----
+    // ---- all weight gradients of the block: one grouped launch ----
     {
-      const int slabs = ceil_div(T, BK);
-      auto wgrad = [&](int64_t a_hi, int64_t a_lo, int M, int64_t b_hi, int64_t b_lo, int Nrows,
-                       int Nvalid, int shift, float* out, long long gm, long long gk, float* gb,
-                       float* gb2, int ones_col) -> int {
-        Maps maps;
-        if (int rc = map3(&maps.m[0], a_hi, a_lo, T, M, B, TM)) return rc;
-        if (int rc = map3(&maps.m[2], b_hi, b_lo, T, Nrows, B, TN)) return rc;
-        for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
-        GemmParams P = {};
-        P.nseg = 1;
-        P.seg[0] = Seg{0, 1, 0, 0, shift, 0, 0};
-        P.x3 = x3; P.B = B; P.T = T;
-        P.M = M; P.N = Nvalid;
-        P.slabs_per_item = slabs; P.chunks_per_b = 1;
-        P.o0 = out; P.gm = gm; P.gk = gk; P.gb = gb; P.gb2 = gb2; P.ones_col = ones_col;
-        dim3 grid(ceil_div(M, TM), ceil_div(Nrows, TN), B);
-        return launch_gemm<EPI_WGRAD>(maps, P, grid, stream);
+      Maps maps;
+      // pairs: 0 gh, 1 x_i, 2 cond, 3 z_i, 4 g_res, 5 g_skip
+      if (int rc = mapmn(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd)) return rc;
+      if (int rc = mapmn(&maps.m[2], xp_hi, xp_lo, Cr)) return rc;
+      if (int rc = mapmn(&maps.m[4], sv + S.cond[0], sv + S.cond[1], Cc)) return rc;
+      if (int rc = mapmn(&maps.m[6], zp_hi, zp_lo, Ch)) return rc;
+      if (int rc = mapmn(&maps.m[8], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr)) return rc;
+      if (int rc = mapmn(&maps.m[10], ws + L.gs_p[0], ws + L.gs_p[1], Cs)) return rc;
+      GemmParams P = {};
+      P.x3 = x3; P.B = B; P.T = T;
+      P.slabs_per_item = ceil_div(T, BK);
+      P.chunks_per_b = 1;
+      int nj = 0;
+      auto add_jobs = [&](int a_map, int M, int b_map, int N, int shift, float* out, long long gm,
+                          long long gk) -> int {
+        for (int m0 = 0; m0 < M; m0 += TM)
+          for (int n0 = 0; n0 < N; n0 += TN) {
+            VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 backward: too many weight-gradient tiles");
+            P.jobs[nj++] = Job{a_map, b_map, m0, n0, shift, M, N, out, gm, gk};
+          }
+        return 0;
       };
-      // x as channel-major planes; a tap delay that is a multiple of 8 samples (16 bytes) is a
-      // TMA box coordinate, any other delay needs its own shifted copy (TMA alignment rule)
-      cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_c[0]), LO(L.x_c[1]), Cr, Cr,
-                                                    T, B, 0);
-      VQW_CHECK_LAUNCH("cvt_planes_kernel(x)");
-      static const bool use_mn = getenv("VQW_WGRAD_MN") && getenv("VQW_WGRAD_MN")[0] == '1';
-      if (use_mn) {
-        // MN-major validation path: gh and x as TIME-major planes, tap delay = row coordinate
-        if (int rc = pack_act_launch(xin, P16(L.x_s[0]), LO(L.x_s[1]), B, Cr, T, stream)) return rc;
-        for (int j = 0; j < fs; ++j) {
-          Maps maps;
-          if (int rc = make_map_mn(&maps.m[0], ws + L.gh_p[0], Cd, Cd, T, B)) return rc;
-          if (int rc = make_map_mn(&maps.m[1], ws + (x3 ? L.gh_p[1] : L.gh_p[0]), Cd, Cd, T, B)) return rc;
-          if (int rc = make_map_mn(&maps.m[2], ws + L.x_s[0], Cr, Cr, T, B)) return rc;
-          if (int rc = make_map_mn(&maps.m[3], ws + (x3 ? L.x_s[1] : L.x_s[0]), Cr, Cr, T, B)) return rc;
-          for (int k = 4; k < 8; ++k) maps.m[k] = maps.m[k - 4];
-          GemmParams P = {};
-          P.nseg = 1;
-          P.seg[0] = Seg{0, 1, 0, 0, -dil * (fs - 1 - j), 0, 0};
-          P.x3 = x3; P.B = B; P.T = T;
-          P.M = Cd; P.N = Cr;
-          P.slabs_per_item = slabs; P.chunks_per_b = 1;
-          P.o0 = gw.conv_w + j; P.gm = (long long)Cr * fs; P.gk = fs; P.ones_col = -1;
-          dim3 grid(ceil_div(Cd, TM), ceil_div(Cr, TN), B);
-          if (int rc = launch_gemm<EPI_WGRAD_MN>(maps, P, grid, stream)) return rc;
-        }
-      } else
-      for (int j = 0; j < fs; ++j) {
-        const int sh = dil * (fs - 1 - j);
-        if (sh % 8 == 0) {
-          if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.x_c[0], L.x_c[1], Cr, Cr, -sh,
-                             gw.conv_w + j, (long long)Cr * fs, fs, nullptr, nullptr, -1))
-            return rc;
-        } else {
-          cvt_planes_kernel<<<GRID1D, 256, 0, stream>>>(xin, nullptr, P16(L.x_s[0]), LO(L.x_s[1]), Cr,
-                                                        Cr, T, B, sh);
-          VQW_CHECK_LAUNCH("cvt_planes_kernel(x shifted)");
-          if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.x_s[0], L.x_s[1], Cr, Cr, 0, gw.conv_w + j,
-                             (long long)Cr * fs, fs, nullptr, nullptr, -1))
-            return rc;
-        }
-      }
-      // cond projection; the appended row of ones gives sum_t gh = gb_conv = gb_cond
-      if (int rc = wgrad(L.gh_c[0], L.gh_c[1], Cd, L.cond_c[0], L.cond_c[1], CcP, Cc, 0,
-                         gw.cond_w, Cc, 1, gw.cond_b, gw.conv_b, Cc))
-        return rc;
-      if (have_gres) {
-        if (int rc = wgrad(L.gr_c[cur][0], L.gr_c[cur][1], Cr, L.z_c[0], L.z_c[1], Ch, Ch, 0,
-                           gw.res_w, Ch, 1, nullptr, nullptr, -1))
+      for (int j = 0; j < fs; ++j)
+        if (int rc = add_jobs(0, Cd, 1, Cr, -dil * (fs - 1 - j), gw.conv_w + j, (long long)Cr * fs, fs))
           return rc;
-        rowsum_kernel<<<dim3(Cr, B), 256, 0, stream>>>(gres_f, gw.res_b, Cr, T);
-        VQW_CHECK_LAUNCH("rowsum_kernel(g_res)");
-      }
-      if (int rc = wgrad(L.gs_c[0], L.gs_c[1], Cs, L.z_c[0], L.z_c[1], Ch, Ch, 0, gw.skip_w, Ch, 1,
-                         nullptr, nullptr, -1))
-        return rc;
-      rowsum_kernel<<<dim3(Cs, B), 256, 0, stream>>>(g_skip, gw.skip_b, Cs, T);
-      VQW_CHECK_LAUNCH("rowsum_kernel(g_skip)");
+      if (int rc = add_jobs(0, Cd, 2, Cc, 0, gw.cond_w, Cc, 1)) return rc;
+      if (have_gres)
+        if (int rc = add_jobs(4, Cr, 3, Ch, 0, gw.res_w, Ch, 1)) return rc;
+      if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
+      P.njobs = nj;
+      if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
     }
+    // ---- bias gradients: column sums of gh (conv_b and cond_b), g_res, g_skip ----
+    colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gh_p[0]), LO(L.gh_p[1]), gw.conv_b,
+                                                     gw.cond_b, Cd, NROWS, RPB);
+    VQW_CHECK_LAUNCH("colsum_planes_kernel(gh)");
+    if (have_gres) {
+      colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LO(L.gr_p[cur][1]),
+                                                       gw.res_b, nullptr, Cr, NROWS, RPB);
+      VQW_CHECK_LAUNCH("colsum_planes_kernel(g_res)");
+    }
+    colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gw.skip_b,
+                                                     nullptr, Cs, NROWS, RPB);
+    VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
     have_gres = true;
     cur = nxt;
   }

@@ -251,7 +251,7 @@ class _ResidualStack(torch.autograd.Function):
 
         # residual[i] = output of block i = saved input of block i+1.  Training keeps all of
         # them; inference chains the blocks through the library's workspace.
-        if need_grad:
+        if need_grad and not tc_mode:
             res = [new(Cr) for _ in range(n - 1)] + [new(Cr) if keep_last_residual else None]
         else:
             res = [None] * (n - 1) + [new(Cr) if keep_last_residual else None]
@@ -278,15 +278,25 @@ class _ResidualStack(torch.autograd.Function):
             garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_forward_workspace(C.byref(d))
         workspace = torch.empty(max(int(ws_bytes), 1), device=x.device, dtype=torch.uint8)
+        # tensor-core training: the library keeps the bf16 hi/lo planes the backward consumes
+        # (condition, every block's input and gated activation) in this caller-owned buffer
+        saved = None
+        if need_grad and tc_mode:
+            saved = torch.empty(int(L.lib.vqw_resnet_saved_bytes(C.byref(d))), device=x.device,
+                                dtype=torch.uint8)
         with L.timed("resnet_forward"):
             L.check(L.lib.vqw_resnet_forward(C.byref(d), L.ptr(x), L.ptr(cond), warr, rarr,
                                              L.ptr(skip), garr_t, garr_s, L.ptr(workspace),
-                                             L.stream()), "vqw_resnet_forward")
+                                             L.ptr(saved), L.stream()), "vqw_resnet_forward")
         xs: List[torch.Tensor] = [x] + [r for r in res[:n - 1]]
+        ctx.tc_saved = saved
+        if saved is not None:
+            xs = [x] + [None] * (n - 1)
         residual = res[n - 1]
         ctx.cfg = (tuple(dilations), fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last_residual)
         if need_grad:
-            ctx.save_for_backward(cond, *xs, *gates, *weights)
+            keep = [t if t is not None else x.new_empty(0) for t in xs]
+            ctx.save_for_backward(cond, *keep, *gates, *weights)
         if keep_last_residual:
             return skip, residual
         return skip
@@ -317,7 +327,9 @@ class _ResidualStack(torch.autograd.Function):
             for j, name in enumerate(names):
                 setattr(warr[i], name, L.ptr(weights[8 * i + j]))
                 setattr(gwarr[i], name, L.ptr(gws[8 * i + j]))
-        rarr = (C.c_void_p * n)(*([L.ptr(xs[i + 1]) for i in range(n - 1)] + [None]))
+        tc_saved = getattr(ctx, "tc_saved", None)
+        rarr = (C.c_void_p * n)(*([None if tc_saved is not None else L.ptr(xs[i + 1])
+                                   for i in range(n - 1)] + [None]))
         garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
         garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_backward_workspace(C.byref(d))
@@ -328,8 +340,8 @@ class _ResidualStack(torch.autograd.Function):
         with L.timed("resnet_backward"):
             L.check(L.lib.vqw_resnet_backward(
                 C.byref(d), L.ptr(g_skip), L.ptr(g_last), L.ptr(xs[0]), L.ptr(cond), rarr, garr_t,
-                garr_s, warr, L.ptr(g_res), L.ptr(gcond), gwarr, L.ptr(workspace), L.stream()),
-                "vqw_resnet_backward")
+                garr_s, warr, L.ptr(g_res), L.ptr(gcond), gwarr, L.ptr(workspace),
+                L.ptr(tc_saved), L.stream()), "vqw_resnet_backward")
         return (g_res, gcond, None, None, None, None, *gws)
 
 

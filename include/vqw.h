@@ -179,14 +179,22 @@ typedef struct {
 } vqw_resnet_desc;
 
 int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc);
+/* Bytes of the caller-owned `saved` buffer (0 in fp32 mode).  Training in the tensor-core modes
+ * passes it to the forward, which keeps there the time-major bf16 hi/lo planes of the condition
+ * and of every block's input and gated activation, and hands it unchanged to the backward;
+ * residuals[] (fp32) is then only needed for the entry the caller wants back (keep_last_residual).
+ * saved = NULL = inference. */
+int64_t vqw_resnet_saved_bytes(const vqw_resnet_desc* desc);
 int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, const float* cond,
                        const vqw_resblock_weights* weights, float* const* residuals, float* skip,
                        float* const* gate_tanh, float* const* gate_sig, void* workspace,
-                       vqw_stream_t stream);
+                       void* saved, vqw_stream_t stream);
 
 /* Backward of the whole stack, blocks walked in reverse with the shared
  * g_skip (B,Cs,T) and the accumulated g_condition.  x = the stack input, residuals[i] /
- * gate_tanh[i] / gate_sig[i] = what vqw_resnet_forward saved.  g_last_res (B,Cr,T) or NULL.
+ * gate_tanh[i] / gate_sig[i] = what vqw_resnet_forward saved (fp32 mode reads x, cond and
+ * residuals[]; the tensor-core modes read `saved` instead and ignore them).  g_last_res
+ * (B,Cr,T) or NULL.
  * gx (B,Cr,T) overwritten (may be NULL); gcond (B,Cc,T) and every weight gradient ACCUMULATED.
  * fp32 mode composes the CUDA-core conv family; the tensor-core modes run tcgen05 GEMMs for
  * the gate-gradient, data-gradient and weight-gradient contractions. */
@@ -195,7 +203,8 @@ int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_skip, const 
                         const float* x, const float* cond, float* const* residuals,
                         float* const* gate_tanh, float* const* gate_sig,
                         const vqw_resblock_weights* weights, float* gx, float* gcond,
-                        const vqw_resblock_wgrads* wgrads, void* workspace, vqw_stream_t stream);
+                        const vqw_resblock_wgrads* wgrads, void* workspace, const void* saved,
+                        vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot
