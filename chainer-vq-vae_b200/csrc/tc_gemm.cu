@@ -477,6 +477,11 @@ colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* 
   }
 }
 
+__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
                     cudaStream_t stream);   // resblock_tc.cu
 
@@ -489,6 +494,7 @@ static inline int pad256(int v) { return (v + 255) / 256 * 256; }   // TMA boxes
 struct BwdLayout {
   int64_t total;
   int64_t gs_p[2], gh_p[2], gr_p[2][2];
+  int64_t gs_sum;   // column sum of g_skip (the same bias gradient for every block)
   int64_t w2t[2], wct[2], wpt[2];
   int64_t wstride;
 };
@@ -499,6 +505,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   const int64_t N = (int64_t)d.B * d.T;
   auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
   for (int p = 0; p < 2; ++p) L.gs_p[p] = take(N * d.Cs * 2);
+  L.gs_sum = take((int64_t)d.Cs * 4);
   for (int p = 0; p < 2; ++p) L.gh_p[p] = take(N * d.Cd * 2);
   for (int q = 0; q < 2; ++q)
     for (int p = 0; p < 2; ++p) L.gr_p[q][p] = take(N * d.Cr * 2);
@@ -538,6 +545,11 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
 
   // ---- once per call: g_skip planes, transposed weight planes of every block ----
   if (int rc = pack_act_launch(g_skip, P16(L.gs_p[0]), LO(L.gs_p[1]), B, Cs, T, stream)) return rc;
+  float* gs_sum = reinterpret_cast<float*>(ws + L.gs_sum);
+  VQW_CHECK_CUDA(cudaMemsetAsync(gs_sum, 0, sizeof(float) * Cs, stream));
+  colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gs_sum, nullptr, Cs,
+                                                   NROWS, RPB);
+  VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
   for (int i = 0; i < d.n_blocks; ++i) {
     const vqw_resblock_weights& w = weights[i];
     const int64_t wo = i * L.wstride;
@@ -674,9 +686,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
                                                        gw.res_b, nullptr, Cr, NROWS, RPB);
       VQW_CHECK_LAUNCH("colsum_planes_kernel(g_res)");
     }
-    colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gw.skip_b,
-                                                     nullptr, Cs, NROWS, RPB);
-    VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
+    add_vec_kernel<<<ceil_div(Cs, 256), 256, 0, stream>>>(gw.skip_b, gs_sum, Cs);
+    VQW_CHECK_LAUNCH("add_vec_kernel(skip_b)");
     have_gres = true;
     cur = nxt;
   }
