@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "fp32"),
+    ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "bf16x3"),
                     choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "generate"])

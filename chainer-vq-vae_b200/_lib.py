@@ -69,6 +69,10 @@ class GenerateDesc(C.Structure):
                 ("set_state", c_int), ("s1", c_int), ("s2", c_int), ("cond_t0", c_int)]
 
 
+class HeadDesc(C.Structure):
+    _fields_ = [("B", c_int), ("T", c_int), ("Cs", c_int), ("Q", c_int), ("mode", c_int)]
+
+
 _SIGNATURES = {
     "vqw_version": (c_int, []),
     "vqw_last_error": (C.c_char_p, []),
@@ -97,6 +101,10 @@ _SIGNATURES = {
     "vqw_generate_workspace": (C.c_int64, [C.POINTER(GenerateDesc)]),
     "vqw_generate": (c_int, [C.POINTER(GenerateDesc), C.POINTER(ResblockWeights)] +
                      [C.c_void_p] * 13),
+    "vqw_head_workspace": (C.c_int64, [C.POINTER(HeadDesc)]),
+    "vqw_head_saved_bytes": (C.c_int64, [C.POINTER(HeadDesc)]),
+    "vqw_head_forward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 9),
+    "vqw_head_backward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 11),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
 }

@@ -71,4 +71,14 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
                        const vqw_resblock_wgrads* wgrads, void* workspace, const void* saved,
                        cudaStream_t stream);
 
+bool head_tc_supported(const vqw_head_desc& d);
+int64_t head_tc_workspace(const vqw_head_desc& d);
+int64_t head_tc_saved_bytes(const vqw_head_desc& d);
+int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                    const float* W2, const float* b2, float* y, void* workspace, void* saved,
+                    cudaStream_t stream);
+int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, const float* W2,
+                     float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
+                     const void* saved, cudaStream_t stream);
+
 }  // namespace vqw

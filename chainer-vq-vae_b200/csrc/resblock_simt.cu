@@ -438,3 +438,37 @@ extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_s
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------
+// output head (modules.py:155-159), tensor-core modes
+// ---------------------------------------------------------------------------------------
+static int head_check(const vqw_head_desc* desc, const char* who) {
+  using namespace vqw;
+  VQW_REQUIRE(desc != nullptr, "%s: null descriptor", who);
+  VQW_REQUIRE(desc->mode == VQW_MODE_BF16X3 || desc->mode == VQW_MODE_BF16,
+              "%s: tensor-core modes only (fp32 runs through vqw_conv_forward)", who);
+  VQW_REQUIRE(head_tc_supported(*desc),
+              "%s: needs skip_channels %% 256 == 0, T >= 128 and T %% 8 == 0 (Cs=%d T=%d)", who,
+              desc->Cs, desc->T);
+  return 0;
+}
+extern "C" int64_t vqw_head_workspace(const vqw_head_desc* desc) {
+  return desc ? vqw::head_tc_workspace(*desc) : -1;
+}
+extern "C" int64_t vqw_head_saved_bytes(const vqw_head_desc* desc) {
+  return desc ? vqw::head_tc_saved_bytes(*desc) : -1;
+}
+extern "C" int vqw_head_forward(const vqw_head_desc* desc, const float* skip, const float* W1,
+                                const float* b1, const float* W2, const float* b2, float* y,
+                                void* workspace, void* saved, vqw_stream_t stream) {
+  if (int rc = head_check(desc, "vqw_head_forward")) return rc;
+  return vqw::head_forward_tc(*desc, skip, W1, b1, W2, b2, y, workspace, saved, (cudaStream_t)stream);
+}
+extern "C" int vqw_head_backward(const vqw_head_desc* desc, const float* gy, const float* W1,
+                                 const float* W2, float* gskip, float* gW1, float* gb1, float* gW2,
+                                 float* gb2, void* workspace, const void* saved,
+                                 vqw_stream_t stream) {
+  if (int rc = head_check(desc, "vqw_head_backward")) return rc;
+  return vqw::head_backward_tc(*desc, gy, W1, W2, gskip, gW1, gb1, gW2, gb2, workspace, saved,
+                               (cudaStream_t)stream);
+}

@@ -404,7 +404,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 // (B,C,T) fp32 -> (B,T,C) bf16 hi/lo planes: 32x32 transpose through shared memory
 __global__ void __launch_bounds__(256)
 pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                __nv_bfloat16* __restrict__ lo, int C, int T) {
+                __nv_bfloat16* __restrict__ lo, int C, int T, int pitch, int relu) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -415,22 +415,28 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     int t = t0 + r, c = c0 + tx;
-    if (t < T && c < C) {
+    if (t < T && c < pitch) {          // channels in [C, pitch) are zero padding
       __nv_bfloat16 h, l;
-      split_bf16(tile[tx][r], h, l);
-      const int64_t off = ((int64_t)b * T + t) * C + c;
+      float v = tile[tx][r];
+      if (relu) v = fmaxf(v, 0.0f);
+      split_bf16(v, h, l);
+      const int64_t off = ((int64_t)b * T + t) * pitch + c;
       hi[off] = h;
       if (lo) lo[off] = l;
     }
   }
 }
 
-int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
-                    cudaStream_t stream) {
-  dim3 g(ceil_div(T, 32), ceil_div(C, 32), B);
-  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T);
+int pack_act_launch_ex(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
+                       int pitch, int relu, cudaStream_t stream) {
+  dim3 g(ceil_div(T, 32), ceil_div(pitch, 32), B);
+  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T, pitch, relu);
   VQW_CHECK_LAUNCH("pack_act_kernel");
   return 0;
+}
+int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
+                    cudaStream_t stream) {
+  return pack_act_launch_ex(in, hi, lo, B, C, T, C, 0, stream);
 }
 
 // W1 packed [512 rows in phase order][K1 = fs*Cr + Cc]: row r -> original row
@@ -597,9 +603,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   // pack the two inputs and every block's weights
   {
     dim3 g1(ceil_div(d.T, 32), ceil_div(d.Cr, 32), d.B), g2(ceil_div(d.T, 32), ceil_div(d.Cc, 32), d.B);
-    pack_act_kernel<<<g1, 256, 0, stream>>>(x, x_hi[0], x3 ? x_lo[0] : nullptr, d.Cr, d.T);
+    pack_act_kernel<<<g1, 256, 0, stream>>>(x, x_hi[0], x3 ? x_lo[0] : nullptr, d.Cr, d.T, d.Cr, 0);
     VQW_CHECK_LAUNCH("pack_act_kernel(x)");
-    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, d.Cc, d.T);
+    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, d.Cc, d.T, d.Cc, 0);
     VQW_CHECK_LAUNCH("pack_act_kernel(cond)");
     for (int i = 0; i < d.n_blocks; ++i) {
       const vqw_resblock_weights& w = weights[i];

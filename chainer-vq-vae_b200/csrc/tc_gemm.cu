@@ -12,6 +12,8 @@
 //                   row shifts of the TMA box; rows past T are out of bounds = zero) -> planes of
 //                   the next g_res (and fp32 (B,Cr,T) for the gradient handed back to autograd)
 //     EPI_ACCUM     gcond += Wp^T gh   (fp32 (B,Cc,T), read-modify-write)
+//     EPI_HEAD      out = [mask] [relu] (acc + bias) -> planes and/or fp32 (B,C,T): the 1x1
+//                   projections of the WaveNet head (modules.py:155-159) and their data gradients
 //   "wgrad" flavour -- tile rows = 128 output channels, K = time.  Time is the ROW axis of the
 //   planes, so both operands are MN-major tiles (128-byte swizzle, TMA boxes {64 channels, 32
 //   steps}); the per-tap delay is a row coordinate.  All weight gradients of a block -- fs conv
@@ -35,7 +37,7 @@ constexpr int GW_TMA = G_EPI_WARPS, GW_MMA = G_EPI_WARPS + 1;
 constexpr int MAX_SEG = 4;
 constexpr int MAX_JOBS = 48;
 constexpr int NMAPS = 12;
-enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3 };
+enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3, EPI_HEAD = 4 };
 
 struct Seg {
   int a_map, b_map;   // tensor-map pair index: hi plane = maps[2*i], lo plane = maps[2*i+1]
@@ -69,6 +71,9 @@ struct GemmParams {
   __nv_bfloat16* p_hi;         // GATE_BWD / GX: output planes (B,T,C) or null
   __nv_bfloat16* p_lo;
   int Cout;
+  const float* bias;           // HEAD: per-output-channel bias or null
+  int relu;                    // HEAD: relu on the result
+  const __nv_bfloat16* mask_hi;  // HEAD: (B,T,Cout) plane; result is zeroed where mask <= 0
   int njobs;
   Job jobs[MAX_JOBS];
 };
@@ -365,6 +370,63 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             }
           }
         }
+      } else if (EPI == EPI_HEAD) {
+        const int cbase = TN * blockIdx.y;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
+          const int ch0 = cbase + 16 * q;
+          if (ch0 >= P.Cout) break;            // Cout is a multiple of 16 for plane outputs
+          float o[16];
+          tmem_ld16(lane_base + 16 * q, o);
+          if (!t_ok) continue;
+          uint32_t mk[8];
+          if (P.mask_hi != nullptr) {
+            const uint4* pm = reinterpret_cast<const uint4*>(
+                P.mask_hi + ((int64_t)b * P.T + t) * P.Cout + ch0);
+            const uint4 m0 = __ldg(pm), m1 = __ldg(pm + 1);
+            mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
+            mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v = o[i];
+            if (P.bias != nullptr && ch0 + i < P.Cout) v += __ldg(P.bias + ch0 + i);
+            if (P.relu) v = fmaxf(v, 0.0f);
+            if (P.mask_hi != nullptr) {
+              const uint32_t w = mk[i >> 1];
+              const float mv = (i & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+              v = (mv > 0.0f) ? v : 0.0f;
+            }
+            o[i] = v;
+          }
+          if (P.o0 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ch0 + i < P.Cout) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i];
+          }
+          if (P.p_hi != nullptr) {
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(o[2 * i], h0, l0);
+              split_bf16(o[2 * i + 1], h1, l1);
+              vh[i] = pack2(h0, h1);
+              vl[i] = pack2(l0, l1);
+            }
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
+            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
+            d0[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]);
+            d0[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
+            if (P.x3) {
+              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
+              e0[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+              e0[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
+            }
+          }
+        }
       } else {
         // EPI_ACCUM: gcond[b, ch, t] += acc for ch = 256*blockIdx.y + col < Cout (fp32, lanes = t)
         const int cbase = TN * blockIdx.y;
@@ -413,8 +475,9 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
   const size_t smem = gemm_smem();
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
-  static const char* names[4] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
-                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>"};
+  static const char* names[5] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
+                                 "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>",
+                                 "tc_gemm_kernel<HEAD>"};
   VQW_CHECK_LAUNCH(names[EPI]);
   return 0;
 }
@@ -453,7 +516,7 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
 __global__ void __launch_bounds__(256)
 colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                      float* __restrict__ g0, float* __restrict__ g1, int C, int64_t rows,
-                     int rows_per_block) {
+                     int rows_per_block, int valid) {
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
@@ -468,11 +531,13 @@ colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* 
         s1 += __uint_as_float(l & 0xffff0000u);
       }
     }
-    atomicAdd(g0 + 2 * c2, s0);
-    atomicAdd(g0 + 2 * c2 + 1, s1);
-    if (g1) {
-      atomicAdd(g1 + 2 * c2, s0);
-      atomicAdd(g1 + 2 * c2 + 1, s1);
+    if (2 * c2 < valid) {
+      atomicAdd(g0 + 2 * c2, s0);
+      if (g1) atomicAdd(g1 + 2 * c2, s0);
+    }
+    if (2 * c2 + 1 < valid) {
+      atomicAdd(g0 + 2 * c2 + 1, s1);
+      if (g1) atomicAdd(g1 + 2 * c2 + 1, s1);
     }
   }
 }
@@ -484,6 +549,26 @@ __global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict_
 
 int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
                     cudaStream_t stream);   // resblock_tc.cu
+int pack_act_launch_ex(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
+                       int pitch, int relu, cudaStream_t stream);   // resblock_tc.cu
+
+// out[r][k] (out_rows x out_cols bf16 planes) = src[r][k] or src[k][r] (transpose), zero padded
+__global__ void __launch_bounds__(256)
+pack_mat_kernel(const float* __restrict__ src, int src_rows, int src_cols, int transpose,
+                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int out_rows,
+                int out_cols) {
+  const int64_t n = (int64_t)out_rows * out_cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / out_cols), k = (int)(e % out_cols);
+    const int sr = transpose ? k : r, sc = transpose ? r : k;
+    const float v = (sr < src_rows && sc < src_cols) ? src[(int64_t)sr * src_cols + sc] : 0.0f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[e] = h;
+    if (lo) lo[e] = l;
+  }
+}
 
 }  // namespace tc
 
@@ -548,7 +633,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   float* gs_sum = reinterpret_cast<float*>(ws + L.gs_sum);
   VQW_CHECK_CUDA(cudaMemsetAsync(gs_sum, 0, sizeof(float) * Cs, stream));
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gs_sum, nullptr, Cs,
-                                                   NROWS, RPB);
+                                                   NROWS, RPB, Cs);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
   for (int i = 0; i < d.n_blocks; ++i) {
     const vqw_resblock_weights& w = weights[i];
@@ -679,11 +764,11 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     }
     // ---- bias gradients: column sums of gh (conv_b and cond_b), g_res, g_skip ----
     colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gh_p[0]), LO(L.gh_p[1]), gw.conv_b,
-                                                     gw.cond_b, Cd, NROWS, RPB);
+                                                     gw.cond_b, Cd, NROWS, RPB, Cd);
     VQW_CHECK_LAUNCH("colsum_planes_kernel(gh)");
     if (have_gres) {
       colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LO(L.gr_p[cur][1]),
-                                                       gw.res_b, nullptr, Cr, NROWS, RPB);
+                                                       gw.res_b, nullptr, Cr, NROWS, RPB, Cr);
       VQW_CHECK_LAUNCH("colsum_planes_kernel(g_res)");
     }
     add_vec_kernel<<<ceil_div(Cs, 256), 256, 0, stream>>>(gw.skip_b, gs_sum, Cs);
@@ -691,6 +776,188 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     have_gres = true;
     cur = nxt;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// WaveNet output head on the tensor cores: y = proj2(relu(proj1(relu(skip)))), modules.py:155-159
+// ---------------------------------------------------------------------------------------
+static inline int qpad(int Q) { int v = (Q + 31) / 32 * 32; return v < 64 ? 64 : v; }
+
+bool head_tc_supported(const vqw_head_desc& d) {
+  return d.Cs % tc::TN == 0 && d.Q >= 1 && d.T >= tc::TM && d.T % 8 == 0 && d.B >= 1 && d.B <= 65535;
+}
+
+struct HeadLayout {   // workspace (both directions)
+  int64_t w1[2], w2[2], w1t[2], w2t[2], gy[2], gh1[2], total;
+};
+static HeadLayout head_layout(const vqw_head_desc& d) {
+  HeadLayout L;
+  int64_t off = 0;
+  const int64_t N = (int64_t)d.B * d.T;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
+  for (int p = 0; p < 2; ++p) L.w1[p] = take((int64_t)d.Cs * d.Cs * 2);
+  for (int p = 0; p < 2; ++p) L.w2[p] = take((int64_t)pad256(d.Q) * d.Cs * 2);
+  for (int p = 0; p < 2; ++p) L.w1t[p] = take((int64_t)d.Cs * d.Cs * 2);
+  for (int p = 0; p < 2; ++p) L.w2t[p] = take((int64_t)d.Cs * qpad(d.Q) * 2);
+  for (int p = 0; p < 2; ++p) L.gy[p] = take(N * qpad(d.Q) * 2);
+  for (int p = 0; p < 2; ++p) L.gh1[p] = take(N * d.Cs * 2);
+  L.total = off + 1024;
+  return L;
+}
+struct HeadSaved { int64_t s[2], h1[2], total; };
+static HeadSaved head_saved(const vqw_head_desc& d) {
+  HeadSaved S;
+  const int64_t plane = al((int64_t)d.B * d.T * d.Cs * 2);
+  S.s[0] = 0; S.s[1] = plane; S.h1[0] = 2 * plane; S.h1[1] = 3 * plane;
+  S.total = 4 * plane + 1024;
+  return S;
+}
+
+int64_t head_tc_workspace(const vqw_head_desc& d) { return head_layout(d).total; }
+int64_t head_tc_saved_bytes(const vqw_head_desc& d) { return head_saved(d).total; }
+
+int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                    const float* W2, const float* b2, float* y, void* workspace, void* saved,
+                    cudaStream_t stream) {
+  using namespace tc;
+  VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: needs skip_channels %% 256 == 0, T >= 128, T %% 8 == 0");
+  VQW_REQUIRE(skip && W1 && b1 && W2 && b2 && y && workspace, "vqw_head_forward: null argument");
+  const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const HeadLayout L = head_layout(d);
+  const HeadSaved S = head_saved(d);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
+  // without a `saved` buffer (inference) the activation planes live in the gradient scratch
+  uint8_t* sv = saved ? reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)saved)) : nullptr;
+  auto W16 = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  __nv_bfloat16* s_hi = sv ? reinterpret_cast<__nv_bfloat16*>(sv + S.s[0]) : W16(L.gh1[0]);
+  __nv_bfloat16* s_lo = sv ? reinterpret_cast<__nv_bfloat16*>(sv + S.s[1]) : W16(L.gh1[1]);
+  __nv_bfloat16* h_hi = sv ? reinterpret_cast<__nv_bfloat16*>(sv + S.h1[0]) : W16(L.gy[0]);
+  __nv_bfloat16* h_lo = sv ? reinterpret_cast<__nv_bfloat16*>(sv + S.h1[1]) : W16(L.gy[1]);
+  VQW_REQUIRE(sv || qpad(d.Q) >= d.Cs, "vqw_head_forward: inference scratch too small; pass `saved`");
+  const int B = d.B, T = d.T, Cs = d.Cs, Q = d.Q;
+  auto LOW = [&](__nv_bfloat16* p) { return x3 ? p : nullptr; };
+  // relu(skip) planes, weight planes
+  if (int rc = pack_act_launch_ex(skip, s_hi, LOW(s_lo), B, Cs, T, Cs, 1, stream)) return rc;
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 0, W16(L.w1[0]), LOW(W16(L.w1[1])), Cs, Cs);
+  VQW_CHECK_LAUNCH("pack_mat_kernel(W1)");
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 0, W16(L.w2[0]), LOW(W16(L.w2[1])), pad256(Q), Cs);
+  VQW_CHECK_LAUNCH("pack_mat_kernel(W2)");
+  auto mapk = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t inner, uint64_t rows,
+                  uint64_t batch, uint32_t box_rows) -> int {
+    if (int rc = make_map(&m[0], hi, 3, inner, rows, batch, box_rows)) return rc;
+    return make_map(&m[1], x3 ? lo : hi, 3, inner, rows, batch, box_rows);
+  };
+  {   // h1 = relu(W1 s + b1) -> planes
+    Maps maps;
+    if (int rc = mapk(&maps.m[0], s_hi, s_lo, Cs, T, B, TM)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w1[0], ws + L.w1[1], Cs, Cs, 1, TN)) return rc;
+    for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
+    GemmParams P = {};
+    P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
+    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs; P.bias = b1; P.relu = 1;
+    P.p_hi = h_hi; P.p_lo = LOW(h_lo);
+    if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
+  }
+  {   // y = W2 h1 + b2 -> fp32 (B,Q,T)
+    Maps maps;
+    if (int rc = mapk(&maps.m[0], h_hi, h_lo, Cs, T, B, TM)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w2[0], ws + L.w2[1], Cs, pad256(Q), 1, TN)) return rc;
+    for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
+    GemmParams P = {};
+    P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
+    P.x3 = x3; P.B = B; P.T = T; P.Cout = Q; P.bias = b2; P.o0 = y;
+    if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), ceil_div(Q, TN), B), stream)) return rc;
+  }
+  return 0;
+}
+
+int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, const float* W2,
+                     float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
+                     const void* saved, cudaStream_t stream) {
+  using namespace tc;
+  VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: unsupported shape");
+  VQW_REQUIRE(gy && W1 && W2 && gskip && gW1 && gb1 && gW2 && gb2 && workspace && saved,
+              "vqw_head_backward: null argument");
+  const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const HeadLayout L = head_layout(d);
+  const HeadSaved S = head_saved(d);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(al((int64_t)(uintptr_t)saved));
+  auto W16 = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto LOW = [&](__nv_bfloat16* p) { return x3 ? p : nullptr; };
+  const int B = d.B, T = d.T, Cs = d.Cs, Q = d.Q, Qp = qpad(Q);
+  const int64_t NROWS = (int64_t)B * T;
+  const int RPB = 256, CS_GRID = (int)((NROWS + RPB - 1) / RPB);
+  if (int rc = pack_act_launch_ex(gy, W16(L.gy[0]), LOW(W16(L.gy[1])), B, Q, T, Qp, 0, stream)) return rc;
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 1, W16(L.w2t[0]), LOW(W16(L.w2t[1])), Cs, Qp);
+  VQW_CHECK_LAUNCH("pack_mat_kernel(W2T)");
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 1, W16(L.w1t[0]), LOW(W16(L.w1t[1])), Cs, Cs);
+  VQW_CHECK_LAUNCH("pack_mat_kernel(W1T)");
+  auto mapk = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t inner, uint64_t rows,
+                  uint64_t batch, uint32_t box_rows) -> int {
+    if (int rc = make_map(&m[0], hi, 3, inner, rows, batch, box_rows)) return rc;
+    return make_map(&m[1], x3 ? lo : hi, 3, inner, rows, batch, box_rows);
+  };
+  auto mapmn = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t C) -> int {
+    if (int rc = make_map_mn(&m[0], hi, C, C, T, B)) return rc;
+    return make_map_mn(&m[1], x3 ? lo : hi, C, C, T, B);
+  };
+  {   // g_h1 = (W2^T g_y) * (h1 > 0) -> planes
+    Maps maps;
+    if (int rc = mapk(&maps.m[0], ws + L.gy[0], ws + L.gy[1], Qp, T, B, TM)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w2t[0], ws + L.w2t[1], Qp, Cs, 1, TN)) return rc;
+    for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
+    GemmParams P = {};
+    P.nseg = 1; P.seg[0] = Seg{0, 1, Qp / BK, 0, 0, 0, 0};
+    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs;
+    P.mask_hi = reinterpret_cast<const __nv_bfloat16*>(sv + S.h1[0]);
+    P.p_hi = W16(L.gh1[0]); P.p_lo = LOW(W16(L.gh1[1]));
+    if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
+  }
+  {   // g_skip = (W1^T g_h1) * (skip > 0) -> fp32 (B,Cs,T)
+    Maps maps;
+    if (int rc = mapk(&maps.m[0], ws + L.gh1[0], ws + L.gh1[1], Cs, T, B, TM)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w1t[0], ws + L.w1t[1], Cs, Cs, 1, TN)) return rc;
+    for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
+    GemmParams P = {};
+    P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
+    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs;
+    P.mask_hi = reinterpret_cast<const __nv_bfloat16*>(sv + S.s[0]);
+    P.o0 = gskip;
+    if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
+  }
+  {   // gW2 = g_y (x) h1, gW1 = g_h1 (x) relu(skip): one grouped launch
+    Maps maps;
+    if (int rc = mapmn(&maps.m[0], ws + L.gy[0], ws + L.gy[1], Qp)) return rc;
+    if (int rc = mapmn(&maps.m[2], sv + S.h1[0], sv + S.h1[1], Cs)) return rc;
+    if (int rc = mapmn(&maps.m[4], ws + L.gh1[0], ws + L.gh1[1], Cs)) return rc;
+    if (int rc = mapmn(&maps.m[6], sv + S.s[0], sv + S.s[1], Cs)) return rc;
+    for (int k = 8; k < NMAPS; ++k) maps.m[k] = maps.m[k % 8];
+    GemmParams P = {};
+    P.x3 = x3; P.B = B; P.T = T;
+    P.slabs_per_item = ceil_div(T, BK);
+    P.chunks_per_b = 1;
+    int nj = 0;
+    for (int m0 = 0; m0 < Q; m0 += TM)
+      for (int n0 = 0; n0 < Cs; n0 += TN) {
+        VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 head: too many weight-gradient tiles");
+        P.jobs[nj++] = Job{0, 1, m0, n0, 0, Q, Cs, gW2, Cs, 1};
+      }
+    for (int m0 = 0; m0 < Cs; m0 += TM)
+      for (int n0 = 0; n0 < Cs; n0 += TN) {
+        VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 head: too many weight-gradient tiles");
+        P.jobs[nj++] = Job{2, 3, m0, n0, 0, Cs, Cs, gW1, Cs, 1};
+      }
+    P.njobs = nj;
+    if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+  }
+  colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gy[0]), LOW(W16(L.gy[1])), gb2, nullptr, Qp,
+                                                   NROWS, RPB, Q);
+  VQW_CHECK_LAUNCH("colsum_planes_kernel(gy)");
+  colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gh1[0]), LOW(W16(L.gh1[1])), gb1, nullptr,
+                                                   Cs, NROWS, RPB, Cs);
+  VQW_CHECK_LAUNCH("colsum_planes_kernel(gh1)");
   return 0;
 }
 

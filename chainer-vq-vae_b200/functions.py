@@ -385,3 +385,63 @@ class _EmbedGather(torch.autograd.Function):
 def embed_gather(q, W, b):
     """q (B,T) int32 -> (B,Cr,T,1); W is the embed conv's weight (Cr, Q, 2, 1)."""
     return _EmbedGather.apply(q, W, b)
+
+
+# ---------------------------------------------------------------------------------------
+# output head on the tensor cores (modules.py:155-159)
+# ---------------------------------------------------------------------------------------
+def head_supported(skip: torch.Tensor, mode: int) -> bool:
+    B, Cs, T = _as3(skip)
+    return mode != L.MODE_FP32 and Cs % 256 == 0 and T >= 128 and T % 8 == 0 and B >= 1
+
+
+class _Head(torch.autograd.Function):
+    """y = proj2(relu(proj1(relu(skip)))) as two tcgen05 GEMMs; the backward is two data-gradient
+    GEMMs (ReLU masks applied in the epilogue) and one grouped weight-gradient launch."""
+
+    @staticmethod
+    def forward(ctx, skip, W1, b1, W2, b2, mode):
+        skip, W1, b1, W2, b2 = (_f32c(t) for t in (skip, W1, b1, W2, b2))
+        B, Cs, T = _as3(skip)
+        Q = W2.shape[0]
+        d = L.HeadDesc()
+        d.B, d.T, d.Cs, d.Q, d.mode = B, T, Cs, Q, mode
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty((B, Q, T, 1), device=skip.device, dtype=torch.float32)
+        ws = torch.empty(int(L.lib.vqw_head_workspace(C.byref(d))), device=skip.device,
+                         dtype=torch.uint8)
+        saved = torch.empty(int(L.lib.vqw_head_saved_bytes(C.byref(d))), device=skip.device,
+                            dtype=torch.uint8)
+        with L.timed("head_forward"):
+            L.check(L.lib.vqw_head_forward(C.byref(d), L.ptr(skip), L.ptr(W1), L.ptr(b1), L.ptr(W2),
+                                           L.ptr(b2), L.ptr(y), L.ptr(ws), L.ptr(saved), L.stream()),
+                    "vqw_head_forward")
+        if need_grad:
+            ctx.cfg = (B, T, Cs, Q, mode)
+            ctx.tc_saved = saved
+            ctx.save_for_backward(W1, W2)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, T, Cs, Q, mode = ctx.cfg
+        W1, W2 = ctx.saved_tensors
+        gy = _f32c(gy)
+        d = L.HeadDesc()
+        d.B, d.T, d.Cs, d.Q, d.mode = B, T, Cs, Q, mode
+        dev = gy.device
+        gskip = torch.empty((B, Cs, T, 1), device=dev, dtype=torch.float32)
+        gW1, gW2 = torch.zeros_like(W1), torch.zeros_like(W2)
+        gb1 = torch.zeros(Cs, device=dev, dtype=torch.float32)
+        gb2 = torch.zeros(Q, device=dev, dtype=torch.float32)
+        ws = torch.empty(int(L.lib.vqw_head_workspace(C.byref(d))), device=dev, dtype=torch.uint8)
+        with L.timed("head_backward"):
+            L.check(L.lib.vqw_head_backward(C.byref(d), L.ptr(gy), L.ptr(W1), L.ptr(W2),
+                                            L.ptr(gskip), L.ptr(gW1), L.ptr(gb1), L.ptr(gW2),
+                                            L.ptr(gb2), L.ptr(ws), L.ptr(ctx.tc_saved), L.stream()),
+                    "vqw_head_backward")
+        return gskip, gW1, gb1, gW2, gb2, None
+
+
+def head(skip, W1, b1, W2, b2, mode):
+    return _Head.apply(skip, W1, b1, W2, b2, mode)

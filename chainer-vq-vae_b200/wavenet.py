@@ -107,6 +107,9 @@ class WaveNet(nn.Module):
         else:
             h = self.embed(x, out_len=x.shape[2])                              # :150-152
         z = self.resnet(h, condition)                                          # :155
+        if Fn.head_supported(z, self.resnet.mode):                             # tensor-core head
+            return Fn.head(z, self.proj1.W, self.proj1.b, self.proj2.W, self.proj2.b,
+                           self.resnet.mode)                                   # :155-159
         z = self.proj1(z, relu=True, relu_in=True)                             # :155,158
         return self.proj2(z)                                                   # :159
 

@@ -207,6 +207,27 @@ int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_skip, const 
                         vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * WaveNet output head on the tensor cores.  Replaces relu -> proj1 -> relu -> proj2 of
+ * WaveNet.__call__, modules.py:155-159 (two 1x1 convolutions) and their backward.
+ *   skip (B,Cs,T) f32, W1 (Cs,Cs), b1 (Cs), W2 (Q,Cs), b2 (Q)  ->  y (B,Q,T) f32.
+ * mode = VQW_MODE_BF16X3 / VQW_MODE_BF16; needs Cs % 256 == 0, T >= 128, T % 8 == 0 (other
+ * shapes and fp32 go through vqw_conv_forward).  `saved` (vqw_head_saved_bytes) keeps the
+ * bf16 planes of relu(skip) and of the hidden activation for the backward; NULL = inference.
+ * Backward: gy (B,Q,T) -> gskip (B,Cs,T) overwritten; gW1, gb1, gW2, gb2 ACCUMULATED. */
+typedef struct {
+  int B, T, Cs, Q;
+  int mode;
+} vqw_head_desc;
+int64_t vqw_head_workspace(const vqw_head_desc* desc);
+int64_t vqw_head_saved_bytes(const vqw_head_desc* desc);
+int vqw_head_forward(const vqw_head_desc* desc, const float* skip, const float* W1, const float* b1,
+                     const float* W2, const float* b2, float* y, void* workspace, void* saved,
+                     vqw_stream_t stream);
+int vqw_head_backward(const vqw_head_desc* desc, const float* gy, const float* W1, const float* W2,
+                      float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
+                      const void* saved, vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot
  * tensor, modules.py:151-152: out[b,c,t] = b[c] + W[c,q[t-1],0] + W[c,q[t],1] (t-1<0 dropped).
  *   q (B,T) i32 in [0,Q), W (Cr,Q,2), bias (Cr) -> out (B,Cr,T). */

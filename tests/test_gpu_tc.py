@@ -113,3 +113,75 @@ def test_tc_rejects_unsupported_shapes():
     weights = [p[f"resnet/0/{n}"].to(DEV) for n in ORDER]
     with pytest.raises(V.VqwError):
         V.residual_stack(x.to(DEV), c.to(DEV), [1], 3, weights, L.MODES["bf16x3"])
+
+
+def test_tc_head_matches_conv_path():
+    """relu -> proj1 -> relu -> proj2 (modules.py:155-159) as tcgen05 GEMMs against the fp32
+    conv kernels on the SAME input (identical ReLU masks), forward and every gradient."""
+    from chainer_vq_vae_b200 import functions as Fn
+    torch.manual_seed(0)
+    for Q in (256, 30):                                  # softmax head and the MoL head
+        B, Cs, T = 2, 256, 256
+        skip = torch.randn(B, Cs, T, 1, device=DEV)
+        W1 = torch.randn(Cs, Cs, 1, 1, device=DEV) / 16
+        b1 = torch.randn(Cs, device=DEV) * 0.1
+        W2 = torch.randn(Q, Cs, 1, 1, device=DEV) / 16
+        b2 = torch.randn(Q, device=DEV) * 0.1
+        gy = torch.randn(B, Q, T, 1, device=DEV)
+        out = {}
+        for mode in ("fp32", "tc"):
+            ts = [t.clone().requires_grad_(True) for t in (skip, W1, b1, W2, b2)]
+            if mode == "tc":
+                y = Fn.head(*ts, L.MODE_BF16X3)
+            else:
+                y = Fn.conv(Fn.conv(ts[0], ts[1], ts[2], 1, 0, 1, True, None, True), ts[3], ts[4])
+            y.backward(gy)
+            out[mode] = [y.detach()] + [t.grad for t in ts]
+        for n, a, b in zip(["y", "gskip", "gW1", "gb1", "gW2", "gb2"], out["tc"], out["fp32"]):
+            assert rel_err(a, b) < 1e-4, (Q, n, rel_err(a, b))
+
+
+def test_tc_wavenet_with_head_matches_fp32_path_and_oracle():
+    """Whole decoder (embed -> tcgen05 stack -> tcgen05 head) in bf16x3 against the float64
+    oracle (forward, 1e-4) and the fp32 path (gradients).  The gradient of relu() is
+    discontinuous: a 1e-5 forward difference flips a handful of ReLU masks, and with a random
+    zero-mean upstream gradient the affected sums are cancellation dominated, so gradients are
+    compared by direction (cosine) and a loose bound; the GEMMs themselves are pinned to 2e-4 by
+    test_tc_backward_matches_fp32_path and test_tc_head_matches_conv_path."""
+    for use_logistic in (False, True):
+        cfg = O.Config(batch=2, length=256, n_loop=1, n_layer=3, filter_size=3,
+                       residual_channels=512, dilated_channels=512, skip_channels=256,
+                       use_logistic=use_logistic, input_dim=1 if use_logistic else 256)
+        params = O.make_params(cfg, seed=5)
+        dec = O.sub(params, "decoder/")
+        rng = np.random.default_rng(2)
+        cond = torch.from_numpy(rng.normal(size=(2, cfg.condition_dim, 256, 1)).astype(np.float32))
+        inp = O.make_inputs(cfg)
+        x_dec = torch.from_numpy(inp["x_dec"])
+        with torch.no_grad():
+            y_o = O.wavenet_forward({k: v.double() for k, v in dec.items()}, cfg, x_dec.double(),
+                                    cond.double())
+        gy = torch.from_numpy(rng.normal(size=tuple(y_o.shape)).astype(np.float32)).to(DEV)
+        res = {}
+        for mode in ("fp32", "bf16x3"):
+            wn = V.WaveNet(cfg.n_loop, cfg.n_layer, cfg.filter_size, cfg.input_dim, 512, 512, 256,
+                           cfg.quantize, cfg.use_logistic, cfg.n_mixture, cfg.log_scale_min,
+                           cfg.condition_dim, 0).to(DEV)
+            own = dict(wn.named_parameters())
+            with torch.no_grad():
+                for k, v in dec.items():
+                    own[k.replace("/", ".")].copy_(v)
+            wn.set_mode(mode)
+            c = cond.to(DEV).requires_grad_(True)
+            y = wn(x_dec.to(DEV), c)
+            y.backward(gy)
+            res[mode] = [y.detach(), c.grad.detach()] + [p.grad.detach() for p in wn.parameters()]
+        assert rel_err(res["bf16x3"][0], y_o) < 1e-4
+        names = ["y", "gcond"] + [n for n, _ in wn.named_parameters()]
+        for name, a, b in zip(names, res["bf16x3"], res["fp32"]):
+            if float(b.abs().max()) == 0.0:
+                assert float(a.abs().max()) == 0.0, name      # last block's unused res branch
+                continue
+            cos = float(torch.dot(a.flatten().double(), b.flatten().double()) /
+                        (a.double().norm() * b.double().norm()))
+            assert cos > 0.999 and rel_err(a, b) < 0.15, (use_logistic, name, cos, rel_err(a, b))
