@@ -10,6 +10,7 @@ from .links import Convolution2D, DilatedConvolution2D, EmbedID, namedparams
 from .losses import logistic_loss, softmax_cross_entropy
 from .net import VAE, ConditionEmbed, Encoder
 from .updaters import Adam, GradBucket, VQVAE_ParallelUpdater, VQVAE_StandardUpdater
+from .snapshot import load_chainer_snapshot, save_chainer_snapshot
 from .utils import VQ, ExponentialMovingAverage, MuLaw
 from .wavenet import ResidualBlock, ResidualNet, WaveNet
 
@@ -19,4 +20,5 @@ __all__ = [
     "VQVAE_ParallelUpdater", "Adam", "GradBucket", "softmax_cross_entropy", "logistic_loss",
     "conv", "embed_gather", "residual_stack", "vq_lookup", "Convolution2D",
     "DilatedConvolution2D", "EmbedID", "namedparams", "MODES", "VqwError", "launch_count",
+    "load_chainer_snapshot", "save_chainer_snapshot",
 ]

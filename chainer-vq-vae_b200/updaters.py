@@ -112,12 +112,17 @@ class VQVAE_StandardUpdater:
         self.iteration = 0
 
     def backward_three(self, model, loss1, loss2, loss3) -> None:
+        from . import functions as Fn
         model.zero_grad(set_to_none=False) if not hasattr(self._optimizers["main"], "bucket") \
             else self._optimizers["main"].bucket.zero()             # optimizer.target.cleargrads()
-        loss1.backward(retain_graph=True)                           # :15
-        cleargrads(model.vq)                                        # :16
-        loss2.backward(retain_graph=True)                           # :17
-        loss3.backward()                                            # :18
+        prev, Fn.ACCUMULATE_INTO_GRAD = Fn.ACCUMULATE_INTO_GRAD, True
+        try:
+            loss1.backward(retain_graph=True)                       # :15
+            cleargrads(model.vq)                                    # :16
+            loss2.backward(retain_graph=True)                       # :17
+            loss3.backward()                                        # :18
+        finally:
+            Fn.ACCUMULATE_INTO_GRAD = prev
 
     def update_core(self):
         batch = self._iterators["main"].next()

@@ -66,7 +66,7 @@ class ResidualNet(nn.ModuleList):
         for block in self:
             weights += block.weights()
         return Fn.residual_stack(x, condition, [b.dilation for b in self], self.filter_size,
-                                 weights, self.mode)
+                                 weights, self.mode, grad_targets=tuple(weights))
 
 
 class WaveNet(nn.Module):

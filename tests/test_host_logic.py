@@ -100,3 +100,40 @@ def test_mulaw_roundtrip():
     assert q.min() == 0 and q.max() == 255 and q.dtype == np.int32
     x = m.itransform(q)
     assert np.all(np.diff(x) >= 0) and abs(x[500]) < 0.01
+
+
+def test_chainer_snapshot_roundtrip_and_reference_keys(tmp_path):
+    from helpers import build_model
+    from chainer_vq_vae_b200.snapshot import load_chainer_snapshot, save_chainer_snapshot, PREFIX
+    cfg = O.config_cpu()
+    params = O.make_params(cfg)
+    # a snapshot as the reference would write it (EMA wrapper on): decoder/target + decoder/ema
+    ref = {}
+    for k, v in params.items():
+        if k.startswith("decoder/"):
+            ref[PREFIX + "decoder/target/" + k[len("decoder/"):]] = v.numpy()
+            ref[PREFIX + "decoder/ema/" + k[len("decoder/"):]] = (v * 0.5).numpy()
+        else:
+            ref[PREFIX + k] = v.numpy()
+    ref["updater/optimizer:main/t"] = np.array(7)
+    path = tmp_path / "snapshot_iter_7.npz"
+    np.savez(path, **ref)
+    # generate.py:70-73: a bare WaveNet decoder loads the EMA sub-tree
+    plain = build_model(cfg, O.make_params(cfg, seed=99), device="cpu")
+    missing, unexpected = load_chainer_snapshot(str(path), plain, use_ema=True)
+    assert not missing and not unexpected
+    assert torch.equal(plain.decoder.proj2.W, params["decoder/proj2/W"] * 0.5)
+    assert torch.equal(plain.encoder.conv3.W, params["encoder/conv3/W"])
+    load_chainer_snapshot(str(path), plain, use_ema=False)                 # generate.py:74-76
+    assert torch.equal(plain.decoder.proj2.W, params["decoder/proj2/W"])
+    # a wrapped decoder gets both copies; save -> load round trip
+    wrapped = build_model(cfg, O.make_params(cfg, seed=98), device="cpu", ema_decay=0.9999)
+    load_chainer_snapshot(str(path), wrapped)
+    assert torch.equal(wrapped.decoder.ema.embed.W, params["decoder/embed/W"] * 0.5)
+    assert torch.equal(wrapped.decoder.target.embed.W, params["decoder/embed/W"])
+    p2 = tmp_path / "out.npz"
+    save_chainer_snapshot(str(p2), wrapped)
+    again = build_model(cfg, O.make_params(cfg, seed=97), device="cpu", ema_decay=0.9999)
+    assert load_chainer_snapshot(str(p2), again) == ([], [])
+    for (n, a), (_, b) in zip(wrapped.named_parameters(), again.named_parameters()):
+        assert torch.equal(a, b), n
