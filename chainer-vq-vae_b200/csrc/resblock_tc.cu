@@ -56,7 +56,8 @@ struct Params {
   float* gate_sig;
   __nv_bfloat16* zp_hi; // packed (B,T,Ch) planes of z = tanh*sigmoid, saved for the backward (or null)
   __nv_bfloat16* zp_lo;
-  long long* dbg;       // optional phase timestamps of CTA (0,0) (VQW_TC_TIMELINE=1)
+  long long* dbg;       // optional phase timestamps of one CTA (VQW_TC_TIMELINE=1)
+  int dbg_x, dbg_y;
 };
 
 // ------------------------------------------------------------------ the kernel -------------
@@ -84,6 +85,8 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, t0 = blockIdx.x * TM;
   const int nplanes = P.x3 ? 2 : 1;
+  const bool rec_cta = P.dbg != nullptr && blockIdx.x == P.dbg_x && blockIdx.y == P.dbg_y;
+  if (rec_cta && threadIdx.x == 0) P.dbg[40] = clock64();
   const int chunks_per_tap = P.Cr / BK;
   const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of the first contraction
   const int nk2 = CH / BK;                               // K slabs of the second contraction
@@ -121,6 +124,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (rec_cta && threadIdx.x == 0) P.dbg[41] = clock64();
 
   if (warp == W_TMA) {
     // =============================== TMA producer ===============================
@@ -168,7 +172,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       uint32_t ph = 0;
       int nphase = 0;
       const uint32_t acc = tmem_base + ACC_COL;
-      const bool rec = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0;
+      const bool rec = rec_cta;
       for (int gp = 0; gp < 2; ++gp, ++nphase) {
         if (nphase > 0) {
           mbar_wait(acc_empty, (nphase - 1) & 1);
@@ -237,7 +241,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     const bool t_ok = t < P.T;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     int nphase = 0;
-    const bool rec = P.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && threadIdx.x == 0;
+    const bool rec = rec_cta && threadIdx.x == 0;
     // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), kept in TMEM as bf16 hi/lo planes ----
     for (int gp = 0; gp < 2; ++gp, ++nphase) {
       mbar_wait(acc_full, nphase & 1);
@@ -275,14 +279,8 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
         if (P.zp_hi != nullptr && t_ok) {
           const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
-          uint4* dh = reinterpret_cast<uint4*>(P.zp_hi + zoff);
-          dh[0] = make_uint4(zh[0], zh[1], zh[2], zh[3]);
-          dh[1] = make_uint4(zh[4], zh[5], zh[6], zh[7]);
-          if (P.x3) {
-            uint4* dl = reinterpret_cast<uint4*>(P.zp_lo + zoff);
-            dl[0] = make_uint4(zl[0], zl[1], zl[2], zl[3]);
-            dl[1] = make_uint4(zl[4], zl[5], zl[6], zl[7]);
-          }
+          st256(P.zp_hi + zoff, zh);
+          if (P.x3) st256(P.zp_lo + zoff, zl);
         }
       }
       tmem_wait_st();
@@ -300,18 +298,14 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       const bool is_res = oc < P.Cr / TN;
       const int cbase = is_res ? oc * TN : (oc - P.Cr / TN) * TN;
       float addf[16];
-      uint4 xh[2], xl[2];
+      uint32_t hw[8], lw[8];
       auto fetch = [&](int q) {
         const int ch0 = cbase + 16 * q;
         if (is_res) {
           const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
           if (t_ok) {
-            const uint4* ph = reinterpret_cast<const uint4*>(P.xp_hi + poff);
-            xh[0] = __ldg(ph); xh[1] = __ldg(ph + 1);
-            if (P.x3) {
-              const uint4* pl = reinterpret_cast<const uint4*>(P.xp_lo + poff);
-              xl[0] = __ldg(pl); xl[1] = __ldg(pl + 1);
-            }
+            ld256(P.xp_hi + poff, hw);
+            if (P.x3) ld256(P.xp_lo + poff, lw);
           }
         } else if (P.skip_accumulate && t_ok) {
           const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
@@ -328,8 +322,6 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         float o[16], add[16];
         tmem_ld16(lane_base + ACC_COL + 16 * q, o);
         if (is_res) {
-          const uint32_t hw[8] = {xh[0].x, xh[0].y, xh[0].z, xh[0].w, xh[1].x, xh[1].y, xh[1].z, xh[1].w};
-          const uint32_t lw[8] = {xl[0].x, xl[0].y, xl[0].z, xl[0].w, xl[1].x, xl[1].y, xl[1].z, xl[1].w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float v0 = __uint_as_float(hw[i] << 16), v1 = __uint_as_float(hw[i] & 0xffff0000u);
@@ -367,14 +359,8 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           }
           if (t_ok && P.res_hi != nullptr) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
-            uint4* dh = reinterpret_cast<uint4*>(P.res_hi + poff);
-            dh[0] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-            dh[1] = make_uint4(rh[4], rh[5], rh[6], rh[7]);
-            if (P.x3) {
-              uint4* dl = reinterpret_cast<uint4*>(P.res_lo + poff);
-              dl[0] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
-              dl[1] = make_uint4(rl[4], rl[5], rl[6], rl[7]);
-            }
+            st256(P.res_hi + poff, rh);
+            if (P.x3) st256(P.res_lo + poff, rl);
           }
         } else if (t_ok) {
 #pragma unroll
@@ -397,6 +383,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
                  : "memory");
+    if (rec_cta && lane == 0) P.dbg[42] = clock64();
   }
 }
 
@@ -670,11 +657,13 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
                 "vqw_resnet_forward: gate_tanh/gate_sig of block %d must be given together", i);
     static long long* dbg_buf = nullptr;
     static const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
-    P.dbg = nullptr;
+    P.dbg = nullptr; P.dbg_x = P.dbg_y = 0;
     if (timeline) {
       if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
       cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
       P.dbg = dbg_buf;
+      P.dbg_x = getenv("VQW_TC_TIMELINE_X") ? atoi(getenv("VQW_TC_TIMELINE_X")) : 1;
+      P.dbg_y = getenv("VQW_TC_TIMELINE_Y") ? atoi(getenv("VQW_TC_TIMELINE_Y")) : 0;
     }
     dim3 grid(ceil_div(d.T, TM), d.B);
     resblock_tc_kernel<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
@@ -684,7 +673,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       long long h[64];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[vqw timeline] block %d (cycles rel. to first MMA phase start)\n", i);
+      fprintf(stderr, "[vqw timeline] block %d CTA (%d,%d): entry %lld, setup done %lld, exit %lld "
+                      "(cycles rel. to first MMA phase start)\n", i, P.dbg_x, P.dbg_y, h[40] - h[0],
+              h[41] - h[0], h[42] - h[0]);
       for (int n = 0; n < 5; ++n)
         fprintf(stderr, "  phase %d: mma [%lld, %lld]  epilogue [%lld, %lld]\n", n, h[2 * n] - h[0],
                 h[2 * n + 1] - h[0], h[16 + 2 * n] - h[0], h[16 + 2 * n + 1] - h[0]);

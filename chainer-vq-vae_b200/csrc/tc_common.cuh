@@ -149,13 +149,39 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
 // same, both operands MN-major (bit 15 = A, bit 16 = B)
 constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
 
-// gate non-linearities on the special-function unit (ex2 + fast division), ~1e-6 relative
+// Gate non-linearities.  The epilogue is special-function-unit bound (16 MUFU lanes/cycle/SM):
+// exp stays on the MUFU (ex2), the two reciprocals run on the FMA pipe -- the argument of
+// each is 1 + e with e in (0, 1], so a linear minimax seed (|err| <= 1/17) followed by three
+// Newton steps r <- r * (2 - y r) gives 1/y to ~1e-7 relative without touching the MUFU.
+__device__ __forceinline__ float rcp_1to2(float y) {
+  float r = fmaf(-0.47058824f, y, 1.41176471f);     // 24/17 - 8/17 * y
+  r = r * fmaf(-y, r, 2.0f);
+  r = r * fmaf(-y, r, 2.0f);
+  r = r * fmaf(-y, r, 2.0f);
+  return r;
+}
 __device__ __forceinline__ float sigmoid_fast(float v) {
-  return __fdividef(1.0f, 1.0f + __expf(-v));
+  const float e = __expf(-fabsf(v));                // in (0, 1]
+  const float s = rcp_1to2(1.0f + e);               // sigmoid(|v|)
+  return v >= 0.0f ? s : e * s;                     // sigmoid(-|v|) = e / (1 + e)
 }
 __device__ __forceinline__ float tanh_fast(float v) {
   const float e = __expf(-2.0f * fabsf(v));
-  return copysignf(__fdividef(1.0f - e, 1.0f + e), v);
+  return copysignf((1.0f - e) * rcp_1to2(1.0f + e), v);
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.256): one instruction per 32-byte sector, i.e. per
+// 16 bf16 channels of one time-major plane row
+__device__ __forceinline__ void ld256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

@@ -290,19 +290,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           }
           if (t_ok) {
             const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + 16 * q;
-            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
-            uint4* d1 = reinterpret_cast<uint4*>(P.p_hi + poff + CHh);
-            d0[0] = make_uint4(th_hi[0], th_hi[1], th_hi[2], th_hi[3]);
-            d0[1] = make_uint4(th_hi[4], th_hi[5], th_hi[6], th_hi[7]);
-            d1[0] = make_uint4(sg_hi[0], sg_hi[1], sg_hi[2], sg_hi[3]);
-            d1[1] = make_uint4(sg_hi[4], sg_hi[5], sg_hi[6], sg_hi[7]);
+            st256(P.p_hi + poff, th_hi);
+            st256(P.p_hi + poff + CHh, sg_hi);
             if (P.x3) {
-              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
-              uint4* e1 = reinterpret_cast<uint4*>(P.p_lo + poff + CHh);
-              e0[0] = make_uint4(th_lo[0], th_lo[1], th_lo[2], th_lo[3]);
-              e0[1] = make_uint4(th_lo[4], th_lo[5], th_lo[6], th_lo[7]);
-              e1[0] = make_uint4(sg_lo[0], sg_lo[1], sg_lo[2], sg_lo[3]);
-              e1[1] = make_uint4(sg_lo[4], sg_lo[5], sg_lo[6], sg_lo[7]);
+              st256(P.p_lo + poff, th_lo);
+              st256(P.p_lo + poff + CHh, sg_lo);
             }
           }
         }
@@ -310,16 +302,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         // gx = acc + g_res: the addend and the result are time-major planes (16-byte accesses);
         // the fp32 (B,Cout,T) copy is only written for the gradient handed back to autograd
         const int cbase = TN * blockIdx.y;
-        uint4 ah[2], al[2];
+        uint32_t hw[8], lw[8];
         auto fetch = [&](int q) {
           if (P.a_hi != nullptr && t_ok) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + cbase + 16 * q;
-            const uint4* ph = reinterpret_cast<const uint4*>(P.a_hi + poff);
-            ah[0] = __ldg(ph); ah[1] = __ldg(ph + 1);
-            if (P.x3) {
-              const uint4* pl = reinterpret_cast<const uint4*>(P.a_lo + poff);
-              al[0] = __ldg(pl); al[1] = __ldg(pl + 1);
-            }
+            ld256(P.a_hi + poff, hw);
+            if (P.x3) ld256(P.a_lo + poff, lw);
           }
         };
         fetch(grp);
@@ -330,8 +318,6 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           float o[16];
           tmem_ld16(lane_base + 16 * q, o);
           if (P.a_hi != nullptr && t_ok) {
-            const uint32_t hw[8] = {ah[0].x, ah[0].y, ah[0].z, ah[0].w, ah[1].x, ah[1].y, ah[1].z, ah[1].w};
-            const uint32_t lw[8] = {al[0].x, al[0].y, al[0].z, al[0].w, al[1].x, al[1].y, al[1].z, al[1].w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               o[2 * i] += __uint_as_float(hw[i] << 16);
@@ -360,14 +346,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
               vl[i] = pack2(l0, l1);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
-            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
-            d0[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-            d0[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-            if (P.x3) {
-              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
-              e0[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]);
-              e0[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
-            }
+            st256(P.p_hi + poff, vh);
+            if (P.x3) st256(P.p_lo + poff, vl);
           }
         }
       } else if (EPI == EPI_HEAD) {
@@ -383,11 +363,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (!t_ok) continue;
           uint32_t mk[8];
           if (P.mask_hi != nullptr) {
-            const uint4* pm = reinterpret_cast<const uint4*>(
-                P.mask_hi + ((int64_t)b * P.T + t) * P.Cout + ch0);
-            const uint4 m0 = __ldg(pm), m1 = __ldg(pm + 1);
-            mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
-            mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+            ld256(P.mask_hi + ((int64_t)b * P.T + t) * P.Cout + ch0, mk);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -417,14 +393,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
               vl[i] = pack2(l0, l1);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
-            uint4* d0 = reinterpret_cast<uint4*>(P.p_hi + poff);
-            d0[0] = make_uint4(vh[0], vh[1], vh[2], vh[3]);
-            d0[1] = make_uint4(vh[4], vh[5], vh[6], vh[7]);
-            if (P.x3) {
-              uint4* e0 = reinterpret_cast<uint4*>(P.p_lo + poff);
-              e0[0] = make_uint4(vl[0], vl[1], vl[2], vl[3]);
-              e0[1] = make_uint4(vl[4], vl[5], vl[6], vl[7]);
-            }
+            st256(P.p_hi + poff, vh);
+            if (P.x3) st256(P.p_lo + poff, vl);
           }
         }
       } else {
