@@ -225,13 +225,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the start of the warm-up (nvidia-smi needs ~1 s to deliver its
+    # first sample; the timed region of a short run would otherwise see none) -- warm-up and
+    # timed steps are the same load
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     L.enable_timers(True)
     launches0 = V.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -468,7 +471,7 @@ def run_generate(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "bf16x3"),
