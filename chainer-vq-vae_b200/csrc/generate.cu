@@ -57,7 +57,25 @@ struct GenParams {
   float* h1;                   // [Cs] relu(proj1(relu(skip)))
   float* logit_buf;            // [Q]
   int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none)
+  unsigned int* barrier;       // grid barrier counter (zeroed by the host before the launch)
 };
+
+// Grid-wide barrier (all CTAs are co-resident: cooperative launch): one atomic arrival per CTA
+// on a monotonically increasing counter, then a polling acquire load.  ~3x cheaper than
+// cooperative_groups' grid.sync() at one CTA per SM.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - epoch) < 0);
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -65,29 +83,85 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// dot product of a contiguous weight row segment (global) with a shared-memory vector
-__device__ __forceinline__ float dot_row(const float* __restrict__ w, const float* v, int n, int lane) {
-  float acc = 0.0f;
-  int i = lane * 4;
-  if ((((uintptr_t)w) & 15) == 0) {
-    for (; i + 3 < n; i += 128) {
-      float4 a = __ldg(reinterpret_cast<const float4*>(w + i));
-      acc = fmaf(a.x, v[i], acc);
-      acc = fmaf(a.y, v[i + 1], acc);
-      acc = fmaf(a.z, v[i + 2], acc);
-      acc = fmaf(a.w, v[i + 3], acc);
-    }
-    // tail (n not a multiple of 4)
-    for (int j = (n & ~3) + lane; j < n; j += 32) acc = fmaf(__ldg(w + j), v[j], acc);
-  } else {
-    for (int j = lane; j < n; j += 32) acc = fmaf(__ldg(w + j), v[j], acc);
+// Dot products of contiguous weight row segments (global) with a shared-memory vector.  The
+// kernel is latency bound (one dependent DRAM/L2 round trip per phase), so all loads of a call
+// are issued before the first FMA: up to NV float4 per lane per row are in flight at once.
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ w, int n, int lane, float4* r) {
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int i = lane * 4 + u * 128;
+    r[u] = (i + 3 < n) ? __ldg(reinterpret_cast<const float4*>(w + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  return warp_sum(acc);
+}
+template <int NV>
+__device__ __forceinline__ float fma_row(const float4* r, const float* v, int n, int lane) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int i = lane * 4 + u * 128;
+    if (i + 3 < n) {
+      acc = fmaf(r[u].x, v[i], acc);
+      acc = fmaf(r[u].y, v[i + 1], acc);
+      acc = fmaf(r[u].z, v[i + 2], acc);
+      acc = fmaf(r[u].w, v[i + 3], acc);
+    }
+  }
+  return acc;
+}
+// generic (any length / alignment) fallback and tail handling
+__device__ __forceinline__ float dot_tail(const float* __restrict__ w, const float* v, int from, int n,
+                                          int lane) {
+  float acc = 0.0f;
+  for (int j = from + lane; j < n; j += 32) acc = fmaf(__ldg(w + j), v[j], acc);
+  return acc;
+}
+constexpr int NVMAX = 4;   // 4 float4 per lane = 512 floats per row segment per batch
+
+// two rows (the tanh row and the sigmoid row of a gate pair) against the same vector
+__device__ __forceinline__ void dot2(const float* __restrict__ w0, const float* __restrict__ w1,
+                                     const float* v, int n, int lane, float& o0, float& o1) {
+  float a0 = 0.0f, a1 = 0.0f;
+  const bool aligned = ((((uintptr_t)w0) | ((uintptr_t)w1)) & 15) == 0;
+  int done = 0;
+  if (aligned) {
+    for (; done + 3 < n; done += NVMAX * 128) {
+      float4 r0[NVMAX], r1[NVMAX];
+      load_row<NVMAX>(w0 + done, n - done, lane, r0);
+      load_row<NVMAX>(w1 + done, n - done, lane, r1);
+      a0 += fma_row<NVMAX>(r0, v + done, n - done, lane);
+      a1 += fma_row<NVMAX>(r1, v + done, n - done, lane);
+    }
+    done = n & ~3;
+  }
+  a0 += dot_tail(w0, v, done, n, lane);
+  a1 += dot_tail(w1, v, done, n, lane);
+  o0 = warp_sum(a0);
+  o1 = warp_sum(a1);
+}
+__device__ __forceinline__ float dot_row(const float* __restrict__ w, const float* v, int n, int lane) {
+  float a0 = 0.0f;
+  int done = 0;
+  if ((((uintptr_t)w) & 15) == 0) {
+    for (; done + 3 < n; done += NVMAX * 128) {
+      float4 r0[NVMAX];
+      load_row<NVMAX>(w + done, n - done, lane, r0);
+      a0 += fma_row<NVMAX>(r0, v + done, n - done, lane);
+    }
+    done = n & ~3;
+  }
+  a0 += dot_tail(w, v, done, n, lane);
+  return warp_sum(a0);
+}
+// pull the lines of a weight row segment into L2 ahead of the phase that reads them
+__device__ __forceinline__ void prefetch_row(const float* w, int n, int lane) {
+  for (int i = lane * 32; i < n; i += 32 * 32)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(w + i));
 }
 
 __global__ void __launch_bounds__(GEN_THREADS)
 generate_kernel(const GenParams P) {
-  cg::grid_group grid = cg::this_grid();
+  unsigned int epoch = 0;
   extern __shared__ __align__(16) float sm[];
   const int Ch = P.Cd / 2;
   const int KX = P.fs * P.Cr;           // interleaved tap vector length
@@ -96,11 +170,16 @@ generate_kernel(const GenParams P) {
   float* zs = vc + ((P.Cc + 3) & ~3);   // [Ch]
   float* xs = zs + ((Ch + 3) & ~3);     // [max(Cr, Cs, Q)] scratch vector
   float* ps = xs + ((max(max(P.Cr, P.Cs), P.Q) + 3) & ~3);   // [Q] softmax numerators
+  GenBlock* sblk = reinterpret_cast<GenBlock*>(ps + ((P.Q + 3) & ~3));   // block table copy
   __shared__ int s_sample;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gwarp = blockIdx.x * GEN_WARPS + warp;
   const int nwarps = gridDim.x * GEN_WARPS;
+
+  for (int i = tid; i < P.n_blocks * (int)(sizeof(GenBlock) / 8); i += GEN_THREADS)
+    reinterpret_cast<long long*>(sblk)[i] = reinterpret_cast<const long long*>(P.blocks)[i];
+  __syncthreads();
 
   for (int step = 0; step < P.n_steps; ++step) {
     const int t = P.t_start + step;
@@ -118,10 +197,10 @@ generate_kernel(const GenParams P) {
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cs; c += gridDim.x * GEN_THREADS)
         P.skipacc[c] = 0.0f;
     }
-    grid.sync();
+    grid_barrier(P.barrier, epoch);
 
     for (int l = 0; l < P.n_blocks; ++l) {
-      const GenBlock& blk = P.blocks[l];
+      const GenBlock& blk = sblk[l];
       const float* xin = P.xbuf + (l & 1) * P.Cr;
       float* xout = P.xbuf + ((l + 1) & 1) * P.Cr;
       float* ring = P.queues + blk.qoff;
@@ -130,13 +209,25 @@ generate_kernel(const GenParams P) {
       if (blockIdx.x == 0)
         for (int c = tid; c < P.Cr; c += GEN_THREADS)
           ring[(long long)(t % blk.qlen) * P.Cr + c] = xin[c];
-      for (int i = tid; i < KX; i += GEN_THREADS) {
-        const int c = i / P.fs, j = i - c * P.fs;
-        const int s = blk.dilation * (P.fs - 1 - j);
-        float v = 0.0f;
-        if (s == 0) v = xin[c];
-        else if (t - s >= 0) v = ring[(long long)((t - s) % blk.qlen) * P.Cr + c];
-        vx[i] = v;
+      // gather the interleaved tap vector; the loads of a batch are independent and issued
+      // together (one L2 round trip instead of one per element)
+      for (int i0 = tid; i0 < KX; i0 += 8 * GEN_THREADS) {
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * GEN_THREADS;
+          float v = 0.0f;
+          if (i < KX) {
+            const int c = i / P.fs, j = i - c * P.fs;
+            const int s = blk.dilation * (P.fs - 1 - j);
+            if (s == 0) v = __ldcg(xin + c);
+            else if (t - s >= 0) v = __ldcg(ring + (long long)((t - s) % blk.qlen) * P.Cr + c);
+          }
+          tmp[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u * GEN_THREADS < KX) vx[i0 + u * GEN_THREADS] = tmp[u];
       }
       for (int i = tid; i < P.Cc; i += GEN_THREADS) vc[i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
       __syncthreads();
@@ -148,13 +239,15 @@ generate_kernel(const GenParams P) {
           const int k0 = kc * clen4;
           const int n = max(0, min(clen4, KX - k0));
           float at = 0.0f, ag = 0.0f;
-          if (n > 0) {
-            at = dot_row(blk.conv_w + (long long)p * KX + k0, vx + k0, n, lane);
-            ag = dot_row(blk.conv_w + (long long)(Ch + p) * KX + k0, vx + k0, n, lane);
-          }
-          if (kc == 0) {
-            at += dot_row(blk.cond_w + (long long)p * P.Cc, vc, P.Cc, lane);
-            ag += dot_row(blk.cond_w + (long long)(Ch + p) * P.Cc, vc, P.Cc, lane);
+          if (n > 0)
+            dot2(blk.conv_w + (long long)p * KX + k0, blk.conv_w + (long long)(Ch + p) * KX + k0,
+                 vx + k0, n, lane, at, ag);
+          if (kc == KCH - 1) {   // the last chunk is the shortest: it also takes the condition part
+            float ct, cgv;
+            dot2(blk.cond_w + (long long)p * P.Cc, blk.cond_w + (long long)(Ch + p) * P.Cc, vc, P.Cc,
+                 lane, ct, cgv);
+            at += ct;
+            ag += cgv;
           }
           if (lane == 0) {
             P.partial[(p * KCH + kc) * 2 + 0] = at;
@@ -162,7 +255,11 @@ generate_kernel(const GenParams P) {
           }
         }
       }
-      grid.sync();
+      // rows this warp reads in phase B: bring them into L2 while waiting at the barrier
+      for (int r = gwarp; r < P.Cr + P.Cs; r += nwarps)
+        prefetch_row(r < P.Cr ? blk.res_w + (long long)r * Ch : blk.skip_w + (long long)(r - P.Cr) * Ch,
+                     Ch, lane);
+      grid_barrier(P.barrier, epoch);
       // ---- phase B ----
       for (int p = tid; p < Ch; p += GEN_THREADS) {
         float ht = __ldg(blk.conv_b + p) + __ldg(blk.cond_b + p);
@@ -188,7 +285,21 @@ generate_kernel(const GenParams P) {
           }
         }
       }
-      grid.sync();
+      if (l + 1 < P.n_blocks) {   // next block's phase-A rows
+        const GenBlock& nb = sblk[l + 1];
+        const int chunk = (KX + KCH - 1) / KCH, clen4 = (chunk + 3) & ~3;
+        for (int item = gwarp; item < Ch * KCH; item += nwarps) {
+          const int p = item / KCH, kc = item - p * KCH, k0 = kc * clen4;
+          const int n = max(0, min(clen4, KX - k0));
+          prefetch_row(nb.conv_w + (long long)p * KX + k0, n, lane);
+          prefetch_row(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane);
+          if (kc == KCH - 1) {
+            prefetch_row(nb.cond_w + (long long)p * P.Cc, P.Cc, lane);
+            prefetch_row(nb.cond_w + (long long)(Ch + p) * P.Cc, P.Cc, lane);
+          }
+        }
+      }
+      grid_barrier(P.barrier, epoch);
     }
 
     // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
@@ -198,14 +309,14 @@ generate_kernel(const GenParams P) {
       float v = dot_row(P.proj1_w + (long long)r * P.Cs, xs, P.Cs, lane);
       if (lane == 0) P.h1[r] = fmaxf(v + __ldg(P.proj1_b + r), 0.0f);
     }
-    grid.sync();
+    grid_barrier(P.barrier, epoch);
     for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = P.h1[i];
     __syncthreads();
     for (int r = gwarp; r < P.Q; r += nwarps) {
       float v = dot_row(P.proj2_w + (long long)r * P.Cs, xs, P.Cs, lane);
       if (lane == 0) P.logit_buf[r] = v + __ldg(P.proj2_b + r);
     }
-    grid.sync();
+    grid_barrier(P.barrier, epoch);
 
     // ---- softmax + draw: every CTA does it redundantly (identical inputs -> identical result)
     __syncthreads();
@@ -246,12 +357,12 @@ generate_kernel(const GenParams P) {
         for (int i = tid; i < P.Q; i += GEN_THREADS) P.logits[(long long)step * P.Q + i] = xs[i];
       if (tid == 0) P.samples[step] = pick;
     }
-    grid.sync();   // everyone has read state/logit_buf before they change
+    grid_barrier(P.barrier, epoch);   // everyone has read state/logit_buf before they change
     if (blockIdx.x == 0 && tid == 0) {
       P.state[1] = P.state[0];
       P.state[0] = fed;
     }
-    grid.sync();
+    grid_barrier(P.barrier, epoch);
   }
 }
 
@@ -260,7 +371,7 @@ generate_kernel(const GenParams P) {
 static inline int64_t gen_align(int64_t v) { return (v + 255) / 256 * 256; }
 
 struct GenLayout {
-  int64_t blocks, queues, partial, xbuf, skipacc, h1, logit, state, total;
+  int64_t blocks, queues, partial, xbuf, skipacc, h1, logit, state, barrier, total;
 };
 
 static GenLayout gen_layout(const vqw_generate_desc& d) {
@@ -277,6 +388,7 @@ static GenLayout gen_layout(const vqw_generate_desc& d) {
   L.h1 = take((int64_t)d.Cs * 4);
   L.logit = take((int64_t)d.Q * 4);
   L.state = take(16);
+  L.barrier = take(16);
   L.total = off + 256;
   return L;
 }
@@ -352,12 +464,15 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   P.h1 = reinterpret_cast<float*>(ws + L.h1);
   P.logit_buf = reinterpret_cast<float*>(ws + L.logit);
   P.state = reinterpret_cast<int32_t*>(ws + L.state);
+  P.barrier = reinterpret_cast<unsigned int*>(ws + L.barrier);
+  VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.barrier, 0, 16, st));
 
   const int KX = d.fs * d.Cr, Ch = d.Cd / 2;
   int mx = d.Cr > d.Cs ? d.Cr : d.Cs;
   if (d.Q > mx) mx = d.Q;
   size_t smem = sizeof(float) * (((KX + 3) & ~3) + ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) +
-                                 ((mx + 3) & ~3) + d.Q + 8);
+                                 ((mx + 3) & ~3) + ((d.Q + 3) & ~3) + 8) +
+                sizeof(GenBlock) * d.n_blocks;
   VQW_REQUIRE(smem <= 200 * 1024, "vqw_generate: channel counts too large for shared memory");
   VQW_CHECK_CUDA(cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
