@@ -105,6 +105,9 @@ _SIGNATURES = {
     "vqw_head_saved_bytes": (C.c_int64, [C.POINTER(HeadDesc)]),
     "vqw_head_forward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 9),
     "vqw_head_backward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 11),
+    "vqw_softmax_ce": (c_int, [C.c_void_p] * 4 + [c_int] * 3 + [C.c_void_p]),
+    "vqw_adam_step": (c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_void_p]),
+    "vqw_ema_update": (c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_float, C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
 }

@@ -1,0 +1,118 @@
+// Optimiser-side elementwise kernels over flat fp32 ranges (HBM bound, one pass each).
+//
+// vqw_adam_step   chainer.optimizers.Adam's update rule (train.py:101) [dep]:
+//                   m += (1-b1)(g-m);  v += (1-b2)(g*g-v);  p -= lr * m / (sqrt(v) + eps)
+//                 with lr = alpha*sqrt(1-b2^t)/(1-b1^t) computed by the caller (eps is NOT bias
+//                 corrected).  Replaces ~250 per-parameter update launches.
+// vqw_ema_update  ExponentialMovingAverage.__call__, utils.py:153-154:
+//                   ema = decay*target + (1-decay)*ema   (decay multiplies the TARGET)
+// vqw_softmax_ce  chainer.functions.softmax_cross_entropy (train.py:95): loss and d loss / d y
+//                 in one pass over the logits.
+#include "common.cuh"
+
+namespace vqw {
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      M[k] += (1.0f - b1) * (G[k] - M[k]);
+      V[k] += (1.0f - b2) * (G[k] * G[k] - V[k]);
+      P[k] -= lr * M[k] / (sqrtf(V[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    m[i] += (1.0f - b1) * (g[i] - m[i]);
+    v[i] += (1.0f - b2) * (g[i] * g[i] - v[i]);
+    p[i] -= lr * m[i] / (sqrtf(v[i]) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ema_kernel(float* __restrict__ ema, const float* __restrict__ target, int64_t n, float decay) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    ema[i] = decay * target[i] + (1.0f - decay) * ema[i];
+}
+
+// one warp per (b, t) column of y (B,Q,T): lanes stride over the Q classes
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const float* __restrict__ y, const int32_t* __restrict__ tgt,
+                  float* __restrict__ gy, double* __restrict__ loss, int B, int Q, int T,
+                  float inv_n) {
+  // thread = one time step (coalesced along T); loops over the Q classes three times
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  double local = 0.0;
+  if (t < T) {
+    const float* yc = y + (int64_t)b * Q * T + t;
+    float mx = -INFINITY;
+    for (int q = 0; q < Q; ++q) mx = fmaxf(mx, __ldg(yc + (int64_t)q * T));
+    float s = 0.0f;
+    for (int q = 0; q < Q; ++q) s += expf(__ldg(yc + (int64_t)q * T) - mx);
+    const float lse = mx + logf(s);
+    const int k = tgt[(int64_t)b * T + t];
+    local = (double)(lse - __ldg(yc + (int64_t)k * T));
+    if (gy) {
+      float* gc = gy + (int64_t)b * Q * T + t;
+      for (int q = 0; q < Q; ++q) {
+        const float pq = expf(__ldg(yc + (int64_t)q * T) - lse);
+        gc[(int64_t)q * T] = (pq - (q == k ? 1.0f : 0.0f)) * inv_n;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(loss, local * (double)inv_n);
+}
+
+}  // namespace vqw
+
+extern "C" int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
+                             float beta1, float beta2, float eps, vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(n >= 0, "vqw_adam_step: negative size");
+  if (n == 0) return 0;
+  VQW_REQUIRE(p && g && m && v, "vqw_adam_step: null pointer");
+  VQW_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                  ((uintptr_t)v % 16 == 0), "vqw_adam_step: buffers must be 16-byte aligned");
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps);
+  VQW_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+extern "C" int vqw_ema_update(float* ema, const float* target, long long n, float decay,
+                              vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(n >= 0, "vqw_ema_update: negative size");
+  if (n == 0) return 0;
+  VQW_REQUIRE(ema && target, "vqw_ema_update: null pointer");
+  ema_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(ema, target, n, decay);
+  VQW_CHECK_LAUNCH("ema_kernel");
+  return 0;
+}
+
+extern "C" int vqw_softmax_ce(const float* y, const int32_t* t, float* gy, double* loss, int B, int Q,
+                              int T, vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(B >= 0 && Q > 0 && T >= 0, "vqw_softmax_ce: bad sizes");
+  if (B == 0 || T == 0) return 0;
+  VQW_REQUIRE(y && t && loss, "vqw_softmax_ce: null pointer");
+  VQW_REQUIRE(B <= 65535, "vqw_softmax_ce: B > 65535");
+  dim3 grid(ceil_div(T, 256), B);
+  softmax_ce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, t, gy, loss, B, Q, T,
+                                                         1.0f / ((float)B * (float)T));
+  VQW_CHECK_LAUNCH("softmax_ce_kernel");
+  return 0;
+}

@@ -269,11 +269,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               __stcs(P.gate_sig + off, sg);
             }
           }
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(z2[0], h0, l0);
-          split_bf16(z2[1], h1, l1);
-          zh[i >> 1] = pack2(h0, h1);
-          zl[i >> 1] = pack2(l0, l1);
+          split_pair(z2[0], z2[1], zh[i >> 1], zl[i >> 1]);
         }
         tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
         if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
@@ -351,11 +347,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                 __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v2[0], h0, l0);
-            split_bf16(v2[1], h1, l1);
-            rh[i >> 1] = pack2(h0, h1);
-            rl[i >> 1] = pack2(l0, l1);
+            split_pair(v2[0], v2[1], rh[i >> 1], rl[i >> 1]);
           }
           if (t_ok && P.res_hi != nullptr) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;

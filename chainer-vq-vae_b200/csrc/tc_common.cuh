@@ -188,6 +188,16 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+// two values -> packed bf16x2 hi and lo words (low half = first value): one F2FP pack
+// instruction per plane instead of one conversion per value
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16),
+                                                 v1 - __uint_as_float(hb & 0xffff0000u));
+  hi = hb;
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -207,7 +217,9 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
 
 // Layout of the caller-owned `saved` buffer the tensor-core forward fills for the backward:
 // time-major (B,T,C) bf16 hi/lo planes of the condition, of every block's input x_i and of
-// every block's gated activation z_i (all offsets 1024-byte aligned).
+// every block's gated activation z_i (all offsets 1024-byte aligned).  (Saving the gate
+// derivative as planes too was measured: the extra bf16 splits cost the SFU-bound forward
+// gate epilogue more than the backward saved, so tanh/sigmoid stay fp32 tensors.)
 struct TcSaved {
   int64_t cond[2];
   int64_t x0, x_plane, x_stride;   // block i: hi at x0 + i*x_stride, lo at + x_plane

@@ -273,29 +273,21 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 #pragma unroll
           for (int i = 0; i < 16; ++i) { th[i] = pt[i]; sg[i] = ps[i]; }
           if (q + NG < TN / 16) fetch(q + NG);
+          if (!t_ok) continue;
           uint32_t th_hi[8], th_lo[8], sg_hi[8], sg_lo[8];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            __nv_bfloat16 h[2][2], l[2][2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float g = gz[i + u], a = th[i + u], s = sg[i + u];
-              split_bf16(g * s * (1.0f - a * a), h[0][u], l[0][u]);
-              split_bf16(g * a * s * (1.0f - s), h[1][u], l[1][u]);
-            }
-            th_hi[i >> 1] = pack2(h[0][0], h[0][1]);
-            th_lo[i >> 1] = pack2(l[0][0], l[0][1]);
-            sg_hi[i >> 1] = pack2(h[1][0], h[1][1]);
-            sg_lo[i >> 1] = pack2(l[1][0], l[1][1]);
+          for (int i = 0; i < 8; ++i) {
+            const float g0 = gz[2 * i], a0 = th[2 * i], s0 = sg[2 * i];
+            const float g1 = gz[2 * i + 1], a1 = th[2 * i + 1], s1 = sg[2 * i + 1];
+            split_pair(g0 * s0 * (1.0f - a0 * a0), g1 * s1 * (1.0f - a1 * a1), th_hi[i], th_lo[i]);
+            split_pair(g0 * a0 * s0 * (1.0f - s0), g1 * a1 * s1 * (1.0f - s1), sg_hi[i], sg_lo[i]);
           }
-          if (t_ok) {
-            const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + 16 * q;
-            st256(P.p_hi + poff, th_hi);
-            st256(P.p_hi + poff + CHh, sg_hi);
-            if (P.x3) {
-              st256(P.p_lo + poff, th_lo);
-              st256(P.p_lo + poff + CHh, sg_lo);
-            }
+          const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + 16 * q;
+          st256(P.p_hi + poff, th_hi);
+          st256(P.p_hi + poff + CHh, sg_hi);
+          if (P.x3) {
+            st256(P.p_lo + poff, th_lo);
+            st256(P.p_lo + poff + CHh, sg_lo);
           }
         }
       } else if (EPI == EPI_GX) {
@@ -339,11 +331,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             uint32_t vh[8], vl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(o[2 * i], h0, l0);
-              split_bf16(o[2 * i + 1], h1, l1);
-              vh[i] = pack2(h0, h1);
-              vl[i] = pack2(l0, l1);
+              split_pair(o[2 * i], o[2 * i + 1], vh[i], vl[i]);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
             st256(P.p_hi + poff, vh);
@@ -386,11 +374,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             uint32_t vh[8], vl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(o[2 * i], h0, l0);
-              split_bf16(o[2 * i + 1], h1, l1);
-              vh[i] = pack2(h0, h1);
-              vl[i] = pack2(l0, l1);
+              split_pair(o[2 * i], o[2 * i + 1], vh[i], vl[i]);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
             st256(P.p_hi + poff, vh);

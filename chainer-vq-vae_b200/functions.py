@@ -281,7 +281,7 @@ class _ResidualStack(torch.autograd.Function):
                 setattr(warr[i], name, L.ptr(t))
         rarr = (C.c_void_p * n)(*[L.ptr(r) for r in res])
         garr_t = garr_s = None
-        if need_grad:
+        if gates:
             garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
             garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_forward_workspace(C.byref(d))
@@ -316,6 +316,7 @@ class _ResidualStack(torch.autograd.Function):
         saved = ctx.saved_tensors
         cond = saved[0]
         xs = saved[1:1 + n]
+        tc_saved = getattr(ctx, "tc_saved", None)
         gates = saved[1 + n:1 + 3 * n]
         weights = saved[1 + 3 * n:]
         g_skip = _f32c(g_skip)
@@ -338,11 +339,12 @@ class _ResidualStack(torch.autograd.Function):
             for j, name in enumerate(names):
                 setattr(warr[i], name, L.ptr(weights[8 * i + j]))
                 setattr(gwarr[i], name, L.ptr(gws[8 * i + j]))
-        tc_saved = getattr(ctx, "tc_saved", None)
         rarr = (C.c_void_p * n)(*([None if tc_saved is not None else L.ptr(xs[i + 1])
                                    for i in range(n - 1)] + [None]))
-        garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
-        garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
+        garr_t = garr_s = None
+        if gates:
+            garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
+            garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_backward_workspace(C.byref(d))
         workspace = torch.empty(int(ws_bytes), device=dev, dtype=torch.uint8)
         g_last = _f32c(g_last_res) if (keep_last and g_last_res is not None) else None

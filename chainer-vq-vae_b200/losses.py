@@ -6,9 +6,37 @@ import torch
 import torch.nn.functional as F
 
 
+class _SoftmaxCE(torch.autograd.Function):
+    """Loss and d loss / d y in one pass over the logits (vqw_softmax_ce)."""
+
+    @staticmethod
+    def forward(ctx, y, t):
+        import ctypes as C
+        from . import _lib as L
+        yc = y.contiguous()
+        B, Q, T = yc.shape[0], yc.shape[1], yc.shape[2]
+        tc = t.reshape(B, T).to(torch.int32).contiguous()
+        need = ctx.needs_input_grad[0]
+        gy = torch.empty_like(yc) if need else None
+        loss = torch.zeros(1, device=y.device, dtype=torch.float64)
+        L.check(L.lib.vqw_softmax_ce(L.ptr(yc), L.ptr(tc), L.ptr(gy), L.ptr(loss), B, Q, T, L.stream()),
+                "vqw_softmax_ce")
+        if need:
+            ctx.save_for_backward(gy)
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gy,) = ctx.saved_tensors
+        return gy * g, None
+
+
 def softmax_cross_entropy(y, t):
     """chainer.functions.softmax_cross_entropy: log-softmax over axis 1, mean over all labels.
-    y (B,Q,T,1) f32, t (B,T,1) int."""
+    y (B,Q,T,1) f32, t (B,T,1) int.  CUDA tensors run the fused libvqw kernel; the torch
+    formula below is the generic definition for other tensors."""
+    if y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[3] == 1:
+        return _SoftmaxCE.apply(y, t)
     logp = F.log_softmax(y, dim=1)
     picked = torch.gather(logp, 1, t.long().unsqueeze(1))
     return -picked.sum() / t.numel()

@@ -58,8 +58,23 @@ class Adam:
         self.target = model
         self.bucket = GradBucket(model, extra)
         self.params = self.bucket.params
-        self.m = [torch.zeros_like(p) for p in self.params]
-        self.v = [torch.zeros_like(p) for p in self.params]
+        n = self.bucket.n_grad
+        dev = self.params[0].device
+        # parameters and both moments as views of flat buffers (same order as the gradient
+        # bucket): on CUDA the whole update is ONE libvqw kernel over the flat range
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m, self.v = [], []
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)
+                self.m.append(self.flat_m[off:off + k].view_as(p))
+                self.v.append(self.flat_v[off:off + k].view_as(p))
+                off += k
         return self
 
     @property
@@ -70,6 +85,13 @@ class Adam:
     @torch.no_grad()
     def update(self) -> None:
         self.t += 1
+        if self.flat_p.is_cuda:
+            from . import _lib as L
+            n = self.bucket.n_grad
+            L.check(L.lib.vqw_adam_step(L.ptr(self.flat_p), L.ptr(self.bucket.flat), L.ptr(self.flat_m),
+                                        L.ptr(self.flat_v), n, self.lr, self.beta1, self.beta2,
+                                        self.eps, L.stream()), "vqw_adam_step")
+            return
         grads = [p.grad for p in self.params]
         # m += (1-b1)(g-m)
         torch._foreach_lerp_(self.m, grads, 1 - self.beta1)

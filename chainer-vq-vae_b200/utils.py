@@ -92,10 +92,35 @@ class ExponentialMovingAverage(nn.Module):
             ys = self.ema(*args, **kwargs)
         return ys
 
+    @staticmethod
+    def _flat_range(params):
+        """(first tensor, numel) if the parameters are adjacent views of one buffer, else None."""
+        if not params or not params[0].is_cuda:
+            return None
+        ptr, total = params[0].data_ptr(), 0
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.data_ptr() != ptr + 4 * total:
+                return None
+            total += p.numel()
+        return params[0], total
+
     @torch.no_grad()
     def update_average(self):
         tp = [p for p in self.target.parameters()]
         ep = [p for p in self.ema.parameters()]
         # same pairing as the reference's name match (utils.py:146-148), without the O(P^2) loop
+        if tp and tp[0].is_cuda and self._flat_range(ep) is None:
+            flat = torch.cat([p.detach().reshape(-1) for p in ep])
+            off = 0
+            for p in ep:
+                p.data = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._ema_flat = flat
+        rt, re = self._flat_range(tp), self._flat_range(ep)
+        if rt is not None and re is not None and rt[1] == re[1]:
+            from . import _lib as L          # one kernel over the flat ranges (Adam.setup made
+            L.check(L.lib.vqw_ema_update(re[0].data_ptr(), rt[0].data_ptr(), rt[1],   # them flat)
+                                         float(self.decay), L.stream()), "vqw_ema_update")
+            return
         torch._foreach_mul_(ep, 1.0 - self.decay)
         torch._foreach_add_(ep, tp, alpha=self.decay)

@@ -238,6 +238,21 @@ int vqw_embed_gather_backward(const int32_t* q, const float* gout, float* gW, fl
                               int T, int Cr, int Q, vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Loss and optimiser passes over flat fp32 ranges (one HBM-bound kernel each).
+ *   vqw_softmax_ce  chainer.functions.softmax_cross_entropy (train.py:95): y (B,Q,T) f32 logits,
+ *                   t (B,T) i32 labels -> *loss (f64, ACCUMULATED: zero it first) = mean NLL and
+ *                   gy (B,Q,T) = d loss / d y (or NULL).
+ *   vqw_adam_step   chainer.optimizers.Adam's rule (train.py:101): m += (1-b1)(g-m);
+ *                   v += (1-b2)(g*g-v); p -= lr*m/(sqrt(v)+eps); lr already bias corrected.
+ *   vqw_ema_update  ExponentialMovingAverage, utils.py:153-154: ema = decay*target + (1-decay)*ema.
+ */
+int vqw_softmax_ce(const float* y, const int32_t* t, float* gy, double* loss, int B, int Q, int T,
+                   vqw_stream_t stream);
+int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, vqw_stream_t stream);
+int vqw_ema_update(float* ema, const float* target, long long n, float decay, vqw_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Persistent autoregressive generation.  Replaces the sample loop of generate.py:109-145 and
  * the queue-based incremental decoder it drives (WaveNet.initialize / generate,
  * modules.py:232-255; ResidualNet.generate :102-110; ResidualBlock.push / pop :58-74) with ONE
