@@ -16,11 +16,15 @@
 //     searchsorted(side='right')), so a run is comparable with generate.py:139-141 given the
 //     same draws.  The first input is all-zeros, not a one-hot (generate.py:51).
 //
-// Per block two phases:
-//   A  h = conv_b + cond_b + Wp cond[t] + sum_j Wc[:,:,j] x_l[t - dil*(fs-1-j)]   (K split in 4:
-//      one (gate pair, K chunk) item per warp, partial sums to global -- deterministic)
-//   B  every CTA rebuilds z = tanh(h_t) * sigmoid(h_s) from the partials, then one output row
-//      per warp: x_{l+1} = Wr z + br + x_l (pushed into the next block's ring), skip += Ws z + bs
+// One phase + one grid barrier per block.  Block l's gate needs x_l, which block l-1 produces in
+// the same step; to avoid a second barrier the current-tap product is re-associated:
+//   Wc_cur x_l = Wc_cur (x_{l-1} + br_{l-1}) + (Wc_cur Wr_{l-1}) z_{l-1}
+// with M_l = Wc_cur_l Wr_{l-1} (Cd x Cd/2) and c_l = Wc_cur_l br_{l-1} computed once per
+// utterance (fp32, vqw conv kernel).  Phase l then only depends on z_{l-1} and x_{l-1}:
+//   T1  (2 gate pairs x 4 K chunks per CTA, one warp each; partials reduced in shared memory)
+//       h_l = b + Wp cond[t] + past taps of ring_l + Wc_cur x_{l-1} + M_l z_{l-1} + c_l -> z_l
+//   T2  (one output row per warp)   x_l = Wr_{l-1} z_{l-1} + br_{l-1} + x_{l-1}  -> ring_l,
+//       skip += Ws_{l-1} z_{l-1} + bs_{l-1}
 // then the head (relu, proj1, relu, proj2), softmax and the draw.
 #include "common.cuh"
 #include <cooperative_groups.h>
@@ -31,13 +35,14 @@ namespace vqw {
 
 constexpr int GEN_THREADS = 256;
 constexpr int GEN_WARPS = GEN_THREADS / 32;
-constexpr int KCH = 4;   // K chunks per gate pair in phase A
 
 struct GenBlock {
   const float *conv_w, *conv_b, *cond_w, *cond_b, *res_w, *res_b, *skip_w, *skip_b;
   int dilation;
   int qlen;        // dil*(fs-1)+1 ring slots
   long long qoff;  // offset (floats) of this block's ring in the queue area
+  const float* mmat;   // M_l = Wc_cur_l Wr_{l-1}  (Cd, Cd/2), null for l = 0
+  const float* cvec;   // c_l = Wc_cur_l br_{l-1}  (Cd), null for l = 0
 };
 
 struct GenParams {
@@ -51,8 +56,8 @@ struct GenParams {
   int32_t* samples;            // n_steps
   float* logits;               // n_steps * Q or null
   float* queues;               // rings
-  float* partial;              // [Cd/2][KCH][2]
-  float* xbuf;                 // [2][Cr] current block input / output (ping-pong)
+  float* zbuf;                 // [2][Cd/2] gated activations (ping-pong over blocks)
+  float* xbuf;                 // [2][Cr] block inputs (ping-pong over blocks)
   float* skipacc;              // [Cs]
   float* h1;                   // [Cs] relu(proj1(relu(skip)))
   float* logit_buf;            // [Q]
@@ -159,158 +164,267 @@ __device__ __forceinline__ void prefetch_row(const float* w, int n, int lane) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(w + i));
 }
 
-__global__ void __launch_bounds__(GEN_THREADS)
+__global__ void __launch_bounds__(GEN_THREADS, 1)
 generate_kernel(const GenParams P) {
   unsigned int epoch = 0;
   extern __shared__ __align__(16) float sm[];
   const int Ch = P.Cd / 2;
   const int KX = P.fs * P.Cr;           // interleaved tap vector length
-  float* vx = sm;                       // [KX]  v[c*fs + j] = x_l[t - s_j][c]
-  float* vc = vx + ((KX + 3) & ~3);     // [Cc]  cond[:, t]
-  float* zs = vc + ((P.Cc + 3) & ~3);   // [Ch]
+  const int KXp = (KX + 3) & ~3, Ccp = (P.Cc + 3) & ~3;
+  float* vx2 = sm;                      // [2][KX] v[c*fs + j] = x[t - s_j][c]; current tap = x_{l-1}+br
+  float* vc2 = vx2 + 2 * KXp;           // [2][Cc] cond[:, t]
+  float* zs = vc2 + 2 * Ccp;            // [Ch]  z_{l-1}
   float* xs = zs + ((Ch + 3) & ~3);     // [max(Cr, Cs, Q)] scratch vector
   float* ps = xs + ((max(max(P.Cr, P.Cs), P.Q) + 3) & ~3);   // [Q] softmax numerators
-  GenBlock* sblk = reinterpret_cast<GenBlock*>(ps + ((P.Q + 3) & ~3));   // block table copy
+  float* part = ps + ((P.Q + 3) & ~3);  // [2 pairs][4 chunks][2] partial sums
+  GenBlock* sblk = reinterpret_cast<GenBlock*>(part + 16);   // block table copy
   __shared__ int s_sample;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gwarp = blockIdx.x * GEN_WARPS + warp;
   const int nwarps = gridDim.x * GEN_WARPS;
+  // K chunks of a gate row: 3 over the tap vector, the 4th = condition + M_l z_{l-1}
+  const int c3 = (((KX + 2) / 3) + 3) & ~3;
+  const int npb = (Ch + 1) / 2;         // pair blocks (2 pairs each)
 
   for (int i = tid; i < P.n_blocks * (int)(sizeof(GenBlock) / 8); i += GEN_THREADS)
     reinterpret_cast<long long*>(sblk)[i] = reinterpret_cast<const long long*>(P.blocks)[i];
   __syncthreads();
+
+  // Register prefetch of the NEXT phase's weight rows: the rows a warp reads in phase l depend
+  // only on (l, warp), never on data, so their loads are issued before the barrier that ends
+  // phase l-1 and the DRAM latency hides behind it.  Fast path: every row segment fits 4 (tap
+  // chunk, condition) or 2 (M_l, Wr/Ws rows) float4 per lane and one pair block per CTA.
+  const bool fastp = (c3 <= 512) && (P.Cc <= 512) && (Ch <= 256) && (npb <= (int)gridDim.x) &&
+                     ((KX & 3) == 0) && ((P.Cc & 3) == 0) && ((Ch & 3) == 0);
+  float4 r0[4], r1[4], m0[2], m1[2], q4[2];
+  float pb_t = 0.0f, pb_g = 0.0f, pb_row = 0.0f;   // prefetched biases (gate pair / T2 row)
+  const int t2_first = (npb * GEN_WARPS) % nwarps;
+  // past taps and condition of phase l into buffer l&1 (known before phase l-1 ends)
+  auto gather_past = [&](int l, int t) {
+    if (l >= P.n_blocks) return;
+    const GenBlock& nb = sblk[l];
+    float* vx = vx2 + (l & 1) * KXp;
+    float* vc = vc2 + (l & 1) * Ccp;
+    const float* ring = P.queues + nb.qoff;
+    for (int i0 = tid; i0 < KX; i0 += 8 * GEN_THREADS) {
+      float tmp[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * GEN_THREADS;
+        float v = 0.0f;
+        if (i < KX) {
+          const int c = i / P.fs, j = i - c * P.fs;
+          const int s = nb.dilation * (P.fs - 1 - j);
+          if (s > 0 && t - s >= 0) v = __ldcg(ring + (long long)((t - s) % nb.qlen) * P.Cr + c);
+        }
+        tmp[u] = v;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * GEN_THREADS;
+        if (i < KX && (i % P.fs) != P.fs - 1) vx[i] = tmp[u];
+      }
+    }
+    for (int i = tid; i < P.Cc; i += GEN_THREADS)
+      vc[i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
+  };
+  auto prefetch_phase = [&](int l) {
+    if (l > P.n_blocks) return;
+    if (l < P.n_blocks && tid < 2 && 2 * (int)blockIdx.x + tid < Ch) {
+      const GenBlock& nb = sblk[l];
+      const int pp = 2 * blockIdx.x + tid;
+      pb_t = __ldg(nb.conv_b + pp) + __ldg(nb.cond_b + pp);
+      pb_g = __ldg(nb.conv_b + Ch + pp) + __ldg(nb.cond_b + Ch + pp);
+    }
+    if (l >= 1 && lane == 0) {
+      const bool t1 = l < P.n_blocks;
+      const int R = (t1 ? P.Cr : 0) + P.Cs, r_off = t1 ? 0 : P.Cr;
+      const int r = (gwarp - t2_first + nwarps) % nwarps;
+      if (r < R) {
+        const int rr = r + r_off;
+        // x_l rows carry the NEXT block's residual bias (see T2), skip rows their own bias
+        pb_row = rr < P.Cr ? __ldg(sblk[l].res_b + rr) : __ldg(sblk[l - 1].skip_b + (rr - P.Cr));
+      }
+    }
+    if (!fastp) return;
+    if (l < P.n_blocks) {
+      const GenBlock& nb = sblk[l];
+      const int p = 2 * blockIdx.x + (warp >> 2), kc = warp & 3;
+      if ((int)blockIdx.x < npb && p < Ch) {
+        if (kc < 3) {
+          const int k0 = kc * c3, n = max(0, min(c3, KX - k0));
+          load_row<4>(nb.conv_w + (long long)p * KX + k0, n, lane, r0);
+          load_row<4>(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane, r1);
+        } else {
+          load_row<4>(nb.cond_w + (long long)p * P.Cc, P.Cc, lane, r0);
+          load_row<4>(nb.cond_w + (long long)(Ch + p) * P.Cc, P.Cc, lane, r1);
+          if (l >= 1) {
+            load_row<2>(nb.mmat + (long long)p * Ch, Ch, lane, m0);
+            load_row<2>(nb.mmat + (long long)(Ch + p) * Ch, Ch, lane, m1);
+          }
+        }
+      }
+    }
+    if (l >= 1) {
+      const GenBlock& pbk = sblk[l - 1];
+      const bool t1 = l < P.n_blocks;
+      const int R = (t1 ? P.Cr : 0) + P.Cs, r_off = t1 ? 0 : P.Cr;
+      const int r = (gwarp - t2_first + nwarps) % nwarps;
+      if (r < R) {
+        const int rr = r + r_off;
+        load_row<2>(rr < P.Cr ? pbk.res_w + (long long)rr * Ch : pbk.skip_w + (long long)(rr - P.Cr) * Ch,
+                    Ch, lane, q4);
+      }
+    }
+  };
 
   for (int step = 0; step < P.n_steps; ++step) {
     const int t = P.t_start + step;
     // ---- embed: x_0 = b + W[:, s(t-2), 0] + W[:, s(t-1), 1]   (modules.py:246-247; zeros at start)
     {
       const int s1 = P.state[0], s2 = P.state[1];
-      float* x0 = P.xbuf;   // slot 0
+      float* ring0 = P.queues + sblk[0].qoff + (long long)(t % sblk[0].qlen) * P.Cr;
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cr; c += gridDim.x * GEN_THREADS) {
         float v = __ldg(P.embed_b + c);
         const float* wr = P.embed_w + (long long)c * P.Q * 2;
         if (s2 >= 0) v += __ldg(wr + 2 * s2);
         if (s1 >= 0) v += __ldg(wr + 2 * s1 + 1);
-        x0[c] = v;
+        P.xbuf[c] = v + __ldg(sblk[0].res_b + c);   // slot 0 holds x_0 + br_0 (see T2)
+        ring0[c] = v;                               // push (modules.py:72)
       }
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cs; c += gridDim.x * GEN_THREADS)
         P.skipacc[c] = 0.0f;
     }
+    gather_past(0, t);
+    prefetch_phase(0);
     grid_barrier(P.barrier, epoch);
 
-    for (int l = 0; l < P.n_blocks; ++l) {
-      const GenBlock& blk = sblk[l];
-      const float* xin = P.xbuf + (l & 1) * P.Cr;
-      float* xout = P.xbuf + ((l + 1) & 1) * P.Cr;
-      float* ring = P.queues + blk.qoff;
-      // ---- phase A ----
-      // push x_l into the ring (one CTA writes; everyone reads the value from xin directly)
-      if (blockIdx.x == 0)
-        for (int c = tid; c < P.Cr; c += GEN_THREADS)
-          ring[(long long)(t % blk.qlen) * P.Cr + c] = xin[c];
-      // gather the interleaved tap vector; the loads of a batch are independent and issued
-      // together (one L2 round trip instead of one per element)
-      for (int i0 = tid; i0 < KX; i0 += 8 * GEN_THREADS) {
-        float tmp[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * GEN_THREADS;
-          float v = 0.0f;
-          if (i < KX) {
-            const int c = i / P.fs, j = i - c * P.fs;
-            const int s = blk.dilation * (P.fs - 1 - j);
-            if (s == 0) v = __ldcg(xin + c);
-            else if (t - s >= 0) v = __ldcg(ring + (long long)((t - s) % blk.qlen) * P.Cr + c);
-          }
-          tmp[u] = v;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (i0 + u * GEN_THREADS < KX) vx[i0 + u * GEN_THREADS] = tmp[u];
+    // phase l = 0..n-1 computes z_l (T1) and, for l >= 1, x_l and the skip rows of block l-1
+    // (T2); phase n only runs T2 for the last block's skip rows.
+    for (int l = 0; l <= P.n_blocks; ++l) {
+      const bool has_t1 = l < P.n_blocks, has_t2 = l >= 1;
+      const GenBlock& blk = sblk[has_t1 ? l : l - 1];     // T1's block
+      const GenBlock& pb = sblk[has_t2 ? l - 1 : 0];      // T2's block (l-1)
+      const float* xprev = P.xbuf + (has_t2 ? ((l - 1) & 1) : 0) * P.Cr;   // x_{l-1} (x_0 for l=0)
+      float* xout = P.xbuf + (l & 1) * P.Cr;                               // x_l
+      const float* zprev = P.zbuf + ((l - 1) & 1) * Ch;                    // z_{l-1}
+      float* zout = P.zbuf + (l & 1) * Ch;
+      // ---- stage what depended on the previous phase: the current-tap entries and z_{l-1} ----
+      float* vx = vx2 + (l & 1) * KXp;
+      float* vc = vc2 + (l & 1) * Ccp;
+      if (has_t1) {
+        // l = 0: plain x_0 (just pushed into ring_0); l >= 1: x_{l-1} + br_{l-1} (xbuf)
+        const float* cur = has_t2 ? xprev : P.queues + blk.qoff + (long long)(t % blk.qlen) * P.Cr;
+        for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = __ldcg(cur + c);
       }
-      for (int i = tid; i < P.Cc; i += GEN_THREADS) vc[i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
+      if (has_t2)
+        for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = __ldcg(zprev + i);
       __syncthreads();
-      {
-        const int chunk = (KX + KCH - 1) / KCH;
-        const int clen4 = (chunk + 3) & ~3;           // keep chunks float4 aligned
-        for (int item = gwarp; item < Ch * KCH; item += nwarps) {
-          const int p = item / KCH, kc = item - p * KCH;
-          const int k0 = kc * clen4;
-          const int n = max(0, min(clen4, KX - k0));
+
+      // ---- T1: gate pairs ----
+      if (has_t1) {
+        for (int pblk = blockIdx.x; pblk < npb; pblk += gridDim.x) {
+          const int p = 2 * pblk + (warp >> 2), kc = warp & 3;
           float at = 0.0f, ag = 0.0f;
-          if (n > 0)
-            dot2(blk.conv_w + (long long)p * KX + k0, blk.conv_w + (long long)(Ch + p) * KX + k0,
-                 vx + k0, n, lane, at, ag);
-          if (kc == KCH - 1) {   // the last chunk is the shortest: it also takes the condition part
-            float ct, cgv;
-            dot2(blk.cond_w + (long long)p * P.Cc, blk.cond_w + (long long)(Ch + p) * P.Cc, vc, P.Cc,
-                 lane, ct, cgv);
-            at += ct;
-            ag += cgv;
+          if (fastp && p < Ch) {
+            if (kc < 3) {
+              const int k0 = kc * c3, n = max(0, min(c3, KX - k0));
+              at = fma_row<4>(r0, vx + k0, n, lane);
+              ag = fma_row<4>(r1, vx + k0, n, lane);
+            } else {
+              at = fma_row<4>(r0, vc, P.Cc, lane);
+              ag = fma_row<4>(r1, vc, P.Cc, lane);
+              if (has_t2) {
+                at += fma_row<2>(m0, zs, Ch, lane);
+                ag += fma_row<2>(m1, zs, Ch, lane);
+              }
+            }
+            at = warp_sum(at);
+            ag = warp_sum(ag);
+          } else if (p < Ch) {
+            if (kc < 3) {
+              const int k0 = kc * c3;
+              const int n = max(0, min(c3, KX - k0));
+              if (n > 0)
+                dot2(blk.conv_w + (long long)p * KX + k0, blk.conv_w + (long long)(Ch + p) * KX + k0,
+                     vx + k0, n, lane, at, ag);
+            } else {
+              dot2(blk.cond_w + (long long)p * P.Cc, blk.cond_w + (long long)(Ch + p) * P.Cc, vc, P.Cc,
+                   lane, at, ag);
+              if (has_t2) {
+                float mt, mg;
+                dot2(blk.mmat + (long long)p * Ch, blk.mmat + (long long)(Ch + p) * Ch, zs, Ch, lane,
+                     mt, mg);
+                at += mt;
+                ag += mg;
+              }
+            }
           }
           if (lane == 0) {
-            P.partial[(p * KCH + kc) * 2 + 0] = at;
-            P.partial[(p * KCH + kc) * 2 + 1] = ag;
+            part[((warp >> 2) * 4 + kc) * 2 + 0] = at;
+            part[((warp >> 2) * 4 + kc) * 2 + 1] = ag;
           }
-        }
-      }
-      // rows this warp reads in phase B: bring them into L2 while waiting at the barrier
-      for (int r = gwarp; r < P.Cr + P.Cs; r += nwarps)
-        prefetch_row(r < P.Cr ? blk.res_w + (long long)r * Ch : blk.skip_w + (long long)(r - P.Cr) * Ch,
-                     Ch, lane);
-      grid_barrier(P.barrier, epoch);
-      // ---- phase B ----
-      for (int p = tid; p < Ch; p += GEN_THREADS) {
-        float ht = __ldg(blk.conv_b + p) + __ldg(blk.cond_b + p);
-        float hg = __ldg(blk.conv_b + Ch + p) + __ldg(blk.cond_b + Ch + p);
+          __syncthreads();
+          if (tid < 2 && 2 * pblk + tid < Ch) {
+            const int pp = 2 * pblk + tid;
+            float ht = pb_t, hg = pb_g;
+            if (pblk != (int)blockIdx.x) {     // only the first pair block of a CTA is prefetched
+              ht = __ldg(blk.conv_b + pp) + __ldg(blk.cond_b + pp);
+              hg = __ldg(blk.conv_b + Ch + pp) + __ldg(blk.cond_b + Ch + pp);
+            }
+            // the current tap saw x_{l-1} + br_{l-1}; c_l is NOT added (it is inside that sum)
 #pragma unroll
-        for (int kc = 0; kc < KCH; ++kc) {
-          ht += P.partial[(p * KCH + kc) * 2 + 0];
-          hg += P.partial[(p * KCH + kc) * 2 + 1];
+            for (int k = 0; k < 4; ++k) {
+              ht += part[(tid * 4 + k) * 2 + 0];
+              hg += part[(tid * 4 + k) * 2 + 1];
+            }
+            zout[pp] = tanhf(ht) * (1.0f / (1.0f + expf(-hg)));
+          }
+          __syncthreads();
         }
-        zs[p] = tanhf(ht) * (1.0f / (1.0f + expf(-hg)));
       }
-      __syncthreads();
-      {
-        const int R = P.Cr + P.Cs;
-        for (int r = gwarp; r < R; r += nwarps) {
-          if (r < P.Cr) {
-            float v = dot_row(blk.res_w + (long long)r * Ch, zs, Ch, lane);
-            if (lane == 0) xout[r] = v + __ldg(blk.res_b + r) + xin[r];
+      // ---- T2: x_l = Wr z + br + x_{l-1} (pushed into ring_l), skip += Ws z + bs ----
+      if (has_t2) {
+        const int R = (has_t1 ? P.Cr : 0) + P.Cs;      // the last block's residual is unused
+        const int r_off = has_t1 ? 0 : P.Cr;
+        const int first = t2_first;                    // start after the warps T1 keeps busiest
+        for (int r = (gwarp - first + nwarps) % nwarps; r < R; r += nwarps) {
+          const int rr = r + r_off;
+          const bool pre = fastp && r < nwarps;        // the first row of a warp was prefetched
+          if (rr < P.Cr) {
+            const float v = pre ? warp_sum(fma_row<2>(q4, zs, Ch, lane))
+                                : dot_row(pb.res_w + (long long)rr * Ch, zs, Ch, lane);
+            if (lane == 0) {
+              // xbuf holds x_{l-1} + br_{l-1}; it gets x_l + br_l for the next phase
+              const float xv = v + __ldcg(xprev + rr);
+              const float bnext = (r < nwarps) ? pb_row : __ldg(blk.res_b + rr);
+              xout[rr] = xv + bnext;
+              P.queues[blk.qoff + (long long)(t % blk.qlen) * P.Cr + rr] = xv;
+            }
           } else {
-            const int s = r - P.Cr;
-            float v = dot_row(blk.skip_w + (long long)s * Ch, zs, Ch, lane);
-            if (lane == 0) P.skipacc[s] += v + __ldg(blk.skip_b + s);
+            const int sidx = rr - P.Cr;
+            const float v = pre ? warp_sum(fma_row<2>(q4, zs, Ch, lane))
+                                : dot_row(pb.skip_w + (long long)sidx * Ch, zs, Ch, lane);
+            if (lane == 0)
+              P.skipacc[sidx] += v + ((r < nwarps) ? pb_row : __ldg(pb.skip_b + sidx));
           }
         }
       }
-      if (l + 1 < P.n_blocks) {   // next block's phase-A rows
-        const GenBlock& nb = sblk[l + 1];
-        const int chunk = (KX + KCH - 1) / KCH, clen4 = (chunk + 3) & ~3;
-        for (int item = gwarp; item < Ch * KCH; item += nwarps) {
-          const int p = item / KCH, kc = item - p * KCH, k0 = kc * clen4;
-          const int n = max(0, min(clen4, KX - k0));
-          prefetch_row(nb.conv_w + (long long)p * KX + k0, n, lane);
-          prefetch_row(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane);
-          if (kc == KCH - 1) {
-            prefetch_row(nb.cond_w + (long long)p * P.Cc, P.Cc, lane);
-            prefetch_row(nb.cond_w + (long long)(Ch + p) * P.Cc, P.Cc, lane);
-          }
-        }
-      }
+      gather_past(l + 1, t);
+      prefetch_phase(l + 1);
       grid_barrier(P.barrier, epoch);
     }
 
     // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
-    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = fmaxf(P.skipacc[i], 0.0f);
+    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = fmaxf(__ldcg(P.skipacc + i), 0.0f);
     __syncthreads();
     for (int r = gwarp; r < P.Cs; r += nwarps) {
       float v = dot_row(P.proj1_w + (long long)r * P.Cs, xs, P.Cs, lane);
       if (lane == 0) P.h1[r] = fmaxf(v + __ldg(P.proj1_b + r), 0.0f);
     }
     grid_barrier(P.barrier, epoch);
-    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = P.h1[i];
+    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = __ldcg(P.h1 + i);
     __syncthreads();
     for (int r = gwarp; r < P.Q; r += nwarps) {
       float v = dot_row(P.proj2_w + (long long)r * P.Cs, xs, P.Cs, lane);
@@ -319,8 +433,7 @@ generate_kernel(const GenParams P) {
     grid_barrier(P.barrier, epoch);
 
     // ---- softmax + draw: every CTA does it redundantly (identical inputs -> identical result)
-    __syncthreads();
-    for (int i = tid; i < P.Q; i += GEN_THREADS) xs[i] = P.logit_buf[i];
+    for (int i = tid; i < P.Q; i += GEN_THREADS) xs[i] = __ldcg(P.logit_buf + i);
     __syncthreads();
     if (warp == 0) {
       float m = -INFINITY;
@@ -371,7 +484,7 @@ generate_kernel(const GenParams P) {
 static inline int64_t gen_align(int64_t v) { return (v + 255) / 256 * 256; }
 
 struct GenLayout {
-  int64_t blocks, queues, partial, xbuf, skipacc, h1, logit, state, barrier, total;
+  int64_t blocks, queues, zbuf, mmat, xbuf, skipacc, h1, logit, state, barrier, total;
 };
 
 static GenLayout gen_layout(const vqw_generate_desc& d) {
@@ -382,7 +495,8 @@ static GenLayout gen_layout(const vqw_generate_desc& d) {
   int64_t q = 0;
   for (int i = 0; i < d.n_blocks; ++i) q += (int64_t)(d.dilations[i] * (d.fs - 1) + 1) * d.Cr;
   L.queues = take(q * 4);
-  L.partial = take((int64_t)(d.Cd / 2) * vqw::KCH * 2 * 4);
+  L.zbuf = take((int64_t)2 * (d.Cd / 2) * 4);
+  L.mmat = take((int64_t)d.n_blocks * d.Cd * (d.Cd / 2) * 4);
   L.xbuf = take((int64_t)2 * d.Cr * 4);
   L.skipacc = take((int64_t)d.Cs * 4);
   L.h1 = take((int64_t)d.Cs * 4);
@@ -436,10 +550,25 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
     g.qlen = d.dilations[i] * (d.fs - 1) + 1;
     g.qoff = qoff;
     qoff += (long long)g.qlen * d.Cr;
+    g.mmat = (i == 0) ? nullptr
+                      : reinterpret_cast<const float*>(ws + L.mmat) + (long long)i * d.Cd * (d.Cd / 2);
+    g.cvec = nullptr;
   }
   VQW_CHECK_CUDA(cudaMemcpyAsync(ws + L.blocks, host_blocks, sizeof(GenBlock) * d.n_blocks,
                                  cudaMemcpyHostToDevice, st));
   if (d.t_start == 0) {
+    // M_l = Wc_cur_l Wr_{l-1}: a (Cd x Cr) by (Cr x Cd/2) product per block boundary, through the
+    // fp32 conv kernel (Wr viewed as a (Cr channels, Cd/2 steps) signal, Wc_cur as a 1x1 filter)
+    for (int i = 1; i < d.n_blocks; ++i) {
+      vqw_conv_desc c = {};
+      c.B = 1; c.M = d.Cd; c.T = d.Cd / 2;
+      c.nsrc = 1;
+      c.src[0] = {blocks[i - 1].res_w, blocks[i].conv_w + (d.fs - 1), nullptr, d.Cr, d.Cd / 2,
+                  d.Cr * d.fs, d.fs, 1, 0, 1, 0};
+      if (int rc = launch_conv(c, reinterpret_cast<float*>(ws + L.mmat) + (long long)i * d.Cd * (d.Cd / 2),
+                               st))
+        return rc;
+    }
     // WaveNet.initialize(): zero queues (modules.py:59-66,236-243); no previous samples
     VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.queues, 0, (size_t)qoff * 4, st));
     VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.state, 0xff, 16, st));
@@ -458,7 +587,7 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   P.proj2_w = proj2_w; P.proj2_b = proj2_b;
   P.cond = cond; P.uniforms = uniforms; P.forced = forced; P.samples = samples; P.logits = logits;
   P.queues = reinterpret_cast<float*>(ws + L.queues);
-  P.partial = reinterpret_cast<float*>(ws + L.partial);
+  P.zbuf = reinterpret_cast<float*>(ws + L.zbuf);
   P.xbuf = reinterpret_cast<float*>(ws + L.xbuf);
   P.skipacc = reinterpret_cast<float*>(ws + L.skipacc);
   P.h1 = reinterpret_cast<float*>(ws + L.h1);
@@ -470,8 +599,8 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   const int KX = d.fs * d.Cr, Ch = d.Cd / 2;
   int mx = d.Cr > d.Cs ? d.Cr : d.Cs;
   if (d.Q > mx) mx = d.Q;
-  size_t smem = sizeof(float) * (((KX + 3) & ~3) + ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) +
-                                 ((mx + 3) & ~3) + ((d.Q + 3) & ~3) + 8) +
+  size_t smem = sizeof(float) * (2 * ((KX + 3) & ~3) + 2 * ((d.Cc + 3) & ~3) + ((Ch + 3) & ~3) +
+                                 ((mx + 3) & ~3) + ((d.Q + 3) & ~3) + 16 + 8) +
                 sizeof(GenBlock) * d.n_blocks;
   VQW_REQUIRE(smem <= 200 * 1024, "vqw_generate: channel counts too large for shared memory");
   VQW_CHECK_CUDA(cudaFuncSetAttribute(generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
