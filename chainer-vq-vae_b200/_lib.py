@@ -110,6 +110,8 @@ _SIGNATURES = {
     "vqw_ema_update": (c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_float, C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
+    "vqw_embed_gather_backward_tc_workspace": (C.c_int64, [c_int] * 4),
+    "vqw_embed_gather_backward_tc": (c_int, [C.c_void_p] * 4 + [c_int] * 5 + [C.c_void_p] * 2),
 }
 
 

@@ -81,4 +81,9 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
                      float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
                      const void* saved, cudaStream_t stream);
 
+bool embed_bwd_tc_supported(int B, int T, int Cr, int Q);
+int64_t embed_bwd_tc_workspace(int B, int T, int Cr, int Q);
+int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, int B, int T, int Cr,
+                      int Q, int mode, void* workspace, cudaStream_t stream);
+
 }  // namespace vqw

@@ -97,3 +97,16 @@ extern "C" int vqw_embed_gather_backward(const int32_t* q, const float* gout, fl
   VQW_CHECK_LAUNCH("embed_gather_bwd_kernel");
   return 0;
 }
+
+// tensor-core variant (see tc_gemm.cu): mode = VQW_MODE_BF16X3 / VQW_MODE_BF16
+extern "C" int64_t vqw_embed_gather_backward_tc_workspace(int B, int T, int Cr, int Q) {
+  return vqw::embed_bwd_tc_supported(B, T, Cr, Q) ? vqw::embed_bwd_tc_workspace(B, T, Cr, Q) : -1;
+}
+extern "C" int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW, float* gb,
+                                            int B, int T, int Cr, int Q, int mode, void* workspace,
+                                            vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(mode == VQW_MODE_BF16X3 || mode == VQW_MODE_BF16,
+              "vqw_embed_gather_backward_tc: tensor-core modes only");
+  return embed_backward_tc(q, gout, gW, gb, B, T, Cr, Q, mode, workspace, (cudaStream_t)stream);
+}

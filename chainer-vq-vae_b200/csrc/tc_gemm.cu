@@ -61,6 +61,7 @@ struct GemmParams {
   Seg seg[MAX_SEG];
   int x3;
   int B, T;
+  int b_exact;                 // wgrad: B has no lo plane (exact bf16 values, e.g. a one-hot)
   int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
   int chunks_per_b;            // wgrad: work items per batch item
   const float* f0;             // GATE_BWD: tanh (B,256,T)
@@ -146,7 +147,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
             const uint32_t fb = full0 + 8 * stage;
             const uint32_t sa = base + stage * STAGE_BYTES;
-            mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
+            const bool blo = P.x3 && !P.b_exact;
+            mbar_expect_tx(fb, nplanes * A_PLANE + (blo ? 2 : 1) * B_PLANE);
             const int ta = tk + i * BK, tb = ta + jb.shift;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -156,7 +158,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               tma_load_3d(sa + 2 * A_PLANE + h * 4096, mb, fb, jb.n0 + 64 * h, tb, bb);
-              if (P.x3)
+              if (blo)
                 tma_load_3d(sa + 2 * A_PLANE + B_PLANE + h * 4096, mb + 1, fb, jb.n0 + 64 * h, tb, bb);
             }
             if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
@@ -213,7 +215,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           mma_ss(tmem_base, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
           if (P.x3) {
             mma_ss(tmem_base, a_lo, b_hi, ID, 1u);
-            mma_ss(tmem_base, a_hi, b_lo, ID, 1u);
+            if (!(WG && P.b_exact)) mma_ss(tmem_base, a_hi, b_lo, ID, 1u);
           }
         }
         tc_commit(empty0 + 8 * stage);
@@ -912,6 +914,76 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gh1[0]), LOW(W16(L.gh1[1])), gb1, nullptr,
                                                    Cs, NROWS, RPB, Cs);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(gh1)");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Embed weight gradient on the tensor cores (modules.py:151-152 differentiated):
+//   gW[c, q, j] = sum_{b,t} g[b, c, t] * onehot(q[b, t - 1 + j])[q]
+// i.e. two K=time GEMMs of the gradient planes against a one-hot plane (exact in bf16, so it
+// has no lo plane), through the grouped weight-gradient kernel; gb = column sums of g.
+// ---------------------------------------------------------------------------------------
+namespace tc {
+__global__ void __launch_bounds__(256)
+onehot_planes_kernel(const int32_t* __restrict__ q, __nv_bfloat16* __restrict__ oh, int64_t n, int Qp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int k = q[i];
+    if (k >= 0 && k < Qp) oh[i * Qp + k] = __float2bfloat16_rn(1.0f);
+  }
+}
+}  // namespace tc
+
+bool embed_bwd_tc_supported(int B, int T, int Cr, int Q) {
+  return B >= 1 && B <= 65535 && T >= tc::TM && T % 8 == 0 && Cr % 64 == 0 && Q >= 1;
+}
+int64_t embed_bwd_tc_workspace(int B, int T, int Cr, int Q) {
+  const int64_t N = (int64_t)B * T;
+  return 2 * al(N * Cr * 2) + al(N * pad256(Q) * 2) + 2048;
+}
+int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, int B, int T, int Cr,
+                      int Q, int mode, void* workspace, cudaStream_t stream) {
+  using namespace tc;
+  VQW_REQUIRE(embed_bwd_tc_supported(B, T, Cr, Q), "tcgen05 embed backward: unsupported shape");
+  VQW_REQUIRE(q && g && gW && workspace, "vqw_embed_gather_backward_tc: null pointer");
+  const bool x3 = mode == VQW_MODE_BF16X3;
+  const int Qp = pad256(Q);
+  const int64_t N = (int64_t)B * T;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
+  __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* g_lo = reinterpret_cast<__nv_bfloat16*>(ws + al(N * Cr * 2));
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(ws + 2 * al(N * Cr * 2));
+  if (int rc = pack_act_launch(g, g_hi, x3 ? g_lo : nullptr, B, Cr, T, stream)) return rc;
+  VQW_CHECK_CUDA(cudaMemsetAsync(oh, 0, (size_t)N * Qp * 2, stream));
+  onehot_planes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(q, oh, N, Qp);
+  VQW_CHECK_LAUNCH("onehot_planes_kernel");
+  Maps maps;
+  if (int rc = make_map_mn(&maps.m[0], g_hi, Cr, Cr, T, B)) return rc;
+  if (int rc = make_map_mn(&maps.m[1], x3 ? g_lo : g_hi, Cr, Cr, T, B)) return rc;
+  if (int rc = make_map_mn(&maps.m[2], oh, Qp, Qp, T, B)) return rc;
+  maps.m[3] = maps.m[2];
+  for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
+  GemmParams P = {};
+  P.x3 = x3; P.B = B; P.T = T;
+  P.b_exact = 1;
+  P.slabs_per_item = ceil_div(T, BK);
+  P.chunks_per_b = 1;
+  int nj = 0;
+  for (int j = 0; j < 2; ++j)
+    for (int m0 = 0; m0 < Cr; m0 += TM)
+      for (int n0 = 0; n0 < Q; n0 += TN) {
+        VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 embed backward: too many tiles");
+        // tap j reads the index at t - 1 + j  (j = 0: previous sample, j = 1: current sample)
+        P.jobs[nj++] = Job{0, 1, m0, n0, j - 1, Cr, Q, gW + j, (long long)Q * 2, 2};
+      }
+  P.njobs = nj;
+  if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+  if (gb) {
+    const int RPB = 256;
+    colsum_planes_kernel<<<(int)((N + RPB - 1) / RPB), 256, 0, stream>>>(g_hi, x3 ? g_lo : nullptr, gb,
+                                                                        nullptr, Cr, N, RPB, Cr);
+    VQW_CHECK_LAUNCH("colsum_planes_kernel(embed)");
+  }
   return 0;
 }
 

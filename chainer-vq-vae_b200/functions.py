@@ -371,7 +371,7 @@ def residual_stack(x, cond, dilations, fs, weights, mode=L.MODE_FP32, keep_last_
 # ---------------------------------------------------------------------------------------
 class _EmbedGather(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, W, b):
+    def forward(ctx, q, W, b, mode=L.MODE_FP32):
         W = _f32c(W)
         if q.dtype != torch.int32:
             raise TypeError("embed indices must be int32")
@@ -382,26 +382,36 @@ class _EmbedGather(torch.autograd.Function):
         L.check(L.lib.vqw_embed_gather_forward(L.ptr(q), L.ptr(W), L.ptr(b), L.ptr(out), B, T, Cr,
                                                Q, L.stream()), "vqw_embed_gather_forward")
         ctx.save_for_backward(q)
-        ctx.cfg = (tuple(W.shape), b is not None)
+        ctx.cfg = (tuple(W.shape), b is not None, mode)
         return out
 
     @staticmethod
     def backward(ctx, g):
         (q,) = ctx.saved_tensors
-        wshape, has_b = ctx.cfg
+        wshape, has_b, mode = ctx.cfg
         g = _f32c(g)
         Cr, Q = wshape[0], wshape[1]
+        B, T = q.shape[0], q.shape[1]
         gW = torch.zeros(wshape, device=g.device, dtype=torch.float32)
         gb = torch.zeros(Cr, device=g.device, dtype=torch.float32) if has_b else None
-        L.check(L.lib.vqw_embed_gather_backward(L.ptr(q), L.ptr(g), L.ptr(gW), L.ptr(gb),
-                                                q.shape[0], q.shape[1], Cr, Q, L.stream()),
-                "vqw_embed_gather_backward")
-        return None, gW, gb
+        ws_bytes = -1
+        if mode != L.MODE_FP32:
+            ws_bytes = int(L.lib.vqw_embed_gather_backward_tc_workspace(B, T, Cr, Q))
+        if ws_bytes > 0:      # two tcgen05 GEMMs against a one-hot plane
+            ws = torch.empty(ws_bytes, device=g.device, dtype=torch.uint8)
+            L.check(L.lib.vqw_embed_gather_backward_tc(L.ptr(q), L.ptr(g), L.ptr(gW), L.ptr(gb), B, T,
+                                                       Cr, Q, mode, L.ptr(ws), L.stream()),
+                    "vqw_embed_gather_backward_tc")
+        else:                 # shared-memory histogram on the CUDA cores
+            L.check(L.lib.vqw_embed_gather_backward(L.ptr(q), L.ptr(g), L.ptr(gW), L.ptr(gb), B, T,
+                                                    Cr, Q, L.stream()), "vqw_embed_gather_backward")
+        return None, gW, gb, None
 
 
-def embed_gather(q, W, b):
-    """q (B,T) int32 -> (B,Cr,T,1); W is the embed conv's weight (Cr, Q, 2, 1)."""
-    return _EmbedGather.apply(q, W, b)
+def embed_gather(q, W, b, mode=L.MODE_FP32):
+    """q (B,T) int32 -> (B,Cr,T,1); W is the embed conv's weight (Cr, Q, 2, 1).  `mode` selects
+    the weight-gradient kernel (tensor-core GEMMs in the bf16 modes)."""
+    return _EmbedGather.apply(q, W, b, mode)
 
 
 # ---------------------------------------------------------------------------------------

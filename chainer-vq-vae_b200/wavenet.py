@@ -103,7 +103,7 @@ class WaveNet(nn.Module):
         same arithmetic without materialising the one-hot -- a (B, T) int32 tensor of mu-law
         indices when input_dim == quantize."""
         if x.dtype == torch.int32:
-            h = Fn.embed_gather(x, self.embed.W, self.embed.b)                  # :151-152
+            h = Fn.embed_gather(x, self.embed.W, self.embed.b, self.resnet.mode)  # :151-152
         else:
             h = self.embed(x, out_len=x.shape[2])                              # :150-152
         z = self.resnet(h, condition)                                          # :155

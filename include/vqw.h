@@ -236,6 +236,13 @@ int vqw_embed_gather_forward(const int32_t* q, const float* W, const float* bias
 /* gW (Cr,Q,2) and gb (Cr) accumulated. */
 int vqw_embed_gather_backward(const int32_t* q, const float* gout, float* gW, float* gb, int B,
                               int T, int Cr, int Q, vqw_stream_t stream);
+/* Same gradient as two K=time tcgen05 GEMMs of the gradient planes against a one-hot plane
+ * (mode = VQW_MODE_BF16X3 / VQW_MODE_BF16; needs Cr % 64 == 0, T >= 128, T % 8 == 0; the
+ * workspace query returns -1 for unsupported shapes).  gW, gb accumulated. */
+int64_t vqw_embed_gather_backward_tc_workspace(int B, int T, int Cr, int Q);
+int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW, float* gb, int B,
+                                 int T, int Cr, int Q, int mode, void* workspace,
+                                 vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Loss and optimiser passes over flat fp32 ranges (one HBM-bound kernel each).

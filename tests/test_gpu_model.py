@@ -30,7 +30,7 @@ def test_vae_forward_matches_oracle(cpu_case, indices):
         "VQ indices must be bit-identical to the reference formulation"
     assert rel_err(model.y, inter["y"]) < TOL
     for got, want in zip((l1, l2, l3), losses):
-        assert abs(float(got) - float(want)) <= TOL * abs(float(want))
+        assert abs(float(got.detach()) - float(want)) <= TOL * abs(float(want))
 
 
 def test_three_loss_backward_ordering(cpu_case):

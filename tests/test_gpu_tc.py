@@ -185,3 +185,32 @@ def test_tc_wavenet_with_head_matches_fp32_path_and_oracle():
             cos = float(torch.dot(a.flatten().double(), b.flatten().double()) /
                         (a.double().norm() * b.double().norm()))
             assert cos > 0.999 and rel_err(a, b) < 0.15, (use_logistic, name, cos, rel_err(a, b))
+
+
+@pytest.mark.parametrize("B,T,Cr,Q", [(2, 256, 512, 256), (1, 136, 128, 100), (3, 384, 64, 300)])
+@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_BF16])
+def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
+    """Embed backward (modules.py:151-152 differentiated) as one-hot tcgen05 GEMMs against the
+    CUDA-core histogram kernel and a float64 restatement."""
+    rng = np.random.default_rng(T + Cr)
+    q = torch.from_numpy(rng.integers(0, Q, size=(B, T)).astype(np.int32)).to(DEV)
+    W = torch.from_numpy(rng.normal(size=(Cr, Q, 2, 1)).astype(np.float32)).to(DEV)
+    b = torch.zeros(Cr, device=DEV)
+    g = torch.from_numpy(rng.normal(size=(B, Cr, T, 1)).astype(np.float32)).to(DEV)
+    out = {}
+    for m in (L.MODE_FP32, mode):
+        Wm, bm = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = V.embed_gather(q, Wm, bm, m)
+        (y * g).sum().backward()
+        out[m] = (Wm.grad.clone(), bm.grad.clone())
+    # float64 restatement: gW[c,k,1] = sum g[b,c,t] [q[b,t]==k];  gW[c,k,0] uses q[b,t-1]
+    g64 = g[..., 0].double().cpu()
+    oh = torch.nn.functional.one_hot(q.long().cpu(), Q).double()          # (B,T,Q)
+    ref1 = torch.einsum("bct,btk->ck", g64, oh)
+    ref0 = torch.einsum("bct,btk->ck", g64[:, :, 1:], oh[:, :-1])
+    tol = 1e-5 if mode == L.MODE_BF16X3 else 5e-3
+    assert rel_err(out[mode][0][:, :, 1, 0], ref1) < tol
+    assert rel_err(out[mode][0][:, :, 0, 0], ref0) < tol
+    assert rel_err(out[L.MODE_FP32][0][:, :, 1, 0], ref1) < 1e-5
+    assert rel_err(out[mode][1], g64.sum((0, 2))) < tol
+    assert rel_err(out[mode][0], out[L.MODE_FP32][0]) < tol
