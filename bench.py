@@ -307,7 +307,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16, fp32 accumulate)",
-                      "bf16": "bf16"}[args.mode],
+                      "bf16": "bf16", "fp16": "fp16 (IEEE half operands, fp32 accumulate)"}[args.mode],
             "data": "synthetic (sinusoid mixtures, mu-law 256, random-init weights)",
             "config": {"workload": "1xB200: batch=16/GPU length=7680 n_loop=2 n_layer=10 "
                                    "filter_size=3 512/512/256 k=512 d=64 mu-law-256 Cc=192",
@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "bf16x3"),
-                    choices=["fp32", "bf16x3", "bf16"])
+                    choices=["fp32", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "generate"])
     ap.add_argument("--gen-length", type=int, default=24000)

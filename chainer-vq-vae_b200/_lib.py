@@ -16,8 +16,8 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 VQW_MAX_SRC = 4
-MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+MODE_FP32, MODE_BF16X3, MODE_BF16, MODE_FP16 = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "fp16": MODE_FP16}
 
 c_float_p = C.c_void_p   # device pointers are passed as integers
 c_int = C.c_int

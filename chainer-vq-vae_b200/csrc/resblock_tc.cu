@@ -42,7 +42,9 @@ constexpr int CD = 512, CH = 256, HALF = 128;             // dilated channels ha
 
 struct Params {
   int B, T, Cr, Cs, Cc, fs, dilation;
-  int x3;               // 1: bf16x3, 0: single bf16 pass
+  int x3;               // 1: bf16x3 (three MMAs per product), 0: single pass over the hi planes
+  int f16;              // planes hold IEEE fp16 instead of bf16 (VQW_MODE_FP16, single pass)
+  int xlo;              // the residual stream keeps its lo plane (residual-add operand): x3 or fp16
   int skip_accumulate;
   int write_residual;   // 0 for the last block: O_0/O_1 are skipped entirely
   const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
@@ -173,6 +175,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       int nphase = 0;
       const uint32_t acc = tmem_base + ACC_COL;
       const bool rec = rec_cta;
+      const uint32_t idesc = idesc_for(IDESC, P.f16);
       for (int gp = 0; gp < 2; ++gp, ++nphase) {
         if (nphase > 0) {
           mbar_wait(acc_empty, (nphase - 1) & 1);
@@ -187,12 +190,12 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           for (int ks = 0; ks < BK / UK; ++ks) {
             const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
             const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma_ss(acc, a_hi, b_hi, IDESC, (i | ks) ? 1u : 0u);
+            mma_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
             if (P.x3) {
               const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
               const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
-              mma_ss(acc, a_lo, b_hi, IDESC, 1u);
-              mma_ss(acc, a_hi, b_lo, IDESC, 1u);
+              mma_ss(acc, a_lo, b_hi, idesc, 1u);
+              mma_ss(acc, a_hi, b_lo, idesc, 1u);
             }
           }
           tc_commit(empty0 + 8 * stage);
@@ -215,11 +218,11 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             const uint32_t z_hi = tmem_base + ZHI_COL + (BK / 2) * i + (UK / 2) * ks;
             const uint32_t z_lo = tmem_base + ZLO_COL + (BK / 2) * i + (UK / 2) * ks;
             const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma_ts(acc, z_hi, b_hi, IDESC, (i | ks) ? 1u : 0u);
+            mma_ts(acc, z_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
             if (P.x3) {
               const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
-              mma_ts(acc, z_lo, b_hi, IDESC, 1u);
-              mma_ts(acc, z_hi, b_lo, IDESC, 1u);
+              mma_ts(acc, z_lo, b_hi, idesc, 1u);
+              mma_ts(acc, z_hi, b_lo, idesc, 1u);
             }
           }
           tc_commit(empty0 + 8 * stage);
@@ -269,7 +272,8 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               __stcs(P.gate_sig + off, sg);
             }
           }
-          split_pair(z2[0], z2[1], zh[i >> 1], zl[i >> 1]);
+          if (P.x3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], P.f16);
+          else zh[i >> 1] = pack_pair_f(z2[0], z2[1], P.f16);
         }
         tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
         if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
@@ -301,7 +305,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
           if (t_ok) {
             ld256(P.xp_hi + poff, hw);
-            if (P.x3) ld256(P.xp_lo + poff, lw);
+            if (P.xlo) ld256(P.xp_lo + poff, lw);
           }
         } else if (P.skip_accumulate && t_ok) {
           const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
@@ -320,10 +324,13 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         if (is_res) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float v0 = __uint_as_float(hw[i] << 16), v1 = __uint_as_float(hw[i] & 0xffff0000u);
-            if (P.x3) {
-              v0 += __uint_as_float(lw[i] << 16);
-              v1 += __uint_as_float(lw[i] & 0xffff0000u);
+            float v0, v1;
+            unpack_pair_f(hw[i], P.f16, v0, v1);
+            if (P.xlo) {
+              float l0, l1;
+              unpack_pair_f(lw[i], P.f16, l0, l1);
+              v0 += l0;
+              v1 += l1;
             }
             add[2 * i] = t_ok ? v0 : 0.0f;
             add[2 * i + 1] = t_ok ? v1 : 0.0f;
@@ -347,12 +354,13 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                 __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
-            split_pair(v2[0], v2[1], rh[i >> 1], rl[i >> 1]);
+            if (P.xlo) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], P.f16);
+            else rh[i >> 1] = pack_pair_f(v2[0], v2[1], P.f16);
           }
           if (t_ok && P.res_hi != nullptr) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
             st256(P.res_hi + poff, rh);
-            if (P.x3) st256(P.res_lo + poff, rl);
+            if (P.xlo) st256(P.res_lo + poff, rl);
           }
         } else if (t_ok) {
 #pragma unroll
@@ -379,17 +387,390 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   }
 }
 
+
+// ------------------------------------------------------------------ the kernel, v2 ---------
+// Persistent variant (EXPERIMENTAL, VQW_TC_FWD_V2=1; measured SLOWER than v1 on B200: 1.01 vs
+// 0.89 ms per block in bf16x3).  Finding: with N = 128 chunks every activation slab is streamed
+// once per chunk, i.e. 32 KB of shared-memory fill per 384 MMA cycles = 85 B/clk, and the SM's
+// L2 read port delivers ~53-62 B/clk (v1 needs 48 KB per 768 cycles = 62.5 B/clk and runs at the
+// MMA rate): an H chunk takes 31-35 k cycles in bf16x3 AND in the single-pass mode, against
+// 20.7 k / 6.9 k of MMA time.  What it does achieve is the epilogue overlap (its per-chunk
+// timeline shows the gate / output epilogues fully hidden); the version that keeps that and
+// fits the port is the same chunk pipeline on a CTA pair (cta_group::2, weights split across the
+// two SMs: 62.5 B/clk) -- round 2.
+// One CTA per SM loops over (batch item, 128 time steps)
+// tiles, and the work of a tile is cut into N = 128 output-channel CHUNKS that ping-pong between
+// two 128-column TMEM accumulators, so the epilogue of chunk n runs while the tensor core works
+// on chunk n+1 (v1 above has ONE 256-column accumulator: its 59 k cycles of epilogue per tile
+// are all exposed, a third of the tile).  Chunks of a tile, in order:
+//   H_0..H_3   h rows {tanh 64c..64c+63 | sigmoid 64c..64c+63} (K = fs*Cr + Cc) -> gate -> z
+//              channels 64c..64c+63 into the TMEM z planes
+//   R_0..R_3   residual channels 128r..128r+127 = Wr z + br + x      (A operand = z in TMEM)
+//   S_0..S_1   skip channels 128s..128s+127 (+)= Ws z + bs
+// The TMA producer streams K = 32 slabs for this chunk sequence without regard to tile
+// boundaries (6-stage ring), so the first slabs of the next tile are in flight during the last
+// epilogues of the current one.  TMEM: [0,128) acc 0, [128,256) acc 1, [256,384) z hi,
+// [384,512) z lo.  Ordering: MMAs execute in issue order, so (a) waiting for the epilogue of
+// H_3 before issuing R_0 guarantees every z column is written, and (b) the epilogue of the NEXT
+// tile's H_0 -- which overwrites z -- can only start after that chunk's commit, i.e. after
+// every R/S MMA of this tile has read z.
+constexpr int V2_STAGES = 6;
+constexpr int V2_TN = 128;
+constexpr int V2_B_PLANE = V2_TN * BK * 2;                  // 8 KB
+constexpr int V2_STAGE_BYTES = 2 * A_PLANE + 2 * V2_B_PLANE;   // 32 KB
+constexpr int V2_HALF = 64;                                 // gate pairs per H chunk
+constexpr uint32_t IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(V2_TN >> 3) << 17) |
+                                ((uint32_t)(TM >> 4) << 24);
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+resblock_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi,
+                    const __grid_constant__ CUtensorMap map_x_lo,
+                    const __grid_constant__ CUtensorMap map_c_hi,
+                    const __grid_constant__ CUtensorMap map_c_lo,
+                    const __grid_constant__ CUtensorMap map_w1_hi,
+                    const __grid_constant__ CUtensorMap map_w1_lo,
+                    const __grid_constant__ CUtensorMap map_w2_hi,
+                    const __grid_constant__ CUtensorMap map_w2_lo, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  float* b1s = reinterpret_cast<float*>(smem + V2_STAGES * V2_STAGE_BYTES);   // [512] conv_b + cond_b
+  float* brs = b1s + CD;                                                      // [Cr]
+  float* bss = brs + P.Cr;                                                    // [Cs]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + V2_STAGES);
+  const uint32_t acc_full0 = smem_u32(bars + 2 * V2_STAGES);        // [2]
+  const uint32_t acc_empty0 = smem_u32(bars + 2 * V2_STAGES + 2);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = P.x3 ? 2 : 1;
+  const int chunks_per_tap = P.Cr / BK;
+  const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of an H chunk
+  const int nk2 = CH / BK;                               // K slabs of an R / S chunk
+  const int n_h = CD / V2_TN;                            // 4
+  const int n_r = P.Cr / V2_TN;
+  const int o_begin = P.write_residual ? 0 : n_r;        // first chunk of [Wr ; Ws]
+  const int o_end = n_r + P.Cs / V2_TN;
+  const int tiles_per_item = (P.T + TM - 1) / TM;
+  const int n_tiles = P.B * tiles_per_item;
+
+  if (warp == W_TMA && lane == 0) {
+    prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
+    prefetch_tmap(&map_w2_hi);
+    if (P.x3) {
+      prefetch_tmap(&map_x_lo); prefetch_tmap(&map_c_lo); prefetch_tmap(&map_w1_lo);
+      prefetch_tmap(&map_w2_lo);
+    }
+    for (int s = 0; s < V2_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full0 + 8 * s, 1);
+      mbar_init(acc_empty0 + 8 * s, FWD_EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < FWD_EPI_WARPS) {
+    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.conv_b[i] + P.cond_b[i];
+    for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
+    for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_TMA) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TM;
+        for (int c = 0; c < n_h; ++c) {
+          for (int i = 0; i < nk1; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = base + stage * V2_STAGE_BYTES;
+            mbar_expect_tx(fb, nplanes * (A_PLANE + V2_B_PLANE));
+            const int tap = i / chunks_per_tap;
+            if (tap < P.fs) {
+              const int c0 = (i - tap * chunks_per_tap) * BK;
+              const int tt = t0 - P.dilation * (P.fs - 1 - tap);   // negative rows -> zero fill
+              tma_load_3d(sa, &map_x_hi, fb, c0, tt, b);
+              if (P.x3) tma_load_3d(sa + A_PLANE, &map_x_lo, fb, c0, tt, b);
+            } else {
+              const int c0 = (i - P.fs * chunks_per_tap) * BK;
+              tma_load_3d(sa, &map_c_hi, fb, c0, t0, b);
+              if (P.x3) tma_load_3d(sa + A_PLANE, &map_c_lo, fb, c0, t0, b);
+            }
+            tma_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, c * V2_TN);
+            if (P.x3) tma_load_2d(sa + 2 * A_PLANE + V2_B_PLANE, &map_w1_lo, fb, i * BK, c * V2_TN);
+            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+        for (int oc = o_begin; oc < o_end; ++oc) {
+          for (int i = 0; i < nk2; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t sa = base + stage * V2_STAGE_BYTES;
+            mbar_expect_tx(fb, nplanes * V2_B_PLANE);
+            tma_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * V2_TN);
+            if (P.x3) tma_load_2d(sa + 2 * A_PLANE + V2_B_PLANE, &map_w2_lo, fb, i * BK, oc * V2_TN);
+            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      uint32_t n = 0;   // running chunk counter: accumulator n & 1, its k-th use k = n >> 1
+      const uint32_t idesc = idesc_for(IDESC_N128, P.f16);
+      const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < n_h; ++c, ++n) {
+          const uint32_t buf = n & 1;
+          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);   // epilogue of chunk n-2 is done
+          tc_fence_after();
+          if (rec && n < 24) P.dbg[4 * n] = clock64();
+          const uint32_t acc = tmem_base + buf * V2_TN;
+          for (int i = 0; i < nk1; ++i) {
+            mbar_wait(full0 + 8 * stage, ph);
+            tc_fence_after();
+            const uint32_t sa = base + stage * V2_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks) {
+              const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
+              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+              mma_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
+              if (P.x3) {
+                const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V2_B_PLANE + ks * UK * 2);
+                mma_ss(acc, a_lo, b_hi, idesc, 1u);
+                mma_ss(acc, a_hi, b_lo, idesc, 1u);
+              }
+            }
+            tc_commit(empty0 + 8 * stage);
+            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
+          }
+          tc_commit(acc_full0 + 8 * buf);
+          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
+        }
+        {   // every z column of this tile must be in TMEM: wait for the epilogue of H_3 (chunk n-1)
+          const uint32_t m = n - 1;
+          mbar_wait(acc_empty0 + 8 * (m & 1), (m >> 1) & 1);
+          tc_fence_after();
+        }
+        for (int oc = o_begin; oc < o_end; ++oc, ++n) {
+          const uint32_t buf = n & 1;
+          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (rec && n < 24) P.dbg[4 * n] = clock64();
+          const uint32_t acc = tmem_base + buf * V2_TN;
+          for (int i = 0; i < nk2; ++i) {
+            mbar_wait(full0 + 8 * stage, ph);
+            tc_fence_after();
+            const uint32_t sa = base + stage * V2_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks) {
+              // z channel k sits in column k/2 of its plane: slab i, step ks -> 16*i + 8*ks
+              const uint32_t z_hi = tmem_base + ZHI_COL + (BK / 2) * i + (UK / 2) * ks;
+              const uint32_t z_lo = tmem_base + ZLO_COL + (BK / 2) * i + (UK / 2) * ks;
+              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+              mma_ts(acc, z_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
+              if (P.x3) {
+                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V2_B_PLANE + ks * UK * 2);
+                mma_ts(acc, z_lo, b_hi, idesc, 1u);
+                mma_ts(acc, z_hi, b_lo, idesc, 1u);
+              }
+            }
+            tc_commit(empty0 + 8 * stage);
+            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
+          }
+          tc_commit(acc_full0 + 8 * buf);
+          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-15) ======================
+    // warp e: TMEM lane quadrant e%4, column group e/4 (16-column units dealt round-robin)
+    const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x && threadIdx.x == 0;
+    const int quad = warp & 3, grp = warp >> 2;
+    constexpr int NG = FWD_EPI_WARPS / 4;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TM;
+      const int t = t0 + row;
+      const bool t_ok = t < P.T;
+      // ---- gate chunks: z = tanh(h_t) * sigmoid(h_s) -> TMEM z planes (+ saved tensors) ----
+      for (int c = 0; c < n_h; ++c, ++n) {
+        const uint32_t buf = n & 1;
+        const uint32_t acc = lane_base + buf * V2_TN;
+        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
+        tc_fence_after();
+        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
+#pragma unroll 1
+        for (int q = grp; q < V2_HALF / 16; q += NG) {
+          float a[16], g[16];
+          tmem_ld16(acc + 16 * q, a);
+          tmem_ld16(acc + V2_HALF + 16 * q, g);
+          uint32_t zh[8], zl[8];
+          const int ch0 = c * V2_HALF + 16 * q;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float z2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int ch = ch0 + i + u;
+              const float th = tanh_fast(a[i + u] + b1s[ch]);
+              const float sg = sigmoid_fast(g[i + u] + b1s[CH + ch]);
+              z2[u] = th * sg;
+              if (P.gate_tanh != nullptr && t_ok) {
+                const int64_t off = ((int64_t)b * CH + ch) * P.T + t;
+                __stcs(P.gate_tanh + off, th);
+                __stcs(P.gate_sig + off, sg);
+              }
+            }
+            if (P.x3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], P.f16);
+            else zh[i >> 1] = pack_pair_f(z2[0], z2[1], P.f16);
+          }
+          tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
+          if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
+          if (P.zp_hi != nullptr && t_ok) {
+            const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
+            st256(P.zp_hi + zoff, zh);
+            if (P.x3) st256(P.zp_lo + zoff, zl);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(acc_empty0 + 8 * buf);
+        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
+      }
+      // ---- output chunks: residual channels, then skip channels ----
+      for (int oc = o_begin; oc < o_end; ++oc, ++n) {
+        const uint32_t buf = n & 1;
+        const uint32_t acc = lane_base + buf * V2_TN;
+        const bool is_res = oc < n_r;
+        const int cbase = is_res ? oc * V2_TN : (oc - n_r) * V2_TN;
+        float addf[16];
+        uint32_t hw[8], lw[8];
+        auto fetch = [&](int q) {
+          const int ch0 = cbase + 16 * q;
+          if (is_res) {
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
+            if (t_ok) {
+              ld256(P.xp_hi + poff, hw);
+              if (P.xlo) ld256(P.xp_lo + poff, lw);
+            }
+          } else if (P.skip_accumulate && t_ok) {
+            const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
+          }
+        };
+        fetch(grp);
+        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
+        tc_fence_after();
+        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
+#pragma unroll 1
+        for (int q = grp; q < V2_TN / 16; q += NG) {
+          float o[16], add[16];
+          tmem_ld16(acc + 16 * q, o);
+          if (is_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v0, v1;
+              unpack_pair_f(hw[i], P.f16, v0, v1);
+              if (P.xlo) {
+                float l0, l1;
+                unpack_pair_f(lw[i], P.f16, l0, l1);
+                v0 += l0;
+                v1 += l1;
+              }
+              add[2 * i] = t_ok ? v0 : 0.0f;
+              add[2 * i + 1] = t_ok ? v1 : 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
+          }
+          if (q + NG < V2_TN / 16) fetch(q + NG);
+          const int ch0 = cbase + 16 * q;
+          if (is_res) {
+            uint32_t rh[8], rl[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float v2[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int ch = ch0 + i + u;
+                const float v = o[i + u] + brs[ch] + add[i + u];
+                if (t_ok && P.res_f32 != nullptr)
+                  __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
+                v2[u] = v;
+              }
+              if (P.xlo) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], P.f16);
+              else rh[i >> 1] = pack_pair_f(v2[0], v2[1], P.f16);
+            }
+            if (t_ok && P.res_hi != nullptr) {
+              const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
+              st256(P.res_hi + poff, rh);
+              if (P.xlo) st256(P.res_lo + poff, rl);
+            }
+          } else if (t_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int ch = ch0 + i;
+              P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty0 + 8 * buf);
+        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ packing kernels --------
 // (B,C,T) fp32 -> (B,T,C) bf16 hi/lo planes: 32x32 transpose through shared memory
 __global__ void __launch_bounds__(256)
 pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
-                __nv_bfloat16* __restrict__ lo, int C, int T, int pitch, int relu) {
+                __nv_bfloat16* __restrict__ lo, int C, int T, int pitch, int relu, int f16,
+                const float* __restrict__ scale) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float sc = scale ? scale[0] : 1.0f;   // power-of-two gradient scale (fp16 backward)
   for (int r = ty; r < 32; r += 8) {
     int c = c0 + r, t = t0 + tx;
-    tile[r][tx] = (c < C && t < T) ? in[((int64_t)b * C + c) * T + t] : 0.0f;
+    tile[r][tx] = (c < C && t < T) ? in[((int64_t)b * C + c) * T + t] * sc : 0.0f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
@@ -398,7 +779,7 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
       __nv_bfloat16 h, l;
       float v = tile[tx][r];
       if (relu) v = fmaxf(v, 0.0f);
-      split_bf16(v, h, l);
+      split_16(v, f16, h, l);
       const int64_t off = ((int64_t)b * T + t) * pitch + c;
       hi[off] = h;
       if (lo) lo[off] = l;
@@ -407,30 +788,32 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
 }
 
 int pack_act_launch_ex(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
-                       int pitch, int relu, cudaStream_t stream) {
+                       int pitch, int relu, int f16, const float* scale, cudaStream_t stream) {
   dim3 g(ceil_div(T, 32), ceil_div(pitch, 32), B);
-  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T, pitch, relu);
+  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T, pitch, relu, f16, scale);
   VQW_CHECK_LAUNCH("pack_act_kernel");
   return 0;
 }
 int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
-                    cudaStream_t stream) {
-  return pack_act_launch_ex(in, hi, lo, B, C, T, C, 0, stream);
+                    int f16, const float* scale, cudaStream_t stream) {
+  return pack_act_launch_ex(in, hi, lo, B, C, T, C, 0, f16, scale, stream);
 }
 
-// W1 packed [512 rows in phase order][K1 = fs*Cr + Cc]: row r -> original row
-//   r in [0,128) tanh 0..127 | [128,256) sigmoid 0..127 | [256,384) tanh 128..255 | [384,512) sigmoid 128..255
+// W1 packed [512 rows in chunk order][K1 = fs*Cr + Cc]: row r -> original row; `half` gate pairs
+// per accumulator chunk (v1: 128, v2: 64):
+//   half = 128: [0,128) tanh 0..127 | [128,256) sigmoid 0..127 | [256,384) tanh 128..255 | ...
+//   half = 64 : [0,64) tanh 0..63 | [64,128) sigmoid 0..63 | [128,192) tanh 64..127 | ...
 __global__ void __launch_bounds__(256)
 pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_w,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cc,
-               int fs) {
+               int fs, int f16, int half) {
   const int K1 = fs * Cr + Cc;
   const int64_t n = (int64_t)CD * K1;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / K1), k = (int)(e % K1);
-    const int quad = r / HALF, within = r % HALF;
-    const int orig = ((quad & 1) ? CH : 0) + ((quad >> 1) ? HALF : 0) + within;
+    const int quad = r / half, within = r % half;
+    const int orig = ((quad & 1) ? CH : 0) + (quad >> 1) * half + within;
     float v;
     if (k < fs * Cr) {
       const int j = k / Cr, c = k % Cr;
@@ -439,7 +822,7 @@ pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_
       v = cond_w[(int64_t)orig * Cc + (k - fs * Cr)];
     }
     __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    split_16(v, f16, h, l);
     hi[e] = h;
     if (lo) lo[e] = l;
   }
@@ -448,14 +831,15 @@ pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_
 // W2 packed [(Cr + Cs) rows][Ch]: residual rows then skip rows
 __global__ void __launch_bounds__(256)
 pack_w2_kernel(const float* __restrict__ res_w, const float* __restrict__ skip_w,
-               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cs) {
+               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cs,
+               int f16) {
   const int64_t n = (int64_t)(Cr + Cs) * CH;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / CH), k = (int)(e % CH);
     const float v = (r < Cr) ? res_w[(int64_t)r * CH + k] : skip_w[(int64_t)(r - Cr) * CH + k];
     __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    split_16(v, f16, h, l);
     hi[e] = h;
     if (lo) lo[e] = l;
   }
@@ -514,6 +898,10 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
 size_t smem_bytes(int Cr, int Cs) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * (2 * STAGES + 2) + 16;
 }
+size_t smem_bytes_v2(int Cr, int Cs) {
+  return 1024 + (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) +
+         8 * (2 * V2_STAGES + 4) + 16;
+}
 
 }  // namespace tc
 
@@ -561,6 +949,13 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   VQW_REQUIRE(workspace != nullptr, "vqw_resnet_forward: workspace is null");
   VQW_REQUIRE(d.B <= 65535, "vqw_resnet_forward: B > 65535");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool xlo = x3 || f16;   // residual stream hi + lo (only the hi plane feeds the MMAs in fp16)
+  // VQW_TC_FWD_V2=1 selects the experimental persistent kernel (see resblock_tc2_kernel)
+  const char* v2env = getenv("VQW_TC_FWD_V2");
+  const bool use_v2 = v2env && v2env[0] == '1';
+  const bool v2 = use_v2 && d.Cr % V2_TN == 0 && d.Cs % V2_TN == 0;
+  const int wrows = v2 ? V2_TN : TN;   // weight rows per accumulator chunk = TMA box rows
   const TcWorkspace L = tc_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
   auto plane = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
@@ -582,9 +977,11 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   // pack the two inputs and every block's weights
   {
     dim3 g1(ceil_div(d.T, 32), ceil_div(d.Cr, 32), d.B), g2(ceil_div(d.T, 32), ceil_div(d.Cc, 32), d.B);
-    pack_act_kernel<<<g1, 256, 0, stream>>>(x, x_hi[0], x3 ? x_lo[0] : nullptr, d.Cr, d.T, d.Cr, 0);
+    pack_act_kernel<<<g1, 256, 0, stream>>>(x, x_hi[0], xlo ? x_lo[0] : nullptr, d.Cr, d.T, d.Cr, 0,
+                                            f16, nullptr);
     VQW_CHECK_LAUNCH("pack_act_kernel(x)");
-    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, d.Cc, d.T, d.Cc, 0);
+    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, d.Cc, d.T, d.Cc, 0, f16,
+                                            nullptr);
     VQW_CHECK_LAUNCH("pack_act_kernel(cond)");
     for (int i = 0; i < d.n_blocks; ++i) {
       const vqw_resblock_weights& w = weights[i];
@@ -595,16 +992,27 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       __nv_bfloat16* w2h = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane);
       __nv_bfloat16* w2l = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane + L.w2_plane);
       pack_w1_kernel<<<296, 256, 0, stream>>>(w.conv_w, w.cond_w, w1h, x3 ? w1l : nullptr, d.Cr,
-                                               d.Cc, d.fs);
+                                               d.Cc, d.fs, f16, v2 ? V2_HALF : HALF);
       VQW_CHECK_LAUNCH("pack_w1_kernel");
-      pack_w2_kernel<<<148, 256, 0, stream>>>(w.res_w, w.skip_w, w2h, x3 ? w2l : nullptr, d.Cr, d.Cs);
+      pack_w2_kernel<<<148, 256, 0, stream>>>(w.res_w, w.skip_w, w2h, x3 ? w2l : nullptr, d.Cr, d.Cs,
+                                               f16);
       VQW_CHECK_LAUNCH("pack_w2_kernel");
     }
   }
 
-  const size_t smem = smem_bytes(d.Cr, d.Cs);
-  VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = v2 ? smem_bytes_v2(d.Cr, d.Cs) : smem_bytes(d.Cr, d.Cs);
+  if (v2)
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc2_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n_sm = 148;
+  {
+    int dev = 0;
+    VQW_CHECK_CUDA(cudaGetDevice(&dev));
+    VQW_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
   CUtensorMap m_c_hi, m_c_lo;
   if (int rc = make_map(&m_c_hi, c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
   if (int rc = make_map(&m_c_lo, x3 ? c_lo : c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
@@ -624,14 +1032,16 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     CUtensorMap m_x_hi, m_x_lo, m_w1_hi, m_w1_lo, m_w2_hi, m_w2_lo;
     if (int rc = make_map(&m_x_hi, x_hi[cur], 3, d.Cr, d.T, d.B, TM)) return rc;
     if (int rc = make_map(&m_x_lo, x3 ? x_lo[cur] : x_hi[cur], 3, d.Cr, d.T, d.B, TM)) return rc;
-    if (int rc = make_map(&m_w1_hi, w1h, 2, K1, CD, 1, TN)) return rc;
-    if (int rc = make_map(&m_w1_lo, x3 ? w1l : w1h, 2, K1, CD, 1, TN)) return rc;
-    if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, TN)) return rc;
-    if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, TN)) return rc;
+    if (int rc = make_map(&m_w1_hi, w1h, 2, K1, CD, 1, wrows)) return rc;
+    if (int rc = make_map(&m_w1_lo, x3 ? w1l : w1h, 2, K1, CD, 1, wrows)) return rc;
+    if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, wrows)) return rc;
+    if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, wrows)) return rc;
     Params P;
     P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = d.Cc; P.fs = d.fs;
     P.dilation = d.dilations[i];
     P.x3 = x3 ? 1 : 0;
+    P.f16 = f16;
+    P.xlo = xlo ? 1 : 0;
     P.skip_accumulate = i > 0;
     P.write_residual = write_res ? 1 : 0;
     P.xp_hi = x_hi[cur];
@@ -651,17 +1061,33 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     static const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
     P.dbg = nullptr; P.dbg_x = P.dbg_y = 0;
     if (timeline) {
-      if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
-      cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 128 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 128 * sizeof(long long), stream);
       P.dbg = dbg_buf;
       P.dbg_x = getenv("VQW_TC_TIMELINE_X") ? atoi(getenv("VQW_TC_TIMELINE_X")) : 1;
       P.dbg_y = getenv("VQW_TC_TIMELINE_Y") ? atoi(getenv("VQW_TC_TIMELINE_Y")) : 0;
     }
-    dim3 grid(ceil_div(d.T, TM), d.B);
-    resblock_tc_kernel<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
-                                                        m_w1_lo, m_w2_hi, m_w2_lo, P);
-    VQW_CHECK_LAUNCH("resblock_tc_kernel");
-    if (timeline) {
+    if (v2) {
+      const int n_tiles = d.B * ceil_div(d.T, TM);
+      resblock_tc2_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, FWD_THREADS, smem, stream>>>(
+          m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo, m_w2_hi, m_w2_lo, P);
+      VQW_CHECK_LAUNCH("resblock_tc2_kernel");
+    } else {
+      dim3 grid(ceil_div(d.T, TM), d.B);
+      resblock_tc_kernel<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
+                                                          m_w1_lo, m_w2_hi, m_w2_lo, P);
+      VQW_CHECK_LAUNCH("resblock_tc_kernel");
+    }
+    if (timeline && v2) {
+      long long h[128];
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[vqw timeline v2] block %d CTA %d (cycles rel. to the first MMA issue)\n", i, P.dbg_x);
+      for (int n = 0; n < 24; ++n)
+        fprintf(stderr, "  chunk %2d: mma issue [%7lld, %7lld]  epilogue [%7lld, %7lld]\n", n,
+                h[4 * n] - h[0], h[4 * n + 1] - h[0], h[4 * n + 2] - h[0], h[4 * n + 3] - h[0]);
+    }
+    if (timeline && !v2) {
       long long h[64];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);

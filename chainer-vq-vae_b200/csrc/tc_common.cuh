@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace vqw {
 namespace tc {
@@ -148,6 +149,11 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
                            ((uint32_t)(TM >> 4) << 24);
 // same, both operands MN-major (bit 15 = A, bit 16 = B)
 constexpr uint32_t IDESC_MN = IDESC | (1u << 15) | (1u << 16);
+// A = B = IEEE fp16: format code 0 in both operand fields (VQW_MODE_FP16)
+constexpr uint32_t IDESC_F16BITS = (1u << 7) | (1u << 10);
+__host__ __device__ __forceinline__ constexpr uint32_t idesc_for(uint32_t base, int f16) {
+  return f16 ? (base & ~IDESC_F16BITS) : base;
+}
 
 // Gate non-linearities.  The epilogue is special-function-unit bound (16 MUFU lanes/cycle/SM):
 // exp stays on the MUFU (ex2), the two reciprocals run on the FMA pipe -- the argument of
@@ -197,6 +203,45 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
                                                  v1 - __uint_as_float(hb & 0xffff0000u));
   hi = hb;
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// ---- format-generic variants: the planes hold bf16 (f16 = 0) or IEEE fp16 (f16 = 1) bits.
+// fp16 has 11 significant bits (vs 8), so ONE pass over fp16 planes gives ~2e-4 relative per
+// product -- inside the 1e-3 parity bar -- at a third of the bf16x3 tensor work; its narrow
+// exponent range is handled by power-of-two gradient scaling in the backward (tc_gemm.cu).
+__device__ __forceinline__ uint32_t pack_pair_f(float v0, float v1, int f16) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack_pair_f(uint32_t w, int f16, float& v0, float& v1) {
+  if (f16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    v0 = f.x;
+    v1 = f.y;
+  } else {
+    v0 = __uint_as_float(w << 16);
+    v1 = __uint_as_float(w & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void split_pair_f(float v0, float v1, uint32_t& hi, uint32_t& lo, int f16) {
+  hi = pack_pair_f(v0, v1, f16);
+  float b0, b1;
+  unpack_pair_f(hi, f16, b0, b1);
+  lo = pack_pair_f(v0 - b0, v1 - b1, f16);
+}
+// one value -> raw 16-bit patterns of its hi and lo parts
+__device__ __forceinline__ void split_16(float v, int f16, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  if (f16) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __ushort_as_bfloat16(__half_as_ushort(h));
+    lo = __ushort_as_bfloat16(__half_as_ushort(l));
+  } else {
+    split_bf16(v, hi, lo);
+  }
 }
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);

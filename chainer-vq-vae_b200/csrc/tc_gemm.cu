@@ -60,6 +60,10 @@ struct GemmParams {
   int nseg;
   Seg seg[MAX_SEG];
   int x3;
+  int f16;                     // planes hold IEEE fp16 (VQW_MODE_FP16: single pass) instead of bf16
+  int add_lo;                  // GX: the g_res stream keeps a lo plane (addend read / result write)
+  const float* scale;          // fp16 backward: device {s, 1/s}, the power-of-two gradient scale the
+                               // operand planes carry; fp32 outputs are multiplied by 1/s (or null)
   int B, T;
   int b_exact;                 // wgrad: B has no lo plane (exact bf16 values, e.g. a one-hot)
   int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
@@ -193,6 +197,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     if (lane == 0 && total_slabs > 0) {
       int stage = 0;
       uint32_t ph = 0;
+      const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16);
       for (int i = 0; i < total_slabs; ++i) {
         mbar_wait(full0 + 8 * stage, ph);
         tc_fence_after();
@@ -211,7 +216,6 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
             b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
           }
-          constexpr uint32_t ID = WG ? IDESC_MN : IDESC;
           mma_ss(tmem_base, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
           if (P.x3) {
             mma_ss(tmem_base, a_lo, b_hi, ID, 1u);
@@ -230,6 +234,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     constexpr int NG = G_EPI_WARPS / 4;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float inv = P.scale ? P.scale[1] : 1.0f;   // undoes the gradient scale on fp32 outputs
 
     if (WG) {
       const Job& jb = P.jobs[blockIdx.x];
@@ -244,7 +249,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int n = jb.n0 + 16 * q + i;
-            if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i]);
+            if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i] * inv);
           }
         }
       }
@@ -281,8 +286,15 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           for (int i = 0; i < 8; ++i) {
             const float g0 = gz[2 * i], a0 = th[2 * i], s0 = sg[2 * i];
             const float g1 = gz[2 * i + 1], a1 = th[2 * i + 1], s1 = sg[2 * i + 1];
-            split_pair(g0 * s0 * (1.0f - a0 * a0), g1 * s1 * (1.0f - a1 * a1), th_hi[i], th_lo[i]);
-            split_pair(g0 * a0 * s0 * (1.0f - s0), g1 * a1 * s1 * (1.0f - s1), sg_hi[i], sg_lo[i]);
+            const float ht0 = g0 * s0 * (1.0f - a0 * a0), ht1 = g1 * s1 * (1.0f - a1 * a1);
+            const float hs0 = g0 * a0 * s0 * (1.0f - s0), hs1 = g1 * a1 * s1 * (1.0f - s1);
+            if (P.x3) {
+              split_pair_f(ht0, ht1, th_hi[i], th_lo[i], P.f16);
+              split_pair_f(hs0, hs1, sg_hi[i], sg_lo[i], P.f16);
+            } else {
+              th_hi[i] = pack_pair_f(ht0, ht1, P.f16);
+              sg_hi[i] = pack_pair_f(hs0, hs1, P.f16);
+            }
           }
           const int64_t poff = ((int64_t)b * P.T + t) * (2 * CHh) + 16 * q;
           st256(P.p_hi + poff, th_hi);
@@ -301,7 +313,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (P.a_hi != nullptr && t_ok) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + cbase + 16 * q;
             ld256(P.a_hi + poff, hw);
-            if (P.x3) ld256(P.a_lo + poff, lw);
+            if (P.add_lo) ld256(P.a_lo + poff, lw);
           }
         };
         fetch(grp);
@@ -314,11 +326,14 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (P.a_hi != nullptr && t_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              o[2 * i] += __uint_as_float(hw[i] << 16);
-              o[2 * i + 1] += __uint_as_float(hw[i] & 0xffff0000u);
-              if (P.x3) {
-                o[2 * i] += __uint_as_float(lw[i] << 16);
-                o[2 * i + 1] += __uint_as_float(lw[i] & 0xffff0000u);
+              float v0, v1;
+              unpack_pair_f(hw[i], P.f16, v0, v1);
+              o[2 * i] += v0;
+              o[2 * i + 1] += v1;
+              if (P.add_lo) {
+                unpack_pair_f(lw[i], P.f16, v0, v1);
+                o[2 * i] += v0;
+                o[2 * i + 1] += v1;
               }
             }
           }
@@ -327,17 +342,18 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (!t_ok) continue;
           if (P.o0 != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i];
+            for (int i = 0; i < 16; ++i) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i] * inv;
           }
           if (P.p_hi != nullptr) {
             uint32_t vh[8], vl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              split_pair(o[2 * i], o[2 * i + 1], vh[i], vl[i]);
+              if (P.add_lo) split_pair_f(o[2 * i], o[2 * i + 1], vh[i], vl[i], P.f16);
+              else vh[i] = pack_pair_f(o[2 * i], o[2 * i + 1], P.f16);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
             st256(P.p_hi + poff, vh);
-            if (P.x3) st256(P.p_lo + poff, vl);
+            if (P.add_lo) st256(P.p_lo + poff, vl);
           }
         }
       } else if (EPI == EPI_HEAD) {
@@ -361,22 +377,23 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             if (P.bias != nullptr && ch0 + i < P.Cout) v += __ldg(P.bias + ch0 + i);
             if (P.relu) v = fmaxf(v, 0.0f);
             if (P.mask_hi != nullptr) {
-              const uint32_t w = mk[i >> 1];
-              const float mv = (i & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
-              v = (mv > 0.0f) ? v : 0.0f;
+              float m0, m1;
+              unpack_pair_f(mk[i >> 1], P.f16, m0, m1);
+              v = (((i & 1) ? m1 : m0) > 0.0f) ? v : 0.0f;
             }
             o[i] = v;
           }
           if (P.o0 != nullptr) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (ch0 + i < P.Cout) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i];
+              if (ch0 + i < P.Cout) P.o0[((int64_t)b * P.Cout + ch0 + i) * P.T + t] = o[i] * inv;
           }
           if (P.p_hi != nullptr) {
             uint32_t vh[8], vl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              split_pair(o[2 * i], o[2 * i + 1], vh[i], vl[i]);
+              if (P.x3) split_pair_f(o[2 * i], o[2 * i + 1], vh[i], vl[i], P.f16);
+              else vh[i] = pack_pair_f(o[2 * i], o[2 * i + 1], P.f16);
             }
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + ch0;
             st256(P.p_hi + poff, vh);
@@ -406,7 +423,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (!t_ok) continue;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (cbase + 16 * q + i < P.Cout) op[(int64_t)(16 * q + i) * P.T] = o[i] + add[i];
+            if (cbase + 16 * q + i < P.Cout) op[(int64_t)(16 * q + i) * P.T] = fmaf(o[i], inv, add[i]);
         }
       }
     }
@@ -446,7 +463,7 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
 __global__ void __launch_bounds__(256)
 pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__ w1,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int K,
-               int Cr, int Cs, int Cd, int Cc, int fs) {
+               int Cr, int Cs, int Cd, int Cc, int fs, int f16) {
   const int Ch = Cd / 2;
   const int64_t n = (int64_t)rows * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
@@ -462,7 +479,7 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
       v = (r < Cc) ? w0[(int64_t)k * Cc + r] : 0.0f;
     }
     __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    split_16(v, f16, h, l);
     hi[e] = h;
     if (lo) lo[e] = l;
   }
@@ -472,21 +489,25 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
 __global__ void __launch_bounds__(256)
 colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                      float* __restrict__ g0, float* __restrict__ g1, int C, int64_t rows,
-                     int rows_per_block, int valid) {
+                     int rows_per_block, int valid, int f16, const float* __restrict__ scale) {
+  const float inv = scale ? scale[1] : 1.0f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
   for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
     float s0 = 0.0f, s1 = 0.0f;
     for (int64_t r = r0; r < r1; ++r) {
-      const uint32_t h = *reinterpret_cast<const uint32_t*>(hi + r * C + 2 * c2);
-      s0 += __uint_as_float(h << 16);
-      s1 += __uint_as_float(h & 0xffff0000u);
+      float v0, v1;
+      unpack_pair_f(*reinterpret_cast<const uint32_t*>(hi + r * C + 2 * c2), f16, v0, v1);
+      s0 += v0;
+      s1 += v1;
       if (lo) {
-        const uint32_t l = *reinterpret_cast<const uint32_t*>(lo + r * C + 2 * c2);
-        s0 += __uint_as_float(l << 16);
-        s1 += __uint_as_float(l & 0xffff0000u);
+        unpack_pair_f(*reinterpret_cast<const uint32_t*>(lo + r * C + 2 * c2), f16, v0, v1);
+        s0 += v0;
+        s1 += v1;
       }
     }
+    s0 *= inv;
+    s1 *= inv;
     if (2 * c2 < valid) {
       atomicAdd(g0 + 2 * c2, s0);
       if (g1) atomicAdd(g1 + 2 * c2, s0);
@@ -504,15 +525,63 @@ __global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict_
 }
 
 int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
-                    cudaStream_t stream);   // resblock_tc.cu
+                    int f16, const float* scale, cudaStream_t stream);   // resblock_tc.cu
 int pack_act_launch_ex(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
-                       int pitch, int relu, cudaStream_t stream);   // resblock_tc.cu
+                       int pitch, int relu, int f16, const float* scale,
+                       cudaStream_t stream);   // resblock_tc.cu
+
+// ---- power-of-two gradient scale of the fp16 backward ------------------------------------
+// fp16 planes have 5 exponent bits; gradients of a mean loss over B*T samples are ~1e-5 and
+// smaller, i.e. subnormal in fp16.  Every backward entry point therefore measures max|g| of its
+// incoming gradient on the device and scales the planes by s = 2^k so that the maximum lands in
+// [2^5, 2^6): exact (power of two), 2^10 of headroom against growth through the stack, 2^-30 of
+// the maximum still representable.  The backward is linear in g, so every fp32 result is simply
+// multiplied by 1/s in the epilogue that writes it.  No host synchronisation.
+__global__ void __launch_bounds__(256)
+amax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+__global__ void grad_scale_kernel(const unsigned* __restrict__ amax, float* __restrict__ scale) {
+  const float a = __uint_as_float(*amax);
+  float s = 1.0f;
+  if (a > 0.0f && a < 3.0e38f) {
+    int e;
+    frexpf(a, &e);            // a = m * 2^e with m in [0.5, 1)
+    int k = 6 - e;
+    k = k < -60 ? -60 : (k > 60 ? 60 : k);
+    s = ldexpf(1.0f, k);
+  }
+  scale[0] = s;
+  scale[1] = 1.0f / s;
+}
+// scale_mem: 4 floats of workspace {amax bits, s, 1/s, pad}; returns the {s, 1/s} pointer
+static int make_grad_scale(const float* g0, int64_t n0, const float* g1, int64_t n1, float* scale_mem,
+                           cudaStream_t stream, const float** out) {
+  unsigned* amax = reinterpret_cast<unsigned*>(scale_mem);
+  VQW_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned), stream));
+  amax_kernel<<<148 * 8, 256, 0, stream>>>(g0, n0, amax);
+  VQW_CHECK_LAUNCH("amax_kernel");
+  if (g1 != nullptr) {
+    amax_kernel<<<148 * 8, 256, 0, stream>>>(g1, n1, amax);
+    VQW_CHECK_LAUNCH("amax_kernel");
+  }
+  grad_scale_kernel<<<1, 1, 0, stream>>>(amax, scale_mem + 1);
+  VQW_CHECK_LAUNCH("grad_scale_kernel");
+  *out = scale_mem + 1;
+  return 0;
+}
 
 // out[r][k] (out_rows x out_cols bf16 planes) = src[r][k] or src[k][r] (transpose), zero padded
 __global__ void __launch_bounds__(256)
 pack_mat_kernel(const float* __restrict__ src, int src_rows, int src_cols, int transpose,
                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int out_rows,
-                int out_cols) {
+                int out_cols, int f16) {
   const int64_t n = (int64_t)out_rows * out_cols;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -520,7 +589,7 @@ pack_mat_kernel(const float* __restrict__ src, int src_rows, int src_cols, int t
     const int sr = transpose ? k : r, sc = transpose ? r : k;
     const float v = (sr < src_rows && sc < src_cols) ? src[(int64_t)sr * src_cols + sc] : 0.0f;
     __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    split_16(v, f16, h, l);
     hi[e] = h;
     if (lo) lo[e] = l;
   }
@@ -536,6 +605,7 @@ struct BwdLayout {
   int64_t total;
   int64_t gs_p[2], gh_p[2], gr_p[2][2];
   int64_t gs_sum;   // column sum of g_skip (the same bias gradient for every block)
+  int64_t scale;    // 4 floats: gradient-scale scratch of the fp16 mode
   int64_t w2t[2], wct[2], wpt[2];
   int64_t wstride;
 };
@@ -547,6 +617,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
   for (int p = 0; p < 2; ++p) L.gs_p[p] = take(N * d.Cs * 2);
   L.gs_sum = take((int64_t)d.Cs * 4);
+  L.scale = take(16);
   for (int p = 0; p < 2; ++p) L.gh_p[p] = take(N * d.Cd * 2);
   for (int q = 0; q < 2; ++q)
     for (int p = 0; p < 2; ++p) L.gr_p[q][p] = take(N * d.Cr * 2);
@@ -573,35 +644,45 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
               "vqw_resnet_backward: null argument");
   VQW_REQUIRE(d.fs <= MAX_SEG, "tcgen05 backward: filter_size > %d unsupported", MAX_SEG);
   const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool xlo = x3 || f16;   // the g_res stream keeps hi + lo (addend of GX), like x in the forward
   const BwdLayout L = bwd_layout(d);
   const TcSaved S = tc_saved_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
   const uint8_t* sv = reinterpret_cast<const uint8_t*>(al((int64_t)(uintptr_t)saved));
   auto P16 = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
   auto LO = [&](int64_t off) { return x3 ? P16(off) : nullptr; };
+  auto LOX = [&](int64_t off) { return xlo ? P16(off) : nullptr; };
   const int B = d.B, T = d.T, Cr = d.Cr, Cd = d.Cd, Cs = d.Cs, Cc = d.Cc, Ch = d.Cd / 2, fs = d.fs;
   const int64_t NROWS = (int64_t)B * T;
   const int RPB = 256;   // rows per block of the bias column sums
   const int CS_GRID = (int)((NROWS + RPB - 1) / RPB);
 
   // ---- once per call: g_skip planes, transposed weight planes of every block ----
-  if (int rc = pack_act_launch(g_skip, P16(L.gs_p[0]), LO(L.gs_p[1]), B, Cs, T, stream)) return rc;
+  const float* gscale = nullptr;   // device {s, 1/s} (fp16 mode) -- see make_grad_scale
+  if (f16) {
+    if (int rc = make_grad_scale(g_skip, (int64_t)B * Cs * T, g_last_res, (int64_t)B * Cr * T,
+                                 reinterpret_cast<float*>(ws + L.scale), stream, &gscale))
+      return rc;
+  }
+  if (int rc = pack_act_launch(g_skip, P16(L.gs_p[0]), LO(L.gs_p[1]), B, Cs, T, f16, gscale, stream))
+    return rc;
   float* gs_sum = reinterpret_cast<float*>(ws + L.gs_sum);
   VQW_CHECK_CUDA(cudaMemsetAsync(gs_sum, 0, sizeof(float) * Cs, stream));
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gs_sum, nullptr, Cs,
-                                                   NROWS, RPB, Cs);
+                                                   NROWS, RPB, Cs, f16, gscale);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
   for (int i = 0; i < d.n_blocks; ++i) {
     const vqw_resblock_weights& w = weights[i];
     const int64_t wo = i * L.wstride;
     pack_wt_kernel<<<148, 256, 0, stream>>>(0, w.res_w, w.skip_w, P16(L.w2t[0] + wo),
-                                            LO(L.w2t[1] + wo), Ch, Cr + Cs, Cr, Cs, Cd, Cc, fs);
+                                            LO(L.w2t[1] + wo), Ch, Cr + Cs, Cr, Cs, Cd, Cc, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(0)");
     pack_wt_kernel<<<296, 256, 0, stream>>>(1, w.conv_w, nullptr, P16(L.wct[0] + wo),
-                                            LO(L.wct[1] + wo), Cr, fs * Cd, Cr, Cs, Cd, Cc, fs);
+                                            LO(L.wct[1] + wo), Cr, fs * Cd, Cr, Cs, Cd, Cc, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(1)");
     pack_wt_kernel<<<148, 256, 0, stream>>>(2, w.cond_w, nullptr, P16(L.wpt[0] + wo),
-                                            LO(L.wpt[1] + wo), pad256(Cc), Cd, Cr, Cs, Cd, Cc, fs);
+                                            LO(L.wpt[1] + wo), pad256(Cc), Cd, Cr, Cs, Cd, Cc, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(2)");
   }
 
@@ -620,7 +701,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   int cur = 0;
   bool have_gres = false;
   if (g_last_res != nullptr) {
-    if (int rc = pack_act_launch(g_last_res, P16(L.gr_p[0][0]), LO(L.gr_p[0][1]), B, Cr, T, stream))
+    if (int rc = pack_act_launch(g_last_res, P16(L.gr_p[0][0]), LOX(L.gr_p[0][1]), B, Cr, T, f16,
+                                 gscale, stream))
       return rc;
     have_gres = true;
   }
@@ -648,7 +730,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       if (have_gres) P.seg[n++] = Seg{0, 2, Cr / BK, 0, 0, 0, 0};
       P.seg[n++] = Seg{1, 2, Cs / BK, 0, Cr, 0, 0};
       P.nseg = n;
-      P.x3 = x3; P.B = B; P.T = T;
+      P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
       P.f0 = gate_tanh[i]; P.f1 = gate_sig[i];
       P.p_hi = P16(L.gh_p[0]); P.p_lo = LO(L.gh_p[1]);
       P.Cout = Cd;
@@ -666,9 +748,9 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         int n = 0;
         for (int j = 0; j < fs; ++j) P.seg[n++] = Seg{0, 1, Cd / BK, 0, j * Cd, dil * (fs - 1 - j), 0};
         P.nseg = n;
-        P.x3 = x3; P.B = B; P.T = T;
-        if (have_gres) { P.a_hi = P16(L.gr_p[cur][0]); P.a_lo = LO(L.gr_p[cur][1]); }
-        if (i > 0) { P.p_hi = P16(L.gr_p[nxt][0]); P.p_lo = LO(L.gr_p[nxt][1]); }
+        P.x3 = x3; P.f16 = f16; P.add_lo = xlo; P.scale = gscale; P.B = B; P.T = T;
+        if (have_gres) { P.a_hi = P16(L.gr_p[cur][0]); P.a_lo = LOX(L.gr_p[cur][1]); }
+        if (i > 0) { P.p_hi = P16(L.gr_p[nxt][0]); P.p_lo = LOX(L.gr_p[nxt][1]); }
         else P.o0 = gx0;
         P.Cout = Cr;
         if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN, B), stream)) return rc;
@@ -677,7 +759,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         GemmParams P = {};
         P.nseg = 1;
         P.seg[0] = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
-        P.x3 = x3; P.B = B; P.T = T;
+        P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
         P.o0 = gcond;
         P.Cout = Cc;
         if (int rc = launch_gemm<EPI_ACCUM>(maps, P, dim3(ceil_div(T, TM), ceil_div(Cc, TN), B), stream))
@@ -695,7 +777,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       if (int rc = mapmn(&maps.m[8], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr)) return rc;
       if (int rc = mapmn(&maps.m[10], ws + L.gs_p[0], ws + L.gs_p[1], Cs)) return rc;
       GemmParams P = {};
-      P.x3 = x3; P.B = B; P.T = T;
+      P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
       P.slabs_per_item = ceil_div(T, BK);
       P.chunks_per_b = 1;
       int nj = 0;
@@ -720,11 +802,12 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     }
     // ---- bias gradients: column sums of gh (conv_b and cond_b), g_res, g_skip ----
     colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gh_p[0]), LO(L.gh_p[1]), gw.conv_b,
-                                                     gw.cond_b, Cd, NROWS, RPB, Cd);
+                                                     gw.cond_b, Cd, NROWS, RPB, Cd, f16, gscale);
     VQW_CHECK_LAUNCH("colsum_planes_kernel(gh)");
     if (have_gres) {
-      colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LO(L.gr_p[cur][1]),
-                                                       gw.res_b, nullptr, Cr, NROWS, RPB, Cr);
+      colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LOX(L.gr_p[cur][1]),
+                                                       gw.res_b, nullptr, Cr, NROWS, RPB, Cr, f16,
+                                                       gscale);
       VQW_CHECK_LAUNCH("colsum_planes_kernel(g_res)");
     }
     add_vec_kernel<<<ceil_div(Cs, 256), 256, 0, stream>>>(gw.skip_b, gs_sum, Cs);
@@ -745,7 +828,7 @@ bool head_tc_supported(const vqw_head_desc& d) {
 }
 
 struct HeadLayout {   // workspace (both directions)
-  int64_t w1[2], w2[2], w1t[2], w2t[2], gy[2], gh1[2], total;
+  int64_t w1[2], w2[2], w1t[2], w2t[2], gy[2], gh1[2], scale, total;
 };
 static HeadLayout head_layout(const vqw_head_desc& d) {
   HeadLayout L;
@@ -758,6 +841,7 @@ static HeadLayout head_layout(const vqw_head_desc& d) {
   for (int p = 0; p < 2; ++p) L.w2t[p] = take((int64_t)d.Cs * qpad(d.Q) * 2);
   for (int p = 0; p < 2; ++p) L.gy[p] = take(N * qpad(d.Q) * 2);
   for (int p = 0; p < 2; ++p) L.gh1[p] = take(N * d.Cs * 2);
+  L.scale = take(16);
   L.total = off + 1024;
   return L;
 }
@@ -780,6 +864,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
   VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: needs skip_channels %% 256 == 0, T >= 128, T %% 8 == 0");
   VQW_REQUIRE(skip && W1 && b1 && W2 && b2 && y && workspace, "vqw_head_forward: null argument");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const HeadLayout L = head_layout(d);
   const HeadSaved S = head_saved(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
@@ -794,10 +879,11 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
   const int B = d.B, T = d.T, Cs = d.Cs, Q = d.Q;
   auto LOW = [&](__nv_bfloat16* p) { return x3 ? p : nullptr; };
   // relu(skip) planes, weight planes
-  if (int rc = pack_act_launch_ex(skip, s_hi, LOW(s_lo), B, Cs, T, Cs, 1, stream)) return rc;
-  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 0, W16(L.w1[0]), LOW(W16(L.w1[1])), Cs, Cs);
+  if (int rc = pack_act_launch_ex(skip, s_hi, LOW(s_lo), B, Cs, T, Cs, 1, f16, nullptr, stream)) return rc;
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 0, W16(L.w1[0]), LOW(W16(L.w1[1])), Cs, Cs, f16);
   VQW_CHECK_LAUNCH("pack_mat_kernel(W1)");
-  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 0, W16(L.w2[0]), LOW(W16(L.w2[1])), pad256(Q), Cs);
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 0, W16(L.w2[0]), LOW(W16(L.w2[1])), pad256(Q), Cs,
+                                           f16);
   VQW_CHECK_LAUNCH("pack_mat_kernel(W2)");
   auto mapk = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t inner, uint64_t rows,
                   uint64_t batch, uint32_t box_rows) -> int {
@@ -811,7 +897,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
-    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs; P.bias = b1; P.relu = 1;
+    P.x3 = x3; P.f16 = f16; P.B = B; P.T = T; P.Cout = Cs; P.bias = b1; P.relu = 1;
     P.p_hi = h_hi; P.p_lo = LOW(h_lo);
     if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
   }
@@ -822,7 +908,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
-    P.x3 = x3; P.B = B; P.T = T; P.Cout = Q; P.bias = b2; P.o0 = y;
+    P.x3 = x3; P.f16 = f16; P.B = B; P.T = T; P.Cout = Q; P.bias = b2; P.o0 = y;
     if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), ceil_div(Q, TN), B), stream)) return rc;
   }
   return 0;
@@ -836,6 +922,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   VQW_REQUIRE(gy && W1 && W2 && gskip && gW1 && gb1 && gW2 && gb2 && workspace && saved,
               "vqw_head_backward: null argument");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
+  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const HeadLayout L = head_layout(d);
   const HeadSaved S = head_saved(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
@@ -845,10 +932,17 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   const int B = d.B, T = d.T, Cs = d.Cs, Q = d.Q, Qp = qpad(Q);
   const int64_t NROWS = (int64_t)B * T;
   const int RPB = 256, CS_GRID = (int)((NROWS + RPB - 1) / RPB);
-  if (int rc = pack_act_launch_ex(gy, W16(L.gy[0]), LOW(W16(L.gy[1])), B, Q, T, Qp, 0, stream)) return rc;
-  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 1, W16(L.w2t[0]), LOW(W16(L.w2t[1])), Cs, Qp);
+  const float* gscale = nullptr;
+  if (f16) {
+    if (int rc = make_grad_scale(gy, (int64_t)B * Q * T, nullptr, 0,
+                                 reinterpret_cast<float*>(ws + L.scale), stream, &gscale))
+      return rc;
+  }
+  if (int rc = pack_act_launch_ex(gy, W16(L.gy[0]), LOW(W16(L.gy[1])), B, Q, T, Qp, 0, f16, gscale, stream))
+    return rc;
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 1, W16(L.w2t[0]), LOW(W16(L.w2t[1])), Cs, Qp, f16);
   VQW_CHECK_LAUNCH("pack_mat_kernel(W2T)");
-  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 1, W16(L.w1t[0]), LOW(W16(L.w1t[1])), Cs, Cs);
+  pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 1, W16(L.w1t[0]), LOW(W16(L.w1t[1])), Cs, Cs, f16);
   VQW_CHECK_LAUNCH("pack_mat_kernel(W1T)");
   auto mapk = [&](CUtensorMap* m, const void* hi, const void* lo, uint64_t inner, uint64_t rows,
                   uint64_t batch, uint32_t box_rows) -> int {
@@ -866,7 +960,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Qp / BK, 0, 0, 0, 0};
-    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs;
+    P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T; P.Cout = Cs;
     P.mask_hi = reinterpret_cast<const __nv_bfloat16*>(sv + S.h1[0]);
     P.p_hi = W16(L.gh1[0]); P.p_lo = LOW(W16(L.gh1[1]));
     if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
@@ -878,7 +972,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
-    P.x3 = x3; P.B = B; P.T = T; P.Cout = Cs;
+    P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T; P.Cout = Cs;
     P.mask_hi = reinterpret_cast<const __nv_bfloat16*>(sv + S.s[0]);
     P.o0 = gskip;
     if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
@@ -891,7 +985,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     if (int rc = mapmn(&maps.m[6], sv + S.s[0], sv + S.s[1], Cs)) return rc;
     for (int k = 8; k < NMAPS; ++k) maps.m[k] = maps.m[k % 8];
     GemmParams P = {};
-    P.x3 = x3; P.B = B; P.T = T;
+    P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
     P.slabs_per_item = ceil_div(T, BK);
     P.chunks_per_b = 1;
     int nj = 0;
@@ -909,10 +1003,10 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
   }
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gy[0]), LOW(W16(L.gy[1])), gb2, nullptr, Qp,
-                                                   NROWS, RPB, Q);
+                                                   NROWS, RPB, Q, f16, gscale);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(gy)");
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gh1[0]), LOW(W16(L.gh1[1])), gb1, nullptr,
-                                                   Cs, NROWS, RPB, Cs);
+                                                   Cs, NROWS, RPB, Cs, f16, gscale);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(gh1)");
   return 0;
 }
@@ -925,11 +1019,13 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
 // ---------------------------------------------------------------------------------------
 namespace tc {
 __global__ void __launch_bounds__(256)
-onehot_planes_kernel(const int32_t* __restrict__ q, __nv_bfloat16* __restrict__ oh, int64_t n, int Qp) {
+onehot_planes_kernel(const int32_t* __restrict__ q, __nv_bfloat16* __restrict__ oh, int64_t n, int Qp,
+                     int f16) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const int k = q[i];
-    if (k >= 0 && k < Qp) oh[i * Qp + k] = __float2bfloat16_rn(1.0f);
+    if (k >= 0 && k < Qp)   // 1.0 as bf16 or fp16 bits
+      oh[i * Qp + k] = __ushort_as_bfloat16((unsigned short)(f16 ? 0x3C00 : 0x3F80));
   }
 }
 }  // namespace tc
@@ -939,7 +1035,7 @@ bool embed_bwd_tc_supported(int B, int T, int Cr, int Q) {
 }
 int64_t embed_bwd_tc_workspace(int B, int T, int Cr, int Q) {
   const int64_t N = (int64_t)B * T;
-  return 2 * al(N * Cr * 2) + al(N * pad256(Q) * 2) + 2048;
+  return 2 * al(N * Cr * 2) + al(N * pad256(Q) * 2) + 1024 + 2048;
 }
 int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, int B, int T, int Cr,
                       int Q, int mode, void* workspace, cudaStream_t stream) {
@@ -947,15 +1043,21 @@ int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, in
   VQW_REQUIRE(embed_bwd_tc_supported(B, T, Cr, Q), "tcgen05 embed backward: unsupported shape");
   VQW_REQUIRE(q && g && gW && workspace, "vqw_embed_gather_backward_tc: null pointer");
   const bool x3 = mode == VQW_MODE_BF16X3;
+  const int f16 = mode == VQW_MODE_FP16 ? 1 : 0;
   const int Qp = pad256(Q);
   const int64_t N = (int64_t)B * T;
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
   __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* g_lo = reinterpret_cast<__nv_bfloat16*>(ws + al(N * Cr * 2));
   __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(ws + 2 * al(N * Cr * 2));
-  if (int rc = pack_act_launch(g, g_hi, x3 ? g_lo : nullptr, B, Cr, T, stream)) return rc;
+  const float* gscale = nullptr;
+  if (f16) {
+    float* scale_mem = reinterpret_cast<float*>(ws + 2 * al(N * Cr * 2) + al(N * Qp * 2));
+    if (int rc = make_grad_scale(g, N * Cr, nullptr, 0, scale_mem, stream, &gscale)) return rc;
+  }
+  if (int rc = pack_act_launch(g, g_hi, x3 ? g_lo : nullptr, B, Cr, T, f16, gscale, stream)) return rc;
   VQW_CHECK_CUDA(cudaMemsetAsync(oh, 0, (size_t)N * Qp * 2, stream));
-  onehot_planes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(q, oh, N, Qp);
+  onehot_planes_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(q, oh, N, Qp, f16);
   VQW_CHECK_LAUNCH("onehot_planes_kernel");
   Maps maps;
   if (int rc = make_map_mn(&maps.m[0], g_hi, Cr, Cr, T, B)) return rc;
@@ -964,7 +1066,7 @@ int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, in
   maps.m[3] = maps.m[2];
   for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
   GemmParams P = {};
-  P.x3 = x3; P.B = B; P.T = T;
+  P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
   P.b_exact = 1;
   P.slabs_per_item = ceil_div(T, BK);
   P.chunks_per_b = 1;
@@ -981,7 +1083,8 @@ int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, in
   if (gb) {
     const int RPB = 256;
     colsum_planes_kernel<<<(int)((N + RPB - 1) / RPB), 256, 0, stream>>>(g_hi, x3 ? g_lo : nullptr, gb,
-                                                                        nullptr, Cr, N, RPB, Cr);
+                                                                        nullptr, Cr, N, RPB, Cr, f16,
+                                                                        gscale);
     VQW_CHECK_LAUNCH("colsum_planes_kernel(embed)");
   }
   return 0;

@@ -69,6 +69,27 @@ def test_tc_bf16x3_matches_oracle(dilations, B, T):
     assert e_skip < 1e-4 and e_res < 1e-4          # well inside the 1e-3 parity bar
 
 
+@pytest.mark.parametrize("dilations,B,T", [([1], 1, 128), ([1, 2, 4], 2, 256), ([64, 128, 512], 1, 384),
+                                           ([2, 1], 2, 200)])
+def test_tc_fp16_matches_oracle(dilations, B, T):
+    """VQW_MODE_FP16: ONE tensor-core pass over IEEE-fp16 planes (11 significant bits) -- the
+    bench's mode.  Bar: the north star's 1e-3 relative on activations."""
+    (skip, res), skip_o, coll = _run("fp16", dilations, B, T, keep_last=True)
+    e_skip, e_res = rel_err(skip, skip_o), rel_err(res, coll[-1])
+    print(f"fp16 dil={dilations} skip err {e_skip:.2e} residual err {e_res:.2e}")
+    assert e_skip < TOL and e_res < TOL
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
+def test_tc_persistent_chunked_kernel_matches_oracle(mode, monkeypatch):
+    """The experimental persistent forward kernel (N = 128 chunks on two ping-pong accumulators,
+    VQW_TC_FWD_V2=1) computes the same block."""
+    monkeypatch.setenv("VQW_TC_FWD_V2", "1")
+    (skip, res), skip_o, coll = _run(mode, [1, 2, 4], 3, 640, keep_last=True)
+    tol = 1e-4 if mode == "bf16x3" else TOL
+    assert rel_err(skip, skip_o) < tol and rel_err(res, coll[-1]) < tol
+
+
 def test_tc_bf16_throughput_mode_is_close():
     skip, skip_o, coll = _run("bf16", [1, 2, 4], 2, 256)
     e = rel_err(skip, skip_o)
@@ -108,6 +129,42 @@ def test_tc_backward_matches_fp32_path(dil, B, T, keep_last):
         assert e < 2e-4, (name, e)
 
 
+@pytest.mark.parametrize("gscale", [1.0, 3e-7, 4e4])
+@pytest.mark.parametrize("dil,B,T,keep_last", [([1, 2], 2, 256, False), ([8], 2, 200, True)])
+def test_tc_fp16_backward_matches_fp32_path(dil, B, T, keep_last, gscale):
+    """fp16 single-pass backward against the fp32 CUDA-core path.  `gscale` moves the upstream
+    gradients far below fp16's normal range (a mean loss over B*T samples) and far above it: the
+    device-side power-of-two gradient scale must make the result independent of it."""
+    cfg, p, x, c = _stack_case(dil, B, T, seed=3)
+    rng = np.random.default_rng(9)
+    g_skip = torch.from_numpy(rng.normal(size=(B, 256, T, 1)).astype(np.float32)).to(DEV) * gscale
+    g_res = torch.from_numpy(rng.normal(size=(B, 512, T, 1)).astype(np.float32)).to(DEV) * gscale
+    outs = {}
+    for mode in ("fp32", "fp16"):
+        weights = []
+        for i in range(len(dil)):
+            weights += [p[f"resnet/{i}/{n}"].to(DEV).requires_grad_(True) for n in ORDER]
+        xg = x.to(DEV).requires_grad_(True)
+        cg = c.to(DEV).requires_grad_(True)
+        out = V.residual_stack(xg, cg, dil, cfg.filter_size, weights, L.MODES[mode],
+                               keep_last_residual=keep_last)
+        if keep_last:
+            skip, res = out
+            ((skip * g_skip).sum() + (res * g_res).sum()).backward()
+        else:
+            skip = out
+            (skip * g_skip).sum().backward()
+        outs[mode] = [skip.detach(), xg.grad.detach(), cg.grad.detach()] + \
+                     [w.grad.detach() for w in weights]
+    names = ["skip", "gx", "gcond"] + [f"{i}/{n}" for i in range(len(dil)) for n in ORDER]
+    worst = 0.0
+    for name, a, b in zip(names, outs["fp16"], outs["fp32"]):
+        e = rel_err(a, b)
+        worst = max(worst, e)
+        assert e < TOL, (name, e)
+    print(f"fp16 backward dil={dil} gscale={gscale:g}: worst rel err {worst:.2e}")
+
+
 def test_tc_rejects_unsupported_shapes():
     cfg, p, x, c = _stack_case([1], 1, 128, Cr=32, Cd=32, Cs=32, Cc=192)
     weights = [p[f"resnet/0/{n}"].to(DEV) for n in ORDER]
@@ -129,16 +186,23 @@ def test_tc_head_matches_conv_path():
         b2 = torch.randn(Q, device=DEV) * 0.1
         gy = torch.randn(B, Q, T, 1, device=DEV)
         out = {}
-        for mode in ("fp32", "tc"):
+        for mode in ("fp32", "tc", "fp16"):
             ts = [t.clone().requires_grad_(True) for t in (skip, W1, b1, W2, b2)]
-            if mode == "tc":
-                y = Fn.head(*ts, L.MODE_BF16X3)
+            if mode != "fp32":
+                y = Fn.head(*ts, L.MODE_BF16X3 if mode == "tc" else L.MODE_FP16)
             else:
                 y = Fn.conv(Fn.conv(ts[0], ts[1], ts[2], 1, 0, 1, True, None, True), ts[3], ts[4])
             y.backward(gy)
             out[mode] = [y.detach()] + [t.grad for t in ts]
         for n, a, b in zip(["y", "gskip", "gW1", "gb1", "gW2", "gb2"], out["tc"], out["fp32"]):
             assert rel_err(a, b) < 1e-4, (Q, n, rel_err(a, b))
+        # fp16 single pass: y within the bar; a 2e-4 forward difference flips the mask of ~1e-4 of
+        # the hidden ReLUs, each flip changing one gradient element by O(1) -- compare directions
+        assert rel_err(out["fp16"][0], out["fp32"][0]) < TOL
+        for n, a, b in zip(["gskip", "gW1", "gb1", "gW2", "gb2"], out["fp16"][1:], out["fp32"][1:]):
+            cos = float(torch.dot(a.flatten().double(), b.flatten().double()) /
+                        (a.double().norm() * b.double().norm()))
+            assert cos > 0.9995, (Q, n, cos)
 
 
 def test_tc_wavenet_with_head_matches_fp32_path_and_oracle():
@@ -188,7 +252,7 @@ def test_tc_wavenet_with_head_matches_fp32_path_and_oracle():
 
 
 @pytest.mark.parametrize("B,T,Cr,Q", [(2, 256, 512, 256), (1, 136, 128, 100), (3, 384, 64, 300)])
-@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_BF16])
+@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_BF16, L.MODE_FP16])
 def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
     """Embed backward (modules.py:151-152 differentiated) as one-hot tcgen05 GEMMs against the
     CUDA-core histogram kernel and a float64 restatement."""
@@ -208,9 +272,59 @@ def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
     oh = torch.nn.functional.one_hot(q.long().cpu(), Q).double()          # (B,T,Q)
     ref1 = torch.einsum("bct,btk->ck", g64, oh)
     ref0 = torch.einsum("bct,btk->ck", g64[:, :, 1:], oh[:, :-1])
-    tol = 1e-5 if mode == L.MODE_BF16X3 else 5e-3
+    tol = {L.MODE_BF16X3: 1e-5, L.MODE_BF16: 5e-3, L.MODE_FP16: 5e-4}[mode]
     assert rel_err(out[mode][0][:, :, 1, 0], ref1) < tol
     assert rel_err(out[mode][0][:, :, 0, 0], ref0) < tol
     assert rel_err(out[L.MODE_FP32][0][:, :, 1, 0], ref1) < 1e-5
     assert rel_err(out[mode][1], g64.sum((0, 2))) < tol
     assert rel_err(out[mode][0], out[L.MODE_FP32][0]) < tol
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
+def test_full_depth_step_matches_oracle(mode):
+    """The bench configuration at full depth and length (BASELINE.json configs[1]: 20 blocks,
+    512/512/256, T=7680; two items instead of 16) against the oracle's forward + three-loss
+    backward.  bf16x3 (the bench's mode) must hold the north star's bar: VQ indices bit-exact,
+    logits, losses and every gradient within 1e-3 (max error over max magnitude).  The opt-in
+    single-pass fp16 mode is measured at 1.4e-3 on the logits in that max norm (3e-4 in the
+    relative L2 norm): just outside the bar, which is why it is not the bench's mode; it is held
+    to 1e-3 in L2 and 3e-3 in the max norm."""
+    from helpers import build_model, grads_by_name, to_dev
+    cfg = O.config_b200()
+    cfg.batch = 2
+    params = O.make_params(cfg)
+    inp = O.make_inputs(cfg)
+    args = [torch.from_numpy(inp[k]) for k in ("x_enc", "x_dec", "speaker", "t")]
+    torch.set_num_threads(max(1, (__import__("os").cpu_count() or 2)))
+    losses, grads, inter = O.three_loss_grads(params, cfg, *args)
+    model = build_model(cfg, params, mode=mode)
+    opt = V.Adam(2e-4).setup(model)
+    upd = V.VQVAE_StandardUpdater(None, opt)
+    l1, l2, l3 = model(*to_dev(inp, cfg, indices=True))
+    upd.backward_three(model, l1, l2, l3)
+    torch.cuda.synchronize()
+    assert np.array_equal(model.vq.indexes.cpu().numpy(), inter["indexes"])
+    def l2_err(a, b):
+        a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+        return float((a - b).norm() / b.norm())
+
+    e_y, e_y2 = rel_err(model.y, inter["y"]), l2_err(model.y, inter["y"])
+    print(f"{mode} full depth: logits max-norm rel err {e_y:.2e}, L2 rel err {e_y2:.2e}")
+    assert e_y < (TOL if mode == "bf16x3" else 3e-3) and e_y2 < TOL
+    for got, want in zip((l1, l2, l3), losses):
+        assert abs(float(got.detach()) - float(want)) <= TOL * abs(float(want))
+    got = grads_by_name(model)
+    worst, worst_name, worst2 = 0.0, None, 0.0
+    for name, g in grads.items():
+        if float(g.abs().max()) == 0.0:
+            continue
+        e = rel_err(got[name], g)
+        worst2 = max(worst2, l2_err(got[name], g))
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"{mode} full depth: worst gradient max-norm rel err {worst:.2e} ({worst_name}), "
+          f"worst L2 rel err {worst2:.2e}")
+    if mode == "bf16x3":
+        assert worst < TOL, (worst_name, worst)
+    else:
+        assert worst2 < 5e-3, worst2
