@@ -66,7 +66,8 @@ class GenerateDesc(C.Structure):
     _fields_ = [("n_blocks", c_int), ("dilations", C.POINTER(c_int)), ("fs", c_int),
                 ("Cr", c_int), ("Cd", c_int), ("Cs", c_int), ("Cc", c_int), ("Q", c_int),
                 ("T_total", c_int), ("n_steps", c_int), ("t_start", c_int),
-                ("set_state", c_int), ("s1", c_int), ("s2", c_int), ("cond_t0", c_int)]
+                ("set_state", c_int), ("s1", c_int), ("s2", c_int), ("cond_t0", c_int),
+                ("use_logistic", c_int), ("log_scale_min", C.c_float)]
 
 
 class HeadDesc(C.Structure):
@@ -106,6 +107,9 @@ _SIGNATURES = {
     "vqw_head_forward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 9),
     "vqw_head_backward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 11),
     "vqw_softmax_ce": (c_int, [C.c_void_p] * 4 + [c_int] * 3 + [C.c_void_p]),
+    "vqw_mol_loss": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_float, C.c_void_p]),
+    "vqw_upsample_concat_forward": (c_int, [C.c_void_p] * 3 + [c_int] * 5 + [C.c_void_p]),
+    "vqw_upsample_concat_backward": (c_int, [C.c_void_p] * 3 + [c_int] * 5 + [C.c_void_p]),
     "vqw_adam_step": (c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_void_p]),
     "vqw_ema_update": (c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_float, C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),

@@ -48,12 +48,14 @@ struct GenBlock {
 struct GenParams {
   int n_blocks, fs, Cr, Cd, Cs, Cc, Q;
   int T_total, n_steps, t_start, cond_t0;
+  int mol;                     // mixture-of-logistics decoder: scalar input, Q = 3 * nr_mix outputs
+  float log_scale_min;
   const GenBlock* blocks;      // device array
   const float *embed_w, *embed_b, *proj1_w, *proj1_b, *proj2_w, *proj2_b;
   const float* cond;           // (Cc, T_total)
-  const double* uniforms;      // n_steps
+  const double* uniforms;      // n_steps (mol: n_steps * nr_mix)
   const int32_t* forced;       // n_steps or null: teacher forcing (sample still recorded)
-  int32_t* samples;            // n_steps
+  int32_t* samples;            // n_steps (mol: the float32 values, as bits)
   float* logits;               // n_steps * Q or null
   float* queues;               // rings
   float* zbuf;                 // [2][Cd/2] gated activations (ping-pong over blocks)
@@ -61,7 +63,7 @@ struct GenParams {
   float* skipacc;              // [Cs]
   float* h1;                   // [Cs] relu(proj1(relu(skip)))
   float* logit_buf;            // [Q]
-  int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none)
+  int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none; mol: float bits)
   unsigned int* barrier;       // grid barrier counter (zeroed by the host before the launch)
 };
 
@@ -287,9 +289,14 @@ generate_kernel(const GenParams P) {
       float* ring0 = P.queues + sblk[0].qoff + (long long)(t % sblk[0].qlen) * P.Cr;
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cr; c += gridDim.x * GEN_THREADS) {
         float v = __ldg(P.embed_b + c);
-        const float* wr = P.embed_w + (long long)c * P.Q * 2;
-        if (s2 >= 0) v += __ldg(wr + 2 * s2);
-        if (s1 >= 0) v += __ldg(wr + 2 * s1 + 1);
+        if (P.mol) {   // one input channel carrying the previous values (generate.py:137)
+          const float* wr = P.embed_w + (long long)c * 2;
+          v += __ldg(wr) * __int_as_float(s2) + __ldg(wr + 1) * __int_as_float(s1);
+        } else {
+          const float* wr = P.embed_w + (long long)c * P.Q * 2;
+          if (s2 >= 0) v += __ldg(wr + 2 * s2);
+          if (s1 >= 0) v += __ldg(wr + 2 * s1 + 1);
+        }
         P.xbuf[c] = v + __ldg(sblk[0].res_b + c);   // slot 0 holds x_0 + br_0 (see T2)
         ring0[c] = v;                               // push (modules.py:72)
       }
@@ -435,7 +442,36 @@ generate_kernel(const GenParams P) {
     // ---- softmax + draw: every CTA does it redundantly (identical inputs -> identical result)
     for (int i = tid; i < P.Q; i += GEN_THREADS) xs[i] = __ldcg(P.logit_buf + i);
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && P.mol) {
+      // generate.py:116-137: one logistic draw from EVERY component, mixed by the softmax weights
+      // (float32 softmax, float64 draw and sum, cast to float32, / 127.5, clip to [-1, 1])
+      const int nr = P.Q / 3;
+      float m = -INFINITY;
+      for (int i = lane; i < nr; i += 32) m = fmaxf(m, xs[i]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      float s = 0.0f;
+      for (int i = lane; i < nr; i += 32) {
+        const float e = expf(xs[i] - m);
+        ps[i] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      __syncwarp();
+      if (lane == 0) {
+        double acc = 0.0;
+        for (int k = 0; k < nr; ++k) {
+          const float sc = expf(fmaxf(xs[2 * nr + k], P.log_scale_min));
+          const double u = P.uniforms[(long long)step * nr + k];
+          const double r = (double)xs[nr + k] + (double)sc * (log(u) - log(1.0 - u));
+          acc += r * (double)(ps[k] / s);
+        }
+        float v = (float)acc;
+        v = v / 127.5f;
+        v = fminf(fmaxf(v, -1.0f), 1.0f);
+        s_sample = __float_as_int(v);
+      }
+    } else if (warp == 0) {
       float m = -INFINITY;
       for (int i = lane; i < P.Q; i += 32) m = fmaxf(m, xs[i]);
 #pragma unroll
@@ -571,7 +607,8 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
     }
     // WaveNet.initialize(): zero queues (modules.py:59-66,236-243); no previous samples
     VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.queues, 0, (size_t)qoff * 4, st));
-    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.state, 0xff, 16, st));
+    // no previous samples: index -1 (categorical) / value 0.0 (mixture of logistics), generate.py:51
+    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.state, d.use_logistic ? 0 : 0xff, 16, st));
   }
   if (d.set_state) {
     static thread_local int32_t hs[4];
@@ -582,6 +619,10 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   GenParams P;
   P.n_blocks = d.n_blocks; P.fs = d.fs; P.Cr = d.Cr; P.Cd = d.Cd; P.Cs = d.Cs; P.Cc = d.Cc; P.Q = d.Q;
   P.T_total = d.T_total; P.n_steps = d.n_steps; P.t_start = d.t_start; P.cond_t0 = d.cond_t0;
+  P.mol = d.use_logistic ? 1 : 0;
+  P.log_scale_min = d.log_scale_min;
+  VQW_REQUIRE(!d.use_logistic || (d.Q % 3 == 0 && d.Q >= 3),
+              "vqw_generate: use_logistic needs Q = 3 * n_mixtures output channels (got %d)", d.Q);
   P.blocks = reinterpret_cast<const GenBlock*>(ws + L.blocks);
   P.embed_w = embed_w; P.embed_b = embed_b; P.proj1_w = proj1_w; P.proj1_b = proj1_b;
   P.proj2_w = proj2_w; P.proj2_b = proj2_b;

@@ -472,3 +472,37 @@ class _Head(torch.autograd.Function):
 
 def head(skip, W1, b1, W2, b2, mode):
     return _Head.apply(skip, W1, b1, W2, b2, mode)
+
+
+# ---------------------------------------------------------------------------------------
+# ConditionEmbed tail: x64 linear upsampling + speaker broadcast + concat (net.py:58-63)
+# ---------------------------------------------------------------------------------------
+class _UpsampleConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, local, glob, out_len):
+        local, glob = _f32c(local), _f32c(glob)
+        B, Cl, H = _as3(local)
+        Cg = glob.shape[1]
+        if glob.shape[0] != B:
+            raise ValueError("local and global condition batch sizes differ")
+        out = torch.empty((B, Cl + Cg, out_len, 1), device=local.device, dtype=torch.float32)
+        L.check(L.lib.vqw_upsample_concat_forward(L.ptr(local), L.ptr(glob), L.ptr(out), B, Cl, Cg, H,
+                                                  out_len, L.stream()), "vqw_upsample_concat_forward")
+        ctx.cfg = (B, Cl, Cg, H, out_len)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cl, Cg, H, out_len = ctx.cfg
+        g = _f32c(g)
+        g_local = torch.empty((B, Cl, H, 1), device=g.device, dtype=torch.float32)
+        g_glob = torch.empty((B, Cg), device=g.device, dtype=torch.float32)
+        L.check(L.lib.vqw_upsample_concat_backward(L.ptr(g), L.ptr(g_local), L.ptr(g_glob), B, Cl, Cg, H,
+                                                   out_len, L.stream()), "vqw_upsample_concat_backward")
+        return g_local, g_glob, None
+
+
+def upsample_concat(local, glob, out_len):
+    """local (B,Cl,H,1), glob (B,Cg) -> (B, Cl+Cg, out_len, 1): F.resize_images of both (the
+    global one from length 1 = broadcast) and F.concat, net.py:58-63."""
+    return _UpsampleConcat.apply(local, glob, out_len)

@@ -25,6 +25,8 @@ def _desc(wavenet, T_total, n_steps, t_start):
     d.fs, d.Cr, d.Cd = wavenet.filter_size, wavenet.residual_channels, wavenet.dilated_channels
     d.Cs, d.Cc, d.Q = wavenet.skip_channels, wavenet.condition_dim, wavenet.proj2.W.shape[0]
     d.T_total, d.n_steps, d.t_start = T_total, n_steps, t_start
+    d.use_logistic = 1 if wavenet.input_dim == 1 else 0
+    d.log_scale_min = float(wavenet.log_scale_min)
     warr = (L.ResblockWeights * n)()
     for i, b in enumerate(blocks):
         for name, t in zip(("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b", "skip_w",
@@ -39,12 +41,11 @@ class WaveNetState:
     def __init__(self, wavenet, n):
         if n != 1:
             raise NotImplementedError("generation supports n = 1, like generate.py:42")
-        if wavenet.input_dim == 1:
-            raise NotImplementedError("persistent generation covers the categorical decoder; "
-                                      "the mixture-of-logistics sampler is not implemented")
         self.w = wavenet
+        self.mol = wavenet.input_dim == 1   # mixture of logistics: scalar input (generate.py:137)
         self.t = 0
-        self.prev = -1                      # input of the previous step (-1 = all zeros)
+        # input of the previous step: index (-1 = all zeros) or, for MoL, the float's bit pattern
+        self.prev = 0 if self.mol else -1
         self.workspace = None
 
     def _launch(self, cond2d, t_start, n_steps, uniforms, forced, want_logits, state=None,
@@ -74,9 +75,13 @@ class WaveNetState:
         if x.shape[0] != 1 or x.shape[2] != 1:
             raise ValueError("generate() takes one time step of one utterance")
         xv = x.reshape(-1)
-        cur = int(torch.argmax(xv)) if bool((xv != 0).any()) else -1
+        if self.mol:
+            cur = int(xv.float().cpu().view(torch.int32)[0])
+        else:
+            cur = int(torch.argmax(xv)) if bool((xv != 0).any()) else -1
         cond2d = condition.reshape(condition.shape[1], 1).contiguous().float()
-        u = torch.zeros(1, device=cond2d.device, dtype=torch.float64)
+        u = torch.full((max(1, self.w.proj2.W.shape[0] // 3),), 0.5, device=cond2d.device,
+                       dtype=torch.float64)
         _, logits = self._launch(cond2d, self.t, 1, u, None, True, state=(cur, self.prev),
                                  cond_t0=self.t)
         self.prev = cur
@@ -97,12 +102,17 @@ def generate_utterance(wavenet, condition: torch.Tensor, uniforms, n_steps: Opti
     steps = T - 1 if n_steps is None else min(n_steps, T - 1)
     dev = condition.device
     cond2d = condition.reshape(condition.shape[1], T).contiguous().float()
-    u = torch.as_tensor(numpy.asarray(uniforms, dtype=numpy.float64)[:steps]).to(dev)
+    mol = wavenet.input_dim == 1
+    u = numpy.asarray(uniforms, dtype=numpy.float64)
+    if mol:     # one draw per mixture component and step (generate.py:124)
+        u = u.reshape(-1, wavenet.proj2.W.shape[0] // 3)
+    u = torch.as_tensor(numpy.ascontiguousarray(u[:steps])).to(dev)
     f = None
     if forced is not None:
-        f = torch.as_tensor(numpy.asarray(forced, dtype=numpy.int32)[:steps]).to(dev)
+        fa = numpy.asarray(forced, dtype=numpy.float32 if mol else numpy.int32)[:steps]
+        f = torch.as_tensor(fa.view(numpy.int32) if mol else fa).to(dev)
     st = WaveNetState(wavenet, 1)
     samples, logits = st._launch(cond2d, 0, steps, u, f, return_logits)
     out = torch.zeros(T, device=dev, dtype=torch.float64)
-    out[:steps] = samples.double()
+    out[:steps] = (samples.view(torch.float32) if mol else samples).double()
     return (out, logits) if return_logits else out

@@ -42,8 +42,36 @@ def softmax_cross_entropy(y, t):
     return -picked.sum() / t.numel()
 
 
+class _MolLoss(torch.autograd.Function):
+    """modules.py:169-230 and its gradient in one pass over the decoder output (vqw_mol_loss)."""
+
+    @staticmethod
+    def forward(ctx, y, t, quantize, log_scale_min):
+        from . import _lib as L
+        yc = y.contiguous()
+        B, C3, T = yc.shape[0], yc.shape[1], yc.shape[2]
+        tc = t.reshape(B, T).to(torch.float32).contiguous()
+        need = ctx.needs_input_grad[0]
+        gy = torch.empty_like(yc) if need else None
+        loss = torch.zeros(1, device=y.device, dtype=torch.float64)
+        L.check(L.lib.vqw_mol_loss(L.ptr(yc), L.ptr(tc), L.ptr(gy), L.ptr(loss), B, C3 // 3, T,
+                                   int(quantize), float(log_scale_min), L.stream()), "vqw_mol_loss")
+        if need:
+            ctx.save_for_backward(gy)
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gy,) = ctx.saved_tensors
+        return gy * g, None, None, None
+
+
 def logistic_loss(y, t, quantize, log_scale_min):
-    """modules.py:169-230, term by term."""
+    """modules.py:169-230.  CUDA tensors run the fused libvqw kernel; the torch formula below is
+    the same definition term by term for other tensors."""
+    if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[3] == 1
+            and y.shape[1] % 3 == 0 and t.numel() == y.shape[0] * y.shape[2]):
+        return _MolLoss.apply(y, t, quantize, log_scale_min)
     nr_mix = y.shape[1] // 3
     logit_probs = y[:, :nr_mix]
     means = y[:, nr_mix:2 * nr_mix]

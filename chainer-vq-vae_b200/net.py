@@ -89,11 +89,9 @@ class ConditionEmbed(nn.Module):
         h = self.local_embed3(h, relu=True)
         h = self.local_embed4(h, relu=True)
         h = self.local_embed5(h, relu=True)
-        h = resize_images_h(h, self.upscale_factor * h.shape[2])
-        g = self.global_embed(global_condition)
-        g = g.reshape(g.shape + (1, 1))
-        g = resize_images_h(g, h.shape[2])
-        return torch.cat((h, g), dim=1).contiguous()
+        g = self.global_embed(global_condition)                         # :59
+        # resize (:58), broadcast-resize of the speaker embedding (:60-61) and concat (:63): one kernel
+        return Fn.upsample_concat(h, g, self.upscale_factor * h.shape[2])
 
 
 class VAE(nn.Module):

@@ -258,6 +258,19 @@ int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW,
  */
 int vqw_softmax_ce(const float* y, const int32_t* t, float* gy, double* loss, int B, int Q, int T,
                    vqw_stream_t stream);
+/* WaveNet.calculate_logistic_loss, modules.py:169-230 (discretised mixture of logistics), and
+ * its gradient: y (B,3*n_mix,T) f32 = {logit_probs, means, log_scales}, t (B,T) f32 in [-1,1]
+ * -> *loss (f64, ACCUMULATED: zero it first) = -mean logsumexp, gy (B,3*n_mix,T) or NULL. */
+int vqw_mol_loss(const float* y, const float* t, float* gy, double* loss, int B, int n_mix, int T,
+                 int quantize, float log_scale_min, vqw_stream_t stream);
+/* Tail of ConditionEmbed.__call__, net.py:58-63: out (B,Cl+Cg,T_out) = concat(align-corners
+ * linear resize of local (B,Cl,H) to T_out steps [F.resize_images, exact integer coordinates],
+ * glob (B,Cg) broadcast over time).  Backward: g (B,Cl+Cg,T_out) -> g_local (B,Cl,H), g_glob
+ * (B,Cg), both overwritten. */
+int vqw_upsample_concat_forward(const float* local, const float* glob, float* out, int B, int Cl,
+                                int Cg, int H, int T_out, vqw_stream_t stream);
+int vqw_upsample_concat_backward(const float* g, float* g_local, float* g_glob, int B, int Cl, int Cg,
+                                 int H, int T_out, vqw_stream_t stream);
 int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, vqw_stream_t stream);
 int vqw_ema_update(float* ema, const float* target, long long n, float decay, vqw_stream_t stream);
@@ -285,6 +298,13 @@ typedef struct {
   int T_total, n_steps, t_start;
   int set_state, s1, s2;
   int cond_t0;   /* time index of cond's first column (0 for a whole-utterance condition) */
+  /* mixture-of-logistics decoder (generate.py:116-137): embed_w is (Cr,1,2), Q = 3*nr_mix output
+   * channels {logit_probs, means, log_scales}; uniforms is (n_steps, nr_mix) f64; the value fed
+   * back is sum_k softmax_k * (mean_k + exp(max(log_scale_k, log_scale_min)) * logit(u_k)) / 127.5
+   * clipped to [-1, 1]; samples / forced / s1 / s2 then hold float32 values as their bit
+   * patterns (initial state = 0.0). */
+  int use_logistic;
+  float log_scale_min;
 } vqw_generate_desc;
 
 int64_t vqw_generate_workspace(const vqw_generate_desc* desc);

@@ -98,3 +98,61 @@ def test_generate_b200_channels_smoke():
         out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps, return_logits=True)
     assert rel_err(logits_g, logits_o) < TOL
     assert np.array_equal(out_g.cpu().numpy()[:steps], out_o[:steps])
+
+
+def _mol_case(length):
+    cfg = O.config_cpu()
+    cfg.use_logistic, cfg.input_dim = True, 1
+    params, inp = _case(cfg, length)
+    model = build_model(cfg, params).eval()
+    with torch.no_grad():
+        cond = model.condition_embed(model.vq(model.encoder(torch.from_numpy(inp["x_enc"]).cuda())),
+                                     torch.from_numpy(inp["speaker"]).cuda())
+    return cfg, params, inp, model, cond
+
+
+def test_generate_mixture_of_logistics_matches_oracle():
+    """generate.py:116-137 in the persistent kernel: scalar input, one logistic draw from every
+    mixture component mixed by the softmax weights, / 127.5, clip.  Free running from the same
+    uniforms (the fed-back value is continuous, so differences of the last float32 bit are
+    carried forward: values within 1e-3 of their [-1, 1] range, logits within 1e-3)."""
+    cfg, params, inp, model, cond = _mol_case(192)
+    steps, nr = 60, cfg.n_mixture // 3
+    u = np.random.default_rng(3).uniform(0.02, 0.98, size=(steps, nr))
+    out_o, logits_o = O.generate_loop(params, cfg, inp["x_enc"], inp["speaker"], u, n_steps=steps,
+                                      return_logits=True)
+    with torch.no_grad():
+        out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps, return_logits=True)
+    out_g = out_g.cpu().numpy()
+    assert out_g.shape == out_o.shape and out_g[-1] == 0
+    assert np.abs(out_g[:steps]).max() <= 1.0 and np.abs(out_g[:steps]).max() > 0
+    err_v = np.abs(out_g[:steps] - out_o[:steps]).max()
+    print(f"MoL generation: max value diff {err_v:.2e}, logits rel err {rel_err(logits_g, logits_o):.2e}")
+    assert err_v < 1e-3
+    assert rel_err(logits_g, logits_o) < TOL
+
+
+def test_generate_mixture_of_logistics_teacher_forced_and_stepwise():
+    cfg, params, inp, model, cond = _mol_case(160)
+    dec = model.decoder
+    steps, nr = 32, cfg.n_mixture // 3
+    forced = inp["x_enc"][0, 0, 1:steps + 1, 0].astype(np.float32)      # raw waveform values
+    u = np.full((steps, nr), 0.5)
+    with torch.no_grad():
+        _, logits = generate_utterance(dec, cond, u, n_steps=steps, forced=forced, return_logits=True)
+        dec.initialize(1)
+        x = torch.zeros(1, 1, 1, 1, device="cuda")
+        outs = []
+        for i in range(steps):
+            outs.append(dec.generate(x, cond[:, :, i:i + 1])[0, :, 0, 0])
+            x = torch.full((1, 1, 1, 1), float(forced[i]), device="cuda")
+        outs = torch.stack(outs)
+    assert rel_err(outs, logits) < 1e-6
+    gen = O.WaveNetGenerator(O.sub(params, "decoder/"), cfg, 1)
+    xo = torch.zeros(1, 1, 1, 1)
+    ref = []
+    with torch.no_grad():
+        for i in range(steps):
+            ref.append(gen.generate(xo, cond[:, :, i:i + 1].cpu())[0, :, 0, 0])
+            xo = torch.full((1, 1, 1, 1), float(forced[i]))
+    assert rel_err(logits, torch.stack(ref)) < TOL

@@ -192,3 +192,59 @@ def test_resblock_rejects_bad_arguments():
         blk(x.cpu(), torch.zeros(2, 16, 64, 1))                  # CPU tensors: no fallback
     with pytest.raises(NotImplementedError):
         V.ResidualBlock(3, 1, 32, 32, 32, 16, 0.05)
+
+
+def test_mol_loss_kernel_matches_literal_and_autograd():
+    """vqw_mol_loss against (a) the NumPy-literal float32 evaluation of modules.py:169-230 on a
+    well-conditioned case (wide logistics: no cdf cancellation) at 1e-5, including the +-0.999
+    edge branches and the log_scale floor, and (b) torch autograd of the float64 oracle formula
+    for the gradient."""
+    from chainer_vq_vae_b200.losses import logistic_loss
+    cfg = O.config_cpu()
+    cfg.use_logistic, cfg.input_dim = True, 1
+    rng = np.random.default_rng(5)
+    B, nr, T = 3, 10, 333
+    y = np.concatenate([rng.normal(0, 1, (B, nr, T, 1)), rng.normal(0, 40, (B, nr, T, 1)),
+                        rng.normal(3.5, 0.3, (B, nr, T, 1))], axis=1).astype(np.float32)
+    y[:, 2 * nr:, :40] = -50.0                                   # below log_scale_min = -40
+    t = rng.uniform(-1, 1, (B, 1, T, 1)).astype(np.float32)
+    t[:, :, :7] = -1.0                                           # x < -0.999 * 127.5
+    t[:, :, 7:15] = 1.0                                          # x >  0.999 * 127.5
+    want = O.calculate_logistic_loss_numpy(cfg, y, t)
+    yg = torch.from_numpy(y).cuda().requires_grad_(True)
+    loss = logistic_loss(yg, torch.from_numpy(t).cuda(), cfg.quantize, cfg.log_scale_min)
+    assert abs(float(loss) - want) <= 1e-5 * abs(want), (float(loss), want)
+    loss.backward()
+    y64 = torch.from_numpy(y).double().requires_grad_(True)
+    O.calculate_logistic_loss(cfg, y64, torch.from_numpy(t).double()).backward()
+    assert rel_err(yg.grad, y64.grad) < 1e-4
+    # every group of channels on its own scale (float32 cdf_plus - cdf_min keeps ~1e-3 here)
+    for k in range(3):
+        assert rel_err(yg.grad[:, k * nr:(k + 1) * nr], y64.grad[:, k * nr:(k + 1) * nr]) < 2e-3
+
+
+@pytest.mark.parametrize("B,Cl,Cg,H,f", [(2, 64, 128, 16, 64), (1, 5, 3, 375, 64), (3, 4, 2, 7, 3),
+                                         (2, 6, 0, 9, 64)])
+def test_upsample_concat_matches_resize_images(B, Cl, Cg, H, f):
+    """net.py:58-63 (F.resize_images x64 + speaker broadcast + concat) in one kernel against the
+    oracle's float64-coordinate restatement; backward against autograd of it."""
+    from chainer_vq_vae_b200 import functions as Fn
+    rng = np.random.default_rng(H)
+    local = torch.from_numpy(rng.normal(size=(B, Cl, H, 1)).astype(np.float32))
+    glob = torch.from_numpy(rng.normal(size=(B, Cg)).astype(np.float32))
+    T = H * f
+    lo = local.double().requires_grad_(True)
+    go = glob.double().requires_grad_(True)
+    parts = [O.resize_images_h(lo, T)]
+    if Cg:
+        parts.append(O.resize_images_h(go.reshape(B, Cg, 1, 1), T))
+    want = torch.cat(parts, dim=1)
+    lg, gg = local.cuda().requires_grad_(True), glob.cuda().requires_grad_(True)
+    got = Fn.upsample_concat(lg, gg, T)
+    assert got.shape == want.shape and rel_err(got, want) < 1e-6
+    g = torch.from_numpy(rng.normal(size=tuple(want.shape)).astype(np.float32))
+    (want * g.double()).sum().backward()
+    (got * g.cuda()).sum().backward()
+    assert rel_err(lg.grad, lo.grad) < 1e-5
+    if Cg:
+        assert rel_err(gg.grad, go.grad) < 1e-5
