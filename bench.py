@@ -53,7 +53,7 @@ def peaks():
 # ------------------------------------------------------------------------------------------
 # synthetic data: sinusoid mixtures + noise, peak-normalised, mu-law 256
 # ------------------------------------------------------------------------------------------
-def synthetic_examples(n_items: int, length: int, seed: int, n_speaker: int = 109):
+def synthetic_examples(n_items: int, length: int, seed: int, n_speaker: int = 109, mol=False):
     """List of Preprocess-shaped tuples (utils.py:100-110) with x_dec as int32 mu-law indices
     (the one-hot of the reference carries the same information)."""
     import chainer_vq_vae_b200 as V
@@ -69,7 +69,10 @@ def synthetic_examples(n_items: int, length: int, seed: int, n_speaker: int = 10
         raw = (w / np.abs(w).max()).astype(np.float32)
         q = mulaw.transform(raw)
         spk = np.int32(rng.integers(0, n_speaker))
-        out.append((raw[None, :, None], q[:-1].astype(np.int32), spk, q[1:, None].astype(np.int32)))
+        if mol:   # utils.py:104,107: the decoder reads and predicts the raw waveform
+            out.append((raw[None, :, None], raw[None, :-1, None], spk, raw[None, 1:, None]))
+        else:
+            out.append((raw[None, :, None], q[:-1].astype(np.int32), spk, q[1:, None].astype(np.int32)))
     return out
 
 
@@ -184,6 +187,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = dict(CFG)
+    mol = args.workload == "train-mol"
+    if mol:            # BASELINE.json configs[3]: use_logistic=True n_mixture=10 input_dim=1
+        cfg.update(use_logistic=True, input_dim=1, n_mixture=30)
     B, T = cfg["batch"], cfg["length"]
 
     model = build_model(cfg, dev, args.mode)
@@ -196,7 +202,7 @@ def run_ours(args):
         def __init__(self):
             # weak scaling: the global batch is world*B items; each rank only materialises the
             # items it will consume (its strided slice), which is what split() then returns.
-            self.mine = synthetic_examples(B, T, 71 + rank)
+            self.mine = synthetic_examples(B, T, 71 + rank, mol=mol)
 
         def next(self):
             # interleave so that batch[rank::world] == this rank's items
@@ -207,18 +213,16 @@ def run_ours(args):
             return out
 
     it = Iter()
-    upd = V.VQVAE_ParallelUpdater(it, opt, device=dev)
+    # --graph: the whole step is captured into a CUDA graph after 3 ordinary steps and replayed
+    # (measured: no gain at this size -- the step is power-capped tensor work, not launch bound)
+    upd = V.VQVAE_ParallelUpdater(it, opt, device=dev, use_cuda_graph=args.graph)
 
     # ---- device-resident arm ----
     dev_batch = V.updaters.concat_examples(it.mine, dev)
     torch.cuda.synchronize()
 
     def step_resident():
-        l1, l2, l3 = model(*dev_batch)
-        upd.backward_three(model, l1, l2, l3)
-        opt.bucket.allreduce()
-        opt.update()
-        return l1
+        return upd.update_from_arrays(dev_batch)[0]
 
     def barrier():
         if world > 1:
@@ -232,8 +236,20 @@ def run_ours(args):
     sampler.start()
     for _ in range(args.warmup):
         step_resident()
+    launches_per_step = None
+    if upd.use_cuda_graph:            # make sure the capture happens before the timed region
+        for _ in range(8):
+            if upd._graph is not None or not upd.use_cuda_graph:
+                break
+            n0 = V.launch_count()
+            step_resident()
+            if upd._graph is not None:
+                launches_per_step = V.launch_count() - n0     # launches recorded into the graph
+        step_resident()
+    graphed = upd._graph is not None
     barrier()
-    L.enable_timers(True)
+    if not graphed:
+        L.enable_timers(True)
     launches0 = V.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -243,7 +259,16 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     launches = V.launch_count() - launches0
+    if graphed:
+        launches = launches_per_step * args.steps     # replayed from the graph, not re-issued
     ms_total = e0.elapsed_time(e1)
+    if graphed:
+        # CUDA events cannot bracket kernels inside a replayed graph: the per-kernel timers (and the
+        # roofline's launch duration) come from the same step issued eagerly right after
+        L.enable_timers(True)
+        for _ in range(min(args.steps, 5)):
+            upd._step(dev_batch)
+        torch.cuda.synchronize()
     timers = L.timer_summary()
     L.enable_timers(False)
     t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -284,6 +309,8 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": (achieved_tf / pk["bf16_tflops_sustained"]) if nfw else None,
         "traffic": None, "peak_source": pk_src + " (sustained bf16, kernel timed inside a long step)",
         "launch_ms": fw_ms, "launches_timed": nfw,
+        "timed_in": ("the same steps issued eagerly right after the graph-replayed timed region"
+                     if graphed else "the timed region"),
         "algorithmic_gflop_per_launch": flops / 1e9, "algorithmic_mb_per_launch": bytes_ / 1e6,
         "hbm": {"achieved": bytes_ / (fw_ms * 1e-3) / 1e9 if nfw else None, "peak": pk["hbm_gbs"],
                 "unit": "GB/s",
@@ -309,10 +336,12 @@ def run_ours(args):
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16, fp32 accumulate)",
                       "bf16": "bf16", "fp16": "fp16 (IEEE half operands, fp32 accumulate)"}[args.mode],
             "data": "synthetic (sinusoid mixtures, mu-law 256, random-init weights)",
-            "config": {"workload": "1xB200: batch=16/GPU length=7680 n_loop=2 n_layer=10 "
+            "config": {"workload": ("MoL decoder (use_logistic, n_mixture=10, input_dim=1): " if mol
+                                    else "1xB200: ") +
+                                   "batch=16/GPU length=7680 n_loop=2 n_layer=10 "
                                    "filter_size=3 512/512/256 k=512 d=64 mu-law-256 Cc=192",
                        "global_batch": B * world, "parallelism": f"dp{world}",
-                       "mode": args.mode,
+                       "mode": args.mode, "cuda_graph": graphed,
                        "l2": "per-step working set (>10 GB of activations) far exceeds the "
                              "126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "audio-samples/s", "h2d_bytes_per_step": h2d,
@@ -477,12 +506,18 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "bf16x3"),
                     choices=["fp32", "bf16x3", "bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "generate"])
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the training step from a CUDA graph (updater use_cuda_graph=True)")
+    ap.add_argument("--workload", default="train", choices=["train", "train-mol", "generate"],
+                    help="train = BASELINE configs[1]/[2]; train-mol = configs[3] (mixture-of-"
+                         "logistics decoder, scalar input); generate = configs[4]")
     ap.add_argument("--gen-length", type=int, default=24000)
     ap.add_argument("--gen-steps", type=int, default=0)
     args = ap.parse_args()
     if args.workload == "generate":
         run_generate(args)
+    elif args.impl == "reference" and args.workload == "train-mol":
+        raise SystemExit("--impl reference times the categorical configs[1] workload")
     elif args.impl == "reference":
         run_reference(args)
     else:

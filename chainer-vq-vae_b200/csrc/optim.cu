@@ -14,7 +14,10 @@ namespace vqw {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps) {
+            float* __restrict__ v, int64_t n, float lr_value, const float* __restrict__ lr_ptr,
+            float b1, float b2, float eps) {
+  // lr from device memory when the step is replayed from a CUDA graph (it changes every step)
+  const float lr = lr_ptr ? __ldg(lr_ptr) : lr_value;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -87,7 +90,21 @@ extern "C" int vqw_adam_step(float* p, const float* g, float* m, float* v, long 
   VQW_REQUIRE(p && g && m && v, "vqw_adam_step: null pointer");
   VQW_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                   ((uintptr_t)v % 16 == 0), "vqw_adam_step: buffers must be 16-byte aligned");
-  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps);
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, nullptr, beta1, beta2, eps);
+  VQW_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+extern "C" int vqw_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
+                                 const float* lr_dev, float beta1, float beta2, float eps,
+                                 vqw_stream_t stream) {
+  using namespace vqw;
+  VQW_REQUIRE(n >= 0, "vqw_adam_step_dev: negative size");
+  if (n == 0) return 0;
+  VQW_REQUIRE(p && g && m && v && lr_dev, "vqw_adam_step_dev: null pointer");
+  VQW_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+                  ((uintptr_t)v % 16 == 0), "vqw_adam_step_dev: buffers must be 16-byte aligned");
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.0f, lr_dev, beta1, beta2, eps);
   VQW_CHECK_LAUNCH("adam_kernel");
   return 0;
 }

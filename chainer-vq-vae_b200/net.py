@@ -124,5 +124,5 @@ class VAE(nn.Module):
         loss = loss1 + loss2 + loss3
         self.observation = {"loss1": loss1.detach(), "loss2": loss2.detach(),
                             "loss3": loss3.detach(), "loss": loss.detach()}   # reporter, :93-95
-        self.y = y
+        self.y = y.detach()
         return loss1, loss2, loss3

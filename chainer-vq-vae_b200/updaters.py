@@ -92,6 +92,20 @@ class Adam:
                                         L.ptr(self.flat_v), n, self.lr, self.beta1, self.beta2,
                                         self.eps, L.stream()), "vqw_adam_step")
             return
+        self._update_torch()
+
+    def update_captured(self, lr_dev: torch.Tensor) -> None:
+        """The same update with the learning rate read from `lr_dev` (a 1-element CUDA tensor)
+        and WITHOUT advancing `t`: the form recorded into a CUDA graph; the caller advances `t`
+        and refreshes `lr_dev` before every replay."""
+        from . import _lib as L
+        L.check(L.lib.vqw_adam_step_dev(L.ptr(self.flat_p), L.ptr(self.bucket.flat), L.ptr(self.flat_m),
+                                        L.ptr(self.flat_v), self.bucket.n_grad, L.ptr(lr_dev),
+                                        self.beta1, self.beta2, self.eps, L.stream()),
+                "vqw_adam_step_dev")
+
+    @torch.no_grad()
+    def _update_torch(self) -> None:
         grads = [p.grad for p in self.params]
         # m += (1-b1)(g-m)
         torch._foreach_lerp_(self.m, grads, 1 - self.beta1)
@@ -125,13 +139,21 @@ class VQVAE_StandardUpdater:
     """updaters.py:5-19."""
 
     def __init__(self, iterator, optimizer: Adam, converter: Callable = concat_examples,
-                 device=None, loss_func=None):
+                 device=None, loss_func=None, use_cuda_graph: bool = False, graph_warmup: int = 3):
         self._iterators = {"main": iterator}
         self._optimizers = {"main": optimizer}
         self.converter = converter
         self.device = device
         self.loss_func = loss_func
         self.iteration = 0
+        # use_cuda_graph: after `graph_warmup` ordinary steps the whole step (forward, three
+        # backward passes, gradient reduction, Adam, weight EMA: ~500 kernel launches) is
+        # captured once into a CUDA graph and replayed from then on; batches are copied into the
+        # graph's static input buffers.  Same kernels, same order, same results.
+        self.use_cuda_graph = use_cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graph = None
+        self._eager_steps = 0
 
     def backward_three(self, model, loss1, loss2, loss3) -> None:
         from . import functions as Fn
@@ -146,15 +168,62 @@ class VQVAE_StandardUpdater:
         finally:
             Fn.ACCUMULATE_INTO_GRAD = prev
 
-    def update_core(self):
-        batch = self._iterators["main"].next()
-        in_arrays = self.converter(batch, self.device)
+    def _reduce(self, optimizer) -> None:
+        """gradient exchange between replicas (none for the single-device updater)"""
+
+    def _step(self, in_arrays, captured_lr=None):
         optimizer = self._optimizers["main"]
         loss_func = self.loss_func or optimizer.target
         loss1, loss2, loss3 = loss_func(*in_arrays)                 # :13
-        self.backward_three(optimizer.target, loss1, loss2, loss3)
-        optimizer.update()                                          # :19
-        return loss1, loss2, loss3
+        self.backward_three(optimizer.target, loss1, loss2, loss3)  # :14-18
+        self._reduce(optimizer)
+        if captured_lr is None:
+            optimizer.update()                                      # :19
+        else:
+            optimizer.update_captured(captured_lr)
+        # detached: nothing may keep this step's autograd graph (and its AccumulateGrad nodes,
+        # which are bound to the stream they were created on) alive into a later graph capture
+        return loss1.detach(), loss2.detach(), loss3.detach()
+
+    def update_from_arrays(self, in_arrays):
+        """One step on already converted (device-resident) arrays."""
+        if not (self.use_cuda_graph and in_arrays[0].is_cuda):
+            return self._step(in_arrays)
+        optimizer = self._optimizers["main"]
+        sig = tuple((tuple(t.shape), t.dtype) for t in in_arrays)
+        if self._graph is not None and sig != self._graph_sig:
+            self._graph = None                                      # new batch shape: re-capture
+        if self._graph is None:
+            if self._eager_steps < self.graph_warmup:
+                self._eager_steps += 1
+                return self._step(in_arrays)
+            self._static_in = tuple(t.clone() for t in in_arrays)
+            self._lr_dev = torch.zeros(1, device=in_arrays[0].device, dtype=torch.float32)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            try:
+                with torch.cuda.graph(graph):
+                    self._static_out = self._step(self._static_in, captured_lr=self._lr_dev)
+            except Exception as exc:                                # capture unsupported here:
+                import sys                                          # stay on the ordinary path
+                print(f"[vqw] CUDA-graph capture of the training step failed ({exc!r}); "
+                      "continuing without it", file=sys.stderr)
+                self.use_cuda_graph = False
+                torch.cuda.synchronize()
+                return self._step(in_arrays)
+            self._graph, self._graph_sig = graph, sig
+        else:
+            for dst, src in zip(self._static_in, in_arrays):
+                dst.copy_(src, non_blocking=True)
+        optimizer.t += 1
+        self._lr_dev.fill_(optimizer.lr)
+        self._graph.replay()
+        return tuple(o.detach().clone() for o in self._static_out)
+
+    def update_core(self):
+        batch = self._iterators["main"].next()
+        in_arrays = self.converter(batch, self.device)
+        return self.update_from_arrays(in_arrays)
 
     def update(self):
         out = self.update_core()
@@ -169,8 +238,10 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
     updaters.py:76-77)."""
 
     def __init__(self, iterator, optimizer: Adam, converter: Callable = concat_examples,
-                 device=None, loss_func=None, group=None):
-        super().__init__(iterator, optimizer, converter, device, loss_func)
+                 device=None, loss_func=None, group=None, use_cuda_graph: bool = False,
+                 graph_warmup: int = 3):
+        super().__init__(iterator, optimizer, converter, device, loss_func, use_cuda_graph,
+                         graph_warmup)
         self.group = group
 
     @staticmethod
@@ -182,10 +253,7 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         batch = self._iterators["main"].next()
         in_arrays = self.converter(self.split(batch, rank, n), self.device)
-        optimizer = self._optimizers["main"]
-        loss_func = self.loss_func or optimizer.target
-        loss1, loss2, loss3 = loss_func(*in_arrays)
-        self.backward_three(optimizer.target, loss1, loss2, loss3)
-        optimizer.bucket.allreduce(self.group)
-        optimizer.update()
-        return loss1, loss2, loss3
+        return self.update_from_arrays(in_arrays)
+
+    def _reduce(self, optimizer) -> None:
+        optimizer.bucket.allreduce(self.group)                      # addgrads, :71-72

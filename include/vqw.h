@@ -273,6 +273,10 @@ int vqw_upsample_concat_backward(const float* g, float* g_local, float* g_glob, 
                                  int H, int T_out, vqw_stream_t stream);
 int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, vqw_stream_t stream);
+/* same, with the (bias-corrected) learning rate read from device memory: the form a CUDA-graph
+ * replay of the training step uses, where lr changes every step but kernel arguments cannot */
+int vqw_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev,
+                      float beta1, float beta2, float eps, vqw_stream_t stream);
 int vqw_ema_update(float* ema, const float* target, long long n, float decay, vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

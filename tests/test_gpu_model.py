@@ -141,3 +141,38 @@ def test_mol_vae_matches_oracle():
     a, b = got["decoder/proj2/W"].flatten().double(), grads["decoder/proj2/W"].flatten().double()
     assert torch.isfinite(a).all()
     assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.99
+
+
+def test_cuda_graph_updater_matches_eager_updater():
+    """VQVAE_StandardUpdater(use_cuda_graph=True): three ordinary steps, one capture, then replays
+    -- same losses and parameters as issuing every step eagerly (different batch every step, the
+    bias-corrected Adam learning rate read from device memory)."""
+    cfg = O.config_cpu()
+    cfg.length = 256
+    params = O.make_params(cfg)
+    batches = [O.make_inputs(cfg, seed=100 + i) for i in range(7)]
+
+    class It:
+        def __init__(self):
+            self.i = 0
+
+        def next(self):
+            inp = batches[self.i]
+            self.i += 1
+            return [(inp["x_enc"][b], inp["quantized"][b, :-1].astype(np.int32), inp["speaker"][b],
+                     inp["t"][b]) for b in range(cfg.batch)]
+
+    out = {}
+    for graph in (False, True):
+        model = build_model(cfg, params, ema_decay=0.9999)
+        model.train()
+        opt = V.Adam(1e-3).setup(model)
+        upd = V.VQVAE_StandardUpdater(It(), opt, device="cuda", use_cuda_graph=graph, graph_warmup=3)
+        losses = [[float(v) for v in upd.update()] for _ in range(len(batches))]
+        assert (upd._graph is not None) == graph
+        assert opt.t == len(batches)
+        out[graph] = (losses, {n: p.detach().clone() for n, p in model.named_parameters()})
+    for a, b in zip(out[True][0], out[False][0]):
+        assert np.allclose(a, b, rtol=2e-4, atol=1e-7), (a, b)
+    for n, p in out[False][1].items():
+        assert rel_err(out[True][1][n], p) < 2e-4, n
