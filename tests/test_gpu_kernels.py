@@ -248,3 +248,33 @@ def test_upsample_concat_matches_resize_images(B, Cl, Cg, H, f):
     assert rel_err(lg.grad, lo.grad) < 1e-5
     if Cg:
         assert rel_err(gg.grad, go.grad) < 1e-5
+
+
+def test_vq_full_size_bit_exact_and_properties():
+    """BASELINE configs[1]/[2] VQ size (B=16, d=64, T_z=120, k=512) and a 64x longer one: indices
+    bit-identical to the NumPy formulation of utils.py:189-203, idempotence (quantising the
+    codebook vectors returns the same indices and vectors), first-minimum ties."""
+    rng = np.random.default_rng(2)
+    for B, d, T, k in ((16, 64, 120, 512), (4, 64, 7680, 512)):
+        W = rng.normal(0, 1 / np.sqrt(d), size=(k, d)).astype(np.float32)
+        W[37] = W[5]                                             # duplicate rows: tie -> lowest k
+        z = rng.normal(size=(B, d, T, 1)).astype(np.float32)
+        z[0, :, 3, 0] = W[37]
+        e, idx, cnt, zsum, sq = Fn_vq(torch.from_numpy(z).cuda(), torch.from_numpy(W).cuda())
+        want = O.vq_indexes(z, W)                 # sequential-over-d restatement (any size)
+        if T <= 120:
+            assert np.array_equal(want, O.vq_indexes_numpy(z, W))   # == the literal (B,k,d,T,1) form
+        got = idx.cpu().numpy()
+        assert np.array_equal(got, want)
+        assert got[0, 3, 0] == 5
+        assert int(cnt.sum()) == B * T and np.array_equal(
+            cnt.cpu().numpy().astype(np.int64), np.bincount(want.ravel(), minlength=k))
+        # gather: e = W[idx] exactly, and quantising e again is a fixed point
+        assert np.array_equal(e.cpu().numpy()[:, :, :, 0], W[want[:, :, 0]].transpose(0, 2, 1))
+        e2, idx2, _, _, _ = Fn_vq(e, torch.from_numpy(W).cuda())
+        assert torch.equal(idx2, idx) and torch.equal(e2, e)
+
+
+def Fn_vq(z, W):
+    from chainer_vq_vae_b200 import functions as Fn
+    return Fn.vq_lookup(z, W, stats=True)

@@ -335,3 +335,39 @@ def test_full_depth_step_matches_oracle(mode):
         assert worst_cos > 0.9999 and worst2 < 1e-2, (worst_name, worst_cos, worst2)
     else:
         assert worst_cos > 0.999 and worst2 < 5e-2, (worst_name, worst_cos, worst2)
+
+
+def test_full_size_stack_is_causal_and_batch_independent():
+    """Size-independent properties at the BASELINE configs[1] size (20 blocks, dilations 1..512
+    twice, 512/512/256, T = 7680): (a) causality -- perturbing x and the condition from t0 on
+    leaves every output before t0 BIT-identical (modules.py:16,41: the pad/slice makes the conv
+    causal; here the negative-time TMA rows are the zero pad); (b) the receptive field is exactly
+    n_loop*(fs-1)*(2^n_layer-1)+1 steps of the stack input; (c) items of a batch do not see each
+    other (what makes the batch shard over GPUs, updaters.py:36-38)."""
+    dil = [2 ** i for i in range(10)] * 2
+    B, T, fs = 2, 7680, 3
+    cfg, p, x, c = _stack_case(dil, B, T, seed=11)
+    weights = [p[f"resnet/{i}/{n}"].to(DEV) for i in range(len(dil)) for n in ORDER]
+    xg, cg = x.to(DEV), c.to(DEV)
+    with torch.no_grad():
+        base = V.residual_stack(xg, cg, dil, fs, weights, L.MODE_BF16X3)
+        t0 = 5000
+        x2, c2 = xg.clone(), cg.clone()
+        x2[:, :, t0:] += 1.0
+        c2[:, :, t0:] -= 0.5
+        pert = V.residual_stack(x2, c2, dil, fs, weights, L.MODE_BF16X3)
+        assert torch.equal(base[:, :, :t0], pert[:, :, :t0])
+        assert not torch.equal(base[:, :, t0:], pert[:, :, t0:])
+        # receptive field: an impulse at t1 reaches exactly rf - 1 later steps
+        rf = 2 * (fs - 1) * (2 ** 10 - 1) + 1
+        t1 = 100
+        x3 = xg.clone()
+        x3[0, :, t1] += 1.0
+        imp = V.residual_stack(x3, cg, dil, fs, weights, L.MODE_BF16X3)
+        changed = ((imp[0] - base[0]).abs().amax(dim=(0, 2)) > 0).nonzero().flatten()
+        assert int(changed.min()) == t1 and int(changed.max()) == t1 + rf - 1
+        assert torch.equal(imp[1], base[1])                       # the other item is untouched
+        # batch independence: item 1 alone gives the same bits as item 1 inside the batch
+        alone = V.residual_stack(xg[1:2].contiguous(), cg[1:2].contiguous(), dil, fs, weights,
+                                 L.MODE_BF16X3)
+        assert torch.equal(alone[0], base[1])
