@@ -215,7 +215,9 @@ def run_ours(args):
     it = Iter()
     # --graph: the whole step is captured into a CUDA graph after 3 ordinary steps and replayed
     # (measured: no gain at this size -- the step is power-capped tensor work, not launch bound)
-    upd = V.VQVAE_ParallelUpdater(it, opt, device=dev, use_cuda_graph=args.graph)
+    # (single process only here: a process group must not be destroyed while a captured graph
+    # still holds its NCCL kernels -- measured as a hang at exit; see release_graph())
+    upd = V.VQVAE_ParallelUpdater(it, opt, device=dev, use_cuda_graph=args.graph and world == 1)
 
     # ---- device-resident arm ----
     dev_batch = V.updaters.concat_examples(it.mine, dev)
@@ -354,6 +356,7 @@ def run_ours(args):
             "loss1": float(loss),
         }
         print(json.dumps(line))
+    upd.release_graph()
     if world > 1:
         dist.destroy_process_group()
 

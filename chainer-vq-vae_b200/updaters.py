@@ -220,6 +220,16 @@ class VQVAE_StandardUpdater:
         self._graph.replay()
         return tuple(o.detach().clone() for o in self._static_out)
 
+    def release_graph(self) -> None:
+        """Drop the captured step (and its static buffers).  Call it before tearing down a
+        process group whose collectives were captured: destroying the NCCL communicator while a
+        live graph still references its kernels hangs."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static_in = self._static_out = None
+            torch.cuda.synchronize()
+
     def update_core(self):
         batch = self._iterators["main"].next()
         in_arrays = self.converter(batch, self.device)
