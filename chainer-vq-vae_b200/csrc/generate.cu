@@ -28,6 +28,7 @@
 // then the head (relu, proj1, relu, proj2), softmax and the draw.
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -65,6 +66,8 @@ struct GenParams {
   float* logit_buf;            // [Q]
   int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none; mol: float bits)
   unsigned int* barrier;       // grid barrier counter (zeroed by the host before the launch)
+  long long* dbg;              // VQW_GEN_TIMELINE=1: per-phase clock64 stamps of one CTA (or null)
+  int dbg_cta, dbg_step;
 };
 
 // Grid-wide barrier (all CTAs are co-resident: cooperative launch): one atomic arrival per CTA
@@ -74,8 +77,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release-add without a return value: the CTA's writes (ordered before this thread by the
+    // bar.sync above) become visible to whoever acquires the counter; no round trip to wait for
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
@@ -200,7 +204,8 @@ generate_kernel(const GenParams P) {
   const bool fastp = (c3 <= 512) && (P.Cc <= 512) && (Ch <= 256) && (npb <= (int)gridDim.x) &&
                      ((KX & 3) == 0) && ((P.Cc & 3) == 0) && ((Ch & 3) == 0);
   float4 r0[4], r1[4], m0[2], m1[2], q4[2];
-  float pb_t = 0.0f, pb_g = 0.0f, pb_row = 0.0f;   // prefetched biases (gate pair / T2 row)
+  // prefetched biases (gate pair: conv + cond parts, summed at use so the loads stay in flight)
+  float pb_t = 0.0f, pb_t2 = 0.0f, pb_g = 0.0f, pb_g2 = 0.0f, pb_row = 0.0f;
   const int t2_first = (npb * GEN_WARPS) % nwarps;
   // past taps and condition of phase l into buffer l&1 (known before phase l-1 ends)
   auto gather_past = [&](int l, int t) {
@@ -231,13 +236,52 @@ generate_kernel(const GenParams P) {
     for (int i = tid; i < P.Cc; i += GEN_THREADS)
       vc[i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
   };
+  // Software-pipelined form of the same gather (measured: the blocking gather above was ~45 % of a
+  // phase -- two dependent HBM round trips, the rings are evicted from L2 by the 175 MB weight
+  // stream).  The past taps of EVERY layer at step t were written in earlier steps, so the loads
+  // for phase l+2 are issued during phase l and only stored to shared memory one phase later;
+  // the condition column is the same for all layers and is loaded once per step.
+  constexpr int GQ = 4;
+  const int npast = (P.fs - 1) * P.Cr;
+  const bool gfast = npast <= GQ * GEN_THREADS;
+  float gt[GQ];
+  auto gather_issue = [&](int l, int t) {
+    if (l >= P.n_blocks) return;
+    const GenBlock& nb = sblk[l];
+    const float* ring = P.queues + nb.qoff;
+#pragma unroll
+    for (int u = 0; u < GQ; ++u) {
+      const int e = tid + u * GEN_THREADS;
+      float v = 0.0f;
+      if (e < npast) {
+        const int j = e / P.Cr, c = e - j * P.Cr;
+        const int s = nb.dilation * (P.fs - 1 - j);
+        if (t - s >= 0) v = __ldcg(ring + (long long)((t - s) % nb.qlen) * P.Cr + c);
+      }
+      gt[u] = v;
+    }
+  };
+  auto gather_commit = [&](int l) {
+    if (l >= P.n_blocks) return;
+    float* vx = vx2 + (l & 1) * KXp;
+#pragma unroll
+    for (int u = 0; u < GQ; ++u) {
+      const int e = tid + u * GEN_THREADS;
+      if (e < npast) {
+        const int j = e / P.Cr, c = e - j * P.Cr;
+        vx[c * P.fs + j] = gt[u];
+      }
+    }
+  };
   auto prefetch_phase = [&](int l) {
     if (l > P.n_blocks) return;
     if (l < P.n_blocks && tid < 2 && 2 * (int)blockIdx.x + tid < Ch) {
       const GenBlock& nb = sblk[l];
       const int pp = 2 * blockIdx.x + tid;
-      pb_t = __ldg(nb.conv_b + pp) + __ldg(nb.cond_b + pp);
-      pb_g = __ldg(nb.conv_b + Ch + pp) + __ldg(nb.cond_b + Ch + pp);
+      pb_t = __ldg(nb.conv_b + pp);
+      pb_t2 = __ldg(nb.cond_b + pp);
+      pb_g = __ldg(nb.conv_b + Ch + pp);
+      pb_g2 = __ldg(nb.cond_b + Ch + pp);
     }
     if (l >= 1 && lane == 0) {
       const bool t1 = l < P.n_blocks;
@@ -303,14 +347,24 @@ generate_kernel(const GenParams P) {
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cs; c += gridDim.x * GEN_THREADS)
         P.skipacc[c] = 0.0f;
     }
-    gather_past(0, t);
+    if (gfast) {
+      gather_issue(0, t);
+      for (int i = tid; i < P.Cc; i += GEN_THREADS)      // cond[:, t]: once per step, both buffers
+        vc2[i] = vc2[Ccp + i] = __ldg(P.cond + (long long)i * P.T_total + (t - P.cond_t0));
+      gather_commit(0);
+      gather_issue(1, t);
+    } else {
+      gather_past(0, t);
+    }
     prefetch_phase(0);
     grid_barrier(P.barrier, epoch);
 
     // phase l = 0..n-1 computes z_l (T1) and, for l >= 1, x_l and the skip rows of block l-1
     // (T2); phase n only runs T2 for the last block's skip rows.
+    const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_cta && step == P.dbg_step && tid == 0;
     for (int l = 0; l <= P.n_blocks; ++l) {
       const bool has_t1 = l < P.n_blocks, has_t2 = l >= 1;
+      if (rec && l < 12) P.dbg[8 * l] = clock64();
       const GenBlock& blk = sblk[has_t1 ? l : l - 1];     // T1's block
       const GenBlock& pb = sblk[has_t2 ? l - 1 : 0];      // T2's block (l-1)
       const float* xprev = P.xbuf + (has_t2 ? ((l - 1) & 1) : 0) * P.Cr;   // x_{l-1} (x_0 for l=0)
@@ -328,6 +382,7 @@ generate_kernel(const GenParams P) {
       if (has_t2)
         for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = __ldcg(zprev + i);
       __syncthreads();
+      if (rec && l < 12) P.dbg[8 * l + 1] = clock64();
 
       // ---- T1: gate pairs ----
       if (has_t1) {
@@ -375,7 +430,7 @@ generate_kernel(const GenParams P) {
           __syncthreads();
           if (tid < 2 && 2 * pblk + tid < Ch) {
             const int pp = 2 * pblk + tid;
-            float ht = pb_t, hg = pb_g;
+            float ht = pb_t + pb_t2, hg = pb_g + pb_g2;
             if (pblk != (int)blockIdx.x) {     // only the first pair block of a CTA is prefetched
               ht = __ldg(blk.conv_b + pp) + __ldg(blk.cond_b + pp);
               hg = __ldg(blk.conv_b + Ch + pp) + __ldg(blk.cond_b + Ch + pp);
@@ -391,6 +446,7 @@ generate_kernel(const GenParams P) {
           __syncthreads();
         }
       }
+      if (rec && l < 12) P.dbg[8 * l + 2] = clock64();
       // ---- T2: x_l = Wr z + br + x_{l-1} (pushed into ring_l), skip += Ws z + bs ----
       if (has_t2) {
         const int R = (has_t1 ? P.Cr : 0) + P.Cs;      // the last block's residual is unused
@@ -404,7 +460,7 @@ generate_kernel(const GenParams P) {
                                 : dot_row(pb.res_w + (long long)rr * Ch, zs, Ch, lane);
             if (lane == 0) {
               // xbuf holds x_{l-1} + br_{l-1}; it gets x_l + br_l for the next phase
-              const float xv = v + __ldcg(xprev + rr);
+              const float xv = v + vx[rr * P.fs + P.fs - 1];   // x_{l-1} + br_{l-1}, staged above
               const float bnext = (r < nwarps) ? pb_row : __ldg(blk.res_b + rr);
               xout[rr] = xv + bnext;
               P.queues[blk.qoff + (long long)(t % blk.qlen) * P.Cr + rr] = xv;
@@ -418,9 +474,17 @@ generate_kernel(const GenParams P) {
           }
         }
       }
-      gather_past(l + 1, t);
+      if (rec && l < 12) P.dbg[8 * l + 3] = clock64();
+      if (gfast) {
+        gather_commit(l + 1);          // loaded during the previous phase
+        gather_issue(l + 2, t);
+      } else {
+        gather_past(l + 1, t);
+      }
       prefetch_phase(l + 1);
+      if (rec && l < 12) P.dbg[8 * l + 4] = clock64();
       grid_barrier(P.barrier, epoch);
+      if (rec && l < 12) P.dbg[8 * l + 5] = clock64();
     }
 
     // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
@@ -636,6 +700,16 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   P.state = reinterpret_cast<int32_t*>(ws + L.state);
   P.barrier = reinterpret_cast<unsigned int*>(ws + L.barrier);
   VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.barrier, 0, 16, st));
+  static long long* gen_dbg = nullptr;
+  static const bool gen_timeline = getenv("VQW_GEN_TIMELINE") && getenv("VQW_GEN_TIMELINE")[0] == '1';
+  P.dbg = nullptr; P.dbg_cta = 0; P.dbg_step = 0;
+  if (gen_timeline && d.n_steps > 8) {
+    if (!gen_dbg) cudaMalloc(&gen_dbg, 128 * sizeof(long long));
+    cudaMemsetAsync(gen_dbg, 0, 128 * sizeof(long long), st);
+    P.dbg = gen_dbg;
+    P.dbg_cta = getenv("VQW_GEN_TIMELINE_CTA") ? atoi(getenv("VQW_GEN_TIMELINE_CTA")) : 0;
+    P.dbg_step = 8;
+  }
 
   const int KX = d.fs * d.Cr, Ch = d.Cd / 2;
   int mx = d.Cr > d.Cs ? d.Cr : d.Cs;
@@ -659,5 +733,16 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   VQW_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)generate_kernel, dim3(grid), dim3(GEN_THREADS),
                                              args, smem, st));
   VQW_CHECK_LAUNCH("generate_kernel");
+  if (P.dbg) {
+    long long h[128];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, gen_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[vqw generate timeline] CTA %d, step %d (cycles rel. to the start of phase 0)\n",
+            P.dbg_cta, P.dbg_step);
+    for (int l = 0; l < 12; ++l)
+      fprintf(stderr, "  phase %2d: start %6lld staged %6lld T1 %6lld T2 %6lld prefetch issued %6lld "
+                      "barrier passed %6lld\n", l, h[8 * l] - h[0], h[8 * l + 1] - h[0],
+              h[8 * l + 2] - h[0], h[8 * l + 3] - h[0], h[8 * l + 4] - h[0], h[8 * l + 5] - h[0]);
+  }
   return 0;
 }
