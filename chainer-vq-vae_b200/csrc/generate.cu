@@ -185,6 +185,7 @@ generate_kernel(const GenParams P) {
   float* part = ps + ((P.Q + 3) & ~3);  // [2 pairs][4 chunks][2] partial sums
   GenBlock* sblk = reinterpret_cast<GenBlock*>(part + 16);   // block table copy
   __shared__ int s_sample;
+  __shared__ int s_slot[256];   // t % qlen of every block, refreshed once per step (<= 256 blocks)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gwarp = blockIdx.x * GEN_WARPS + warp;
@@ -207,6 +208,16 @@ generate_kernel(const GenParams P) {
   // prefetched biases (gate pair: conv + cond parts, summed at use so the loads stay in flight)
   float pb_t = 0.0f, pb_t2 = 0.0f, pb_g = 0.0f, pb_g2 = 0.0f, pb_row = 0.0f;
   const int t2_first = (npb * GEN_WARPS) % nwarps;
+  // loop invariants of the per-phase code (integer division and modulo are ~25 dependent
+  // instructions each; measured: they were most of the ~3 k cycles between T2 and the barrier)
+  const int r_t2 = (gwarp - t2_first + nwarps) % nwarps;      // this warp's T2 row
+  // A warp owns the same skip row in every phase but the last one, so the running skip sum of a
+  // step lives in a register of its lane 0 and reaches memory once (instead of a dependent global
+  // read-modify-write per block)
+  const bool skreg = (P.Cr + P.Cs) <= nwarps && P.n_blocks >= 2;
+  float skip_reg = 0.0f;
+  const int p_t1 = 2 * blockIdx.x + (warp >> 2), kc_t1 = warp & 3;
+  const int k0_t1 = kc_t1 * c3, n_t1 = max(0, min(c3, KX - k0_t1));
   // past taps and condition of phase l into buffer l&1 (known before phase l-1 ends)
   auto gather_past = [&](int l, int t) {
     if (l >= P.n_blocks) return;
@@ -245,6 +256,13 @@ generate_kernel(const GenParams P) {
   const int npast = (P.fs - 1) * P.Cr;
   const bool gfast = npast <= GQ * GEN_THREADS;
   float gt[GQ];
+  int gj[GQ], gc[GQ];          // tap and channel of this thread's elements (step independent)
+#pragma unroll
+  for (int u = 0; u < GQ; ++u) {
+    const int e = tid + u * GEN_THREADS;
+    gj[u] = e / P.Cr;
+    gc[u] = e - gj[u] * P.Cr;
+  }
   auto gather_issue = [&](int l, int t) {
     if (l >= P.n_blocks) return;
     const GenBlock& nb = sblk[l];
@@ -254,9 +272,12 @@ generate_kernel(const GenParams P) {
       const int e = tid + u * GEN_THREADS;
       float v = 0.0f;
       if (e < npast) {
-        const int j = e / P.Cr, c = e - j * P.Cr;
-        const int s = nb.dilation * (P.fs - 1 - j);
-        if (t - s >= 0) v = __ldcg(ring + (long long)((t - s) % nb.qlen) * P.Cr + c);
+        const int s = nb.dilation * (P.fs - 1 - gj[u]);       // 1 <= s < qlen
+        if (t - s >= 0) {
+          int slot = s_slot[l] - s;                            // (t - s) % qlen without dividing
+          if (slot < 0) slot += nb.qlen;
+          v = __ldcg(ring + (long long)slot * P.Cr + gc[u]);
+        }
       }
       gt[u] = v;
     }
@@ -267,10 +288,7 @@ generate_kernel(const GenParams P) {
 #pragma unroll
     for (int u = 0; u < GQ; ++u) {
       const int e = tid + u * GEN_THREADS;
-      if (e < npast) {
-        const int j = e / P.Cr, c = e - j * P.Cr;
-        vx[c * P.fs + j] = gt[u];
-      }
+      if (e < npast) vx[gc[u] * P.fs + gj[u]] = gt[u];
     }
   };
   auto prefetch_phase = [&](int l) {
@@ -286,7 +304,7 @@ generate_kernel(const GenParams P) {
     if (l >= 1 && lane == 0) {
       const bool t1 = l < P.n_blocks;
       const int R = (t1 ? P.Cr : 0) + P.Cs, r_off = t1 ? 0 : P.Cr;
-      const int r = (gwarp - t2_first + nwarps) % nwarps;
+      const int r = r_t2;
       if (r < R) {
         const int rr = r + r_off;
         // x_l rows carry the NEXT block's residual bias (see T2), skip rows their own bias
@@ -296,10 +314,10 @@ generate_kernel(const GenParams P) {
     if (!fastp) return;
     if (l < P.n_blocks) {
       const GenBlock& nb = sblk[l];
-      const int p = 2 * blockIdx.x + (warp >> 2), kc = warp & 3;
+      const int p = p_t1, kc = kc_t1;
       if ((int)blockIdx.x < npb && p < Ch) {
         if (kc < 3) {
-          const int k0 = kc * c3, n = max(0, min(c3, KX - k0));
+          const int k0 = k0_t1, n = n_t1;
           load_row<4>(nb.conv_w + (long long)p * KX + k0, n, lane, r0);
           load_row<4>(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane, r1);
         } else {
@@ -316,7 +334,7 @@ generate_kernel(const GenParams P) {
       const GenBlock& pbk = sblk[l - 1];
       const bool t1 = l < P.n_blocks;
       const int R = (t1 ? P.Cr : 0) + P.Cs, r_off = t1 ? 0 : P.Cr;
-      const int r = (gwarp - t2_first + nwarps) % nwarps;
+      const int r = r_t2;
       if (r < R) {
         const int rr = r + r_off;
         load_row<2>(rr < P.Cr ? pbk.res_w + (long long)rr * Ch : pbk.skip_w + (long long)(rr - P.Cr) * Ch,
@@ -328,9 +346,11 @@ generate_kernel(const GenParams P) {
   for (int step = 0; step < P.n_steps; ++step) {
     const int t = P.t_start + step;
     // ---- embed: x_0 = b + W[:, s(t-2), 0] + W[:, s(t-1), 1]   (modules.py:246-247; zeros at start)
+    if (tid < P.n_blocks) s_slot[tid] = t % sblk[tid].qlen;
+    __syncthreads();
     {
       const int s1 = P.state[0], s2 = P.state[1];
-      float* ring0 = P.queues + sblk[0].qoff + (long long)(t % sblk[0].qlen) * P.Cr;
+      float* ring0 = P.queues + sblk[0].qoff + (long long)s_slot[0] * P.Cr;
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cr; c += gridDim.x * GEN_THREADS) {
         float v = __ldg(P.embed_b + c);
         if (P.mol) {   // one input channel carrying the previous values (generate.py:137)
@@ -376,7 +396,7 @@ generate_kernel(const GenParams P) {
       float* vc = vc2 + (l & 1) * Ccp;
       if (has_t1) {
         // l = 0: plain x_0 (just pushed into ring_0); l >= 1: x_{l-1} + br_{l-1} (xbuf)
-        const float* cur = has_t2 ? xprev : P.queues + blk.qoff + (long long)(t % blk.qlen) * P.Cr;
+        const float* cur = has_t2 ? xprev : P.queues + blk.qoff + (long long)s_slot[l] * P.Cr;
         for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = __ldcg(cur + c);
       }
       if (has_t2)
@@ -451,8 +471,7 @@ generate_kernel(const GenParams P) {
       if (has_t2) {
         const int R = (has_t1 ? P.Cr : 0) + P.Cs;      // the last block's residual is unused
         const int r_off = has_t1 ? 0 : P.Cr;
-        const int first = t2_first;                    // start after the warps T1 keeps busiest
-        for (int r = (gwarp - first + nwarps) % nwarps; r < R; r += nwarps) {
+        for (int r = r_t2; r < R; r += nwarps) {
           const int rr = r + r_off;
           const bool pre = fastp && r < nwarps;        // the first row of a warp was prefetched
           if (rr < P.Cr) {
@@ -463,14 +482,24 @@ generate_kernel(const GenParams P) {
               const float xv = v + vx[rr * P.fs + P.fs - 1];   // x_{l-1} + br_{l-1}, staged above
               const float bnext = (r < nwarps) ? pb_row : __ldg(blk.res_b + rr);
               xout[rr] = xv + bnext;
-              P.queues[blk.qoff + (long long)(t % blk.qlen) * P.Cr + rr] = xv;
+              P.queues[blk.qoff + (long long)s_slot[l] * P.Cr + rr] = xv;
             }
           } else {
             const int sidx = rr - P.Cr;
             const float v = pre ? warp_sum(fma_row<2>(q4, zs, Ch, lane))
                                 : dot_row(pb.skip_w + (long long)sidx * Ch, zs, Ch, lane);
-            if (lane == 0)
-              P.skipacc[sidx] += v + ((r < nwarps) ? pb_row : __ldg(pb.skip_b + sidx));
+            if (lane == 0) {
+              const float add = v + ((r < nwarps) ? pb_row : __ldg(pb.skip_b + sidx));
+              if (skreg && has_t1) {
+                skip_reg += add;
+                if (l == P.n_blocks - 1) {        // last phase in which this warp owns the row
+                  P.skipacc[sidx] = skip_reg;
+                  skip_reg = 0.0f;
+                }
+              } else {
+                P.skipacc[sidx] += add;
+              }
+            }
           }
         }
       }
