@@ -494,8 +494,9 @@ def run_generate(args):
                      "frac": wbytes / per_step_s / 1e9 / pk["hbm_gbs"], "traffic": None,
                      "peak_source": pk_src,
                      "note": "algorithmic bytes = every weight read once per sample (174.9 MB "
-                             "fp32); the weights fit the 126 MB L2 only partly, the kernel is "
-                             "grid-barrier latency bound (82 barriers per sample)"},
+                             "fp32, streamed from HBM: L2 hit rate 10 %); the kernel is bound by the "
+                             "dependent chain of 41 phases per sample (one tagged store->load "
+                             "exchange each, ~3.5 us per phase) plus 6 grid barriers"},
         "cpu_baseline": cpu, "first_samples": [int(v) for v in out[:8].tolist()],
     }))
 

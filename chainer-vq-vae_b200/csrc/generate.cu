@@ -62,10 +62,14 @@ struct GenParams {
   float* zbuf;                 // [2][Cd/2] gated activations (ping-pong over blocks)
   float* xbuf;                 // [2][Cr] block inputs (ping-pong over blocks)
   float* skipacc;              // [Cs]
+  float* skiplast;             // [Cs] skip rows of the last block (tagged-exchange mode)
+  uint2* xtag;                 // [2][Cr] {x_l + br_l bits, tag}: tagged exchange between phases
+  uint2* ztag;                 // [2][Cd/2] {z_l bits, tag}
   float* h1;                   // [Cs] relu(proj1(relu(skip)))
   float* logit_buf;            // [Q]
   int32_t* state;              // [0] = sample(t-1), [1] = sample(t-2)  (-1 = none; mol: float bits)
   unsigned int* barrier;       // grid barrier counter (zeroed by the host before the launch)
+  int use_tags;                // tagged exchange between phases instead of grid barriers
   long long* dbg;              // VQW_GEN_TIMELINE=1: per-phase clock64 stamps of one CTA (or null)
   int dbg_cta, dbg_step;
 };
@@ -87,6 +91,28 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   }
   __syncthreads();
 }
+
+// Tagged exchange.  The values one phase hands to the next (x_l + br_l and z_l: 768 floats) are
+// written as 8-byte {value, tag} words and the consumers poll the words themselves until the
+// tag is the one of (step, phase): an 8-byte aligned store is single-copy atomic, so a matching
+// tag means the value next to it is the new one.  This replaces "grid barrier, then load" (two
+// dependent round trips plus the arrival skew, ~3.5 k cycles of an ~8.7 k-cycle phase) by one
+// store -> load propagation.  Ping-pong over two buffers is enough: a CTA can only be two phases
+// ahead of another after consuming something that CTA produced after its own reads.
+__device__ __forceinline__ void st_tagged(uint2* p, float v, uint32_t tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ float ld_tagged(const uint2* p, uint32_t tag) {
+  uint32_t v, g;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {   // bounded: never hang the GPU
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(g) : "l"(p) : "memory");
+    if (g == tag) return __uint_as_float(v);
+  }
+  __trap();
+  return 0.0f;
+}
+__device__ __forceinline__ uint32_t phase_tag(int t, int l) { return (uint32_t)t * 512u + (uint32_t)l + 1u; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -216,6 +242,9 @@ generate_kernel(const GenParams P) {
   // read-modify-write per block)
   const bool skreg = (P.Cr + P.Cs) <= nwarps && P.n_blocks >= 2;
   float skip_reg = 0.0f;
+  const bool tagx = skreg && P.use_tags && P.n_blocks < 500;   // tagged exchange instead of barriers
+  // a CTA without gate pairs and without T2 rows neither produces nor polls the exchanged vectors
+  const bool cta_works = __syncthreads_or((int)blockIdx.x < npb || r_t2 < P.Cr + P.Cs) != 0;
   const int p_t1 = 2 * blockIdx.x + (warp >> 2), kc_t1 = warp & 3;
   const int k0_t1 = kc_t1 * c3, n_t1 = max(0, min(c3, KX - k0_t1));
   // past taps and condition of phase l into buffer l&1 (known before phase l-1 ends)
@@ -291,8 +320,30 @@ generate_kernel(const GenParams P) {
       if (e < npast) vx[gc[u] * P.fs + gj[u]] = gt[u];
     }
   };
-  auto prefetch_phase = [&](int l) {
+  // part 1 = the gate rows (r0, r1, m0, m1: dead as soon as this phase's T1 products are done, so
+  // they are re-filled right there and the loads overlap the reduction, T2 and the exchange);
+  // part 2 = biases, the T2 row and the rest, after T2
+  auto prefetch_phase = [&](int l, bool part1, bool part2) {
     if (l > P.n_blocks) return;
+    if (part1 && fastp && l < P.n_blocks) {
+      const GenBlock& nb = sblk[l];
+      const int p = p_t1, kc = kc_t1;
+      if ((int)blockIdx.x < npb && p < Ch) {
+        if (kc < 3) {
+          const int k0 = k0_t1, n = n_t1;
+          load_row<4>(nb.conv_w + (long long)p * KX + k0, n, lane, r0);
+          load_row<4>(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane, r1);
+        } else {
+          load_row<4>(nb.cond_w + (long long)p * P.Cc, P.Cc, lane, r0);
+          load_row<4>(nb.cond_w + (long long)(Ch + p) * P.Cc, P.Cc, lane, r1);
+          if (l >= 1) {
+            load_row<2>(nb.mmat + (long long)p * Ch, Ch, lane, m0);
+            load_row<2>(nb.mmat + (long long)(Ch + p) * Ch, Ch, lane, m1);
+          }
+        }
+      }
+    }
+    if (!part2) return;
     if (l < P.n_blocks && tid < 2 && 2 * (int)blockIdx.x + tid < Ch) {
       const GenBlock& nb = sblk[l];
       const int pp = 2 * blockIdx.x + tid;
@@ -312,24 +363,6 @@ generate_kernel(const GenParams P) {
       }
     }
     if (!fastp) return;
-    if (l < P.n_blocks) {
-      const GenBlock& nb = sblk[l];
-      const int p = p_t1, kc = kc_t1;
-      if ((int)blockIdx.x < npb && p < Ch) {
-        if (kc < 3) {
-          const int k0 = k0_t1, n = n_t1;
-          load_row<4>(nb.conv_w + (long long)p * KX + k0, n, lane, r0);
-          load_row<4>(nb.conv_w + (long long)(Ch + p) * KX + k0, n, lane, r1);
-        } else {
-          load_row<4>(nb.cond_w + (long long)p * P.Cc, P.Cc, lane, r0);
-          load_row<4>(nb.cond_w + (long long)(Ch + p) * P.Cc, P.Cc, lane, r1);
-          if (l >= 1) {
-            load_row<2>(nb.mmat + (long long)p * Ch, Ch, lane, m0);
-            load_row<2>(nb.mmat + (long long)(Ch + p) * Ch, Ch, lane, m1);
-          }
-        }
-      }
-    }
     if (l >= 1) {
       const GenBlock& pbk = sblk[l - 1];
       const bool t1 = l < P.n_blocks;
@@ -361,7 +394,9 @@ generate_kernel(const GenParams P) {
           if (s2 >= 0) v += __ldg(wr + 2 * s2);
           if (s1 >= 0) v += __ldg(wr + 2 * s1 + 1);
         }
-        P.xbuf[c] = v + __ldg(sblk[0].res_b + c);   // slot 0 holds x_0 + br_0 (see T2)
+        // slot 0 holds x_0 + br_0 (see T2)
+        if (tagx) st_tagged(P.xtag + c, v + __ldg(sblk[0].res_b + c), phase_tag(t, 0));
+        else P.xbuf[c] = v + __ldg(sblk[0].res_b + c);
         ring0[c] = v;                               // push (modules.py:72)
       }
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cs; c += gridDim.x * GEN_THREADS)
@@ -376,7 +411,7 @@ generate_kernel(const GenParams P) {
     } else {
       gather_past(0, t);
     }
-    prefetch_phase(0);
+    prefetch_phase(0, true, true);
     grid_barrier(P.barrier, epoch);
 
     // phase l = 0..n-1 computes z_l (T1) and, for l >= 1, x_l and the skip rows of block l-1
@@ -394,13 +429,25 @@ generate_kernel(const GenParams P) {
       // ---- stage what depended on the previous phase: the current-tap entries and z_{l-1} ----
       float* vx = vx2 + (l & 1) * KXp;
       float* vc = vc2 + (l & 1) * Ccp;
-      if (has_t1) {
-        // l = 0: plain x_0 (just pushed into ring_0); l >= 1: x_{l-1} + br_{l-1} (xbuf)
-        const float* cur = has_t2 ? xprev : P.queues + blk.qoff + (long long)s_slot[l] * P.Cr;
-        for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = __ldcg(cur + c);
+      if (tagx && has_t2 && !cta_works) {
+        // nothing to read: this CTA computes nothing in any phase
+      } else if (tagx && has_t2) {
+        // poll the producers' {value, tag} words of phase l-1 directly (no barrier in between)
+        const uint32_t want = phase_tag(t, l - 1);
+        const uint2* xt = P.xtag + ((l - 1) & 1) * P.Cr;
+        const uint2* zt = P.ztag + ((l - 1) & 1) * Ch;
+        if (has_t1)
+          for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = ld_tagged(xt + c, want);
+        for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = ld_tagged(zt + i, want);
+      } else {
+        if (has_t1) {
+          // l = 0: plain x_0 (just pushed into ring_0); l >= 1: x_{l-1} + br_{l-1} (xbuf)
+          const float* cur = has_t2 ? xprev : P.queues + blk.qoff + (long long)s_slot[l] * P.Cr;
+          for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = __ldcg(cur + c);
+        }
+        if (has_t2)
+          for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = __ldcg(zprev + i);
       }
-      if (has_t2)
-        for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = __ldcg(zprev + i);
       __syncthreads();
       if (rec && l < 12) P.dbg[8 * l + 1] = clock64();
 
@@ -422,6 +469,7 @@ generate_kernel(const GenParams P) {
                 ag += fma_row<2>(m1, zs, Ch, lane);
               }
             }
+            prefetch_phase(l + 1, true, false);   // r0/r1/m0/m1 are free again: next phase's rows
             at = warp_sum(at);
             ag = warp_sum(ag);
           } else if (p < Ch) {
@@ -461,7 +509,9 @@ generate_kernel(const GenParams P) {
               ht += part[(tid * 4 + k) * 2 + 0];
               hg += part[(tid * 4 + k) * 2 + 1];
             }
-            zout[pp] = tanhf(ht) * (1.0f / (1.0f + expf(-hg)));
+            const float zv = tanhf(ht) * (1.0f / (1.0f + expf(-hg)));
+            if (tagx) st_tagged(P.ztag + (l & 1) * Ch + pp, zv, phase_tag(t, l));
+            else zout[pp] = zv;
           }
           __syncthreads();
         }
@@ -481,7 +531,8 @@ generate_kernel(const GenParams P) {
               // xbuf holds x_{l-1} + br_{l-1}; it gets x_l + br_l for the next phase
               const float xv = v + vx[rr * P.fs + P.fs - 1];   // x_{l-1} + br_{l-1}, staged above
               const float bnext = (r < nwarps) ? pb_row : __ldg(blk.res_b + rr);
-              xout[rr] = xv + bnext;
+              if (tagx) st_tagged(P.xtag + (l & 1) * P.Cr + rr, xv + bnext, phase_tag(t, l));
+              else xout[rr] = xv + bnext;
               P.queues[blk.qoff + (long long)s_slot[l] * P.Cr + rr] = xv;
             }
           } else {
@@ -496,6 +547,8 @@ generate_kernel(const GenParams P) {
                   P.skipacc[sidx] = skip_reg;
                   skip_reg = 0.0f;
                 }
+              } else if (tagx) {
+                P.skiplast[sidx] = add;          // last block's rows: summed by the head
               } else {
                 P.skipacc[sidx] += add;
               }
@@ -510,14 +563,15 @@ generate_kernel(const GenParams P) {
       } else {
         gather_past(l + 1, t);
       }
-      prefetch_phase(l + 1);
+      prefetch_phase(l + 1, false, true);
       if (rec && l < 12) P.dbg[8 * l + 4] = clock64();
-      grid_barrier(P.barrier, epoch);
+      if (!tagx || l == P.n_blocks) grid_barrier(P.barrier, epoch);
       if (rec && l < 12) P.dbg[8 * l + 5] = clock64();
     }
 
     // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
-    for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = fmaxf(__ldcg(P.skipacc + i), 0.0f);
+    for (int i = tid; i < P.Cs; i += GEN_THREADS)
+      xs[i] = fmaxf(__ldcg(P.skipacc + i) + (tagx ? __ldcg(P.skiplast + i) : 0.0f), 0.0f);
     __syncthreads();
     for (int r = gwarp; r < P.Cs; r += nwarps) {
       float v = dot_row(P.proj1_w + (long long)r * P.Cs, xs, P.Cs, lane);
@@ -613,7 +667,7 @@ generate_kernel(const GenParams P) {
 static inline int64_t gen_align(int64_t v) { return (v + 255) / 256 * 256; }
 
 struct GenLayout {
-  int64_t blocks, queues, zbuf, mmat, xbuf, skipacc, h1, logit, state, barrier, total;
+  int64_t blocks, queues, zbuf, mmat, xbuf, skipacc, skiplast, xtag, ztag, h1, logit, state, barrier, total;
 };
 
 static GenLayout gen_layout(const vqw_generate_desc& d) {
@@ -628,6 +682,9 @@ static GenLayout gen_layout(const vqw_generate_desc& d) {
   L.mmat = take((int64_t)d.n_blocks * d.Cd * (d.Cd / 2) * 4);
   L.xbuf = take((int64_t)2 * d.Cr * 4);
   L.skipacc = take((int64_t)d.Cs * 4);
+  L.skiplast = take((int64_t)d.Cs * 4);
+  L.xtag = take((int64_t)2 * d.Cr * 8);
+  L.ztag = take((int64_t)2 * (d.Cd / 2) * 8);
   L.h1 = take((int64_t)d.Cs * 4);
   L.logit = take((int64_t)d.Q * 4);
   L.state = take(16);
@@ -700,6 +757,9 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
     }
     // WaveNet.initialize(): zero queues (modules.py:59-66,236-243); no previous samples
     VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.queues, 0, (size_t)qoff * 4, st));
+    // tag 0 is never expected: stale words of a previous utterance must not match
+    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.xtag, 0, (size_t)2 * d.Cr * 8, st));
+    VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.ztag, 0, (size_t)2 * (d.Cd / 2) * 8, st));
     // no previous samples: index -1 (categorical) / value 0.0 (mixture of logistics), generate.py:51
     VQW_CHECK_CUDA(cudaMemsetAsync(ws + L.state, d.use_logistic ? 0 : 0xff, 16, st));
   }
@@ -724,6 +784,9 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
   P.zbuf = reinterpret_cast<float*>(ws + L.zbuf);
   P.xbuf = reinterpret_cast<float*>(ws + L.xbuf);
   P.skipacc = reinterpret_cast<float*>(ws + L.skipacc);
+  P.skiplast = reinterpret_cast<float*>(ws + L.skiplast);
+  P.xtag = reinterpret_cast<uint2*>(ws + L.xtag);
+  P.ztag = reinterpret_cast<uint2*>(ws + L.ztag);
   P.h1 = reinterpret_cast<float*>(ws + L.h1);
   P.logit_buf = reinterpret_cast<float*>(ws + L.logit);
   P.state = reinterpret_cast<int32_t*>(ws + L.state);
@@ -758,6 +821,25 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
                                                               smem));
   VQW_REQUIRE(per_sm >= 1, "vqw_generate: kernel does not fit on an SM");
   int grid = sms;   // one CTA per SM
+  {
+    // Tagged exchange needs every CTA that CONSUMES the exchanged vectors in a phase to also
+    // PRODUCE a tagged word in it (that is what bounds how far CTAs can drift apart, see
+    // st_tagged): true when no CTA holds skip rows only.  Otherwise: grid barriers.
+    const int Ch = d.Cd / 2, nw = grid * (GEN_THREADS / 32), npb = (Ch + 1) / 2;
+    const int t2_first = (npb * (GEN_THREADS / 32)) % nw;
+    bool ok = !(getenv("VQW_GEN_TAGS") && getenv("VQW_GEN_TAGS")[0] == '0') &&
+              (d.Cr + d.Cs) <= nw && d.n_blocks >= 2 && d.n_blocks < 500 && npb <= grid;
+    for (int b = 0; b < grid && ok; ++b) {
+      bool t1 = b < npb, xrow = false, srow = false;
+      for (int w = 0; w < GEN_THREADS / 32; ++w) {
+        const int r = (b * (GEN_THREADS / 32) + w - t2_first + nw) % nw;
+        if (r < d.Cr) xrow = true;
+        else if (r < d.Cr + d.Cs) srow = true;
+      }
+      if (srow && !t1 && !xrow) ok = false;
+    }
+    P.use_tags = ok ? 1 : 0;
+  }
   void* args[] = {(void*)&P};
   VQW_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)generate_kernel, dim3(grid), dim3(GEN_THREADS),
                                              args, smem, st));
