@@ -1,9 +1,8 @@
 #!/bin/bash
 # Build libvqw.so in-tree for sm_100a (cross-compiles without a GPU).
 set -e
-cd "$(dirname "$0")/chainer-vq-vae_b200/csrc"
+cd "$(dirname "$0")/chainer_vq_vae_b200/csrc"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math=false"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 OBJS=""
 for f in *.cu; do

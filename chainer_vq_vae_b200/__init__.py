@@ -1,8 +1,7 @@
-"""chainer-vq-vae_b200: the B200-native hot path of dhgrs/chainer-VQ-VAE.
+"""chainer_vq_vae_b200: the B200-native hot path of dhgrs/chainer-VQ-VAE.
 
-The directory name carries a hyphen, so import it through the `chainer_vq_vae_b200` shim at
-the repository root (or `importlib`); see DESIGN.md.  Importing this package loads
-csrc/libvqw.so and raises if it is missing -- there is no CPU or eager fallback."""
+Importing this package loads csrc/libvqw.so and raises if it is missing -- there is no CPU
+or eager fallback."""
 from . import _lib
 from ._lib import MODES, VqwError, launch_count
 from .functions import conv, embed_gather, residual_stack, straight_through, vq_lookup

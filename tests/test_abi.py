@@ -14,7 +14,7 @@ def _declared():
 
 
 def test_library_exports_every_declared_symbol():
-    lib = ctypes.CDLL(os.path.join(ROOT, "chainer-vq-vae_b200", "csrc", "libvqw.so"))
+    lib = ctypes.CDLL(os.path.join(ROOT, "chainer_vq_vae_b200", "csrc", "libvqw.so"))
     names = _declared()
     assert len(names) >= 15
     for n in names:
@@ -48,7 +48,7 @@ def test_argument_errors_are_reported_before_launch():
 
 def test_no_oracle_or_cpu_fallback_in_the_product():
     """The product package must not import the oracle or route around the CUDA library."""
-    pkg = os.path.join(ROOT, "chainer-vq-vae_b200")
+    pkg = os.path.join(ROOT, "chainer_vq_vae_b200")
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()

@@ -156,3 +156,59 @@ def test_generate_mixture_of_logistics_teacher_forced_and_stepwise():
             ref.append(gen.generate(xo, cond[:, :, i:i + 1].cpu())[0, :, 0, 0])
             xo = torch.full((1, 1, 1, 1), float(forced[i]))
     assert rel_err(logits, torch.stack(ref)) < TOL
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json configs[4] at its own size: n_loop=4 x n_layer=10, 512/512/256, fs=3
+# ---------------------------------------------------------------------------------------
+def _gen_case(length):
+    cfg = O.config_gen()
+    params, inp = _case(cfg, length)
+    model = build_model(cfg, params).eval()
+    with torch.no_grad():
+        cond = model.condition_embed(model.vq(model.encoder(torch.from_numpy(inp["x_enc"]).cuda())),
+                                     torch.from_numpy(inp["speaker"]).cuda())
+    return cfg, params, inp, model, cond
+
+
+def test_generate_config4_teacher_forced_past_the_dilation_512_ring_wrap():
+    """40 blocks, dilations 1..512 four times.  The dilation-512 queue holds 1025 columns
+    (modules.py:59-62), so the kernel's ring buffers wrap for the first time after step 1025:
+    1200 teacher-forced steps against the oracle's concat-shift generator (modules.py:58-74,
+    98-110, 232-255), every step's logits within 1e-3."""
+    steps = 1200
+    cfg, params, inp, model, cond = _gen_case(1280)
+    forced = inp["quantized"][0, 1:steps + 1].astype(np.int32)
+    u = np.full(steps, 0.5)
+    with torch.no_grad():
+        _, logits = generate_utterance(model.decoder, cond, u, n_steps=steps, forced=forced,
+                                       return_logits=True)
+    gen = O.WaveNetGenerator(O.sub(params, "decoder/"), cfg, 1)
+    cond_c = cond.cpu()
+    xo = torch.zeros(1, cfg.input_dim, 1, 1)
+    ref = []
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 2))
+    with torch.no_grad():
+        for i in range(steps):
+            ref.append(gen.generate(xo, cond_c[:, :, i:i + 1])[0, :, 0, 0].clone())
+            xo = torch.zeros(1, cfg.input_dim, 1, 1)
+            xo[0, int(forced[i])] = 1
+    ref = torch.stack(ref)
+    worst = max(rel_err(logits[a:b], ref[a:b]) for a, b in ((0, 400), (400, 1000), (1000, steps)))
+    tail = rel_err(logits[1030:], ref[1030:])       # steps that read wrapped ring slots
+    print(f"configs[4] teacher-forced {steps} steps: worst rel err {worst:.2e}, after the wrap {tail:.2e}")
+    assert worst < TOL and tail < TOL
+
+
+def test_generate_config4_free_running_identical_indices():
+    """300 free-running categorical steps at the configs[4] size: the sampled mu-law indices are
+    identical to the oracle's generate.py loop (numpy.random.choice rule from the same uniforms)."""
+    steps = 300
+    cfg, params, inp, model, cond = _gen_case(320)
+    u = np.random.default_rng(4).uniform(size=steps)
+    out_o, logits_o = O.generate_loop(params, cfg, inp["x_enc"], inp["speaker"], u, n_steps=steps,
+                                      return_logits=True)
+    with torch.no_grad():
+        out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps, return_logits=True)
+    assert np.array_equal(out_g.cpu().numpy()[:steps], out_o[:steps])
+    assert rel_err(logits_g, logits_o) < TOL
