@@ -94,7 +94,7 @@ def build_model(cfg, device, mode, seed=1234):
         for name, p in model.named_parameters():
             if name.endswith(".b"):
                 p.normal_(0.0, 0.01)       # exercise the bias paths
-    wavenet.set_mode(mode)
+    decoder.set_mode(mode)      # both the training copy and the EMA (evaluation) copy
     return model.to(device)
 
 

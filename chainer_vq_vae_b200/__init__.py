@@ -9,7 +9,7 @@ from .links import Convolution2D, DilatedConvolution2D, EmbedID, namedparams
 from .losses import logistic_loss, softmax_cross_entropy
 from .net import VAE, ConditionEmbed, Encoder
 from .updaters import Adam, GradBucket, VQVAE_ParallelUpdater, VQVAE_StandardUpdater
-from .snapshot import load_chainer_snapshot, save_chainer_snapshot
+from .snapshot import load_chainer_snapshot, load_optimizer_state, save_chainer_snapshot
 from .utils import VQ, ExponentialMovingAverage, MuLaw
 from .wavenet import ResidualBlock, ResidualNet, WaveNet
 
@@ -19,5 +19,5 @@ __all__ = [
     "VQVAE_ParallelUpdater", "Adam", "GradBucket", "softmax_cross_entropy", "logistic_loss",
     "conv", "embed_gather", "residual_stack", "vq_lookup", "Convolution2D",
     "DilatedConvolution2D", "EmbedID", "namedparams", "MODES", "VqwError", "launch_count",
-    "load_chainer_snapshot", "save_chainer_snapshot",
+    "load_chainer_snapshot", "save_chainer_snapshot", "load_optimizer_state",
 ]

@@ -22,14 +22,16 @@ embed_gather_fwd_kernel(const int32_t* __restrict__ q, const float* __restrict__
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 16;
   if (t >= T) return;
+  // an index outside [0, Q) is an all-zero input column (generate.py:51 starts from one)
   const int q1 = q[(int64_t)b * T + t];
   const int q0 = (t > 0) ? q[(int64_t)b * T + t - 1] : -1;
+  const bool ok0 = q0 >= 0 && q0 < Q, ok1 = q1 >= 0 && q1 < Q;
 #pragma unroll 4
   for (int c = c0; c < min(c0 + 16, Cr); ++c) {
     float v = bias ? __ldg(bias + c) : 0.0f;
     const float* wr = W + (int64_t)c * Q * 2;
-    if (q0 >= 0) v += __ldg(wr + 2 * q0);
-    v += __ldg(wr + 2 * q1 + 1);
+    if (ok0) v += __ldg(wr + 2 * q0);
+    if (ok1) v += __ldg(wr + 2 * q1 + 1);
     out[((int64_t)b * Cr + c) * T + t] = v;
   }
 }
@@ -46,13 +48,14 @@ embed_gather_bwd_kernel(const int32_t* __restrict__ q, const float* __restrict__
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const int q1 = q[(int64_t)b * T + t];
     const int q0 = (t > 0) ? q[(int64_t)b * T + t - 1] : -1;
+    const bool ok0 = q0 >= 0 && q0 < Q, ok1 = q1 >= 0 && q1 < Q;
 #pragma unroll
     for (int cc = 0; cc < EG_CT; ++cc) {
       int c = c0 + cc;
       if (c >= Cr) break;
       float gv = __ldg(g + ((int64_t)b * Cr + c) * T + t);
-      if (q0 >= 0) atomicAdd(hist + (cc * Q + q0) * 2, gv);
-      atomicAdd(hist + (cc * Q + q1) * 2 + 1, gv);
+      if (ok0) atomicAdd(hist + (cc * Q + q0) * 2, gv);
+      if (ok1) atomicAdd(hist + (cc * Q + q1) * 2 + 1, gv);
       atomicAdd(bsum + cc, gv);
     }
   }

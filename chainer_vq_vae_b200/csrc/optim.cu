@@ -49,30 +49,51 @@ ema_kernel(float* __restrict__ ema, const float* __restrict__ target, int64_t n,
     ema[i] = decay * target[i] + (1.0f - decay) * ema[i];
 }
 
-// one warp per (b, t) column of y (B,Q,T): lanes stride over the Q classes
+// labels outside [0, Q) are ignored (Chainer's ignore_label = -1): they add nothing to the loss,
+// get a zero gradient row and do not count in the normalisation (normalize=True)
+__global__ void __launch_bounds__(256)
+count_valid_kernel(const int32_t* __restrict__ tgt, int64_t n, int Q, double* __restrict__ count) {
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = tgt[i];
+    c += (k >= 0 && k < Q) ? 1 : 0;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (double)c);
+}
+
+// thread = one time step (coalesced along T); loops over the Q classes three times
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ y, const int32_t* __restrict__ tgt,
-                  float* __restrict__ gy, double* __restrict__ loss, int B, int Q, int T,
-                  float inv_n) {
-  // thread = one time step (coalesced along T); loops over the Q classes three times
+                  float* __restrict__ gy, double* __restrict__ loss, int B, int Q, int T) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
+  const double nvalid = loss[1];
+  const float inv_n = nvalid > 0.0 ? (float)(1.0 / nvalid) : 0.0f;
   double local = 0.0;
   if (t < T) {
     const float* yc = y + (int64_t)b * Q * T + t;
-    float mx = -INFINITY;
-    for (int q = 0; q < Q; ++q) mx = fmaxf(mx, __ldg(yc + (int64_t)q * T));
-    float s = 0.0f;
-    for (int q = 0; q < Q; ++q) s += expf(__ldg(yc + (int64_t)q * T) - mx);
-    const float lse = mx + logf(s);
     const int k = tgt[(int64_t)b * T + t];
-    local = (double)(lse - __ldg(yc + (int64_t)k * T));
-    if (gy) {
-      float* gc = gy + (int64_t)b * Q * T + t;
-      for (int q = 0; q < Q; ++q) {
-        const float pq = expf(__ldg(yc + (int64_t)q * T) - lse);
-        gc[(int64_t)q * T] = (pq - (q == k ? 1.0f : 0.0f)) * inv_n;
+    const bool valid = k >= 0 && k < Q;
+    if (valid) {
+      float mx = -INFINITY;
+      for (int q = 0; q < Q; ++q) mx = fmaxf(mx, __ldg(yc + (int64_t)q * T));
+      float s = 0.0f;
+      for (int q = 0; q < Q; ++q) s += expf(__ldg(yc + (int64_t)q * T) - mx);
+      const float lse = mx + logf(s);
+      local = (double)(lse - __ldg(yc + (int64_t)k * T));
+      if (gy) {
+        float* gc = gy + (int64_t)b * Q * T + t;
+        for (int q = 0; q < Q; ++q) {
+          const float pq = expf(__ldg(yc + (int64_t)q * T) - lse);
+          gc[(int64_t)q * T] = (pq - (q == k ? 1.0f : 0.0f)) * inv_n;
+        }
       }
+    } else if (gy) {
+      float* gc = gy + (int64_t)b * Q * T + t;
+      for (int q = 0; q < Q; ++q) gc[(int64_t)q * T] = 0.0f;
     }
   }
 #pragma unroll
@@ -127,9 +148,10 @@ extern "C" int vqw_softmax_ce(const float* y, const int32_t* t, float* gy, doubl
   if (B == 0 || T == 0) return 0;
   VQW_REQUIRE(y && t && loss, "vqw_softmax_ce: null pointer");
   VQW_REQUIRE(B <= 65535, "vqw_softmax_ce: B > 65535");
+  count_valid_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(t, (int64_t)B * T, Q, loss + 1);
+  VQW_CHECK_LAUNCH("count_valid_kernel");
   dim3 grid(ceil_div(T, 256), B);
-  softmax_ce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, t, gy, loss, B, Q, T,
-                                                         1.0f / ((float)B * (float)T));
+  softmax_ce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, t, gy, loss, B, Q, T);
   VQW_CHECK_LAUNCH("softmax_ce_kernel");
   return 0;
 }

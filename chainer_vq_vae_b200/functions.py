@@ -238,7 +238,8 @@ class _ResidualStack(torch.autograd.Function):
     reverse with the shared g_skip and the accumulated g_condition."""
 
     @staticmethod
-    def forward(ctx, x, cond, dilations, fs, mode, keep_last_residual, grad_targets, *weights):
+    def forward(ctx, x, cond, dilations, fs, mode, keep_last_residual, grad_targets,
+                grad_enabled, *weights):
         ctx.grad_targets = grad_targets
         x, cond = _f32c(x), _f32c(cond)
         B, Cr, T = _as3(x)
@@ -251,7 +252,9 @@ class _ResidualStack(torch.autograd.Function):
         Cd = weights[0].shape[0]
         Cs = weights[6].shape[0]
         skip = torch.empty((B, Cs, T, 1), device=x.device, dtype=torch.float32)
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad mirrors requires_grad, NOT the grad mode (inside forward() grad mode
+        # is always off): inference under no_grad must not take the save-for-backward path
+        need_grad = grad_enabled and any(ctx.needs_input_grad)
         tc_mode = mode != L.MODE_FP32
 
         def new(ch):
@@ -357,13 +360,13 @@ class _ResidualStack(torch.autograd.Function):
                 L.ptr(tc_saved), L.stream()), "vqw_resnet_backward")
         if direct:
             gws = [None] * len(gws)
-        return (g_res, gcond, None, None, None, None, None, *gws)
+        return (g_res, gcond, None, None, None, None, None, None, *gws)
 
 
 def residual_stack(x, cond, dilations, fs, weights, mode=L.MODE_FP32, keep_last_residual=False,
                    grad_targets=None):
     return _ResidualStack.apply(x, cond, tuple(dilations), fs, mode, keep_last_residual,
-                                grad_targets, *weights)
+                                grad_targets, torch.is_grad_enabled(), *weights)
 
 
 # ---------------------------------------------------------------------------------------
@@ -427,18 +430,19 @@ class _Head(torch.autograd.Function):
     GEMMs (ReLU masks applied in the epilogue) and one grouped weight-gradient launch."""
 
     @staticmethod
-    def forward(ctx, skip, W1, b1, W2, b2, mode):
+    def forward(ctx, skip, W1, b1, W2, b2, mode, grad_enabled):
         skip, W1, b1, W2, b2 = (_f32c(t) for t in (skip, W1, b1, W2, b2))
         B, Cs, T = _as3(skip)
         Q = W2.shape[0]
         d = L.HeadDesc()
         d.B, d.T, d.Cs, d.Q, d.mode = B, T, Cs, Q, mode
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = grad_enabled and any(ctx.needs_input_grad)
         y = torch.empty((B, Q, T, 1), device=skip.device, dtype=torch.float32)
         ws = torch.empty(int(L.lib.vqw_head_workspace(C.byref(d))), device=skip.device,
                          dtype=torch.uint8)
+        # inference: the activation planes live in the workspace (vqw_head_forward, saved = NULL)
         saved = torch.empty(int(L.lib.vqw_head_saved_bytes(C.byref(d))), device=skip.device,
-                            dtype=torch.uint8)
+                            dtype=torch.uint8) if (need_grad or d.Q < d.Cs) else None
         with L.timed("head_forward"):
             L.check(L.lib.vqw_head_forward(C.byref(d), L.ptr(skip), L.ptr(W1), L.ptr(b1), L.ptr(W2),
                                            L.ptr(b2), L.ptr(y), L.ptr(ws), L.ptr(saved), L.stream()),
@@ -467,11 +471,11 @@ class _Head(torch.autograd.Function):
                                             L.ptr(gskip), L.ptr(gW1), L.ptr(gb1), L.ptr(gW2),
                                             L.ptr(gb2), L.ptr(ws), L.ptr(ctx.tc_saved), L.stream()),
                     "vqw_head_backward")
-        return gskip, gW1, gb1, gW2, gb2, None
+        return gskip, gW1, gb1, gW2, gb2, None, None
 
 
 def head(skip, W1, b1, W2, b2, mode):
-    return _Head.apply(skip, W1, b1, W2, b2, mode)
+    return _Head.apply(skip, W1, b1, W2, b2, mode, torch.is_grad_enabled())
 
 
 # ---------------------------------------------------------------------------------------

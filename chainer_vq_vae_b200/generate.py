@@ -25,7 +25,12 @@ def _desc(wavenet, T_total, n_steps, t_start):
     d.fs, d.Cr, d.Cd = wavenet.filter_size, wavenet.residual_channels, wavenet.dilated_channels
     d.Cs, d.Cc, d.Q = wavenet.skip_channels, wavenet.condition_dim, wavenet.proj2.W.shape[0]
     d.T_total, d.n_steps, d.t_start = T_total, n_steps, t_start
-    d.use_logistic = 1 if wavenet.input_dim == 1 else 0
+    use_logistic = bool(getattr(wavenet, "use_logistic", wavenet.input_dim == 1))
+    if use_logistic != (wavenet.input_dim == 1):
+        raise NotImplementedError(
+            "generation needs use_logistic == (input_dim == 1): generate.py:116-145 feeds a scalar "
+            "back for the mixture-of-logistics decoder and a one-hot for the categorical one")
+    d.use_logistic = 1 if use_logistic else 0
     d.log_scale_min = float(wavenet.log_scale_min)
     warr = (L.ResblockWeights * n)()
     for i, b in enumerate(blocks):

@@ -10,25 +10,26 @@ class _SoftmaxCE(torch.autograd.Function):
     """Loss and d loss / d y in one pass over the logits (vqw_softmax_ce)."""
 
     @staticmethod
-    def forward(ctx, y, t):
-        import ctypes as C
+    def forward(ctx, y, t, grad_enabled):
         from . import _lib as L
         yc = y.contiguous()
         B, Q, T = yc.shape[0], yc.shape[1], yc.shape[2]
         tc = t.reshape(B, T).to(torch.int32).contiguous()
-        need = ctx.needs_input_grad[0]
+        # needs_input_grad reflects requires_grad, not the grad mode: under no_grad / in
+        # evaluation the gradient tensor must not be allocated (ADVICE r1)
+        need = grad_enabled and ctx.needs_input_grad[0]
         gy = torch.empty_like(yc) if need else None
-        loss = torch.zeros(1, device=y.device, dtype=torch.float64)
+        loss = torch.zeros(2, device=y.device, dtype=torch.float64)   # {loss, valid-label count}
         L.check(L.lib.vqw_softmax_ce(L.ptr(yc), L.ptr(tc), L.ptr(gy), L.ptr(loss), B, Q, T, L.stream()),
                 "vqw_softmax_ce")
         if need:
             ctx.save_for_backward(gy)
-        return loss.to(torch.float32).reshape(())
+        return loss[0].to(torch.float32).reshape(())
 
     @staticmethod
     def backward(ctx, g):
         (gy,) = ctx.saved_tensors
-        return gy * g, None
+        return gy * g, None, None
 
 
 def softmax_cross_entropy(y, t):
@@ -36,22 +37,21 @@ def softmax_cross_entropy(y, t):
     y (B,Q,T,1) f32, t (B,T,1) int.  CUDA tensors run the fused libvqw kernel; the torch
     formula below is the generic definition for other tensors."""
     if y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[3] == 1:
-        return _SoftmaxCE.apply(y, t)
-    logp = F.log_softmax(y, dim=1)
-    picked = torch.gather(logp, 1, t.long().unsqueeze(1))
-    return -picked.sum() / t.numel()
+        return _SoftmaxCE.apply(y, t, torch.is_grad_enabled())
+    # generic definition (host-side checks only; CUDA tensors never take it)
+    return F.cross_entropy(y, t.long().reshape(y.shape[0], *y.shape[2:]), ignore_index=-1)
 
 
 class _MolLoss(torch.autograd.Function):
     """modules.py:169-230 and its gradient in one pass over the decoder output (vqw_mol_loss)."""
 
     @staticmethod
-    def forward(ctx, y, t, quantize, log_scale_min):
+    def forward(ctx, y, t, quantize, log_scale_min, grad_enabled):
         from . import _lib as L
         yc = y.contiguous()
         B, C3, T = yc.shape[0], yc.shape[1], yc.shape[2]
         tc = t.reshape(B, T).to(torch.float32).contiguous()
-        need = ctx.needs_input_grad[0]
+        need = grad_enabled and ctx.needs_input_grad[0]
         gy = torch.empty_like(yc) if need else None
         loss = torch.zeros(1, device=y.device, dtype=torch.float64)
         L.check(L.lib.vqw_mol_loss(L.ptr(yc), L.ptr(tc), L.ptr(gy), L.ptr(loss), B, C3 // 3, T,
@@ -63,7 +63,7 @@ class _MolLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (gy,) = ctx.saved_tensors
-        return gy * g, None, None, None
+        return gy * g, None, None, None, None
 
 
 def logistic_loss(y, t, quantize, log_scale_min):
@@ -71,7 +71,7 @@ def logistic_loss(y, t, quantize, log_scale_min):
     the same definition term by term for other tensors."""
     if (y.is_cuda and y.dtype == torch.float32 and y.dim() == 4 and y.shape[3] == 1
             and y.shape[1] % 3 == 0 and t.numel() == y.shape[0] * y.shape[2]):
-        return _MolLoss.apply(y, t, quantize, log_scale_min)
+        return _MolLoss.apply(y, t, quantize, log_scale_min, torch.is_grad_enabled())
     nr_mix = y.shape[1] // 3
     logit_probs = y[:, :nr_mix]
     means = y[:, nr_mix:2 * nr_mix]

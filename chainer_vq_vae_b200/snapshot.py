@@ -59,10 +59,44 @@ def load_chainer_snapshot(path, model, use_ema: bool = True) -> Tuple[List[str],
     return missing, unexpected
 
 
-def save_chainer_snapshot(path, model) -> None:
-    """Write `model`'s parameters under the reference's key layout (the trainer/optimizer state
-    of a full Chainer snapshot is not reproduced)."""
+OPT_PREFIX = "updater/optimizer:main/"
+
+
+def save_chainer_snapshot(path, model, optimizer=None, iteration=None) -> None:
+    """Write `model`'s parameters under the reference's key layout.  With `optimizer` (this
+    package's Adam) the per-parameter moments are stored the way Chainer's serializer lays out
+    an optimizer (`updater/optimizer:main/<param path>/{m,v}`, `.../t`) together with the
+    iteration count, so that training can be resumed (`train.py --resume`).  The file is
+    written through a file object: `path` is used verbatim (numpy.savez would append `.npz`
+    to Chainer's extensionless `snapshot_iter_N` names)."""
     out = {}
     for name, p in model.named_parameters():
         out[PREFIX + name.replace(".", "/")] = p.detach().cpu().numpy()
-    numpy.savez(path, **out)
+    if optimizer is not None:
+        names = {id(p): n for n, p in model.named_parameters()}
+        for p, m, v in zip(optimizer.params, optimizer.m, optimizer.v):
+            key = OPT_PREFIX + names[id(p)].replace(".", "/")
+            out[key + "/m"] = m.detach().cpu().numpy()
+            out[key + "/v"] = v.detach().cpu().numpy()
+        out[OPT_PREFIX + "t"] = numpy.asarray(optimizer.t, dtype=numpy.int64)
+    if iteration is not None:
+        out["updater/iteration"] = numpy.asarray(iteration, dtype=numpy.int64)
+    if hasattr(path, "write"):
+        numpy.savez(path, **out)
+    else:
+        with open(path, "wb") as f:
+            numpy.savez(f, **out)
+
+
+def load_optimizer_state(path, model, optimizer) -> int:
+    """Restore Adam's moments / step count written by save_chainer_snapshot(optimizer=...).
+    Returns the stored iteration (0 if absent)."""
+    npz = numpy.load(path) if not hasattr(path, "files") else path
+    names = {id(p): n for n, p in model.named_parameters()}
+    with torch.no_grad():
+        for p, m, v in zip(optimizer.params, optimizer.m, optimizer.v):
+            key = OPT_PREFIX + names[id(p)].replace(".", "/")
+            m.copy_(torch.from_numpy(numpy.ascontiguousarray(npz[key + "/m"])))
+            v.copy_(torch.from_numpy(numpy.ascontiguousarray(npz[key + "/v"])))
+    optimizer.t = int(npz[OPT_PREFIX + "t"])
+    return int(npz["updater/iteration"]) if "updater/iteration" in npz.files else 0

@@ -253,6 +253,33 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
         super().__init__(iterator, optimizer, converter, device, loss_func, use_cuda_graph,
                          graph_warmup)
         self.group = group
+        self._synced = False
+
+    def sync_replicas(self) -> None:
+        """The reference re-broadcasts the main model's parameters after every step
+        (`copyparams`, updaters.py:76-77).  Here every rank applies the identical Adam update to
+        the identical all-reduced gradient, so ONE broadcast from rank 0 -- parameters, both Adam
+        moments, the step count and the decoder's EMA copy -- before the first step is
+        equivalent and makes the replicas independent of per-process seeds / resume state."""
+        self._synced = True
+        if not (dist.is_available() and dist.is_initialized()) or \
+                dist.get_world_size(self.group) == 1:
+            return
+        opt = self._optimizers["main"]
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        bufs = [getattr(opt, n) for n in ("flat_p", "flat_m", "flat_v") if hasattr(opt, n)]
+        if not bufs:                                   # an optimiser without flat buffers
+            bufs = [p.data for p in opt.target.parameters()]
+        seen = {b.data_ptr() for b in bufs}
+        for m in opt.target.modules():                 # EMA copies are not optimiser parameters
+            ema = getattr(m, "ema", None)
+            if isinstance(ema, nn.Module):
+                bufs += [p.data for p in ema.parameters() if p.data_ptr() not in seen]
+        for b in bufs:
+            dist.broadcast(b, src=src, group=self.group)
+        t = torch.tensor([opt.t], device=bufs[0].device, dtype=torch.int64)
+        dist.broadcast(t, src=src, group=self.group)
+        opt.t = int(t)
 
     @staticmethod
     def split(batch: Sequence, rank: int, n: int):
@@ -264,6 +291,11 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
         batch = self._iterators["main"].next()
         in_arrays = self.converter(self.split(batch, rank, n), self.device)
         return self.update_from_arrays(in_arrays)
+
+    def update_from_arrays(self, in_arrays):
+        if not self._synced:
+            self.sync_replicas()
+        return super().update_from_arrays(in_arrays)
 
     def _reduce(self, optimizer) -> None:
         optimizer.bucket.allreduce(self.group)                      # addgrads, :71-72

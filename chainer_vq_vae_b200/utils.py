@@ -84,6 +84,13 @@ class ExponentialMovingAverage(nn.Module):
         for p in self.ema.parameters():
             p.requires_grad_(False)
 
+    def set_mode(self, mode) -> None:
+        """Arithmetic mode of BOTH copies (the evaluation copy is a deepcopy: it does not see a
+        later set_mode on the target)."""
+        for m in (self.target, self.ema):
+            if hasattr(m, "set_mode"):
+                m.set_mode(mode)
+
     def forward(self, *args, **kwargs):
         if self.training:                                    # configuration.config.train
             ys = self.target(*args, **kwargs)

@@ -59,14 +59,27 @@ class ResidualNet(nn.ModuleList):
         self.filter_size = filter_size
         self.mode = L.MODE_FP32
 
+    def tc_supported(self, x, condition) -> bool:
+        """Shapes the tcgen05 kernels take (resnet_tc_supported, csrc/resblock_tc.cu)."""
+        blk = self[0]
+        Cd, Cr = blk.conv.W.shape[0], blk.conv.W.shape[1]
+        Cs, Cc, T = blk.skip.W.shape[0], condition.shape[1], x.shape[2]
+        return (Cd == 512 and Cr % 256 == 0 and Cs % 256 == 0 and Cc % 32 == 0 and T >= 128
+                and T % 8 == 0 and x.shape[0] <= 65535)
+
     def forward(self, x, condition):
         """Sum of the blocks' skip outputs (modules.py:89-96); the last block's residual is
-        never used by the reference (modules.py:52,91) and is not computed."""
+        never used by the reference (modules.py:52,91) and is not computed.  Shapes outside
+        the tensor-core kernels' tiling (short or odd-length utterances, small channel counts)
+        run the fp32 CUDA-core kernels, like the head does."""
         weights: List[torch.Tensor] = []
         for block in self:
             weights += block.weights()
+        mode = self.mode
+        if mode != L.MODE_FP32 and not self.tc_supported(x, condition):
+            mode = L.MODE_FP32
         return Fn.residual_stack(x, condition, [b.dilation for b in self], self.filter_size,
-                                 weights, self.mode, grad_targets=tuple(weights))
+                                 weights, mode, grad_targets=tuple(weights))
 
 
 class WaveNet(nn.Module):
@@ -84,6 +97,13 @@ class WaveNet(nn.Module):
         output_dim = n_mixture if use_logistic else quantize        # modules.py:137-140
         self.proj2 = Convolution2D(skip_channels, output_dim, 1)
         self.input_dim = input_dim
+        self.use_logistic = bool(use_logistic)
+        if self.use_logistic and input_dim != 1:
+            # generate.py:116-137 feeds the drawn VALUE back as a (1,1,1,1) input; a one-hot
+            # decoder with a mixture-of-logistics output has no feedback rule in the reference
+            import warnings
+            warnings.warn("use_logistic=True with input_dim != 1: training works, generation "
+                          "is undefined in the reference (generate.py:137) and raises here")
         self.quantize = quantize
         self.skip_channels = skip_channels
         self.log_scale_min = log_scale_min

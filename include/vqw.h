@@ -250,8 +250,10 @@ int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW,
 /* ------------------------------------------------------------------------------------
  * Loss and optimiser passes over flat fp32 ranges (one HBM-bound kernel each).
  *   vqw_softmax_ce  chainer.functions.softmax_cross_entropy (train.py:95): y (B,Q,T) f32 logits,
- *                   t (B,T) i32 labels -> *loss (f64, ACCUMULATED: zero it first) = mean NLL and
- *                   gy (B,Q,T) = d loss / d y (or NULL).
+ *                   t (B,T) i32 labels -> loss[0] (f64, ACCUMULATED: zero both first) = mean NLL
+ *                   over the VALID labels, loss[1] = their count (labels outside [0,Q), e.g.
+ *                   Chainer's ignore_label -1, add nothing, get a zero gradient and are not
+ *                   counted: normalize=True), gy (B,Q,T) = d loss / d y (or NULL).
  *   vqw_adam_step   chainer.optimizers.Adam's rule (train.py:101): m += (1-b1)(g-m);
  *                   v += (1-b2)(g*g-v); p -= lr*m/(sqrt(v)+eps); lr already bias corrected.
  *   vqw_ema_update  ExponentialMovingAverage, utils.py:153-154: ema = decay*target + (1-decay)*ema.

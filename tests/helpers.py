@@ -28,7 +28,7 @@ def build_model(cfg: O.Config, params, device="cuda", ema_decay=None, mode="fp32
     loss = wavenet.calculate_logistic_loss if cfg.use_logistic else V.softmax_cross_entropy
     model = V.VAE(encoder, decoder, cond, cfg.d, cfg.k, cfg.beta, loss)
     load_params(model, params, ema=bool(ema_decay))
-    wavenet.set_mode(mode)
+    decoder.set_mode(mode)      # both the training copy and the EMA (evaluation) copy
     return model.to(device)
 
 

@@ -81,3 +81,59 @@ def test_two_rank_gloo_allreduce_equals_reference_parallel_updater():
         p = params[k].clone()
         O.adam_step(p, total[k], torch.zeros_like(p), torch.zeros_like(p), 1, 1e-4)
         assert np.allclose(res[0][2][k], p.numpy(), atol=1e-7), k
+
+
+def _sync_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import chainer_vq_vae_b200 as V
+    torch.set_num_threads(1)
+    torch.manual_seed(100 + rank)                       # replicas built from DIFFERENT seeds
+
+    class Dec(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.randn(7, 5))
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.randn(33))
+            self.decoder = V.ExponentialMovingAverage(Dec(), 0.999)
+            self.vq = torch.nn.Module()
+    model = Holder()
+    with torch.no_grad():
+        model.decoder.ema.w.add_(rank + 1.0)
+    opt = V.Adam(1e-3).setup(model)
+    opt.flat_m.normal_()
+    opt.flat_v.uniform_()
+    opt.t = 10 + rank
+    upd = V.VQVAE_ParallelUpdater(None, opt)
+    upd.sync_replicas()
+    q.put((rank, opt.flat_p.clone().numpy(), opt.flat_m.clone().numpy(), opt.flat_v.clone().numpy(),
+           model.decoder.ema.w.detach().numpy().copy(), opt.t))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_parallel_updater_broadcasts_rank0_state_once():
+    """copyparams (updaters.py:76-77) replaced by one broadcast before the first step: replicas
+    built from different seeds / resume states end up with rank 0's parameters, Adam moments,
+    step count and EMA copy."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i in range(1, 5):
+        assert np.array_equal(res[0][i], res[1][i]), i
+    assert res[0][5] == res[1][5] == 10

@@ -137,3 +137,25 @@ def test_chainer_snapshot_roundtrip_and_reference_keys(tmp_path):
     assert load_chainer_snapshot(str(p2), again) == ([], [])
     for (n, a), (_, b) in zip(wrapped.named_parameters(), again.named_parameters()):
         assert torch.equal(a, b), n
+
+
+def test_snapshot_keeps_optimizer_state_and_extensionless_names(tmp_path):
+    """`--resume` (train.py:152-153): Adam's moments, step count and the iteration survive a
+    save/load; Chainer-style extensionless names are written verbatim (no '.npz' appended)."""
+    import chainer_vq_vae_b200 as V
+    from helpers import build_model
+    cfg = O.config_cpu()
+    model = build_model(cfg, O.make_params(cfg), device="cpu")
+    opt = V.Adam(1e-3).setup(model)
+    opt.flat_m.normal_()
+    opt.flat_v.uniform_()
+    opt.t = 12
+    path = tmp_path / "snapshot_iter_12"
+    V.save_chainer_snapshot(str(path), model, optimizer=opt, iteration=12)
+    assert path.exists() and not (tmp_path / "snapshot_iter_12.npz").exists()
+    model2 = build_model(cfg, O.make_params(cfg, seed=5), device="cpu")
+    opt2 = V.Adam(1e-3).setup(model2)
+    assert V.load_chainer_snapshot(str(path), model2) == ([], [])
+    assert V.load_optimizer_state(str(path), model2, opt2) == 12
+    assert opt2.t == 12 and torch.equal(opt2.flat_m, opt.flat_m) and torch.equal(opt2.flat_v, opt.flat_v)
+    assert torch.equal(opt2.flat_p, opt.flat_p)
