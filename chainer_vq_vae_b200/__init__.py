@@ -6,6 +6,7 @@ from . import _lib
 from ._lib import MODES, VqwError, launch_count
 from .functions import conv, embed_gather, residual_stack, straight_through, vq_lookup
 from .links import Convolution2D, DilatedConvolution2D, EmbedID, namedparams
+from .generate import generate_utterance, output_to_wave, write_wav
 from .losses import logistic_loss, softmax_cross_entropy
 from .net import VAE, ConditionEmbed, Encoder
 from .updaters import Adam, GradBucket, VQVAE_ParallelUpdater, VQVAE_StandardUpdater
@@ -19,5 +20,5 @@ __all__ = [
     "VQVAE_ParallelUpdater", "Adam", "GradBucket", "softmax_cross_entropy", "logistic_loss",
     "conv", "embed_gather", "residual_stack", "vq_lookup", "Convolution2D",
     "DilatedConvolution2D", "EmbedID", "namedparams", "MODES", "VqwError", "launch_count",
-    "load_chainer_snapshot", "save_chainer_snapshot", "load_optimizer_state",
+    "generate_utterance", "output_to_wave", "write_wav", "load_chainer_snapshot", "save_chainer_snapshot", "load_optimizer_state",
 ]

@@ -121,3 +121,25 @@ def generate_utterance(wavenet, condition: torch.Tensor, uniforms, n_steps: Opti
     out = torch.zeros(T, device=dev, dtype=torch.float64)
     out[:steps] = (samples.view(torch.float32) if mol else samples).double()
     return (out, logits) if return_logits else out
+
+
+# ---------------------------------------------------------------------------------------
+# output formats (generate.py:147-153)
+# ---------------------------------------------------------------------------------------
+def output_to_wave(output, quantize: int = 256, use_logistic: bool = False) -> numpy.ndarray:
+    """generate.py:149-152: the mixture-of-logistics decoder emits the waveform itself, the
+    categorical decoder emits mu-law indices that MuLaw(quantize).itransform expands
+    (utils.py:25-29, with its mu**|y| quirk)."""
+    from .utils import MuLaw
+    out = output.detach().cpu().numpy() if torch.is_tensor(output) else numpy.asarray(output)
+    if use_logistic:
+        return out.astype(numpy.float32)
+    return MuLaw(quantize).itransform(out)
+
+
+def write_wav(path, output, sr: int = 16000, quantize: int = 256, use_logistic: bool = False) -> None:
+    """generate.py:153 `librosa.output.write_wav(args.output, wave, params.sr)`: librosa 0.5.1
+    hands the float32 array to scipy.io.wavfile.write, i.e. a 32-bit IEEE-float mono WAVE file."""
+    from scipy.io import wavfile
+    wave = output_to_wave(output, quantize, use_logistic)
+    wavfile.write(str(path), int(sr), wave.astype(numpy.float32))

@@ -1,7 +1,6 @@
 """Encoder / ConditionEmbed / VAE behind the reference's callable surface (net.py:8-96)."""
 from __future__ import annotations
 
-import numpy
 import torch
 from torch import nn
 
@@ -30,37 +29,6 @@ class Encoder(nn.Module):
         h = self.conv4(h, relu=True)
         h = self.conv5(h, relu=True)
         return self.conv6(h)
-
-
-_RESIZE_CACHE = {}
-
-
-def _resize_plan(H, out_h, device):
-    """F.resize_images coordinates for a (H,1) -> (out_h,1) resize [dep], in exact integer
-    form: v = i*(H-1)/(out_h-1), v0 = min(floor v, H-2), frac = v - v0 (SURVEY.md appendix B;
-    fp32 coordinates would drift by 9e-5 at T=24000)."""
-    key = (H, out_h, str(device))
-    if key not in _RESIZE_CACHE:
-        i = numpy.arange(out_h, dtype=numpy.int64)
-        num = i * (H - 1)
-        den = max(out_h - 1, 1)
-        v0 = numpy.minimum(num // den, H - 2)
-        frac = (num - v0 * den).astype(numpy.float64) / den
-        w1 = torch.from_numpy(frac.astype(numpy.float32)).to(device).reshape(1, 1, out_h, 1)
-        w0 = torch.from_numpy((1.0 - frac).astype(numpy.float32)).to(device).reshape(1, 1, out_h, 1)
-        i0 = torch.from_numpy(v0).to(device)
-        _RESIZE_CACHE[key] = (i0, i0 + 1, w0, w1)
-    return _RESIZE_CACHE[key]
-
-
-def resize_images_h(x, out_h):
-    """F.resize_images(x, (out_h, 1)) for width-1 images: 1-D align-corners linear
-    interpolation; H == 1 degenerates to a broadcast (net.py:60-61)."""
-    B, Cn, H, _ = x.shape
-    if H == 1:
-        return x.expand(B, Cn, out_h, 1)
-    i0, i1, w0, w1 = _resize_plan(H, out_h, x.device)
-    return w0 * x.index_select(2, i0) + w1 * x.index_select(2, i1)
 
 
 class ConditionEmbed(nn.Module):
@@ -126,3 +94,28 @@ class VAE(nn.Module):
                             "loss3": loss3.detach(), "loss": loss.detach()}   # reporter, :93-95
         self.y = y.detach()
         return loss1, loss2, loss3
+
+    @torch.no_grad()
+    def generate(self, raw, speaker, use_ema=True, uniforms=None, seed=None, n_steps=None):
+        """The reference's convenience entry (models.py:74-105 / generate.py:104-145): encode
+        `raw` (1,1,T+1,1), quantise, embed the condition, then draw the whole utterance with the
+        persistent kernel.  `use_ema` picks the decoder copy like generate.py:70-76.  `uniforms`
+        are the draws numpy.random.choice / numpy.random.uniform would make (generated from
+        `seed` when omitted).  Returns the `output` array of generate.py:110,145 (length T, last
+        entry 0) as a float64 tensor."""
+        import numpy
+        from .generate import generate_utterance
+        dec = self.decoder
+        if hasattr(dec, "ema") and hasattr(dec, "target"):
+            dec = dec.ema if use_ema else dec.target
+        z = self.encoder(raw)
+        e = self.vq(z)
+        condition = self.condition_embed(e, speaker)
+        T = condition.shape[2]
+        steps = T - 1 if n_steps is None else min(n_steps, T - 1)
+        if uniforms is None:
+            per = dec.proj2.W.shape[0] // 3 if dec.input_dim == 1 else 1
+            uniforms = numpy.random.default_rng(seed).uniform(size=(steps, per))
+            if per == 1:
+                uniforms = uniforms[:, 0]
+        return generate_utterance(dec, condition, uniforms, n_steps=steps)

@@ -212,3 +212,28 @@ def test_generate_config4_free_running_identical_indices():
         out_g, logits_g = generate_utterance(model.decoder, cond, u, n_steps=steps, return_logits=True)
     assert np.array_equal(out_g.cpu().numpy()[:steps], out_o[:steps])
     assert rel_err(logits_g, logits_o) < TOL
+
+
+def test_vae_generate_entry_point_and_wav(tmp_path):
+    """VAE.generate(raw, speaker, use_ema) (the convenience entry of models.py:74-105) draws the
+    same utterance as the oracle's generate.py loop; use_ema selects the decoder copy like
+    generate.py:70-76; the result goes through MuLaw.itransform into a float WAVE file."""
+    from scipy.io import wavfile
+    cfg = O.config_cpu()
+    params, inp = _case(cfg, 256)
+    model = build_model(cfg, params, ema_decay=0.999).eval()
+    with torch.no_grad():                                   # make the two copies differ
+        for p in model.decoder.target.parameters():
+            p.mul_(1.01)
+    steps = 100
+    u = np.random.default_rng(0).uniform(size=steps)
+    out_o = O.generate_loop(params, cfg, inp["x_enc"], inp["speaker"], u, n_steps=steps)
+    raw = torch.from_numpy(inp["x_enc"]).cuda()
+    spk = torch.from_numpy(inp["speaker"]).cuda()
+    out_ema = model.generate(raw, spk, use_ema=True, uniforms=u, n_steps=steps)
+    out_tgt = model.generate(raw, spk, use_ema=False, uniforms=u, n_steps=steps)
+    assert np.array_equal(out_ema.cpu().numpy()[:steps], out_o[:steps])
+    assert not np.array_equal(out_tgt.cpu().numpy()[:steps], out_o[:steps])
+    V.write_wav(tmp_path / "gen.wav", out_ema, sr=16000, quantize=cfg.quantize)
+    sr, wave = wavfile.read(tmp_path / "gen.wav")
+    assert sr == 16000 and np.array_equal(wave, O.MuLaw(256).itransform(out_o))

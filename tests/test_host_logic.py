@@ -5,7 +5,6 @@ import torch
 
 import chainer_vq_vae_b200 as V
 from chainer_vq_vae_b200 import functions as Fn
-from chainer_vq_vae_b200.net import resize_images_h
 from oracle import vqvae_oracle as O
 
 
@@ -45,13 +44,21 @@ def test_straight_through_type_checks():
         V.straight_through(torch.zeros(2, 8, 5, 1, dtype=torch.int64), W)
 
 
-def test_resize_images_matches_chainer_coordinates():
+def test_generated_output_to_wav_matches_reference_formats(tmp_path):
+    """generate.py:147-153: categorical output = mu-law indices -> MuLaw.itransform -> float32
+    WAVE; mixture-of-logistics output is the waveform itself."""
+    from scipy.io import wavfile
     rng = np.random.default_rng(0)
-    for H, f in ((16, 64), (120, 64), (375, 64), (5, 3)):
-        x = torch.from_numpy(rng.normal(size=(2, 3, H, 1)).astype(np.float32))
-        assert torch.allclose(resize_images_h(x, H * f), O.resize_images_h(x, H * f), atol=2e-6)
-    g = torch.randn(2, 4, 1, 1)
-    assert torch.equal(resize_images_h(g, 7), g.expand(2, 4, 7, 1))
+    out = rng.integers(0, 256, size=4000).astype(np.float64)       # generate.py:110: float array
+    out[-1] = 0
+    V.write_wav(tmp_path / "a.wav", torch.from_numpy(out), sr=16000, quantize=256)
+    sr, wave = wavfile.read(tmp_path / "a.wav")
+    assert sr == 16000 and wave.dtype == np.float32 and wave.shape == (4000,)
+    assert np.array_equal(wave, O.MuLaw(256).itransform(out))
+    raw = rng.uniform(-1, 1, size=1000)
+    V.write_wav(tmp_path / "b.wav", raw, sr=22050, use_logistic=True)
+    sr, wave = wavfile.read(tmp_path / "b.wav")
+    assert sr == 22050 and np.array_equal(wave, raw.astype(np.float32))
 
 
 def test_adam_matches_chainer_rule_and_bucket_views():
