@@ -151,6 +151,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_config(mol, world, mode, graphed=False):
+    """The `config` object both arms print (the reference arm times a bounded sample of it)."""
+    B = CFG["batch"]
+    return {"workload": ("MoL decoder (use_logistic, n_mixture=10, input_dim=1): " if mol
+                         else "1xB200: ") +
+                        "batch=16/GPU length=7680 n_loop=2 n_layer=10 "
+                        "filter_size=3 512/512/256 k=512 d=64 mu-law-256 Cc=192",
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "mode": mode, "cuda_graph": graphed,
+            "l2": "per-step working set (>10 GB of activations) far exceeds the "
+                  "126 MB L2; no explicit flush"}
+
+
 def block_flops(cfg, n_samples, with_residual=True):
     Cr, Cd, Cs = cfg["residual_channels"], cfg["dilated_channels"], cfg["skip_channels"]
     Cc = cfg["local_condition_dim"] + cfg["global_condition_dim"]
@@ -172,22 +185,14 @@ def block_bytes(cfg, n_samples):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
+def train_workload(args, mol, steps, warmup, world, rank, local, dev, with_cpu_baseline):
+    """One training workload (categorical configs[1]/[2] or the MoL configs[3]) timed both ways
+    (device-resident and end to end); returns the record rank 0 prints."""
     import torch.distributed as dist
     import chainer_vq_vae_b200 as V
     from chainer_vq_vae_b200 import _lib as L
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libvqw has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     cfg = dict(CFG)
-    mol = args.workload == "train-mol"
     if mol:            # BASELINE.json configs[3]: use_logistic=True n_mixture=10 input_dim=1
         cfg.update(use_logistic=True, input_dim=1, n_mixture=30)
     B, T = cfg["batch"], cfg["length"]
@@ -236,7 +241,7 @@ def run_ours(args):
     # timed steps are the same load
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     launches_per_step = None
     if upd.use_cuda_graph:            # make sure the capture happens before the timed region
@@ -255,20 +260,20 @@ def run_ours(args):
     launches0 = V.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step_resident()
     e1.record()
     barrier()
     clocks = sampler.stop()
     launches = V.launch_count() - launches0
     if graphed:
-        launches = launches_per_step * args.steps     # replayed from the graph, not re-issued
+        launches = launches_per_step * steps          # replayed from the graph, not re-issued
     ms_total = e0.elapsed_time(e1)
     if graphed:
         # CUDA events cannot bracket kernels inside a replayed graph: the per-kernel timers (and the
         # roofline's launch duration) come from the same step issued eagerly right after
         L.enable_timers(True)
-        for _ in range(min(args.steps, 5)):
+        for _ in range(min(steps, 5)):
             upd._step(dev_batch)
         torch.cuda.synchronize()
     timers = L.timer_summary()
@@ -276,22 +281,22 @@ def run_ours(args):
     t_ms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms) / args.steps
+    ms_step = float(t_ms) / steps
     value = world * B * T / (ms_step * 1e-3)
 
     # ---- end-to-end arm: host batches through the public updater API ----
-    for _ in range(min(args.warmup, 3)):
+    for _ in range(min(warmup, 3)):
         upd.update()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         l1, l2, l3 = upd.update()
         host_losses = (float(l1), float(l2), float(l3))       # D2H read of the step's result
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T / (float(e2e_s) / args.steps)
+    e2e_value = world * B * T / (float(e2e_s) / steps)
     h2d = sum(t.numel() * t.element_size() for t in dev_batch)
 
     # ---- roofline of the fused residual-block forward kernel ----
@@ -327,25 +332,19 @@ def run_ours(args):
             pass
 
     cpu_baseline = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+    if with_cpu_baseline and world == 1 and rank == 0 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_sample(cfg, items=2, repeats=1)
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "audio-samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16, fp32 accumulate)",
                       "bf16": "bf16", "fp16": "fp16 (IEEE half operands, fp32 accumulate)"}[args.mode],
             "data": "synthetic (sinusoid mixtures, mu-law 256, random-init weights)",
-            "config": {"workload": ("MoL decoder (use_logistic, n_mixture=10, input_dim=1): " if mol
-                                    else "1xB200: ") +
-                                   "batch=16/GPU length=7680 n_loop=2 n_layer=10 "
-                                   "filter_size=3 512/512/256 k=512 d=64 mu-law-256 Cc=192",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
-                       "mode": args.mode, "cuda_graph": graphed,
-                       "l2": "per-step working set (>10 GB of activations) far exceeds the "
-                             "126 MB L2; no explicit flush"},
+            "config": workload_config(mol, world, args.mode, graphed),
             "e2e": {"value": e2e_value, "unit": "audio-samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 12, "losses": host_losses},
             "gpu_launches": launches,
@@ -355,9 +354,48 @@ def run_ours(args):
             "kernels_ms": {k: {"launches": n, "mean_ms": ms} for k, (n, ms) in timers.items()},
             "loss1": float(loss),
         }
-        print(json.dumps(line))
     upd.release_graph()
+    # free this workload's model, optimiser state and cached activations before the next one
+    del upd, opt, model, dev_batch, it
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_ours(args):
+    """Default run: the categorical training workload (the headline line) plus two sub-records the
+    driver would otherwise never see -- `mol` (BASELINE.json configs[3], at every N) and
+    `generate` (configs[4], one utterance, N = 1 only: generation is replicas-only)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libvqw has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mol_first = args.workload == "train-mol"
+    line = train_workload(args, mol_first, args.steps, args.warmup, world, rank, local, dev, True)
+    if args.workload == "train" and not args.no_sub_records:
+        sub_steps = max(3, min(args.steps, 10))
+        mol = train_workload(args, True, sub_steps, 3, world, rank, local, dev, False)
+        gen = None
+        if world == 1:
+            gen = generate_workload(args, dev, steps=args.gen_steps or 4000,
+                                    length=args.gen_length)
+        if rank == 0:
+            line["mol"] = {k: mol[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup",
+                                               "ms_per_step", "e2e", "gpu_launches", "kernels_ms")}
+            line["mol"]["config"] = mol["config"]
+            line["mol"]["roofline"] = mol["roofline"]
+            line["generate"] = gen
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -414,9 +452,10 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1xB200 config, bounded CPU sample: " + sample},
+        "config": workload_config(False, int(os.environ.get("WORLD_SIZE", "1")), args.mode),
         "cpu_baseline": {"value": value, "unit": "audio-samples/s", "cores": cores,
                          "kind": "port", "sample": sample},
+        "host_cores": cores,
         "e2e": {"value": value, "unit": "audio-samples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }))
@@ -426,25 +465,30 @@ def run_reference(args):
 # generation workload (BASELINE.json configs[4]): 24000-sample utterance, n_loop=4 n_layer=10
 # ------------------------------------------------------------------------------------------
 def run_generate(args):
+    torch.cuda.set_device(0)
+    print(json.dumps(generate_workload(args, torch.device("cuda", 0),
+                                       steps=args.gen_steps or (args.gen_length - 1),
+                                       length=args.gen_length)))
+
+
+def generate_workload(args, dev, steps, length):
     import chainer_vq_vae_b200 as V
     from chainer_vq_vae_b200.generate import generate_utterance
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
     cfg = dict(CFG)
     cfg["n_loop"] = 4
-    T = args.gen_length
+    T = length
     model = build_model(cfg, dev, "fp32").eval()
     ex = synthetic_examples(1, T, 71)[0]
     x_enc = torch.from_numpy(ex[0][None]).to(dev)
     spk = torch.tensor([int(ex[2])], device=dev, dtype=torch.int32)
-    steps = min(args.gen_steps or (T - 1), T - 1)
+    steps = min(steps, T - 1)
     u = np.random.default_rng(0).uniform(size=steps)
     with torch.no_grad():
         cond = model.condition_embed(model.vq(model.encoder(x_enc)), spk)
         dec = model.decoder.ema
         generate_utterance(dec, cond, u, n_steps=min(steps, 200))          # warm-up
         torch.cuda.synchronize()
-        sampler = ClockSampler(0)
+        sampler = ClockSampler(dev.index or 0)
         sampler.start()
         launches0 = V.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -479,7 +523,7 @@ def run_generate(args):
                "sample": f"{n_cpu} steps of the same decoder (n_loop=4, n_layer=10, 512/512/256) "
                          "with the reference's concat-shift queues, oracle on torch-CPU"}
     per_step_s = ms * 1e-3 / steps
-    print(json.dumps({
+    return {
         "metric": "generate samples/sec (one utterance, persistent kernel)",
         "value": steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": steps,
         "warmup": 200, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "replicas only",
@@ -498,7 +542,7 @@ def run_generate(args):
                              "dependent chain of 41 phases per sample (one tagged store->load "
                              "exchange each, ~3.5 us per phase) plus 6 grid barriers"},
         "cpu_baseline": cpu, "first_samples": [int(v) for v in out[:8].tolist()],
-    }))
+    }
 
 
 def main():
@@ -515,6 +559,8 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "train-mol", "generate"],
                     help="train = BASELINE configs[1]/[2]; train-mol = configs[3] (mixture-of-"
                          "logistics decoder, scalar input); generate = configs[4]")
+    ap.add_argument("--no-sub-records", action="store_true",
+                    help="skip the `mol` and `generate` sub-records of the default train run")
     ap.add_argument("--gen-length", type=int, default=24000)
     ap.add_argument("--gen-steps", type=int, default=0)
     args = ap.parse_args()
