@@ -110,10 +110,10 @@ _SIGNATURES = {
     "vqw_mol_loss": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_float, C.c_void_p]),
     "vqw_upsample_concat_forward": (c_int, [C.c_void_p] * 3 + [c_int] * 5 + [C.c_void_p]),
     "vqw_upsample_concat_backward": (c_int, [C.c_void_p] * 3 + [c_int] * 5 + [C.c_void_p]),
-    "vqw_adam_step": (c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_float] * 4 + [C.c_void_p]),
-    "vqw_adam_step_dev": (c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 3 +
+    "vqw_adam_step": (c_int, [C.c_void_p] * 4 + [C.c_longlong] + [C.c_double] * 4 + [C.c_void_p]),
+    "vqw_adam_step_dev": (c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_double] * 3 +
                           [C.c_void_p]),
-    "vqw_ema_update": (c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_float, C.c_void_p]),
+    "vqw_ema_update": (c_int, [C.c_void_p] * 2 + [C.c_longlong, C.c_double, C.c_void_p]),
     "vqw_embed_gather_forward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_void_p]),
     "vqw_embed_gather_backward_tc_workspace": (C.c_int64, [c_int] * 4),

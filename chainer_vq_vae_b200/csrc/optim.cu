@@ -15,7 +15,10 @@ namespace vqw {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float lr_value, const float* __restrict__ lr_ptr,
-            float b1, float b2, float eps) {
+            float omb1, float omb2, float eps) {
+  // omb1 / omb2 = float(1 - beta) with the subtraction done in DOUBLE on the host: NumPy (the
+  // reference's arithmetic) rounds the Python-float scalar 1 - beta2 = 0.001 to float32 once;
+  // 1.0f - 0.999f would be 1.3e-5 off (caught by tests/test_gpu_optim.py)
   // lr from device memory when the step is replayed from a CUDA graph (it changes every step)
   const float lr = lr_ptr ? __ldg(lr_ptr) : lr_value;
   const int64_t n4 = n >> 2;
@@ -26,8 +29,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     float* P = &pp.x; const float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      M[k] += (1.0f - b1) * (G[k] - M[k]);
-      V[k] += (1.0f - b2) * (G[k] * G[k] - V[k]);
+      M[k] += omb1 * (G[k] - M[k]);
+      V[k] += omb2 * (G[k] * G[k] - V[k]);
       P[k] -= lr * M[k] / (sqrtf(V[k]) + eps);
     }
     reinterpret_cast<float4*>(p)[i] = pp;
@@ -36,17 +39,18 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t i = (n4 << 2) + threadIdx.x;
-    m[i] += (1.0f - b1) * (g[i] - m[i]);
-    v[i] += (1.0f - b2) * (g[i] * g[i] - v[i]);
+    m[i] += omb1 * (g[i] - m[i]);
+    v[i] += omb2 * (g[i] * g[i] - v[i]);
     p[i] -= lr * m[i] / (sqrtf(v[i]) + eps);
   }
 }
 
 __global__ void __launch_bounds__(256)
-ema_kernel(float* __restrict__ ema, const float* __restrict__ target, int64_t n, float decay) {
+ema_kernel(float* __restrict__ ema, const float* __restrict__ target, int64_t n, float decay,
+           float omd) {   // omd = float(1 - decay), subtraction in double (see adam_kernel)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
-    ema[i] = decay * target[i] + (1.0f - decay) * ema[i];
+    ema[i] = decay * target[i] + omd * ema[i];
 }
 
 // labels outside [0, Q) are ignored (Chainer's ignore_label = -1): they add nothing to the loss,
@@ -103,21 +107,23 @@ softmax_ce_kernel(const float* __restrict__ y, const int32_t* __restrict__ tgt,
 
 }  // namespace vqw
 
-extern "C" int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
-                             float beta1, float beta2, float eps, vqw_stream_t stream) {
+extern "C" int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr,
+                             double beta1, double beta2, double eps, vqw_stream_t stream) {
   using namespace vqw;
   VQW_REQUIRE(n >= 0, "vqw_adam_step: negative size");
   if (n == 0) return 0;
   VQW_REQUIRE(p && g && m && v, "vqw_adam_step: null pointer");
   VQW_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                   ((uintptr_t)v % 16 == 0), "vqw_adam_step: buffers must be 16-byte aligned");
-  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, nullptr, beta1, beta2, eps);
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)lr, nullptr,
+                                                         (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                         (float)eps);
   VQW_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
 
 extern "C" int vqw_adam_step_dev(float* p, const float* g, float* m, float* v, long long n,
-                                 const float* lr_dev, float beta1, float beta2, float eps,
+                                 const float* lr_dev, double beta1, double beta2, double eps,
                                  vqw_stream_t stream) {
   using namespace vqw;
   VQW_REQUIRE(n >= 0, "vqw_adam_step_dev: negative size");
@@ -125,18 +131,21 @@ extern "C" int vqw_adam_step_dev(float* p, const float* g, float* m, float* v, l
   VQW_REQUIRE(p && g && m && v && lr_dev, "vqw_adam_step_dev: null pointer");
   VQW_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                   ((uintptr_t)v % 16 == 0), "vqw_adam_step_dev: buffers must be 16-byte aligned");
-  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.0f, lr_dev, beta1, beta2, eps);
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.0f, lr_dev,
+                                                         (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                         (float)eps);
   VQW_CHECK_LAUNCH("adam_kernel");
   return 0;
 }
 
-extern "C" int vqw_ema_update(float* ema, const float* target, long long n, float decay,
+extern "C" int vqw_ema_update(float* ema, const float* target, long long n, double decay,
                               vqw_stream_t stream) {
   using namespace vqw;
   VQW_REQUIRE(n >= 0, "vqw_ema_update: negative size");
   if (n == 0) return 0;
   VQW_REQUIRE(ema && target, "vqw_ema_update: null pointer");
-  ema_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(ema, target, n, decay);
+  ema_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(ema, target, n, (float)decay,
+                                                        (float)(1.0 - decay));
   VQW_CHECK_LAUNCH("ema_kernel");
   return 0;
 }

@@ -47,6 +47,7 @@ struct Params {
   int xlo;              // the residual stream keeps its lo plane (residual-add operand): x3 or fp16
   int skip_accumulate;
   int write_residual;   // 0 for the last block: O_0/O_1 are skipped entirely
+  int pf_dist;          // L2 prefetch distance (K slabs) of the activation operand in H_a, 0 = off
   const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
   const __nv_bfloat16* xp_lo;
   const float* conv_b;  const float* cond_b;  const float* res_b;  const float* skip_b;
@@ -133,23 +134,44 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
+      // activation slab i of the first contraction: tap slabs of x (row shift = causal delay,
+      // negative rows are zero-filled by TMA), then the condition slabs
+      auto a_src = [&](int i, const CUtensorMap*& mh, const CUtensorMap*& ml, int& c0, int& tt) {
+        const int tap = i / chunks_per_tap;
+        if (tap < P.fs) {
+          mh = &map_x_hi; ml = &map_x_lo;
+          c0 = (i - tap * chunks_per_tap) * BK;
+          tt = t0 - P.dilation * (P.fs - 1 - tap);
+        } else {
+          mh = &map_c_hi; ml = &map_c_lo;
+          c0 = (i - P.fs * chunks_per_tap) * BK;
+          tt = t0;
+        }
+      };
+      auto a_prefetch = [&](int i) {
+        const CUtensorMap *mh, *ml;
+        int c0, tt;
+        a_src(i, mh, ml, c0, tt);
+        tma_prefetch_3d(mh, c0, tt, b);
+        if (P.x3) tma_prefetch_3d(ml, c0, tt, b);
+      };
+      // H_a reads its activation slabs for the first time (DRAM); H_b re-reads them from L2.
+      // Run an L2 prefetch pf_dist slabs ahead of the ring so that the DRAM latency is not paid
+      // once per ring round trip (measured: H_a 8-22 k cycles slower than H_b without it).
+      const int pf = P.pf_dist < nk1 ? P.pf_dist : nk1;
+      for (int i = 0; i < pf; ++i) a_prefetch(i);
       for (int gp = 0; gp < 2; ++gp) {
         for (int i = 0; i < nk1; ++i) {
+          if (gp == 0 && pf > 0 && i + pf < nk1) a_prefetch(i + pf);
           mbar_wait(empty0 + 8 * stage, ph ^ 1);
           const uint32_t fb = full0 + 8 * stage;
           const uint32_t sa = base + stage * STAGE_BYTES;
           mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
-          const int tap = i / chunks_per_tap;
-          if (tap < P.fs) {
-            const int c0 = (i - tap * chunks_per_tap) * BK;
-            const int tt = t0 - P.dilation * (P.fs - 1 - tap);   // negative rows -> zero fill
-            tma_load_3d(sa, &map_x_hi, fb, c0, tt, b);
-            if (P.x3) tma_load_3d(sa + A_PLANE, &map_x_lo, fb, c0, tt, b);
-          } else {
-            const int c0 = (i - P.fs * chunks_per_tap) * BK;
-            tma_load_3d(sa, &map_c_hi, fb, c0, t0, b);
-            if (P.x3) tma_load_3d(sa + A_PLANE, &map_c_lo, fb, c0, t0, b);
-          }
+          const CUtensorMap *mh, *ml;
+          int c0, tt;
+          a_src(i, mh, ml, c0, tt);
+          tma_load_3d(sa, mh, fb, c0, tt, b);
+          if (P.x3) tma_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
           tma_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, gp * TN);
           if (P.x3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w1_lo, fb, i * BK, gp * TN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
@@ -1495,6 +1517,10 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.xlo = xlo ? 1 : 0;
     P.skip_accumulate = i > 0;
     P.write_residual = write_res ? 1 : 0;
+    {
+      static const int pf_env = getenv("VQW_TC_PREFETCH") ? atoi(getenv("VQW_TC_PREFETCH")) : 12;
+      P.pf_dist = pf_env;
+    }
     P.xp_hi = x_hi[cur];
     P.xp_lo = x_lo[cur];
     P.conv_b = w.conv_b; P.cond_b = w.cond_b; P.res_b = w.res_b; P.skip_b = w.skip_b;

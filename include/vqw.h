@@ -256,6 +256,8 @@ int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW,
  *                   counted: normalize=True), gy (B,Q,T) = d loss / d y (or NULL).
  *   vqw_adam_step   chainer.optimizers.Adam's rule (train.py:101): m += (1-b1)(g-m);
  *                   v += (1-b2)(g*g-v); p -= lr*m/(sqrt(v)+eps); lr already bias corrected.
+ *                   Hyper-parameters are doubles: 1-beta is formed in double and rounded to
+ *                   float32 once, as NumPy does with the reference's Python-float scalars.
  *   vqw_ema_update  ExponentialMovingAverage, utils.py:153-154: ema = decay*target + (1-decay)*ema.
  */
 int vqw_softmax_ce(const float* y, const int32_t* t, float* gy, double* loss, int B, int Q, int T,
@@ -273,13 +275,13 @@ int vqw_upsample_concat_forward(const float* local, const float* glob, float* ou
                                 int Cg, int H, int T_out, vqw_stream_t stream);
 int vqw_upsample_concat_backward(const float* g, float* g_local, float* g_glob, int B, int Cl, int Cg,
                                  int H, int T_out, vqw_stream_t stream);
-int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                  float beta2, float eps, vqw_stream_t stream);
+int vqw_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                  double beta2, double eps, vqw_stream_t stream);
 /* same, with the (bias-corrected) learning rate read from device memory: the form a CUDA-graph
  * replay of the training step uses, where lr changes every step but kernel arguments cannot */
 int vqw_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev,
-                      float beta1, float beta2, float eps, vqw_stream_t stream);
-int vqw_ema_update(float* ema, const float* target, long long n, float decay, vqw_stream_t stream);
+                      double beta1, double beta2, double eps, vqw_stream_t stream);
+int vqw_ema_update(float* ema, const float* target, long long n, double decay, vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Persistent autoregressive generation.  Replaces the sample loop of generate.py:109-145 and
