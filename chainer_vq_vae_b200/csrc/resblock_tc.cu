@@ -55,7 +55,7 @@ struct Params {
   __nv_bfloat16* res_hi;  // packed (B,T,Cr) planes for the next block (null for the last block)
   __nv_bfloat16* res_lo;
   float* skip;          // (B,Cs,T) fp32 in/out
-  float* gate_tanh;     // (B,Ch,T) fp32 or null
+  float* gate_tanh;     // TIME-major (B,T,Ch) fp32 or null (thread = time row in both directions)
   float* gate_sig;
   __nv_bfloat16* zp_hi; // packed (B,T,Ch) planes of z = tanh*sigmoid, saved for the backward (or null)
   __nv_bfloat16* zp_lo;
@@ -64,6 +64,26 @@ struct Params {
 };
 
 // ------------------------------------------------------------------ the kernel -------------
+// TMEM plan (512 columns, fp32 accumulators; one CTA per SM):
+//   [  0,256) accumulator of H_a   (tanh 0..127 | sigmoid 0..127)
+//   [256,512) accumulator of H_b   (tanh 128..255 | sigmoid 128..255)
+// so the MMAs of H_b run while the 16 epilogue warps gate H_a.  The gate writes z IN PLACE: the 16
+// tanh columns of a chunk are overwritten by the 8 + 8 columns of its bf16 hi / lo z pairs (each
+// thread only ever touches the columns it has just read), i.e. z_a ends up in [0,128), z_b in
+// [256,384), interleaved {hi(16 ch), lo(16 ch)} per K = 16 step -- exactly the A-operand tiles of
+// the second contraction.  The two drained sigmoid halves [128,256) and [384,512) become the
+// ping-pong accumulators of the output phase, which runs as N = 128 chunks of [Wr ; Ws] (only the
+// weights stream, z stays in TMEM): the epilogue of chunk c overlaps the MMAs of chunk c + 1.
+// Exposed epilogues per tile: the gate of H_b and the last output chunk (round 1: all five).
+constexpr int ON = 128;                                   // output chunk = UMMA N of the 2nd contraction
+constexpr int OB_PLANE = ON * BK * 2;                     // 8 KB per weight plane and K slab
+constexpr int OACC0 = 128, OACC1 = 384;                   // ping-pong output accumulators
+constexpr uint32_t IDESC_ON = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) |
+                              ((uint32_t)(TM >> 4) << 24);
+constexpr int NBAR = 2 * STAGES + 8;                      // ring + hfull[2] zready[2] ofull[2] oempty[2]
+
+// X3: three MMAs per product over hi/lo planes; F16: the planes hold IEEE fp16 (single pass)
+template <int X3, int F16>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                    const __grid_constant__ CUtensorMap map_x_lo,
@@ -82,24 +102,27 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   float* bss = brs + P.Cr;                                              // [Cs]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
-  const uint32_t acc_full = smem_u32(bars + 2 * STAGES), acc_empty = smem_u32(bars + 2 * STAGES + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  const uint32_t hfull0 = smem_u32(bars + 2 * STAGES), zready0 = hfull0 + 16;
+  const uint32_t ofull0 = hfull0 + 32, oempty0 = hfull0 + 48;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, t0 = blockIdx.x * TM;
-  const int nplanes = P.x3 ? 2 : 1;
+  constexpr int XLO = X3 | F16;   // the residual stream keeps its lo plane (residual-add operand)
+  const int nplanes = X3 ? 2 : 1;
   const bool rec_cta = P.dbg != nullptr && blockIdx.x == P.dbg_x && blockIdx.y == P.dbg_y;
   if (rec_cta && threadIdx.x == 0) P.dbg[40] = clock64();
   const int chunks_per_tap = P.Cr / BK;
   const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of the first contraction
   const int nk2 = CH / BK;                               // K slabs of the second contraction
-  const int o_begin = P.write_residual ? 0 : P.Cr / TN;  // first N chunk of [Wr ; Ws]
-  const int o_end = P.Cr / TN + P.Cs / TN;
+  const int n_res = P.Cr / ON;                           // output chunks: residual rows, then skip rows
+  const int o_begin = P.write_residual ? 0 : n_res;
+  const int o_end = n_res + P.Cs / ON;
 
   if (warp == W_TMA && lane == 0) {
     prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
     prefetch_tmap(&map_w2_hi);
-    if (P.x3) {
+    if (X3) {
       prefetch_tmap(&map_x_lo); prefetch_tmap(&map_c_lo); prefetch_tmap(&map_w1_lo);
       prefetch_tmap(&map_w2_lo);
     }
@@ -107,8 +130,12 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, FWD_EPI_WARPS * 32);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(hfull0 + 8 * g, 1);
+      mbar_init(zready0 + 8 * g, FWD_EPI_WARPS * 32);
+      mbar_init(ofull0 + 8 * g, 1);
+      mbar_init(oempty0 + 8 * g, FWD_EPI_WARPS * 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
@@ -153,11 +180,11 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         int c0, tt;
         a_src(i, mh, ml, c0, tt);
         tma_prefetch_3d(mh, c0, tt, b);
-        if (P.x3) tma_prefetch_3d(ml, c0, tt, b);
+        if (X3) tma_prefetch_3d(ml, c0, tt, b);
       };
       // H_a reads its activation slabs for the first time (DRAM); H_b re-reads them from L2.
-      // Run an L2 prefetch pf_dist slabs ahead of the ring so that the DRAM latency is not paid
-      // once per ring round trip (measured: H_a 8-22 k cycles slower than H_b without it).
+      // An L2 prefetch runs pf_dist slabs ahead of the ring so that the DRAM latency is not paid
+      // once per ring round trip (round 1: H_a 8-22 k cycles slower than H_b).
       const int pf = P.pf_dist < nk1 ? P.pf_dist : nk1;
       for (int i = 0; i < pf; ++i) a_prefetch(i);
       for (int gp = 0; gp < 2; ++gp) {
@@ -171,9 +198,9 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           int c0, tt;
           a_src(i, mh, ml, c0, tt);
           tma_load_3d(sa, mh, fb, c0, tt, b);
-          if (P.x3) tma_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
+          if (X3) tma_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
           tma_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, gp * TN);
-          if (P.x3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w1_lo, fb, i * BK, gp * TN);
+          if (X3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w1_lo, fb, i * BK, gp * TN);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
       }
@@ -182,9 +209,9 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           mbar_wait(empty0 + 8 * stage, ph ^ 1);
           const uint32_t fb = full0 + 8 * stage;
           const uint32_t sa = base + stage * STAGE_BYTES;
-          mbar_expect_tx(fb, nplanes * B_PLANE);
-          tma_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * TN);
-          if (P.x3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w2_lo, fb, i * BK, oc * TN);
+          mbar_expect_tx(fb, nplanes * OB_PLANE);
+          tma_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * ON);
+          if (X3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w2_lo, fb, i * BK, oc * ON);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
       }
@@ -194,16 +221,12 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
-      int nphase = 0;
-      const uint32_t acc = tmem_base + ACC_COL;
       const bool rec = rec_cta;
-      const uint32_t idesc = idesc_for(IDESC, P.f16);
-      for (int gp = 0; gp < 2; ++gp, ++nphase) {
-        if (nphase > 0) {
-          mbar_wait(acc_empty, (nphase - 1) & 1);
-          tc_fence_after();
-        }
-        if (rec) P.dbg[2 * nphase] = clock64();
+      const uint32_t idesc = idesc_for(IDESC, F16);
+      const uint32_t idesc_o = idesc_for(IDESC_ON, F16);
+      for (int gp = 0; gp < 2; ++gp) {
+        const uint32_t acc = tmem_base + 256 * gp;
+        if (rec) P.dbg[2 * gp] = clock64();
         for (int i = 0; i < nk1; ++i) {
           mbar_wait(full0 + 8 * stage, ph);
           tc_fence_after();
@@ -213,7 +236,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
             const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
             mma_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-            if (P.x3) {
+            if (X3) {
               const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
               const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
               mma_ss(acc, a_lo, b_hi, idesc, 1u);
@@ -223,35 +246,44 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           tc_commit(empty0 + 8 * stage);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
-        tc_commit(acc_full);
-        if (rec) P.dbg[2 * nphase + 1] = clock64();
+        tc_commit(hfull0 + 8 * gp);
+        if (rec) P.dbg[2 * gp + 1] = clock64();
       }
-      for (int oc = o_begin; oc < o_end; ++oc, ++nphase) {
-        mbar_wait(acc_empty, (nphase - 1) & 1);   // accumulator drained AND z complete in TMEM
-        tc_fence_after();
-        if (rec) P.dbg[2 * nphase] = clock64();
+      // both halves of z are in TMEM (and both sigmoid halves are drained) from here on
+      mbar_wait(zready0, 0);
+      mbar_wait(zready0 + 8, 0);
+      tc_fence_after();
+      for (int oc = o_begin, j = 0; oc < o_end; ++oc, ++j) {
+        const int buf = j & 1, use = j >> 1;
+        if (use > 0) {
+          mbar_wait(oempty0 + 8 * buf, (use - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (buf ? OACC1 : OACC0);
+        if (rec && j < 6) P.dbg[4 + 2 * j] = clock64();
         for (int i = 0; i < nk2; ++i) {
           mbar_wait(full0 + 8 * stage, ph);
           tc_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / UK; ++ks) {
-            // z channel k sits in column k/2 of its plane: slab i, step ks -> 16*i + 8*ks
-            const uint32_t z_hi = tmem_base + ZHI_COL + (BK / 2) * i + (UK / 2) * ks;
-            const uint32_t z_lo = tmem_base + ZLO_COL + (BK / 2) * i + (UK / 2) * ks;
+            // z channels [32 i + 16 ks, +16): hi pairs in 8 columns, lo pairs in the next 8
+            const int kstep = 2 * i + ks;
+            const uint32_t z_hi = tmem_base + (kstep < 8 ? 0 : 256) + 16 * (kstep & 7);
+            const uint32_t z_lo = z_hi + 8;
             const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma_ts(acc, z_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-            if (P.x3) {
+            mma_ts(acc, z_hi, b_hi, idesc_o, (i | ks) ? 1u : 0u);
+            if (X3) {
               const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
-              mma_ts(acc, z_lo, b_hi, idesc, 1u);
-              mma_ts(acc, z_hi, b_lo, idesc, 1u);
+              mma_ts(acc, z_lo, b_hi, idesc_o, 1u);
+              mma_ts(acc, z_hi, b_lo, idesc_o, 1u);
             }
           }
           tc_commit(empty0 + 8 * stage);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
-        tc_commit(acc_full);
-        if (rec) P.dbg[2 * nphase + 1] = clock64();
+        tc_commit(ofull0 + 8 * buf);
+        if (rec && j < 6) P.dbg[4 + 2 * j + 1] = clock64();
       }
     }
   } else {
@@ -265,60 +297,74 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     const int t = t0 + row;
     const bool t_ok = t < P.T;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    int nphase = 0;
     const bool rec = rec_cta && threadIdx.x == 0;
-    // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), kept in TMEM as bf16 hi/lo planes ----
-    for (int gp = 0; gp < 2; ++gp, ++nphase) {
-      mbar_wait(acc_full, nphase & 1);
+    const bool save_gates = P.gate_tanh != nullptr && t_ok;
+    // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), written over the tanh columns ----
+    for (int gp = 0; gp < 2; ++gp) {
+      mbar_wait(hfull0 + 8 * gp, 0);
       tc_fence_after();
-      if (rec) P.dbg[16 + 2 * nphase] = clock64();
+      if (rec) P.dbg[16 + 2 * gp] = clock64();
+      const uint32_t accb = lane_base + 256 * gp;
 #pragma unroll 1
       for (int q = grp; q < HALF / 16; q += NG) {
-        float a[16], g[16];
-        tmem_ld16(lane_base + ACC_COL + 16 * q, a);
-        tmem_ld16(lane_base + ACC_COL + HALF + 16 * q, g);
+        uint32_t ar[16], gr[16];
+        tmem_ld16_issue(accb + 16 * q, ar);
+        tmem_ld16_issue(accb + HALF + 16 * q, gr);
+        tmem_ld_wait(ar, gr);
         uint32_t zh[8], zl[8];
         const int ch0 = gp * HALF + 16 * q;
+        float bt[16], bs[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(bt + 4 * i) = *reinterpret_cast<const float4*>(b1s + ch0 + 4 * i);
+          *reinterpret_cast<float4*>(bs + 4 * i) = *reinterpret_cast<const float4*>(b1s + CH + ch0 + 4 * i);
+        }
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           float z2[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int ch = ch0 + i + u;
-            const float th = tanh_fast(a[i + u] + b1s[ch]);
-            const float sg = sigmoid_fast(g[i + u] + b1s[CH + ch]);
+            float th, sg;
+            gate_pair(__uint_as_float(ar[i + u]) + bt[i + u], __uint_as_float(gr[i + u]) + bs[i + u],
+                      th, sg);
             z2[u] = th * sg;
-            if (P.gate_tanh != nullptr && t_ok) {
-              const int64_t off = ((int64_t)b * CH + ch) * P.T + t;
-              __stcs(P.gate_tanh + off, th);
-              __stcs(P.gate_sig + off, sg);
-            }
+            ar[i + u] = __float_as_uint(th);     // kept for the backward (gate derivative)
+            gr[i + u] = __float_as_uint(sg);
           }
-          if (P.x3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], P.f16);
-          else zh[i >> 1] = pack_pair_f(z2[0], z2[1], P.f16);
+          if (X3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], F16);
+          else zh[i >> 1] = pack_pair_f(z2[0], z2[1], F16);
         }
-        tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
-        if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
+        if (save_gates) {   // time-major (B,T,Ch) fp32: 64 contiguous bytes per thread and array
+          const int64_t goff = ((int64_t)b * P.T + t) * CH + ch0;
+          st256(P.gate_tanh + goff, ar);
+          st256(P.gate_tanh + goff + 8, ar + 8);
+          st256(P.gate_sig + goff, gr);
+          st256(P.gate_sig + goff + 8, gr + 8);
+        }
+        tmem_st8(accb + 16 * q, zh);
+        if (X3) tmem_st8(accb + 16 * q + 8, zl);
         if (P.zp_hi != nullptr && t_ok) {
           const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
           st256(P.zp_hi + zoff, zh);
-          if (P.x3) st256(P.zp_lo + zoff, zl);
+          if (X3) st256(P.zp_lo + zoff, zl);
         }
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(acc_empty);
-      if (rec) P.dbg[16 + 2 * nphase + 1] = clock64();
+      mbar_arrive(zready0 + 8 * gp);
+      if (rec) P.dbg[16 + 2 * gp + 1] = clock64();
     }
-    // ---- output phases: residual chunks then skip chunks ----
+    // ---- output chunks: residual rows then skip rows, 128 per chunk ----
     // residual = Wr z + br + x with x read back from the packed hi/lo planes (x = hi + lo to
-    // 2^-17: two 16-byte loads per plane per 16 channels instead of 16 strided fp32 loads);
-    // the running skip sum is fp32 (B,Cs,T): lanes are consecutive t, so every access is a
-    // coalesced 128-byte row segment.  Operands of the NEXT chunk are fetched before the
-    // current one is processed.
-    for (int oc = o_begin; oc < o_end; ++oc, ++nphase) {
-      const bool is_res = oc < P.Cr / TN;
-      const int cbase = is_res ? oc * TN : (oc - P.Cr / TN) * TN;
+    // 2^-17: two 32-byte loads per 16 channels instead of 16 strided fp32 loads); the running
+    // skip sum is fp32 (B,Cs,T): lanes are consecutive t, so every access is a coalesced 128-byte
+    // row segment.  Operands of the NEXT 16-column piece are fetched before the current one is
+    // processed.
+    for (int oc = o_begin, j = 0; oc < o_end; ++oc, ++j) {
+      const int buf = j & 1, use = j >> 1;
+      const bool is_res = oc < n_res;
+      const int cbase = (is_res ? oc : oc - n_res) * ON;
+      const uint32_t accb = lane_base + (buf ? OACC1 : OACC0);
       float addf[16];
       uint32_t hw[8], lw[8];
       auto fetch = [&](int q) {
@@ -327,7 +373,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
           if (t_ok) {
             ld256(P.xp_hi + poff, hw);
-            if (P.xlo) ld256(P.xp_lo + poff, lw);
+            if (XLO) ld256(P.xp_lo + poff, lw);
           }
         } else if (P.skip_accumulate && t_ok) {
           const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
@@ -335,22 +381,31 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
         }
       };
+      const bool fine = rec && j == 0;       // per-piece probes of the first chunk (warp 0)
+      if (fine) P.dbg[48] = clock64();
       fetch(grp);
-      mbar_wait(acc_full, nphase & 1);
+      if (fine) P.dbg[49] = clock64();
+      mbar_wait(ofull0 + 8 * buf, use & 1);
       tc_fence_after();
-      if (rec) P.dbg[16 + 2 * nphase] = clock64();
+      if (rec && j < 6) P.dbg[20 + 2 * j] = clock64();
 #pragma unroll 1
-      for (int q = grp; q < TN / 16; q += NG) {
+      for (int q = grp; q < ON / 16; q += NG) {
         float o[16], add[16];
-        tmem_ld16(lane_base + ACC_COL + 16 * q, o);
+        tmem_ld16(accb + 16 * q, o);
+        if (fine && q == grp) {
+          P.dbg[50] = clock64();
+          uint32_t dep;
+          asm volatile("mov.u32 %0, %1;" : "=r"(dep) : "r"(is_res ? hw[0] : __float_as_uint(addf[0])));
+          P.dbg[51] = clock64() + (dep & 0u);
+        }
         if (is_res) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float v0, v1;
-            unpack_pair_f(hw[i], P.f16, v0, v1);
-            if (P.xlo) {
+            unpack_pair_f(hw[i], F16, v0, v1);
+            if (XLO) {
               float l0, l1;
-              unpack_pair_f(lw[i], P.f16, l0, l1);
+              unpack_pair_f(lw[i], F16, l0, l1);
               v0 += l0;
               v1 += l1;
             }
@@ -361,7 +416,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 #pragma unroll
           for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
         }
-        if (q + NG < TN / 16) fetch(q + NG);
+        if (q + NG < ON / 16) fetch(q + NG);
         const int ch0 = cbase + 16 * q;
         if (is_res) {
           uint32_t rh[8], rl[8];
@@ -376,13 +431,13 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                 __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
-            if (P.xlo) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], P.f16);
-            else rh[i >> 1] = pack_pair_f(v2[0], v2[1], P.f16);
+            if (XLO) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
+            else rh[i >> 1] = pack_pair_f(v2[0], v2[1], F16);
           }
           if (t_ok && P.res_hi != nullptr) {
             const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
             st256(P.res_hi + poff, rh);
-            if (P.xlo) st256(P.res_lo + poff, rl);
+            if (XLO) st256(P.res_lo + poff, rl);
           }
         } else if (t_ok) {
 #pragma unroll
@@ -391,10 +446,11 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
           }
         }
+        if (fine) P.dbg[q == grp ? 52 : 53] = clock64();
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);
-      if (rec) P.dbg[16 + 2 * nphase + 1] = clock64();
+      mbar_arrive(oempty0 + 8 * buf);
+      if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
     }
   }
 
@@ -408,817 +464,6 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     if (rec_cta && lane == 0) P.dbg[42] = clock64();
   }
 }
-
-
-// ------------------------------------------------------------------ the kernel, v2 ---------
-// Persistent variant (EXPERIMENTAL, VQW_TC_FWD_V2=1; measured SLOWER than v1 on B200: 1.02 vs
-// 0.89 ms per block in bf16x3).  What it achieves is the epilogue overlap: its per-chunk timeline
-// shows the gate / output epilogues fully hidden.  What it loses: an H chunk takes 33-35 k cycles
-// (in bf16x3 AND in the single-pass mode) against 20.7 k / 6.9 k of MMA time -- ~620 cycles per
-// K = 32 slab whatever the slab's size.  Ruled out by measurement: the issue rate of the TMA
-// producer (three producer warps: same time), the L2 port (the CTA-pair version below stages 25 %
-// fewer bytes per SM and is slower still), any saturated unit (ncu: tensor pipe 47 %, L2 48 %,
-// xbar->SM 30 %, L2 hit rate 89 %).  What is left is latency: ~3.7 k cycles from "stage free" to
-// "stage full" under this load, i.e. 6 stages x 32 KB in flight sustain one slab per 620 cycles, and
-// feeding N = 128 chunks at the MMA rate would need ~300 KB in flight per SM.  v1 (48 KB per 768
-// MMA cycles) needs ~230 KB and has 192: it is close to, but not at, the MMA rate in its first phase.
-// One CTA per SM loops over (batch item, 128 time steps)
-// tiles, and the work of a tile is cut into N = 128 output-channel CHUNKS that ping-pong between
-// two 128-column TMEM accumulators, so the epilogue of chunk n runs while the tensor core works
-// on chunk n+1 (v1 above has ONE 256-column accumulator: its 59 k cycles of epilogue per tile
-// are all exposed, a third of the tile).  Chunks of a tile, in order:
-//   H_0..H_3   h rows {tanh 64c..64c+63 | sigmoid 64c..64c+63} (K = fs*Cr + Cc) -> gate -> z
-//              channels 64c..64c+63 into the TMEM z planes
-//   R_0..R_3   residual channels 128r..128r+127 = Wr z + br + x      (A operand = z in TMEM)
-//   S_0..S_1   skip channels 128s..128s+127 (+)= Ws z + bs
-// The TMA producer streams K = 32 slabs for this chunk sequence without regard to tile
-// boundaries (6-stage ring), so the first slabs of the next tile are in flight during the last
-// epilogues of the current one.  TMEM: [0,128) acc 0, [128,256) acc 1, [256,384) z hi,
-// [384,512) z lo.  Ordering: MMAs execute in issue order, so (a) waiting for the epilogue of
-// H_3 before issuing R_0 guarantees every z column is written, and (b) the epilogue of the NEXT
-// tile's H_0 -- which overwrites z -- can only start after that chunk's commit, i.e. after
-// every R/S MMA of this tile has read z.
-// v2 / v3 use THREE TMA producer warps ({A_hi, A_lo}, B_hi, B_lo): measured,
-// one thread issues a tensor copy every ~170 cycles whatever its size, so with N = 128 chunks (384
-// MMA cycles per K = 32 slab in bf16x3, 128 in the single-pass modes) a single producer thread
-// issuing four copies per slab is the bottleneck (v2 measured 640 cycles per slab, v3 740).
-constexpr int PW = 3;   // 20 warps in all: 96 registers per thread without spills
-constexpr int FWD2_THREADS = (FWD_EPI_WARPS + PW + 1) * 32;
-constexpr int W2_TMA0 = FWD_EPI_WARPS, W2_MMA = FWD_EPI_WARPS + PW;
-constexpr int V2_STAGES = 6;
-constexpr int V2_TN = 128;
-constexpr int V2_B_PLANE = V2_TN * BK * 2;                  // 8 KB
-constexpr int V2_STAGE_BYTES = 2 * A_PLANE + 2 * V2_B_PLANE;   // 32 KB
-constexpr int V2_HALF = 64;                                 // gate pairs per H chunk
-constexpr uint32_t IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(V2_TN >> 3) << 17) |
-                                ((uint32_t)(TM >> 4) << 24);
-
-__global__ void __launch_bounds__(FWD2_THREADS, 1)
-resblock_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi,
-                    const __grid_constant__ CUtensorMap map_x_lo,
-                    const __grid_constant__ CUtensorMap map_c_hi,
-                    const __grid_constant__ CUtensorMap map_c_lo,
-                    const __grid_constant__ CUtensorMap map_w1_hi,
-                    const __grid_constant__ CUtensorMap map_w1_lo,
-                    const __grid_constant__ CUtensorMap map_w2_hi,
-                    const __grid_constant__ CUtensorMap map_w2_lo, const Params P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  float* b1s = reinterpret_cast<float*>(smem + V2_STAGES * V2_STAGE_BYTES);   // [512] conv_b + cond_b
-  float* brs = b1s + CD;                                                      // [Cr]
-  float* bss = brs + P.Cr;                                                    // [Cs]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + V2_STAGES);
-  const uint32_t acc_full0 = smem_u32(bars + 2 * V2_STAGES);        // [2]
-  const uint32_t acc_empty0 = smem_u32(bars + 2 * V2_STAGES + 2);   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V2_STAGES + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nplanes = P.x3 ? 2 : 1;
-  const int chunks_per_tap = P.Cr / BK;
-  const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of an H chunk
-  const int nk2 = CH / BK;                               // K slabs of an R / S chunk
-  const int n_h = CD / V2_TN;                            // 4
-  const int n_r = P.Cr / V2_TN;
-  const int o_begin = P.write_residual ? 0 : n_r;        // first chunk of [Wr ; Ws]
-  const int o_end = n_r + P.Cs / V2_TN;
-  const int tiles_per_item = (P.T + TM - 1) / TM;
-  const int n_tiles = P.B * tiles_per_item;
-
-  if (warp == W2_TMA0 && lane == 0) {
-    prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
-    prefetch_tmap(&map_w2_hi);
-    if (P.x3) {
-      prefetch_tmap(&map_x_lo); prefetch_tmap(&map_c_lo); prefetch_tmap(&map_w1_lo);
-      prefetch_tmap(&map_w2_lo);
-    }
-    for (int s = 0; s < V2_STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(acc_full0 + 8 * s, 1);
-      mbar_init(acc_empty0 + 8 * s, FWD_EPI_WARPS * 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == W2_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp < FWD_EPI_WARPS) {
-    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.conv_b[i] + P.cond_b[i];
-    for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
-    for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= W2_TMA0 && warp < W2_MMA) {
-    // =============================== TMA producers ==============================
-    // producer warp 0 loads the activation planes, 1 the weight hi plane, 2 the weight lo plane; all
-    // three walk the same stage ring, warp 0 also registers the stage's byte count
-    const int pw = warp - W2_TMA0;
-    if (lane == 0 && (pw < 2 || P.x3)) {
-      int stage = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TM;
-        for (int c = 0; c < n_h; ++c) {
-          for (int i = 0; i < nk1; ++i) {
-            mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            const uint32_t fb = full0 + 8 * stage;
-            const uint32_t sa = base + stage * V2_STAGE_BYTES;
-            if (pw == 0) mbar_expect_tx(fb, nplanes * (A_PLANE + V2_B_PLANE));
-            const int tap = i / chunks_per_tap;
-            if (tap < P.fs) {
-              const int c0 = (i - tap * chunks_per_tap) * BK;
-              const int tt = t0 - P.dilation * (P.fs - 1 - tap);   // negative rows -> zero fill
-              if (pw == 0) tma_load_3d(sa, &map_x_hi, fb, c0, tt, b);
-              if (pw == 0 && P.x3) tma_load_3d(sa + A_PLANE, &map_x_lo, fb, c0, tt, b);
-            } else {
-              const int c0 = (i - P.fs * chunks_per_tap) * BK;
-              if (pw == 0) tma_load_3d(sa, &map_c_hi, fb, c0, t0, b);
-              if (pw == 0 && P.x3) tma_load_3d(sa + A_PLANE, &map_c_lo, fb, c0, t0, b);
-            }
-            if (pw == 1) tma_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, c * V2_TN);
-            if (pw == 2) tma_load_2d(sa + 2 * A_PLANE + V2_B_PLANE, &map_w1_lo, fb, i * BK, c * V2_TN);
-            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
-          }
-        }
-        for (int oc = o_begin; oc < o_end; ++oc) {
-          for (int i = 0; i < nk2; ++i) {
-            mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            const uint32_t fb = full0 + 8 * stage;
-            const uint32_t sa = base + stage * V2_STAGE_BYTES;
-            if (pw == 0) mbar_expect_tx(fb, nplanes * V2_B_PLANE);
-            if (pw == 1) tma_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * V2_TN);
-            if (pw == 2) tma_load_2d(sa + 2 * A_PLANE + V2_B_PLANE, &map_w2_lo, fb, i * BK, oc * V2_TN);
-            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == W2_MMA) {
-    // =============================== MMA issuer =================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t ph = 0;
-      uint32_t n = 0;   // running chunk counter: accumulator n & 1, its k-th use k = n >> 1
-      const uint32_t idesc = idesc_for(IDESC_N128, P.f16);
-      const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < n_h; ++c, ++n) {
-          const uint32_t buf = n & 1;
-          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);   // epilogue of chunk n-2 is done
-          tc_fence_after();
-          if (rec && n < 24) P.dbg[4 * n] = clock64();
-          const uint32_t acc = tmem_base + buf * V2_TN;
-          for (int i = 0; i < nk1; ++i) {
-            mbar_wait(full0 + 8 * stage, ph);
-            tc_fence_after();
-            const uint32_t sa = base + stage * V2_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks) {
-              const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-              mma_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-              if (P.x3) {
-                const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V2_B_PLANE + ks * UK * 2);
-                mma_ss(acc, a_lo, b_hi, idesc, 1u);
-                mma_ss(acc, a_hi, b_lo, idesc, 1u);
-              }
-            }
-            tc_commit(empty0 + 8 * stage);
-            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
-          }
-          tc_commit(acc_full0 + 8 * buf);
-          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
-        }
-        {   // every z column of this tile must be in TMEM: wait for the epilogue of H_3 (chunk n-1)
-          const uint32_t m = n - 1;
-          mbar_wait(acc_empty0 + 8 * (m & 1), (m >> 1) & 1);
-          tc_fence_after();
-        }
-        for (int oc = o_begin; oc < o_end; ++oc, ++n) {
-          const uint32_t buf = n & 1;
-          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);
-          tc_fence_after();
-          if (rec && n < 24) P.dbg[4 * n] = clock64();
-          const uint32_t acc = tmem_base + buf * V2_TN;
-          for (int i = 0; i < nk2; ++i) {
-            mbar_wait(full0 + 8 * stage, ph);
-            tc_fence_after();
-            const uint32_t sa = base + stage * V2_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks) {
-              // z channel k sits in column k/2 of its plane: slab i, step ks -> 16*i + 8*ks
-              const uint32_t z_hi = tmem_base + ZHI_COL + (BK / 2) * i + (UK / 2) * ks;
-              const uint32_t z_lo = tmem_base + ZLO_COL + (BK / 2) * i + (UK / 2) * ks;
-              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-              mma_ts(acc, z_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-              if (P.x3) {
-                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V2_B_PLANE + ks * UK * 2);
-                mma_ts(acc, z_lo, b_hi, idesc, 1u);
-                mma_ts(acc, z_hi, b_lo, idesc, 1u);
-              }
-            }
-            tc_commit(empty0 + 8 * stage);
-            if (++stage == V2_STAGES) { stage = 0; ph ^= 1; }
-          }
-          tc_commit(acc_full0 + 8 * buf);
-          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
-        }
-      }
-    }
-  } else {
-    // =============================== epilogue (warps 0-15) ======================
-    // warp e: TMEM lane quadrant e%4, column group e/4 (16-column units dealt round-robin)
-    const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x && threadIdx.x == 0;
-    const int quad = warp & 3, grp = warp >> 2;
-    constexpr int NG = FWD_EPI_WARPS / 4;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TM;
-      const int t = t0 + row;
-      const bool t_ok = t < P.T;
-      // ---- gate chunks: z = tanh(h_t) * sigmoid(h_s) -> TMEM z planes (+ saved tensors) ----
-      for (int c = 0; c < n_h; ++c, ++n) {
-        const uint32_t buf = n & 1;
-        const uint32_t acc = lane_base + buf * V2_TN;
-        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
-        tc_fence_after();
-        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
-#pragma unroll 1
-        for (int q = grp; q < V2_HALF / 16; q += NG) {
-          float a[16], g[16];
-          tmem_ld16(acc + 16 * q, a);
-          tmem_ld16(acc + V2_HALF + 16 * q, g);
-          uint32_t zh[8], zl[8];
-          const int ch0 = c * V2_HALF + 16 * q;
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float z2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int ch = ch0 + i + u;
-              const float th = tanh_fast(a[i + u] + b1s[ch]);
-              const float sg = sigmoid_fast(g[i + u] + b1s[CH + ch]);
-              z2[u] = th * sg;
-              if (P.gate_tanh != nullptr && t_ok) {
-                const int64_t off = ((int64_t)b * CH + ch) * P.T + t;
-                __stcs(P.gate_tanh + off, th);
-                __stcs(P.gate_sig + off, sg);
-              }
-            }
-            if (P.x3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], P.f16);
-            else zh[i >> 1] = pack_pair_f(z2[0], z2[1], P.f16);
-          }
-          tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
-          if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
-          if (P.zp_hi != nullptr && t_ok) {
-            const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
-            st256(P.zp_hi + zoff, zh);
-            if (P.x3) st256(P.zp_lo + zoff, zl);
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(acc_empty0 + 8 * buf);
-        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
-      }
-      // ---- output chunks: residual channels, then skip channels ----
-      for (int oc = o_begin; oc < o_end; ++oc, ++n) {
-        const uint32_t buf = n & 1;
-        const uint32_t acc = lane_base + buf * V2_TN;
-        const bool is_res = oc < n_r;
-        const int cbase = is_res ? oc * V2_TN : (oc - n_r) * V2_TN;
-        float addf[16];
-        uint32_t hw[8], lw[8];
-        auto fetch = [&](int q) {
-          const int ch0 = cbase + 16 * q;
-          if (is_res) {
-            const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
-            if (t_ok) {
-              ld256(P.xp_hi + poff, hw);
-              if (P.xlo) ld256(P.xp_lo + poff, lw);
-            }
-          } else if (P.skip_accumulate && t_ok) {
-            const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
-          }
-        };
-        fetch(grp);
-        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
-        tc_fence_after();
-        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
-#pragma unroll 1
-        for (int q = grp; q < V2_TN / 16; q += NG) {
-          float o[16], add[16];
-          tmem_ld16(acc + 16 * q, o);
-          if (is_res) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float v0, v1;
-              unpack_pair_f(hw[i], P.f16, v0, v1);
-              if (P.xlo) {
-                float l0, l1;
-                unpack_pair_f(lw[i], P.f16, l0, l1);
-                v0 += l0;
-                v1 += l1;
-              }
-              add[2 * i] = t_ok ? v0 : 0.0f;
-              add[2 * i + 1] = t_ok ? v1 : 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
-          }
-          if (q + NG < V2_TN / 16) fetch(q + NG);
-          const int ch0 = cbase + 16 * q;
-          if (is_res) {
-            uint32_t rh[8], rl[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float v2[2];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int ch = ch0 + i + u;
-                const float v = o[i + u] + brs[ch] + add[i + u];
-                if (t_ok && P.res_f32 != nullptr)
-                  __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
-                v2[u] = v;
-              }
-              if (P.xlo) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], P.f16);
-              else rh[i >> 1] = pack_pair_f(v2[0], v2[1], P.f16);
-            }
-            if (t_ok && P.res_hi != nullptr) {
-              const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
-              st256(P.res_hi + poff, rh);
-              if (P.xlo) st256(P.res_lo + poff, rl);
-            }
-          } else if (t_ok) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int ch = ch0 + i;
-              P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(acc_empty0 + 8 * buf);
-        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W2_MMA) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
-                 : "memory");
-  }
-}
-
-// ------------------------------------------------------------------ the kernel, v3 ---------
-// The chunk pipeline of v2 on a CTA PAIR (EXPERIMENTAL, VQW_TC_FWD_V3=1; parity green, measured
-// 1.08 ms per block): a cluster of two CTAs covers 256 time steps, every MMA is a cta_group::2
-// instruction with M = 256 (128 rows per SM) and N = 128, and each SM stages only HALF of a weight
-// slab (64 rows): 24 KB per slab and SM instead of 32.  One thread of the leader CTA issues the
-// MMAs of both SMs; the TMA copies of both CTAs complete on the leader's "full" barrier; "empty"
-// and "accumulator full" are tcgen05.commit multicasts to both CTAs; one elected lane per epilogue
-// warp of both CTAs arrives on the leader's "accumulator empty" barriers.  It validates the whole
-// 2-SM protocol, but the slab interval is latency bound like v2's (740 cycles with 8 stages), so
-// the next step is the pair WITHOUT the N = 128 chunking: v1's N = 256 phases with the weight slab
-// split over the pair need 32 KB per 768 MMA cycles, ~150 KB in flight, which fits.
-constexpr int V3_STAGES = 8;
-constexpr int V3_B_PLANE = (V2_TN / 2) * BK * 2;               // 4 KB: this CTA's 64 weight rows
-constexpr int V3_STAGE_BYTES = 2 * A_PLANE + 2 * V3_B_PLANE;   // 24 KB
-constexpr uint32_t IDESC_M256_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(V2_TN >> 3) << 17) |
-                                     ((uint32_t)((2 * TM) >> 4) << 24);
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                             int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                             int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far are done
-__device__ __forceinline__ void tc_commit2(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          bar),
-      "h"((unsigned short)3)
-      : "memory");
-}
-
-__global__ void __launch_bounds__(FWD2_THREADS, 1)
-resblock_tc3_kernel(const __grid_constant__ CUtensorMap map_x_hi,
-                    const __grid_constant__ CUtensorMap map_x_lo,
-                    const __grid_constant__ CUtensorMap map_c_hi,
-                    const __grid_constant__ CUtensorMap map_c_lo,
-                    const __grid_constant__ CUtensorMap map_w1_hi,
-                    const __grid_constant__ CUtensorMap map_w1_lo,
-                    const __grid_constant__ CUtensorMap map_w2_hi,
-                    const __grid_constant__ CUtensorMap map_w2_lo, const Params P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  float* b1s = reinterpret_cast<float*>(smem + V3_STAGES * V3_STAGE_BYTES);   // [512] conv_b + cond_b
-  float* brs = b1s + CD;                                                      // [Cr]
-  float* bss = brs + P.Cr;                                                    // [Cs]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + V3_STAGES);
-  const uint32_t acc_full0 = smem_u32(bars + 2 * V3_STAGES);        // [2]
-  const uint32_t acc_empty0 = smem_u32(bars + 2 * V3_STAGES + 2);   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_STAGES + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nplanes = P.x3 ? 2 : 1;
-  const uint32_t rank = cluster_ctarank();             // 0 = leader of the CTA pair
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int chunks_per_tap = P.Cr / BK;
-  const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of an H chunk
-  const int nk2 = CH / BK;                               // K slabs of an R / S chunk
-  const int n_h = CD / V2_TN;                            // 4
-  const int n_r = P.Cr / V2_TN;
-  const int o_begin = P.write_residual ? 0 : n_r;        // first chunk of [Wr ; Ws]
-  const int o_end = n_r + P.Cs / V2_TN;
-  const int tiles_per_item = (P.T + 2 * TM - 1) / (2 * TM);   // a pair covers 256 time steps
-  const int n_tiles = P.B * tiles_per_item;
-
-  if (warp == W2_TMA0 && lane == 0) {
-    prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
-    prefetch_tmap(&map_w2_hi);
-    if (P.x3) {
-      prefetch_tmap(&map_x_lo); prefetch_tmap(&map_c_lo); prefetch_tmap(&map_w1_lo);
-      prefetch_tmap(&map_w2_lo);
-    }
-    for (int s = 0; s < V3_STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(acc_full0 + 8 * s, 1);
-      mbar_init(acc_empty0 + 8 * s, 2 * FWD_EPI_WARPS);   // one elected lane per epilogue warp, both CTAs
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == W2_MMA) {   // the same warp in BOTH CTAs of the pair
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  if (warp < FWD_EPI_WARPS) {
-    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.conv_b[i] + P.cond_b[i];
-    for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
-    for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();        // the peer's barriers are initialised before anything remote touches them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= W2_TMA0 && warp < W2_MMA) {
-    // =============================== TMA producers ==============================
-    // producer warp 0 loads the activation planes, 1 the weight hi plane, 2 the weight lo plane; all
-    // three walk the same stage ring, warp 0 also registers the stage's byte count
-    const int pw = warp - W2_TMA0;
-    if (lane == 0 && (pw < 2 || P.x3)) {
-      int stage = 0;
-      uint32_t ph = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * 2 * TM + (int)rank * TM;
-        for (int c = 0; c < n_h; ++c) {
-          for (int i = 0; i < nk1; ++i) {
-            mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
-            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
-            const uint32_t sa = base + stage * V3_STAGE_BYTES;
-            if (rank == 0 && pw == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + V3_B_PLANE));
-            const int tap = i / chunks_per_tap;
-            if (tap < P.fs) {
-              const int c0 = (i - tap * chunks_per_tap) * BK;
-              const int tt = t0 - P.dilation * (P.fs - 1 - tap);   // negative rows -> zero fill
-              if (pw == 0) tma2_load_3d(sa, &map_x_hi, fb, c0, tt, b);
-              if (pw == 0 && P.x3) tma2_load_3d(sa + A_PLANE, &map_x_lo, fb, c0, tt, b);
-            } else {
-              const int c0 = (i - P.fs * chunks_per_tap) * BK;
-              if (pw == 0) tma2_load_3d(sa, &map_c_hi, fb, c0, t0, b);
-              if (pw == 0 && P.x3) tma2_load_3d(sa + A_PLANE, &map_c_lo, fb, c0, t0, b);
-            }
-            // this CTA stages its half (64 rows) of the chunk's 128 weight rows
-            if (pw == 1)
-              tma2_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, c * V2_TN + (int)rank * (V2_TN / 2));
-            if (pw == 2)
-              tma2_load_2d(sa + 2 * A_PLANE + V3_B_PLANE, &map_w1_lo, fb, i * BK,
-                           c * V2_TN + (int)rank * (V2_TN / 2));
-            if (++stage == V3_STAGES) { stage = 0; ph ^= 1; }
-          }
-        }
-        for (int oc = o_begin; oc < o_end; ++oc) {
-          for (int i = 0; i < nk2; ++i) {
-            mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
-            const uint32_t sa = base + stage * V3_STAGE_BYTES;
-            if (rank == 0 && pw == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * V3_B_PLANE);
-            if (pw == 1)
-              tma2_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * V2_TN + (int)rank * (V2_TN / 2));
-            if (pw == 2)
-              tma2_load_2d(sa + 2 * A_PLANE + V3_B_PLANE, &map_w2_lo, fb, i * BK,
-                           oc * V2_TN + (int)rank * (V2_TN / 2));
-            if (++stage == V3_STAGES) { stage = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == W2_MMA) {
-    // =============================== MMA issuer =================================
-    if (lane == 0 && rank == 0) {   // ONE thread of the pair issues the M = 256 MMAs of both SMs
-      int stage = 0;
-      uint32_t ph = 0;
-      uint32_t n = 0;   // running chunk counter: accumulator n & 1, its k-th use k = n >> 1
-      const uint32_t idesc = idesc_for(IDESC_M256_N128, P.f16);
-      const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        for (int c = 0; c < n_h; ++c, ++n) {
-          const uint32_t buf = n & 1;
-          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);   // epilogue of chunk n-2 is done
-          tc_fence_after();
-          if (rec && n < 24) P.dbg[4 * n] = clock64();
-          const uint32_t acc = tmem_base + buf * V2_TN;
-          for (int i = 0; i < nk1; ++i) {
-            mbar_wait(full0 + 8 * stage, ph);
-            tc_fence_after();
-            const uint32_t sa = base + stage * V3_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks) {
-              const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-              mma2_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-              if (P.x3) {
-                const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V3_B_PLANE + ks * UK * 2);
-                mma2_ss(acc, a_lo, b_hi, idesc, 1u);
-                mma2_ss(acc, a_hi, b_lo, idesc, 1u);
-              }
-            }
-            tc_commit2(empty0 + 8 * stage);
-            if (++stage == V3_STAGES) { stage = 0; ph ^= 1; }
-          }
-          tc_commit2(acc_full0 + 8 * buf);
-          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
-        }
-        {   // every z column of this tile must be in TMEM: wait for the epilogue of H_3 (chunk n-1)
-          const uint32_t m = n - 1;
-          mbar_wait(acc_empty0 + 8 * (m & 1), (m >> 1) & 1);
-          tc_fence_after();
-        }
-        for (int oc = o_begin; oc < o_end; ++oc, ++n) {
-          const uint32_t buf = n & 1;
-          mbar_wait(acc_empty0 + 8 * buf, ((n >> 1) & 1) ^ 1);
-          tc_fence_after();
-          if (rec && n < 24) P.dbg[4 * n] = clock64();
-          const uint32_t acc = tmem_base + buf * V2_TN;
-          for (int i = 0; i < nk2; ++i) {
-            mbar_wait(full0 + 8 * stage, ph);
-            tc_fence_after();
-            const uint32_t sa = base + stage * V3_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks) {
-              // z channel k sits in column k/2 of its plane: slab i, step ks -> 16*i + 8*ks
-              const uint32_t z_hi = tmem_base + ZHI_COL + (BK / 2) * i + (UK / 2) * ks;
-              const uint32_t z_lo = tmem_base + ZLO_COL + (BK / 2) * i + (UK / 2) * ks;
-              const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-              mma2_ts(acc, z_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-              if (P.x3) {
-                const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + V3_B_PLANE + ks * UK * 2);
-                mma2_ts(acc, z_lo, b_hi, idesc, 1u);
-                mma2_ts(acc, z_hi, b_lo, idesc, 1u);
-              }
-            }
-            tc_commit2(empty0 + 8 * stage);
-            if (++stage == V3_STAGES) { stage = 0; ph ^= 1; }
-          }
-          tc_commit2(acc_full0 + 8 * buf);
-          if (rec && n < 24) P.dbg[4 * n + 1] = clock64();
-        }
-      }
-    }
-  } else {
-    // =============================== epilogue (warps 0-15) ======================
-    // warp e: TMEM lane quadrant e%4, column group e/4 (16-column units dealt round-robin)
-    const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_x && threadIdx.x == 0;
-    const int quad = warp & 3, grp = warp >> 2;
-    constexpr int NG = FWD_EPI_WARPS / 4;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t n = 0;
-    const uint32_t acc_empty_leader0 = mapa_u32(acc_empty0, 0);   // the leader's barriers
-    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-      const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * 2 * TM + (int)rank * TM;
-      const int t = t0 + row;
-      const bool t_ok = t < P.T;
-      // ---- gate chunks: z = tanh(h_t) * sigmoid(h_s) -> TMEM z planes (+ saved tensors) ----
-      for (int c = 0; c < n_h; ++c, ++n) {
-        const uint32_t buf = n & 1;
-        const uint32_t acc = lane_base + buf * V2_TN;
-        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
-        tc_fence_after();
-        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
-#pragma unroll 1
-        for (int q = grp; q < V2_HALF / 16; q += NG) {
-          float a[16], g[16];
-          tmem_ld16(acc + 16 * q, a);
-          tmem_ld16(acc + V2_HALF + 16 * q, g);
-          uint32_t zh[8], zl[8];
-          const int ch0 = c * V2_HALF + 16 * q;
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float z2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int ch = ch0 + i + u;
-              const float th = tanh_fast(a[i + u] + b1s[ch]);
-              const float sg = sigmoid_fast(g[i + u] + b1s[CH + ch]);
-              z2[u] = th * sg;
-              if (P.gate_tanh != nullptr && t_ok) {
-                const int64_t off = ((int64_t)b * CH + ch) * P.T + t;
-                __stcs(P.gate_tanh + off, th);
-                __stcs(P.gate_sig + off, sg);
-              }
-            }
-            if (P.x3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], P.f16);
-            else zh[i >> 1] = pack_pair_f(z2[0], z2[1], P.f16);
-          }
-          tmem_st8(lane_base + ZHI_COL + (ch0 >> 1), zh);
-          if (P.x3) tmem_st8(lane_base + ZLO_COL + (ch0 >> 1), zl);
-          if (P.zp_hi != nullptr && t_ok) {
-            const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
-            st256(P.zp_hi + zoff, zh);
-            if (P.x3) st256(P.zp_lo + zoff, zl);
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + 8 * buf);
-        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
-      }
-      // ---- output chunks: residual channels, then skip channels ----
-      for (int oc = o_begin; oc < o_end; ++oc, ++n) {
-        const uint32_t buf = n & 1;
-        const uint32_t acc = lane_base + buf * V2_TN;
-        const bool is_res = oc < n_r;
-        const int cbase = is_res ? oc * V2_TN : (oc - n_r) * V2_TN;
-        float addf[16];
-        uint32_t hw[8], lw[8];
-        auto fetch = [&](int q) {
-          const int ch0 = cbase + 16 * q;
-          if (is_res) {
-            const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
-            if (t_ok) {
-              ld256(P.xp_hi + poff, hw);
-              if (P.xlo) ld256(P.xp_lo + poff, lw);
-            }
-          } else if (P.skip_accumulate && t_ok) {
-            const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
-          }
-        };
-        fetch(grp);
-        mbar_wait(acc_full0 + 8 * buf, (n >> 1) & 1);
-        tc_fence_after();
-        if (rec && n < 24) P.dbg[4 * n + 2] = clock64();
-#pragma unroll 1
-        for (int q = grp; q < V2_TN / 16; q += NG) {
-          float o[16], add[16];
-          tmem_ld16(acc + 16 * q, o);
-          if (is_res) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float v0, v1;
-              unpack_pair_f(hw[i], P.f16, v0, v1);
-              if (P.xlo) {
-                float l0, l1;
-                unpack_pair_f(lw[i], P.f16, l0, l1);
-                v0 += l0;
-                v1 += l1;
-              }
-              add[2 * i] = t_ok ? v0 : 0.0f;
-              add[2 * i + 1] = t_ok ? v1 : 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
-          }
-          if (q + NG < V2_TN / 16) fetch(q + NG);
-          const int ch0 = cbase + 16 * q;
-          if (is_res) {
-            uint32_t rh[8], rl[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float v2[2];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int ch = ch0 + i + u;
-                const float v = o[i + u] + brs[ch] + add[i + u];
-                if (t_ok && P.res_f32 != nullptr)
-                  __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
-                v2[u] = v;
-              }
-              if (P.xlo) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], P.f16);
-              else rh[i >> 1] = pack_pair_f(v2[0], v2[1], P.f16);
-            }
-            if (t_ok && P.res_hi != nullptr) {
-              const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
-              st256(P.res_hi + poff, rh);
-              if (P.xlo) st256(P.res_lo + poff, rl);
-            }
-          } else if (t_ok) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int ch = ch0 + i;
-              P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + 8 * buf);
-        if (rec && n < 24) P.dbg[4 * n + 3] = clock64();
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs can still touch it
-  if (warp == W2_MMA) {
-    __syncwarp();
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
-                 : "memory");
-  }
-}
-
 
 // ------------------------------------------------------------------ packing kernels --------
 // (B,C,T) fp32 -> (B,T,C) bf16 hi/lo planes: 32x32 transpose through shared memory
@@ -1358,17 +603,8 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
 }
 
 size_t smem_bytes(int Cr, int Cs) {
-  return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * (2 * STAGES + 2) + 16;
+  return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * NBAR + 16;
 }
-size_t smem_bytes_v3(int Cr, int Cs) {
-  return 1024 + (size_t)V3_STAGES * V3_STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) +
-         8 * (2 * V3_STAGES + 4) + 16;
-}
-size_t smem_bytes_v2(int Cr, int Cs) {
-  return 1024 + (size_t)V2_STAGES * V2_STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) +
-         8 * (2 * V2_STAGES + 4) + 16;
-}
-
 }  // namespace tc
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -1417,15 +653,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   const bool x3 = d.mode == VQW_MODE_BF16X3;
   const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const bool xlo = x3 || f16;   // residual stream hi + lo (only the hi plane feeds the MMAs in fp16)
-  // VQW_TC_FWD_V2=1 selects the experimental persistent kernel (see resblock_tc2_kernel)
-  const char* v2env = getenv("VQW_TC_FWD_V2");
-  const bool use_v2 = v2env && v2env[0] == '1';
-  // VQW_TC_FWD_V3=1: the same chunk pipeline on CTA pairs (cta_group::2), see resblock_tc3_kernel
-  const char* v3env = getenv("VQW_TC_FWD_V3");
-  const bool v3 = v3env && v3env[0] == '1' && d.Cr % V2_TN == 0 && d.Cs % V2_TN == 0;
-  const bool v2 = (use_v2 || v3) && d.Cr % V2_TN == 0 && d.Cs % V2_TN == 0;   // v3 shares v2's packing
-  // weight rows per TMA box: a whole accumulator chunk, or this CTA's half of it (v3)
-  const int wrows = v3 ? V2_TN / 2 : (v2 ? V2_TN : TN);
+  // weight rows per TMA box = UMMA N of the phase that consumes them
+  const int wrows = TN, wrows2 = ON;
   const TcWorkspace L = tc_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
   auto plane = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
@@ -1462,7 +691,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       __nv_bfloat16* w2h = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane);
       __nv_bfloat16* w2l = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane + L.w2_plane);
       pack_w1_kernel<<<296, 256, 0, stream>>>(w.conv_w, w.cond_w, w1h, x3 ? w1l : nullptr, d.Cr,
-                                               d.Cc, d.fs, f16, v2 ? V2_HALF : HALF);
+                                               d.Cc, d.fs, f16, HALF);
       VQW_CHECK_LAUNCH("pack_w1_kernel");
       pack_w2_kernel<<<148, 256, 0, stream>>>(w.res_w, w.skip_w, w2h, x3 ? w2l : nullptr, d.Cr, d.Cs,
                                                f16);
@@ -1470,22 +699,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     }
   }
 
-  const size_t smem = v3 ? smem_bytes_v3(d.Cr, d.Cs) : v2 ? smem_bytes_v2(d.Cr, d.Cs) : smem_bytes(d.Cr, d.Cs);
-  if (v3)
-    VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc3_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else if (v2)
-    VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc2_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else
-    VQW_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int n_sm = 148;
-  {
-    int dev = 0;
-    VQW_CHECK_CUDA(cudaGetDevice(&dev));
-    VQW_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const size_t smem = smem_bytes(d.Cr, d.Cs);
+  auto kern = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
+  VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUtensorMap m_c_hi, m_c_lo;
   if (int rc = make_map(&m_c_hi, c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
   if (int rc = make_map(&m_c_lo, x3 ? c_lo : c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
@@ -1507,8 +723,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     if (int rc = make_map(&m_x_lo, x3 ? x_lo[cur] : x_hi[cur], 3, d.Cr, d.T, d.B, TM)) return rc;
     if (int rc = make_map(&m_w1_hi, w1h, 2, K1, CD, 1, wrows)) return rc;
     if (int rc = make_map(&m_w1_lo, x3 ? w1l : w1h, 2, K1, CD, 1, wrows)) return rc;
-    if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, wrows)) return rc;
-    if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, wrows)) return rc;
+    if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
+    if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
     Params P;
     P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = d.Cc; P.fs = d.fs;
     P.dilation = d.dilations[i];
@@ -1517,10 +733,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.xlo = xlo ? 1 : 0;
     P.skip_accumulate = i > 0;
     P.write_residual = write_res ? 1 : 0;
-    {
-      static const int pf_env = getenv("VQW_TC_PREFETCH") ? atoi(getenv("VQW_TC_PREFETCH")) : 12;
-      P.pf_dist = pf_env;
-    }
+    P.pf_dist = getenv("VQW_TC_PREFETCH") ? atoi(getenv("VQW_TC_PREFETCH")) : 0;   // measured: no gain
     P.xp_hi = x_hi[cur];
     P.xp_lo = x_lo[cur];
     P.conv_b = w.conv_b; P.cond_b = w.cond_b; P.res_b = w.res_b; P.skip_b = w.skip_b;
@@ -1535,7 +748,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     VQW_REQUIRE((P.gate_tanh == nullptr) == (P.gate_sig == nullptr),
                 "vqw_resnet_forward: gate_tanh/gate_sig of block %d must be given together", i);
     static long long* dbg_buf = nullptr;
-    static const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
+    const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
     P.dbg = nullptr; P.dbg_x = P.dbg_y = 0;
     if (timeline) {
       if (!dbg_buf) cudaMalloc(&dbg_buf, 128 * sizeof(long long));
@@ -1544,54 +757,28 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       P.dbg_x = getenv("VQW_TC_TIMELINE_X") ? atoi(getenv("VQW_TC_TIMELINE_X")) : 1;
       P.dbg_y = getenv("VQW_TC_TIMELINE_Y") ? atoi(getenv("VQW_TC_TIMELINE_Y")) : 0;
     }
-    if (v3) {
-      const int n_pair_tiles = d.B * ceil_div(d.T, 2 * TM);
-      const int n_pairs = n_pair_tiles < n_sm / 2 ? n_pair_tiles : n_sm / 2;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * n_pairs);
-      cfg.blockDim = dim3(FWD2_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, resblock_tc3_kernel, m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
-                                        m_w1_lo, m_w2_hi, m_w2_lo, P));
-      VQW_CHECK_LAUNCH("resblock_tc3_kernel");
-    } else if (v2) {
-      const int n_tiles = d.B * ceil_div(d.T, TM);
-      resblock_tc2_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, FWD2_THREADS, smem, stream>>>(
-          m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo, m_w2_hi, m_w2_lo, P);
-      VQW_CHECK_LAUNCH("resblock_tc2_kernel");
-    } else {
-      dim3 grid(ceil_div(d.T, TM), d.B);
-      resblock_tc_kernel<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi,
-                                                          m_w1_lo, m_w2_hi, m_w2_lo, P);
-      VQW_CHECK_LAUNCH("resblock_tc_kernel");
-    }
-    if (timeline && v2) {
-      long long h[128];
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[vqw timeline v2] block %d CTA %d (cycles rel. to the first MMA issue)\n", i, P.dbg_x);
-      for (int n = 0; n < 24; ++n)
-        fprintf(stderr, "  chunk %2d: mma issue [%7lld, %7lld]  epilogue [%7lld, %7lld]\n", n,
-                h[4 * n] - h[0], h[4 * n + 1] - h[0], h[4 * n + 2] - h[0], h[4 * n + 3] - h[0]);
-    }
-    if (timeline && !v2) {
+    dim3 grid(ceil_div(d.T, TM), d.B);
+    kern<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
+                                             m_w2_hi, m_w2_lo, P);
+    VQW_CHECK_LAUNCH("resblock_tc_kernel");
+    if (timeline) {
       long long h[64];
       cudaStreamSynchronize(stream);
       cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[vqw timeline] block %d CTA (%d,%d): entry %lld, setup done %lld, exit %lld "
                       "(cycles rel. to first MMA phase start)\n", i, P.dbg_x, P.dbg_y, h[40] - h[0],
               h[41] - h[0], h[42] - h[0]);
-      for (int n = 0; n < 5; ++n)
-        fprintf(stderr, "  phase %d: mma [%lld, %lld]  epilogue [%lld, %lld]\n", n, h[2 * n] - h[0],
-                h[2 * n + 1] - h[0], h[16 + 2 * n] - h[0], h[16 + 2 * n + 1] - h[0]);
+      {
+        for (int n = 0; n < 2; ++n)
+          fprintf(stderr, "  H_%c : mma [%lld, %lld]  gate epilogue [%lld, %lld]\n", 'a' + n,
+                  h[2 * n] - h[0], h[2 * n + 1] - h[0], h[16 + 2 * n] - h[0], h[16 + 2 * n + 1] - h[0]);
+        for (int n = 0; n < 6; ++n)
+          fprintf(stderr, "  O_%d : mma [%lld, %lld]  epilogue [%lld, %lld]\n", n, h[4 + 2 * n] - h[0],
+                  h[5 + 2 * n] - h[0], h[20 + 2 * n] - h[0], h[21 + 2 * n] - h[0]);
+        fprintf(stderr, "  O_0 warp 0: fetch issue [%lld, %lld]  tmem_ld done %lld  addend arrived %lld  "
+                        "piece 0 done %lld  piece 1 done %lld\n", h[48] - h[0], h[49] - h[0],
+                h[50] - h[0], h[51] - h[0], h[52] - h[0], h[53] - h[0]);
+      }
     }
   }
   return 0;

@@ -68,7 +68,7 @@ struct GemmParams {
   int b_exact;                 // wgrad: B has no lo plane (exact bf16 values, e.g. a one-hot)
   int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
   int chunks_per_b;            // wgrad: work items per batch item
-  const float* f0;             // GATE_BWD: tanh (B,256,T)
+  const float* f0;             // GATE_BWD: tanh, time-major (B,T,256) fp32
   const float* f1;             // GATE_BWD: sigmoid
   const __nv_bfloat16* a_hi;   // GX: addend planes (B,T,Cout) (g_res) or null
   const __nv_bfloat16* a_lo;
@@ -260,14 +260,16 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       if (EPI == EPI_GATE_BWD) {
         // gz -> gh_t = gz*sig*(1-tanh^2), gh_s = gz*tanh*sig*(1-sig)   (modules.py:47-48 differentiated)
         const int CHh = TN;   // 256 gate pairs
-        const float* tp = P.f0 + ((int64_t)b * CHh) * P.T + t;
-        const float* sp = P.f1 + ((int64_t)b * CHh) * P.T + t;
-        float pt[16], ps[16];
+        // saved tanh / sigmoid: time-major (B,T,256) fp32, written by the forward gate epilogue
+        const float* tp = P.f0 + ((int64_t)b * P.T + t) * CHh;
+        const float* sp = P.f1 + ((int64_t)b * P.T + t) * CHh;
+        uint32_t pt[16], ps[16];
         auto fetch = [&](int q) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            pt[i] = t_ok ? __ldcs(tp + (int64_t)(16 * q + i) * P.T) : 0.0f;
-            ps[i] = t_ok ? __ldcs(sp + (int64_t)(16 * q + i) * P.T) : 0.0f;
+          if (t_ok) {
+            ld256(tp + 16 * q, pt);
+            ld256(tp + 16 * q + 8, pt + 8);
+            ld256(sp + 16 * q, ps);
+            ld256(sp + 16 * q + 8, ps + 8);
           }
         };
         fetch(grp);
@@ -278,7 +280,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           float gz[16], th[16], sg[16];
           tmem_ld16(lane_base + 16 * q, gz);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { th[i] = pt[i]; sg[i] = ps[i]; }
+          for (int i = 0; i < 16; ++i) {
+            th[i] = t_ok ? __uint_as_float(pt[i]) : 0.0f;
+            sg[i] = t_ok ? __uint_as_float(ps[i]) : 0.0f;
+          }
           if (q + NG < TN / 16) fetch(q + NG);
           if (!t_ok) continue;
           uint32_t th_hi[8], th_lo[8], sg_hi[8], sg_lo[8];

@@ -171,7 +171,9 @@ int vqw_resblock_backward(const vqw_resblock_desc* desc, const float* g_res, con
  * residuals[i] = (B,Cr,T) fp32 output of block i (the saved input of block i+1; required in
  * the tensor-core modes for i < n_blocks-1, optional -- ping-pong in the workspace -- in fp32
  * mode; the last entry is only written when keep_last_residual), gate_tanh[i] / gate_sig[i] =
- * (B,Cd/2,T) fp32 saved gate factors (arrays may be NULL for inference).
+ * B*(Cd/2)*T fp32 saved gate factors (arrays may be NULL for inference): opaque to the caller --
+ * fp32 mode lays them out (B,Cd/2,T), the tensor-core modes time-major (B,T,Cd/2), because there
+ * one thread owns one time row in the forward gate epilogue and in the backward that reads them.
  */
 typedef struct {
   int B, T, Cr, Cd, Cs, Cc, fs;

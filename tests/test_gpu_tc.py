@@ -80,27 +80,6 @@ def test_tc_fp16_matches_oracle(dilations, B, T):
     assert e_skip < TOL and e_res < TOL
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
-def test_tc_persistent_chunked_kernel_matches_oracle(mode, monkeypatch):
-    """The experimental persistent forward kernel (N = 128 chunks on two ping-pong accumulators,
-    VQW_TC_FWD_V2=1) computes the same block."""
-    monkeypatch.setenv("VQW_TC_FWD_V2", "1")
-    (skip, res), skip_o, coll = _run(mode, [1, 2, 4], 3, 640, keep_last=True)
-    tol = 1e-4 if mode == "bf16x3" else TOL
-    assert rel_err(skip, skip_o) < tol and rel_err(res, coll[-1]) < tol
-
-
-@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
-def test_tc_cta_pair_kernel_matches_oracle(mode, monkeypatch):
-    """The experimental CTA-pair forward kernel (cta_group::2 MMAs with M = 256 over two SMs, each
-    staging half of every weight slab; VQW_TC_FWD_V3=1) computes the same block, including a
-    ragged last pair (T = 640 = 2.5 pairs)."""
-    monkeypatch.setenv("VQW_TC_FWD_V3", "1")
-    (skip, res), skip_o, coll = _run(mode, [1, 2, 4], 3, 640, keep_last=True)
-    tol = 1e-4 if mode == "bf16x3" else TOL
-    assert rel_err(skip, skip_o) < tol and rel_err(res, coll[-1]) < tol
-
-
 def test_tc_bf16_throughput_mode_is_close():
     skip, skip_o, coll = _run("bf16", [1, 2, 4], 2, 256)
     e = rel_err(skip, skip_o)
