@@ -59,7 +59,8 @@ class ResblockWeights(C.Structure):
 class ResnetDesc(C.Structure):
     _fields_ = [("B", c_int), ("T", c_int), ("Cr", c_int), ("Cd", c_int), ("Cs", c_int),
                 ("Cc", c_int), ("fs", c_int), ("n_blocks", c_int),
-                ("dilations", C.POINTER(c_int)), ("mode", c_int), ("keep_last_residual", c_int)]
+                ("dilations", C.POINTER(c_int)), ("mode", c_int), ("keep_last_residual", c_int),
+                ("Cg", c_int), ("cond_global", C.c_void_p), ("g_cond_global", C.c_void_p)]
 
 
 class GenerateDesc(C.Structure):

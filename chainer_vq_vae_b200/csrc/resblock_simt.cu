@@ -351,6 +351,8 @@ extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, c
     return resnet_forward_tc(d, x, cond, weights, residuals, skip, gate_tanh, gate_sig, workspace,
                              saved, st);
   VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_forward: unknown mode %d", d.mode);
+  VQW_REQUIRE(d.Cg == 0, "vqw_resnet_forward: the hoisted global condition (Cg > 0) is a tensor-core "
+                         "mode feature; fp32 mode takes the concatenated condition");
   float* pp[2] = {nullptr, nullptr};
   if (workspace) {
     uintptr_t a = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
@@ -416,6 +418,7 @@ extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_s
                               wgrads, workspace, saved, (cudaStream_t)stream);
   }
   VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_backward: unknown mode %d", d.mode);
+  VQW_REQUIRE(d.Cg == 0, "vqw_resnet_backward: Cg > 0 is a tensor-core mode feature");
   VQW_REQUIRE(x && cond, "vqw_resnet_backward: null tensor");
   VQW_REQUIRE(d.n_blocks == 1 || residuals, "vqw_resnet_backward: residuals[] is required");
   uintptr_t a = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;

@@ -37,7 +37,6 @@ constexpr int STAGES = 4;
 constexpr int FWD_EPI_WARPS = 16;                       // 4 warps per TMEM lane quadrant
 constexpr int FWD_THREADS = (FWD_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
 constexpr int W_TMA = FWD_EPI_WARPS, W_MMA = FWD_EPI_WARPS + 1;
-constexpr int ACC_COL = 0, ZHI_COL = 256, ZLO_COL = 384;
 constexpr int CD = 512, CH = 256, HALF = 128;             // dilated channels handled by this kernel
 
 struct Params {
@@ -50,7 +49,8 @@ struct Params {
   int pf_dist;          // L2 prefetch distance (K slabs) of the activation operand in H_a, 0 = off
   const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
   const __nv_bfloat16* xp_lo;
-  const float* conv_b;  const float* cond_b;  const float* res_b;  const float* skip_b;
+  const float* gbias;   // (B,512): conv_b + cond_b + W_p[:, Cl:] . global condition of the item
+  const float* res_b;  const float* skip_b;
   float* res_f32;       // (B,Cr,T) fp32 or null (saved block input of the next block / API output)
   __nv_bfloat16* res_hi;  // packed (B,T,Cr) planes for the next block (null for the last block)
   __nv_bfloat16* res_lo;
@@ -146,7 +146,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp < FWD_EPI_WARPS) {
-    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.conv_b[i] + P.cond_b[i];
+    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.gbias[(int64_t)b * CD + i];
     for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
     for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
   }
@@ -470,7 +470,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 __global__ void __launch_bounds__(256)
 pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
                 __nv_bfloat16* __restrict__ lo, int C, int T, int pitch, int relu, int f16,
-                const float* __restrict__ scale) {
+                const float* __restrict__ scale, int ones_ch) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -482,9 +482,10 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     int t = t0 + r, c = c0 + tx;
-    if (t < T && c < pitch) {          // channels in [C, pitch) are zero padding
+    if (t < T && c < pitch) {          // channels in [C, pitch) are zero padding ...
       __nv_bfloat16 h, l;
       float v = tile[tx][r];
+      if (c == ones_ch) v = 1.0f;      // ... except the constant-one channel (bias-gradient column)
       if (relu) v = fmaxf(v, 0.0f);
       split_16(v, f16, h, l);
       const int64_t off = ((int64_t)b * T + t) * pitch + c;
@@ -497,7 +498,7 @@ pack_act_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
 int pack_act_launch_ex(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
                        int pitch, int relu, int f16, const float* scale, cudaStream_t stream) {
   dim3 g(ceil_div(T, 32), ceil_div(pitch, 32), B);
-  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T, pitch, relu, f16, scale);
+  pack_act_kernel<<<g, 256, 0, stream>>>(in, hi, lo, C, T, pitch, relu, f16, scale, -1);
   VQW_CHECK_LAUNCH("pack_act_kernel");
   return 0;
 }
@@ -513,8 +514,8 @@ int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B
 __global__ void __launch_bounds__(256)
 pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_w,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cc,
-               int fs, int f16, int half) {
-  const int K1 = fs * Cr + Cc;
+               int Cl, int fs, int f16, int half) {
+  const int K1 = fs * Cr + Cl;         // only the Cl time-varying condition columns are contracted
   const int64_t n = (int64_t)CD * K1;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -550,6 +551,30 @@ pack_w2_kernel(const float* __restrict__ res_w, const float* __restrict__ skip_w
     hi[e] = h;
     if (lo) lo[e] = l;
   }
+}
+
+// Per-(block, item) gate bias: conv_b + cond_b + W_p[:, Cl:] . g_b -- the condition projection of
+// the time-constant (speaker) channels, modules.py:17-18,44 applied to net.py:59-61's broadcast.
+// grid (B, blocks in this launch), 512 threads = dilated channels.
+constexpr int GB_MAX = 32;
+struct GbiasArgs {
+  const float* conv_b[GB_MAX];
+  const float* cond_b[GB_MAX];
+  const float* cond_w[GB_MAX];
+};
+__global__ void __launch_bounds__(CD)
+gbias_kernel(const __grid_constant__ GbiasArgs A, const float* __restrict__ glob,
+             float* __restrict__ out, int B, int Cc, int Cg, int blk0) {
+  const int b = blockIdx.x, i = blockIdx.y, ch = threadIdx.x;
+  float v = A.conv_b[i][ch] + A.cond_b[i][ch];
+  if (Cg > 0) {
+    const float* w = A.cond_w[i] + (int64_t)ch * Cc + (Cc - Cg);
+    const float* g = glob + (int64_t)b * Cg;
+    float acc = 0.0f;
+    for (int k = 0; k < Cg; ++k) acc = fmaf(__ldg(w + k), __ldg(g + k), acc);
+    v += acc;
+  }
+  out[((int64_t)(blk0 + i) * B + b) * CD + ch] = v;
 }
 
 // ------------------------------------------------------------------ host side --------------
@@ -610,20 +635,21 @@ size_t smem_bytes(int Cr, int Cs) {
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 bool resnet_tc_supported(const vqw_resnet_desc& d) {
-  return d.Cd == tc::CD && d.Cr % tc::TN == 0 && d.Cs % tc::TN == 0 && d.Cc % tc::BK == 0 &&
-         d.Cr >= tc::TN && d.Cs >= tc::TN && d.fs >= 1 && d.T >= tc::TM && d.T % 8 == 0 &&
-         d.Cc % 16 == 0;
+  const int Cl = d.Cc - d.Cg;
+  return d.Cd == tc::CD && d.Cr % tc::TN == 0 && d.Cs % tc::TN == 0 && d.Cg >= 0 && Cl >= tc::BK &&
+         Cl % tc::BK == 0 && d.Cr >= tc::TN && d.Cs >= tc::TN && d.fs >= 1 && d.T >= tc::TM &&
+         d.T % 8 == 0;
 }
 
 // workspace: [cond hi|lo] [x ping hi|lo] [x pong hi|lo] [per block: w1 hi|lo, w2 hi|lo]
 struct TcWorkspace {
   int64_t cond_plane, x_plane, w1_plane, w2_plane, block_stride, total;
-  int64_t off_cond, off_x[2], off_w;
+  int64_t off_cond, off_x[2], off_w, off_gbias;
 };
 static TcWorkspace tc_layout(const vqw_resnet_desc& d) {
   TcWorkspace w;
-  const int K1 = d.fs * d.Cr + d.Cc;
-  w.cond_plane = align_up((int64_t)d.B * d.T * d.Cc * 2, 1024);
+  const int K1 = d.fs * d.Cr + cond_local(d);
+  w.cond_plane = align_up((int64_t)d.B * d.T * cond_pitch(d) * 2, 1024);
   w.x_plane = align_up((int64_t)d.B * d.T * d.Cr * 2, 1024);
   w.w1_plane = align_up((int64_t)tc::CD * K1 * 2, 1024);
   w.w2_plane = align_up((int64_t)(d.Cr + d.Cs) * tc::CH * 2, 1024);
@@ -632,7 +658,8 @@ static TcWorkspace tc_layout(const vqw_resnet_desc& d) {
   w.off_x[0] = 2 * w.cond_plane;
   w.off_x[1] = w.off_x[0] + 2 * w.x_plane;
   w.off_w = w.off_x[1] + 2 * w.x_plane;
-  w.total = w.off_w + (int64_t)d.n_blocks * w.block_stride;
+  w.off_gbias = w.off_w + (int64_t)d.n_blocks * w.block_stride;
+  w.total = w.off_gbias + align_up((int64_t)d.n_blocks * d.B * tc::CD * 4, 1024);
   return w;
 }
 
@@ -646,8 +673,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   using namespace tc;
   VQW_REQUIRE(resnet_tc_supported(d),
               "tcgen05 path needs dilated_channels=512, residual/skip channels multiples of 256, "
-              "condition channels a multiple of 32, T >= 128 and T %% 8 == 0 "
-              "(got Cr=%d Cd=%d Cs=%d Cc=%d T=%d)", d.Cr, d.Cd, d.Cs, d.Cc, d.T);
+              "time-varying condition channels a multiple of 32, T >= 128 and T %% 8 == 0 "
+              "(got Cr=%d Cd=%d Cs=%d Cc=%d Cg=%d T=%d)", d.Cr, d.Cd, d.Cs, d.Cc, d.Cg, d.T);
+  VQW_REQUIRE(d.Cg == 0 || d.cond_global != nullptr, "vqw_resnet_forward: Cg > 0 needs cond_global");
   VQW_REQUIRE(workspace != nullptr, "vqw_resnet_forward: workspace is null");
   VQW_REQUIRE(d.B <= 65535, "vqw_resnet_forward: B > 65535");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
@@ -671,17 +699,32 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   };
   __nv_bfloat16* x_hi[2] = {xin_hi(0), nullptr};
   __nv_bfloat16* x_lo[2] = {xin_lo(0), nullptr};
-  const int K1 = d.fs * d.Cr + d.Cc;
+  const int Cl = cond_local(d), CP = cond_pitch(d);
+  const int K1 = d.fs * d.Cr + Cl;
 
+  float* gbias = reinterpret_cast<float*>(ws + L.off_gbias);   // (n_blocks, B, 512) gate biases
   // pack the two inputs and every block's weights
   {
-    dim3 g1(ceil_div(d.T, 32), ceil_div(d.Cr, 32), d.B), g2(ceil_div(d.T, 32), ceil_div(d.Cc, 32), d.B);
+    dim3 g1(ceil_div(d.T, 32), ceil_div(d.Cr, 32), d.B), g2(ceil_div(d.T, 32), ceil_div(CP, 32), d.B);
     pack_act_kernel<<<g1, 256, 0, stream>>>(x, x_hi[0], xlo ? x_lo[0] : nullptr, d.Cr, d.T, d.Cr, 0,
-                                            f16, nullptr);
+                                            f16, nullptr, -1);
     VQW_CHECK_LAUNCH("pack_act_kernel(x)");
-    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, d.Cc, d.T, d.Cc, 0, f16,
-                                            nullptr);
+    // condition planes: Cl channels, the constant-one channel, zero padding (see cond_pitch)
+    pack_act_kernel<<<g2, 256, 0, stream>>>(cond, c_hi, x3 ? c_lo : nullptr, Cl, d.T, CP, 0, f16,
+                                            nullptr, Cl);
     VQW_CHECK_LAUNCH("pack_act_kernel(cond)");
+    for (int i0 = 0; i0 < d.n_blocks; i0 += GB_MAX) {
+      GbiasArgs A = {};
+      const int nb = d.n_blocks - i0 < GB_MAX ? d.n_blocks - i0 : GB_MAX;
+      for (int i = 0; i < nb; ++i) {
+        const vqw_resblock_weights& w = weights[i0 + i];
+        VQW_REQUIRE(w.conv_b && w.cond_b && w.cond_w, "vqw_resnet_forward: block %d has a null weight",
+                    i0 + i);
+        A.conv_b[i] = w.conv_b; A.cond_b[i] = w.cond_b; A.cond_w[i] = w.cond_w;
+      }
+      gbias_kernel<<<dim3(d.B, nb), CD, 0, stream>>>(A, d.cond_global, gbias, d.B, d.Cc, d.Cg, i0);
+      VQW_CHECK_LAUNCH("gbias_kernel");
+    }
     for (int i = 0; i < d.n_blocks; ++i) {
       const vqw_resblock_weights& w = weights[i];
       VQW_REQUIRE(w.conv_w && w.conv_b && w.cond_w && w.cond_b && w.res_w && w.res_b && w.skip_w &&
@@ -691,7 +734,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       __nv_bfloat16* w2h = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane);
       __nv_bfloat16* w2l = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane + L.w2_plane);
       pack_w1_kernel<<<296, 256, 0, stream>>>(w.conv_w, w.cond_w, w1h, x3 ? w1l : nullptr, d.Cr,
-                                               d.Cc, d.fs, f16, HALF);
+                                               d.Cc, Cl, d.fs, f16, HALF);
       VQW_CHECK_LAUNCH("pack_w1_kernel");
       pack_w2_kernel<<<148, 256, 0, stream>>>(w.res_w, w.skip_w, w2h, x3 ? w2l : nullptr, d.Cr, d.Cs,
                                                f16);
@@ -703,8 +746,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   auto kern = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUtensorMap m_c_hi, m_c_lo;
-  if (int rc = make_map(&m_c_hi, c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
-  if (int rc = make_map(&m_c_lo, x3 ? c_lo : c_hi, 3, d.Cc, d.T, d.B, TM)) return rc;
+  if (int rc = make_map(&m_c_hi, c_hi, 3, CP, d.T, d.B, TM)) return rc;
+  if (int rc = make_map(&m_c_lo, x3 ? c_lo : c_hi, 3, CP, d.T, d.B, TM)) return rc;
 
   for (int i = 0; i < d.n_blocks; ++i) {
     const bool last = (i == d.n_blocks - 1);
@@ -726,7 +769,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
     if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
     Params P;
-    P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = d.Cc; P.fs = d.fs;
+    P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = Cl; P.fs = d.fs;   // Cc: contracted channels
     P.dilation = d.dilations[i];
     P.x3 = x3 ? 1 : 0;
     P.f16 = f16;
@@ -736,7 +779,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.pf_dist = getenv("VQW_TC_PREFETCH") ? atoi(getenv("VQW_TC_PREFETCH")) : 0;   // measured: no gain
     P.xp_hi = x_hi[cur];
     P.xp_lo = x_lo[cur];
-    P.conv_b = w.conv_b; P.cond_b = w.cond_b; P.res_b = w.res_b; P.skip_b = w.skip_b;
+    P.gbias = gbias + (int64_t)i * d.B * CD;
+    P.res_b = w.res_b; P.skip_b = w.skip_b;
     P.res_f32 = (write_res && residuals) ? residuals[i] : nullptr;
     P.res_hi = last ? nullptr : x_hi[nxt];
     P.res_lo = last ? nullptr : x_lo[nxt];

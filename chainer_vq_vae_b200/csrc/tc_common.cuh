@@ -315,6 +315,12 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
 // every block's gated activation z_i (all offsets 1024-byte aligned).  (Saving the gate
 // derivative as planes too was measured: the extra bf16 splits cost the SFU-bound forward
 // gate epilogue more than the backward saved, so tanh/sigmoid stay fp32 tensors.)
+// Condition planes hold the Cl = Cc - Cg time-varying channels, then ONE channel that is 1.0 at
+// every time step, zero padded to a pitch of Cl + 32: the weight-gradient GEMM against these
+// planes (N tile = 256 columns, Cl + 1 of them used) then yields the gate-bias gradient -- the
+// column sum of gh -- as column Cl for free, per batch item (tc_gemm.cu, EPI_WGRAD).
+inline int cond_local(const vqw_resnet_desc& d) { return d.Cc - d.Cg; }
+inline int cond_pitch(const vqw_resnet_desc& d) { return d.Cc - d.Cg + 32; }
 struct TcSaved {
   int64_t cond[2];
   int64_t x0, x_plane, x_stride;   // block i: hi at x0 + i*x_stride, lo at + x_plane
@@ -325,7 +331,7 @@ inline TcSaved tc_saved_layout(const vqw_resnet_desc& d) {
   auto al = [](int64_t v) { return (v + 1023) / 1024 * 1024; };
   TcSaved L;
   const int64_t N = (int64_t)d.B * d.T;
-  const int64_t cplane = al(N * d.Cc * 2);
+  const int64_t cplane = al(N * cond_pitch(d) * 2);
   L.cond[0] = 0;
   L.cond[1] = cplane;
   L.x_plane = al(N * d.Cr * 2);

@@ -54,6 +54,11 @@ struct Job {          // one 128 x 256 tile of one weight-gradient GEMM
   int M, N;           // valid extent of the gradient matrix
   float* out;         // gW base (already offset to the tap)
   long long gm, gk;   // strides along m / n
+  // optional column col_n of the product (a constant-one channel of B, see cond_pitch): the sum
+  // over time of A's rows for THIS batch item, stored (not accumulated) at col_out[b*col_stride + m]
+  float* col_out;
+  int col_n;
+  long long col_stride;
 };
 
 struct GemmParams {
@@ -250,6 +255,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           for (int i = 0; i < 16; ++i) {
             const int n = jb.n0 + 16 * q + i;
             if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i] * inv);
+            else if (jb.col_out != nullptr && n == jb.col_n)
+              jb.col_out[(long long)blockIdx.z * jb.col_stride + m] = o[i] * inv;
           }
         }
       }
@@ -464,11 +471,12 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
 // out[r][k] (rows x K, K contiguous) = src(r, k) for the three transposed weight operands
 //   kind 0: W2T [Ch rows][Cr + Cs]   = [Wr ; Ws]^T
 //   kind 1: WcT [Cr rows][fs * Cd]   : WcT[cr][j*Cd + cd] = conv_w[cd][cr][j]
-//   kind 2: WpT [rows >= Cc][Cd]     : WpT[cc][cd] = cond_w[cd][cc], zero rows beyond Cc
+//   kind 2: WpT [rows >= Cl][Cd]     : WpT[cc][cd] = cond_w[cd][cc] for the Cl time-varying
+//           condition channels, zero rows beyond
 __global__ void __launch_bounds__(256)
 pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__ w1,
                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int K,
-               int Cr, int Cs, int Cd, int Cc, int fs, int f16) {
+               int Cr, int Cs, int Cd, int Cc, int Cl, int fs, int f16) {
   const int Ch = Cd / 2;
   const int64_t n = (int64_t)rows * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
@@ -481,7 +489,7 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
       const int j = k / Cd, cd = k % Cd;
       v = w0[((int64_t)cd * Cr + r) * fs + j];
     } else {
-      v = (r < Cc) ? w0[(int64_t)k * Cc + r] : 0.0f;
+      v = (r < Cl) ? w0[(int64_t)k * Cc + r] : 0.0f;   // only the Cl time-varying condition rows
     }
     __nv_bfloat16 h, l;
     split_16(v, f16, h, l);
@@ -527,6 +535,53 @@ colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* 
 __global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
+}
+
+// ---- gradients that flow through the per-(block, item) gate bias (resblock_tc.cu, gbias_kernel) ----
+// S[i][b][m] = sum_t gh_i[b, t, m] (the constant-one column of the weight-gradient GEMM).
+//   conv_b_i[m], cond_b_i[m]  += sum_b S[i][b][m]
+//   cond_w_i[m][Cl + g]       += sum_b S[i][b][m] * glob[b][g]        (grid: blocks, 512 threads)
+//   g_glob[b][g]              += sum_i sum_m cond_w_i[m][Cl + g] * S[i][b][m]   (grid: B, Cg threads)
+constexpr int TAIL_MAX = 32;
+struct TailArgs {
+  const float* cond_w[TAIL_MAX];
+  float* g_conv_b[TAIL_MAX];
+  float* g_cond_b[TAIL_MAX];
+  float* g_cond_w[TAIL_MAX];
+};
+__global__ void __launch_bounds__(512)
+bias_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S,
+                 const float* __restrict__ glob, int B, int Cd, int Cc, int Cg, int blk0) {
+  extern __shared__ float gsm[];                     // glob (B, Cg)
+  for (int i = threadIdx.x; i < B * Cg; i += blockDim.x) gsm[i] = glob[i];
+  __syncthreads();
+  const int i = blockIdx.x, m = threadIdx.x;
+  if (m >= Cd) return;
+  const float* Sb = S + ((int64_t)(blk0 + i) * B) * Cd + m;
+  float sb = 0.0f;
+  for (int b = 0; b < B; ++b) sb += Sb[(int64_t)b * Cd];
+  A.g_conv_b[i][m] += sb;
+  A.g_cond_b[i][m] += sb;
+  float* gw = A.g_cond_w[i] + (int64_t)m * Cc + (Cc - Cg);
+  for (int g = 0; g < Cg; ++g) {
+    float acc = 0.0f;
+    for (int b = 0; b < B; ++b) acc = fmaf(Sb[(int64_t)b * Cd], gsm[b * Cg + g], acc);
+    gw[g] += acc;
+  }
+}
+__global__ void __launch_bounds__(256)
+gglob_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S,
+                  float* __restrict__ g_glob, int B, int Cd, int Cc, int Cg, int blk0, int nblk) {
+  const int b = blockIdx.x;
+  for (int g = threadIdx.x; g < Cg; g += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = 0; i < nblk; ++i) {
+      const float* w = A.cond_w[i] + (Cc - Cg) + g;
+      const float* Sb = S + ((int64_t)(blk0 + i) * B + b) * Cd;
+      for (int m = 0; m < Cd; ++m) acc = fmaf(__ldg(w + (int64_t)m * Cc), Sb[m], acc);
+    }
+    g_glob[(int64_t)b * Cg + g] += acc;
+  }
 }
 
 int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B, int C, int T,
@@ -610,6 +665,7 @@ struct BwdLayout {
   int64_t total;
   int64_t gs_p[2], gh_p[2], gr_p[2][2];
   int64_t gs_sum;   // column sum of g_skip (the same bias gradient for every block)
+  int64_t colS;     // S[i][b][m]: per-item column sums of gh (n_blocks * B * Cd floats)
   int64_t scale;    // 4 floats: gradient-scale scratch of the fp16 mode
   int64_t w2t[2], wct[2], wpt[2];
   int64_t wstride;
@@ -622,6 +678,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
   for (int p = 0; p < 2; ++p) L.gs_p[p] = take(N * d.Cs * 2);
   L.gs_sum = take((int64_t)d.Cs * 4);
+  L.colS = take((int64_t)d.n_blocks * d.B * d.Cd * 4);
   L.scale = take(16);
   for (int p = 0; p < 2; ++p) L.gh_p[p] = take(N * d.Cd * 2);
   for (int q = 0; q < 2; ++q)
@@ -629,7 +686,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   const int64_t wbase = off;
   for (int p = 0; p < 2; ++p) L.w2t[p] = take((int64_t)(d.Cd / 2) * (d.Cr + d.Cs) * 2);
   for (int p = 0; p < 2; ++p) L.wct[p] = take((int64_t)d.Cr * d.fs * d.Cd * 2);
-  for (int p = 0; p < 2; ++p) L.wpt[p] = take((int64_t)pad256(d.Cc) * d.Cd * 2);
+  for (int p = 0; p < 2; ++p) L.wpt[p] = take((int64_t)pad256(cond_local(d)) * d.Cd * 2);
   L.wstride = off - wbase;
   off = wbase + L.wstride * d.n_blocks;
   L.total = off + 1024;
@@ -659,6 +716,10 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   auto LO = [&](int64_t off) { return x3 ? P16(off) : nullptr; };
   auto LOX = [&](int64_t off) { return xlo ? P16(off) : nullptr; };
   const int B = d.B, T = d.T, Cr = d.Cr, Cd = d.Cd, Cs = d.Cs, Cc = d.Cc, Ch = d.Cd / 2, fs = d.fs;
+  const int Cl = cond_local(d), CP = cond_pitch(d), Cg = d.Cg;
+  VQW_REQUIRE(Cg == 0 || (d.cond_global && d.g_cond_global),
+              "vqw_resnet_backward: Cg > 0 needs cond_global and g_cond_global");
+  float* colS = reinterpret_cast<float*>(ws + L.colS);
   const int64_t NROWS = (int64_t)B * T;
   const int RPB = 256;   // rows per block of the bias column sums
   const int CS_GRID = (int)((NROWS + RPB - 1) / RPB);
@@ -681,13 +742,13 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     const vqw_resblock_weights& w = weights[i];
     const int64_t wo = i * L.wstride;
     pack_wt_kernel<<<148, 256, 0, stream>>>(0, w.res_w, w.skip_w, P16(L.w2t[0] + wo),
-                                            LO(L.w2t[1] + wo), Ch, Cr + Cs, Cr, Cs, Cd, Cc, fs, f16);
+                                            LO(L.w2t[1] + wo), Ch, Cr + Cs, Cr, Cs, Cd, Cc, Cl, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(0)");
     pack_wt_kernel<<<296, 256, 0, stream>>>(1, w.conv_w, nullptr, P16(L.wct[0] + wo),
-                                            LO(L.wct[1] + wo), Cr, fs * Cd, Cr, Cs, Cd, Cc, fs, f16);
+                                            LO(L.wct[1] + wo), Cr, fs * Cd, Cr, Cs, Cd, Cc, Cl, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(1)");
     pack_wt_kernel<<<148, 256, 0, stream>>>(2, w.cond_w, nullptr, P16(L.wpt[0] + wo),
-                                            LO(L.wpt[1] + wo), pad256(Cc), Cd, Cr, Cs, Cd, Cc, fs, f16);
+                                            LO(L.wpt[1] + wo), pad256(Cl), Cd, Cr, Cs, Cd, Cc, Cl, fs, f16);
     VQW_CHECK_LAUNCH("pack_wt_kernel(2)");
   }
 
@@ -746,7 +807,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       Maps maps;
       if (int rc = mapk(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd, T, B, TM)) return rc;
       if (int rc = mapk(&maps.m[2], ws + L.wct[0] + wo, ws + L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, TN)) return rc;
-      if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cc), 1, TN)) return rc;
+      if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cl), 1, TN)) return rc;
       for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
       if (i > 0 || gx0 != nullptr) {
         GemmParams P = {};
@@ -765,9 +826,9 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         P.nseg = 1;
         P.seg[0] = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
         P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
-        P.o0 = gcond;
-        P.Cout = Cc;
-        if (int rc = launch_gemm<EPI_ACCUM>(maps, P, dim3(ceil_div(T, TM), ceil_div(Cc, TN), B), stream))
+        P.o0 = gcond;                  // (B, Cl, T): the time-varying condition channels
+        P.Cout = Cl;
+        if (int rc = launch_gemm<EPI_ACCUM>(maps, P, dim3(ceil_div(T, TM), ceil_div(Cl, TN), B), stream))
           return rc;
       }
     }
@@ -777,7 +838,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       // pairs: 0 gh, 1 x_i, 2 cond, 3 z_i, 4 g_res, 5 g_skip
       if (int rc = mapmn(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd)) return rc;
       if (int rc = mapmn(&maps.m[2], xp_hi, xp_lo, Cr)) return rc;
-      if (int rc = mapmn(&maps.m[4], sv + S.cond[0], sv + S.cond[1], Cc)) return rc;
+      if (int rc = mapmn(&maps.m[4], sv + S.cond[0], sv + S.cond[1], CP)) return rc;
       if (int rc = mapmn(&maps.m[6], zp_hi, zp_lo, Ch)) return rc;
       if (int rc = mapmn(&maps.m[8], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr)) return rc;
       if (int rc = mapmn(&maps.m[10], ws + L.gs_p[0], ws + L.gs_p[1], Cs)) return rc;
@@ -786,29 +847,32 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       P.slabs_per_item = ceil_div(T, BK);
       P.chunks_per_b = 1;
       int nj = 0;
+      // `ncols` >= N columns of the product are computed; column `col_n` (if col_out) is the
+      // per-item column sum that the constant-one channel of the condition planes produces
       auto add_jobs = [&](int a_map, int M, int b_map, int N, int shift, float* out, long long gm,
-                          long long gk) -> int {
+                          long long gk, int ncols = 0, float* col_out = nullptr, int col_n = -1) -> int {
+        if (ncols < N) ncols = N;
         for (int m0 = 0; m0 < M; m0 += TM)
-          for (int n0 = 0; n0 < N; n0 += TN) {
+          for (int n0 = 0; n0 < ncols; n0 += TN) {
             VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 backward: too many weight-gradient tiles");
-            P.jobs[nj++] = Job{a_map, b_map, m0, n0, shift, M, N, out, gm, gk};
+            P.jobs[nj++] = Job{a_map, b_map, m0, n0, shift, M, N, out, gm, gk, col_out, col_n,
+                               (long long)Cd};
           }
         return 0;
       };
       for (int j = 0; j < fs; ++j)
         if (int rc = add_jobs(0, Cd, 1, Cr, -dil * (fs - 1 - j), gw.conv_w + j, (long long)Cr * fs, fs))
           return rc;
-      if (int rc = add_jobs(0, Cd, 2, Cc, 0, gw.cond_w, Cc, 1)) return rc;
+      if (int rc = add_jobs(0, Cd, 2, Cl, 0, gw.cond_w, Cc, 1, Cl + 1, colS + (int64_t)i * B * Cd, Cl))
+        return rc;
       if (have_gres)
         if (int rc = add_jobs(4, Cr, 3, Ch, 0, gw.res_w, Ch, 1)) return rc;
       if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
       P.njobs = nj;
       if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
     }
-    // ---- bias gradients: column sums of gh (conv_b and cond_b), g_res, g_skip ----
-    colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gh_p[0]), LO(L.gh_p[1]), gw.conv_b,
-                                                     gw.cond_b, Cd, NROWS, RPB, Cd, f16, gscale);
-    VQW_CHECK_LAUNCH("colsum_planes_kernel(gh)");
+    // ---- bias gradients: gh's column sums come out of the grouped launch above (column Cl of
+    // the condition job, per item) and are folded in after the loop; g_res, g_skip here ----
     if (have_gres) {
       colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LOX(L.gr_p[cur][1]),
                                                        gw.res_b, nullptr, Cr, NROWS, RPB, Cr, f16,
@@ -819,6 +883,24 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     VQW_CHECK_LAUNCH("add_vec_kernel(skip_b)");
     have_gres = true;
     cur = nxt;
+  }
+  // ---- conv_b / cond_b, the global-condition columns of cond_w, and g_cond_global ----
+  for (int i0 = 0; i0 < d.n_blocks; i0 += TAIL_MAX) {
+    TailArgs A = {};
+    const int nb = d.n_blocks - i0 < TAIL_MAX ? d.n_blocks - i0 : TAIL_MAX;
+    for (int i = 0; i < nb; ++i) {
+      A.cond_w[i] = weights[i0 + i].cond_w;
+      A.g_conv_b[i] = wgrads[i0 + i].conv_b;
+      A.g_cond_b[i] = wgrads[i0 + i].cond_b;
+      A.g_cond_w[i] = wgrads[i0 + i].cond_w;
+    }
+    bias_tail_kernel<<<nb, 512, sizeof(float) * (size_t)(B * Cg + 1), stream>>>(A, colS, d.cond_global, B,
+                                                                              Cd, Cc, Cg, i0);
+    VQW_CHECK_LAUNCH("bias_tail_kernel");
+    if (Cg > 0) {
+      gglob_tail_kernel<<<B, 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i0, nb);
+      VQW_CHECK_LAUNCH("gglob_tail_kernel");
+    }
   }
   return 0;
 }

@@ -238,7 +238,7 @@ class _ResidualStack(torch.autograd.Function):
     reverse with the shared g_skip and the accumulated g_condition."""
 
     @staticmethod
-    def forward(ctx, x, cond, dilations, fs, mode, keep_last_residual, grad_targets,
+    def forward(ctx, x, cond, cond_global, dilations, fs, mode, keep_last_residual, grad_targets,
                 grad_enabled, *weights):
         ctx.grad_targets = grad_targets
         x, cond = _f32c(x), _f32c(cond)
@@ -246,6 +246,13 @@ class _ResidualStack(torch.autograd.Function):
         Bc, Cc, Tc = _as3(cond)
         if (Bc, Tc) != (B, T):
             raise ValueError(f"condition shape {tuple(cond.shape)} does not match x {tuple(x.shape)}")
+        Cg = 0
+        if cond_global is not None:      # hoisted time-constant condition channels (B, Cg)
+            cond_global = _f32c(cond_global)
+            if cond_global.dim() != 2 or cond_global.shape[0] != B:
+                raise ValueError("cond_global must be (B, Cg)")
+            Cg = cond_global.shape[1]
+            Cc += Cg                     # Cc = columns of condition_proj.W
         n = len(dilations)
         assert len(weights) == 8 * n
         weights = [_f32c(w) for w in weights]
@@ -277,6 +284,9 @@ class _ResidualStack(torch.autograd.Function):
         dil_arr = (C.c_int * n)(*dilations)
         d.dilations = C.cast(dil_arr, C.POINTER(C.c_int))
         d.mode, d.keep_last_residual = mode, int(keep_last_residual)
+        d.Cg, d.cond_global = Cg, L.ptr(cond_global)
+        if weights[2].shape[1] != Cc:
+            raise ValueError(f"condition_proj expects {weights[2].shape[1]} channels, got {Cc}")
         warr = (L.ResblockWeights * n)()
         for i in range(n):
             for name, t in zip(("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b",
@@ -304,27 +314,29 @@ class _ResidualStack(torch.autograd.Function):
         if saved is not None:
             xs = [x] + [None] * (n - 1)
         residual = res[n - 1]
-        ctx.cfg = (tuple(dilations), fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last_residual)
+        ctx.cfg = (tuple(dilations), fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last_residual, Cg)
         if need_grad:
             keep = [t if t is not None else x.new_empty(0) for t in xs]
-            ctx.save_for_backward(cond, *keep, *gates, *weights)
+            cg = cond_global if cond_global is not None else x.new_empty(0)
+            ctx.save_for_backward(cond, cg, *keep, *gates, *weights)
         if keep_last_residual:
             return skip, residual
         return skip
 
     @staticmethod
     def backward(ctx, g_skip, g_last_res=None):
-        dilations, fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last = ctx.cfg
+        dilations, fs, mode, B, T, Cr, Cd, Cs, Cc, keep_last, Cg = ctx.cfg
         n = len(dilations)
         saved = ctx.saved_tensors
-        cond = saved[0]
-        xs = saved[1:1 + n]
+        cond, cond_global = saved[0], saved[1]
+        xs = saved[2:2 + n]
         tc_saved = getattr(ctx, "tc_saved", None)
-        gates = saved[1 + n:1 + 3 * n]
-        weights = saved[1 + 3 * n:]
+        gates = saved[2 + n:2 + 3 * n]
+        weights = saved[2 + 3 * n:]
         g_skip = _f32c(g_skip)
         dev = g_skip.device
-        gcond = torch.zeros((B, Cc, T, 1), device=dev, dtype=torch.float32)
+        gcond = torch.zeros((B, Cc - Cg, T, 1), device=dev, dtype=torch.float32)
+        g_glob = torch.zeros((B, Cg), device=dev, dtype=torch.float32) if Cg else None
         targets = ctx.grad_targets
         direct = (ACCUMULATE_INTO_GRAD and targets is not None and
                   all(p.grad is not None and p.grad.is_contiguous() for p in targets))
@@ -335,6 +347,7 @@ class _ResidualStack(torch.autograd.Function):
         dil_arr = (C.c_int * n)(*dilations)
         d.dilations = C.cast(dil_arr, C.POINTER(C.c_int))
         d.mode, d.keep_last_residual = mode, int(keep_last)
+        d.Cg, d.cond_global, d.g_cond_global = Cg, (L.ptr(cond_global) if Cg else None), L.ptr(g_glob)
         warr = (L.ResblockWeights * n)()
         gwarr = (L.ResblockWeights * n)()
         names = ("conv_w", "conv_b", "cond_w", "cond_b", "res_w", "res_b", "skip_w", "skip_b")
@@ -360,12 +373,15 @@ class _ResidualStack(torch.autograd.Function):
                 L.ptr(tc_saved), L.stream()), "vqw_resnet_backward")
         if direct:
             gws = [None] * len(gws)
-        return (g_res, gcond, None, None, None, None, None, None, *gws)
+        return (g_res, gcond, g_glob, None, None, None, None, None, None, *gws)
 
 
 def residual_stack(x, cond, dilations, fs, weights, mode=L.MODE_FP32, keep_last_residual=False,
-                   grad_targets=None):
-    return _ResidualStack.apply(x, cond, tuple(dilations), fs, mode, keep_last_residual,
+                   grad_targets=None, cond_global=None):
+    """`cond` (B,Cc,T,1) is the full condition, or -- with `cond_global` (B,Cg), tensor-core modes
+    only -- its Cc-Cg time-varying channels: the time-constant channels are then projected once per
+    (item, block) into the gate bias instead of being contracted at every time step."""
+    return _ResidualStack.apply(x, cond, cond_global, tuple(dilations), fs, mode, keep_last_residual,
                                 grad_targets, torch.is_grad_enabled(), *weights)
 
 
@@ -484,11 +500,14 @@ def head(skip, W1, b1, W2, b2, mode):
 class _UpsampleConcat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, local, glob, out_len):
-        local, glob = _f32c(local), _f32c(glob)
+        local = _f32c(local)
         B, Cl, H = _as3(local)
-        Cg = glob.shape[1]
-        if glob.shape[0] != B:
-            raise ValueError("local and global condition batch sizes differ")
+        Cg = 0
+        if glob is not None:
+            glob = _f32c(glob)
+            Cg = glob.shape[1]
+            if glob.shape[0] != B:
+                raise ValueError("local and global condition batch sizes differ")
         out = torch.empty((B, Cl + Cg, out_len, 1), device=local.device, dtype=torch.float32)
         L.check(L.lib.vqw_upsample_concat_forward(L.ptr(local), L.ptr(glob), L.ptr(out), B, Cl, Cg, H,
                                                   out_len, L.stream()), "vqw_upsample_concat_forward")
@@ -500,7 +519,7 @@ class _UpsampleConcat(torch.autograd.Function):
         B, Cl, Cg, H, out_len = ctx.cfg
         g = _f32c(g)
         g_local = torch.empty((B, Cl, H, 1), device=g.device, dtype=torch.float32)
-        g_glob = torch.empty((B, Cg), device=g.device, dtype=torch.float32)
+        g_glob = torch.empty((B, Cg), device=g.device, dtype=torch.float32) if Cg else None
         L.check(L.lib.vqw_upsample_concat_backward(L.ptr(g), L.ptr(g_local), L.ptr(g_glob), B, Cl, Cg, H,
                                                    out_len, L.stream()), "vqw_upsample_concat_backward")
         return g_local, g_glob, None
@@ -508,5 +527,6 @@ class _UpsampleConcat(torch.autograd.Function):
 
 def upsample_concat(local, glob, out_len):
     """local (B,Cl,H,1), glob (B,Cg) -> (B, Cl+Cg, out_len, 1): F.resize_images of both (the
-    global one from length 1 = broadcast) and F.concat, net.py:58-63."""
+    global one from length 1 = broadcast) and F.concat, net.py:58-63.  glob=None: the resize
+    of the local part alone."""
     return _UpsampleConcat.apply(local, glob, out_len)

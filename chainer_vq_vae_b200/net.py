@@ -51,7 +51,11 @@ class ConditionEmbed(nn.Module):
         self.global_embed = EmbedID(n_global_cond, global_embed_dim)
         self.upscale_factor = upscale_factor
 
-    def forward(self, local_condition, global_condition):
+    def forward(self, local_condition, global_condition, split=False):
+        """`split=True` returns (upsampled local (B,Cl,T,1), speaker embedding (B,Cg)) instead of
+        their concatenation: the decoder's tensor-core path then hoists the projection of the
+        time-constant channels out of the per-step contraction (same arithmetic: W_p is linear
+        and F.resize_images of a length-1 signal is a broadcast, net.py:60-61)."""
         h = self.local_embed1(local_condition, relu=True)
         h = self.local_embed2(h, relu=True)
         h = self.local_embed3(h, relu=True)
@@ -59,6 +63,8 @@ class ConditionEmbed(nn.Module):
         h = self.local_embed5(h, relu=True)
         g = self.global_embed(global_condition)                         # :59
         # resize (:58), broadcast-resize of the speaker embedding (:60-61) and concat (:63): one kernel
+        if split:
+            return Fn.upsample_concat(h, None, self.upscale_factor * h.shape[2]), g
         return Fn.upsample_concat(h, g, self.upscale_factor * h.shape[2])
 
 
@@ -84,7 +90,9 @@ class VAE(nn.Module):
         idx = self.vq.indexes
         zd = z.detach()
         e_ = self.vq(zd, cached=(e.detach(), idx))                     # :83
-        condition = self.condition_embed(e, global_condition)          # :85
+        dec = getattr(self.decoder, "target", self.decoder)
+        split = getattr(getattr(dec, "resnet", None), "mode", 0) != 0   # tensor-core modes hoist it
+        condition = self.condition_embed(e, global_condition, split=split)   # :85
         y = self.decoder(x_dec, condition)                             # :86
         loss1 = self.loss_func(y, t)                                   # :89
         loss2 = torch.mean((zd - e_) ** 2)                             # :90

@@ -59,13 +59,14 @@ class ResidualNet(nn.ModuleList):
         self.filter_size = filter_size
         self.mode = L.MODE_FP32
 
-    def tc_supported(self, x, condition) -> bool:
-        """Shapes the tcgen05 kernels take (resnet_tc_supported, csrc/resblock_tc.cu)."""
+    def tc_supported(self, x, n_local) -> bool:
+        """Shapes the tcgen05 kernels take (resnet_tc_supported, csrc/resblock_tc.cu);
+        n_local = time-varying condition channels that are contracted."""
         blk = self[0]
         Cd, Cr = blk.conv.W.shape[0], blk.conv.W.shape[1]
-        Cs, Cc, T = blk.skip.W.shape[0], condition.shape[1], x.shape[2]
-        return (Cd == 512 and Cr % 256 == 0 and Cs % 256 == 0 and Cc % 32 == 0 and T >= 128
-                and T % 8 == 0 and x.shape[0] <= 65535)
+        Cs, T = blk.skip.W.shape[0], x.shape[2]
+        return (Cd == 512 and Cr % 256 == 0 and Cs % 256 == 0 and n_local >= 32 and
+                n_local % 32 == 0 and T >= 128 and T % 8 == 0 and x.shape[0] <= 65535)
 
     def forward(self, x, condition):
         """Sum of the blocks' skip outputs (modules.py:89-96); the last block's residual is
@@ -76,10 +77,20 @@ class ResidualNet(nn.ModuleList):
         for block in self:
             weights += block.weights()
         mode = self.mode
-        if mode != L.MODE_FP32 and not self.tc_supported(x, condition):
+        cond_global = None
+        if isinstance(condition, (tuple, list)):
+            # (local (B,Cl,T,1), global (B,Cg)) from ConditionEmbed(split=True): the speaker
+            # embedding is constant over time, so its projection is hoisted into the gate bias
+            local, glob = condition
+            if mode != L.MODE_FP32 and self.tc_supported(x, local.shape[1]):
+                condition, cond_global = local, glob
+            else:
+                condition = torch.cat([local, glob.reshape(glob.shape[0], -1, 1, 1).expand(
+                    -1, -1, local.shape[2], 1)], dim=1)
+        if mode != L.MODE_FP32 and cond_global is None and not self.tc_supported(x, condition.shape[1]):
             mode = L.MODE_FP32
         return Fn.residual_stack(x, condition, [b.dilation for b in self], self.filter_size,
-                                 weights, mode, grad_targets=tuple(weights))
+                                 weights, mode, grad_targets=tuple(weights), cond_global=cond_global)
 
 
 class WaveNet(nn.Module):

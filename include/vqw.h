@@ -174,6 +174,14 @@ int vqw_resblock_backward(const vqw_resblock_desc* desc, const float* g_res, con
  * B*(Cd/2)*T fp32 saved gate factors (arrays may be NULL for inference): opaque to the caller --
  * fp32 mode lays them out (B,Cd/2,T), the tensor-core modes time-major (B,T,Cd/2), because there
  * one thread owns one time row in the forward gate epilogue and in the backward that reads them.
+ *
+ * Hoisted global condition (modules.py:17-18,44 with net.py:59-63): the
+ * last Cg of the Cc condition channels may be CONSTANT over time -- the speaker embedding that
+ * ConditionEmbed broadcasts (net.py:60-61).  With Cg > 0 (tensor-core modes only) `cond` holds
+ * only the Cc-Cg time-varying channels, (B,Cc-Cg,T), and `cond_global` (B,Cg) the constant ones:
+ * W_p[:, Cc-Cg:] . g is then one bias vector per (item, block) instead of Cg contraction columns
+ * at every time step, and its gradient a column sum.  The backward writes gcond (B,Cc-Cg,T) and
+ * ACCUMULATES g_cond_global (B,Cg).  Cg = 0: `cond` carries all Cc channels (the reference form).
  */
 typedef struct {
   int B, T, Cr, Cd, Cs, Cc, fs;
@@ -181,6 +189,9 @@ typedef struct {
   const int* dilations;
   int mode;
   int keep_last_residual;
+  int Cg;                       /* trailing time-constant condition channels, 0 = none */
+  const float* cond_global;     /* (B,Cg) f32 or NULL */
+  float* g_cond_global;         /* backward: (B,Cg) f32, accumulated, or NULL */
 } vqw_resnet_desc;
 
 int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc);

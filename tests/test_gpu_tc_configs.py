@@ -165,3 +165,45 @@ def test_reference_default_model_step_matches_oracle():
         worst2 = max(worst2, float((a - b).norm() / b.norm()))
     print(f"reference-default model: gradients worst cosine {worst_cos:.6f}, worst L2 {worst2:.2e}")
     assert worst_cos > 0.9999 and worst2 < 1e-2
+
+
+@pytest.mark.parametrize("fs,Cc,Cg,T,dil", [(3, 192, 128, 384, [1, 2, 512]), (2, 640, 128, 256, [4, 1]),
+                                            (3, 160, 96, 200, [2, 8])])
+def test_tc_hoisted_global_condition_vs_fp64_oracle(fs, Cc, Cg, T, dil):
+    """the projection of the time-constant condition channels (the speaker
+    embedding that net.py:60-61 broadcasts over time) is hoisted out of the per-step contraction
+    into one gate-bias vector per (item, block).  Same function as modules.py:44 on the
+    concatenated condition: forward, gx, the gradient of the time-varying channels, the gradient
+    of the global vector (= time sum of the oracle's gradient of those channels) and every
+    weight gradient -- including the global columns of condition_proj.W -- against float64."""
+    B, Cl = 2, Cc - Cg
+    cfg, p, x, c = _stack_case(dil, B, T, fs=fs, Cc=Cc, seed=Cc + Cg)
+    rng = np.random.default_rng(3)
+    glob = torch.from_numpy(rng.normal(size=(B, Cg)).astype(np.float32))
+    c = c.clone()
+    c[:, Cl:] = glob[:, :, None, None]                       # constant over time
+    g_skip = torch.from_numpy(rng.normal(size=(B, 256, T, 1)).astype(np.float32))
+    g_res = torch.from_numpy(rng.normal(size=(B, 512, T, 1)).astype(np.float32))
+    so, ro, gxo, gco, go = _oracle_grads(cfg, p, x, c, dil, g_skip, g_res)
+    weights = []
+    for i in range(len(dil)):
+        weights += [p[f"resnet/{i}/{n}"].to(DEV).requires_grad_(True) for n in ORDER]
+    xg = x.to(DEV).requires_grad_(True)
+    cl = c[:, :Cl].contiguous().to(DEV).requires_grad_(True)
+    gg = glob.to(DEV).requires_grad_(True)
+    skip, res = V.residual_stack(xg, cl, dil, fs, weights, L.MODE_BF16X3, keep_last_residual=True,
+                                 cond_global=gg)
+    ((skip * g_skip.to(DEV)).sum() + (res * g_res.to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    errs = {"skip": rel_err(skip, so), "res": rel_err(res, ro), "gx": rel_err(xg.grad, gxo),
+            "gcond_local": rel_err(cl.grad, gco[:, :Cl]),
+            "g_global": rel_err(gg.grad, gco[:, Cl:].sum(dim=(2, 3)))}
+    for i in range(len(dil)):
+        for j, n in enumerate(ORDER):
+            g = go[f"resnet/{i}/{n}"]
+            if float(g.abs().max()) > 0:
+                errs[f"{i}/{n}"] = rel_err(weights[8 * i + j].grad, g)
+    bad = {k: v for k, v in errs.items() if v >= 2e-4}
+    print(f"hoisted global condition fs={fs} Cc={Cc} Cg={Cg}: worst {max(errs, key=errs.get)} "
+          f"= {max(errs.values()):.2e}")
+    assert not bad, bad
