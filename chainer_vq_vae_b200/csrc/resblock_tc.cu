@@ -555,26 +555,27 @@ pack_w2_kernel(const float* __restrict__ res_w, const float* __restrict__ skip_w
 
 // Per-(block, item) gate bias: conv_b + cond_b + W_p[:, Cl:] . g_b -- the condition projection of
 // the time-constant (speaker) channels, modules.py:17-18,44 applied to net.py:59-61's broadcast.
-// grid (B, blocks in this launch), 512 threads = dilated channels.
 constexpr int GB_MAX = 32;
 struct GbiasArgs {
   const float* conv_b[GB_MAX];
   const float* cond_b[GB_MAX];
   const float* cond_w[GB_MAX];
 };
-__global__ void __launch_bounds__(CD)
+// grid (blocks, 512 / 8): warp w of CTA (i, y) owns dilated channel 8 y + w; lanes stride the Cg
+// global channels (coalesced weight row), one shuffle reduction per item
+__global__ void __launch_bounds__(256)
 gbias_kernel(const __grid_constant__ GbiasArgs A, const float* __restrict__ glob,
              float* __restrict__ out, int B, int Cc, int Cg, int blk0) {
-  const int b = blockIdx.x, i = blockIdx.y, ch = threadIdx.x;
-  float v = A.conv_b[i][ch] + A.cond_b[i][ch];
-  if (Cg > 0) {
-    const float* w = A.cond_w[i] + (int64_t)ch * Cc + (Cc - Cg);
-    const float* g = glob + (int64_t)b * Cg;
+  const int i = blockIdx.x, ch = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const float base = A.conv_b[i][ch] + A.cond_b[i][ch];
+  const float* w = A.cond_w[i] + (int64_t)ch * Cc + (Cc - Cg);
+  for (int b = 0; b < B; ++b) {
     float acc = 0.0f;
-    for (int k = 0; k < Cg; ++k) acc = fmaf(__ldg(w + k), __ldg(g + k), acc);
-    v += acc;
+    for (int k = lane; k < Cg; k += 32) acc = fmaf(__ldg(w + k), __ldg(glob + (int64_t)b * Cg + k), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[((int64_t)(blk0 + i) * B + b) * CD + ch] = base + acc;
   }
-  out[((int64_t)(blk0 + i) * B + b) * CD + ch] = v;
 }
 
 // ------------------------------------------------------------------ host side --------------
@@ -722,7 +723,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
                     i0 + i);
         A.conv_b[i] = w.conv_b; A.cond_b[i] = w.cond_b; A.cond_w[i] = w.cond_w;
       }
-      gbias_kernel<<<dim3(d.B, nb), CD, 0, stream>>>(A, d.cond_global, gbias, d.B, d.Cc, d.Cg, i0);
+      gbias_kernel<<<dim3(nb, CD / 8), 256, 0, stream>>>(A, d.cond_global, gbias, d.B, d.Cc, d.Cg, i0);
       VQW_CHECK_LAUNCH("gbias_kernel");
     }
     for (int i = 0; i < d.n_blocks; ++i) {

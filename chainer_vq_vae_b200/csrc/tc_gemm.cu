@@ -84,6 +84,16 @@ struct GemmParams {
   const float* bias;           // HEAD: per-output-channel bias or null
   int relu;                    // HEAD: relu on the result
   const __nv_bfloat16* mask_hi;  // HEAD: (B,T,Cout) plane; result is zeroed where mask <= 0
+  // GX launches can carry the ACCUM tiles of the same block as extra blockIdx.y values
+  // (>= alt_y): those CTAs stream gh once more (from L2: the GX tiles of the same rows read the
+  // same slabs) and are bound by that stream, so they overlap the MMA-bound GX tiles instead of
+  // running as a separate launch
+  float* colsum;               // GX: column sums of the result (+= , the bias gradient
+                               // sum_t g_res of the NEXT block to run) or null
+  int alt_y;                   // 0 = no ACCUM tiles in this launch
+  Seg alt_seg;
+  float* alt_out;              // gcond (B, alt_Cout, T)
+  int alt_Cout;
   int njobs;
   Job jobs[MAX_JOBS];
 };
@@ -102,13 +112,20 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + G_STAGES);
   const uint32_t acc_full = smem_u32(bars + 2 * G_STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
+  float* csum = reinterpret_cast<float*>(bars + 2 * G_STAGES + 2);   // [TN] column sums (GX)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool WG = (EPI == EPI_WGRAD);
+  if (EPI == EPI_GX && P.colsum != nullptr)
+    for (int i = threadIdx.x; i < TN; i += G_THREADS) csum[i] = 0.0f;
   const int nplanes = P.x3 ? 2 : 1;
 
+  const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && (int)blockIdx.y >= P.alt_y;
+  const int by = alt ? (int)blockIdx.y - P.alt_y : (int)blockIdx.y;   // N tile within its GEMM
   int total_slabs = 0;
-  if (WG) {
+  if (alt) {
+    total_slabs = P.alt_seg.nslabs;
+  } else if (WG) {
     const int items = P.B * P.chunks_per_b;
     int n_items = 0;
     for (int c = blockIdx.z; c < items; c += gridDim.z) ++n_items;
@@ -175,8 +192,9 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         }
       } else {
         const int t0 = blockIdx.x * TM, bb = blockIdx.z;
-        for (int s = 0; s < P.nseg; ++s) {
-          const Seg& sg = P.seg[s];
+        const int nseg = alt ? 1 : P.nseg;
+        for (int s = 0; s < nseg; ++s) {
+          const Seg& sg = alt ? P.alt_seg : P.seg[s];
           const CUtensorMap* ma = &maps.m[2 * sg.a_map];
           const CUtensorMap* mb = &maps.m[2 * sg.b_map];
           if (s == 0) { prefetch_tmap(ma); prefetch_tmap(mb); }
@@ -186,11 +204,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             const uint32_t sa = base + stage * STAGE_BYTES;
             mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
             tma_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-            tma_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, sg.b_row0 + TN * blockIdx.y, 0);
+            tma_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, sg.b_row0 + TN * by, 0);
             if (P.x3) {
               tma_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
               tma_load_3d(sa + 2 * A_PLANE + B_PLANE, mb + 1, fb, sg.b_c0 + i * BK,
-                          sg.b_row0 + TN * blockIdx.y, 0);
+                          sg.b_row0 + TN * by, 0);
             }
             if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
           }
@@ -316,7 +334,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             st256(P.p_lo + poff + CHh, sg_lo);
           }
         }
-      } else if (EPI == EPI_GX) {
+      } else if (EPI == EPI_GX && !alt) {
         // gx = acc + g_res: the addend and the result are time-major planes (16-byte accesses);
         // the fp32 (B,Cout,T) copy is only written for the gradient handed back to autograd
         const int cbase = TN * blockIdx.y;
@@ -351,6 +369,26 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           }
           if (q + NG < TN / 16) fetch(q + NG);
           const int ch0 = cbase + 16 * q;
+          if (P.colsum != nullptr) {
+            // column sums over the warp's 32 rows by recursive halving: every step exchanges
+            // half of the remaining columns with the lane whose index differs in one bit
+            // (16 shuffles for 16 columns), then one shared-memory atomic per column
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = t_ok ? o[i] : 0.0f;
+#pragma unroll
+            for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+              const bool up = lane & bit;
+#pragma unroll
+              for (int i = 0; i < w; ++i) {
+                const float send = up ? v[i] : v[i + w];
+                const float keep = up ? v[i + w] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+              }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            if ((lane & 1) == 0) atomicAdd(csum + 16 * q + (lane >> 1), v[0]);
+          }
           if (!t_ok) continue;
           if (P.o0 != nullptr) {
 #pragma unroll
@@ -367,6 +405,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             st256(P.p_hi + poff, vh);
             if (P.add_lo) st256(P.p_lo + poff, vl);
           }
+        }
+        if (P.colsum != nullptr) {
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");   // epilogue warps only
+          for (int i = threadIdx.x; i < TN; i += G_EPI_WARPS * 32)
+            atomicAdd(P.colsum + cbase + i, csum[i] * inv);
         }
       } else if (EPI == EPI_HEAD) {
         const int cbase = TN * blockIdx.y;
@@ -413,29 +456,32 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           }
         }
       } else {
-        // EPI_ACCUM: gcond[b, ch, t] += acc for ch = 256*blockIdx.y + col < Cout (fp32, lanes = t)
-        const int cbase = TN * blockIdx.y;
-        float* op = P.o0 + ((int64_t)b * P.Cout + cbase) * P.T + t;
+        // EPI_ACCUM (or an ACCUM tile of a GX launch): gcond[b, ch, t] += acc for
+        // ch = 256 * by + col < Cout (fp32, lanes = t)
+        const int cbase = TN * by;
+        const int Cout = alt ? P.alt_Cout : P.Cout;
+        float* op = (alt ? P.alt_out : P.o0) + ((int64_t)b * Cout + cbase) * P.T + t;
+        const int nq = (Cout - cbase + 15) / 16 < TN / 16 ? (Cout - cbase + 15) / 16 : TN / 16;
         float pre[16];
         auto fetch = [&](int q) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            pre[i] = (t_ok && cbase + 16 * q + i < P.Cout) ? __ldcs(op + (int64_t)(16 * q + i) * P.T) : 0.0f;
+            pre[i] = (t_ok && cbase + 16 * q + i < Cout) ? __ldcs(op + (int64_t)(16 * q + i) * P.T) : 0.0f;
         };
         fetch(grp);
         mbar_wait(acc_full, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int q = grp; q < TN / 16; q += NG) {
+        for (int q = grp; q < nq; q += NG) {      // only the column chunks that exist
           float o[16], add[16];
           tmem_ld16(lane_base + 16 * q, o);
 #pragma unroll
           for (int i = 0; i < 16; ++i) add[i] = pre[i];
-          if (q + NG < TN / 16) fetch(q + NG);
+          if (q + NG < nq) fetch(q + NG);
           if (!t_ok) continue;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (cbase + 16 * q + i < P.Cout) op[(int64_t)(16 * q + i) * P.T] = fmaf(o[i], inv, add[i]);
+            if (cbase + 16 * q + i < Cout) op[(int64_t)(16 * q + i) * P.T] = fmaf(o[i], inv, add[i]);
         }
       }
     }
@@ -452,7 +498,9 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   }
 }
 
-static size_t gemm_smem() { return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * G_STAGES + 1) + 16; }
+static size_t gemm_smem() {
+  return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * G_STAGES + 2) + sizeof(float) * TN + 16;
+}
 
 template <int EPI>
 static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream) {
@@ -540,8 +588,8 @@ __global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict_
 // ---- gradients that flow through the per-(block, item) gate bias (resblock_tc.cu, gbias_kernel) ----
 // S[i][b][m] = sum_t gh_i[b, t, m] (the constant-one column of the weight-gradient GEMM).
 //   conv_b_i[m], cond_b_i[m]  += sum_b S[i][b][m]
-//   cond_w_i[m][Cl + g]       += sum_b S[i][b][m] * glob[b][g]        (grid: blocks, 512 threads)
-//   g_glob[b][g]              += sum_i sum_m cond_w_i[m][Cl + g] * S[i][b][m]   (grid: B, Cg threads)
+//   cond_w_i[m][Cl + g]       += sum_b S[i][b][m] * glob[b][g]
+//   g_glob[b][g]              += sum_i sum_m cond_w_i[m][Cl + g] * S[i][b][m]
 constexpr int TAIL_MAX = 32;
 struct TailArgs {
   const float* cond_w[TAIL_MAX];
@@ -549,38 +597,48 @@ struct TailArgs {
   float* g_cond_b[TAIL_MAX];
   float* g_cond_w[TAIL_MAX];
 };
-__global__ void __launch_bounds__(512)
+// grid (blocks, Cd), Cg' = max(Cg, 1) threads: thread g of CTA (i, m)
+__global__ void __launch_bounds__(256)
 bias_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S,
                  const float* __restrict__ glob, int B, int Cd, int Cc, int Cg, int blk0) {
-  extern __shared__ float gsm[];                     // glob (B, Cg)
-  for (int i = threadIdx.x; i < B * Cg; i += blockDim.x) gsm[i] = glob[i];
-  __syncthreads();
-  const int i = blockIdx.x, m = threadIdx.x;
-  if (m >= Cd) return;
-  const float* Sb = S + ((int64_t)(blk0 + i) * B) * Cd + m;
-  float sb = 0.0f;
-  for (int b = 0; b < B; ++b) sb += Sb[(int64_t)b * Cd];
-  A.g_conv_b[i][m] += sb;
-  A.g_cond_b[i][m] += sb;
+  const int i = blockIdx.x, m = blockIdx.y;
+  const float* Sb = S + ((int64_t)(blk0 + i) * B) * Cd + m;        // S[i][b][m], stride Cd over b
+  if (threadIdx.x == 0) {
+    float sb = 0.0f;
+    for (int b = 0; b < B; ++b) sb += Sb[(int64_t)b * Cd];
+    A.g_conv_b[i][m] += sb;
+    A.g_cond_b[i][m] += sb;
+  }
   float* gw = A.g_cond_w[i] + (int64_t)m * Cc + (Cc - Cg);
-  for (int g = 0; g < Cg; ++g) {
+  for (int g = threadIdx.x; g < Cg; g += blockDim.x) {
     float acc = 0.0f;
-    for (int b = 0; b < B; ++b) acc = fmaf(Sb[(int64_t)b * Cd], gsm[b * Cg + g], acc);
+    for (int b = 0; b < B; ++b) acc = fmaf(Sb[(int64_t)b * Cd], __ldg(glob + (int64_t)b * Cg + g), acc);
     gw[g] += acc;
   }
 }
+// grid (B, blocks): g_glob[b][g] += sum_m cond_w_i[m][Cl + g] * S[i][b][m]  (coalesced over g)
 __global__ void __launch_bounds__(256)
 gglob_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S,
-                  float* __restrict__ g_glob, int B, int Cd, int Cc, int Cg, int blk0, int nblk) {
-  const int b = blockIdx.x;
-  for (int g = threadIdx.x; g < Cg; g += blockDim.x) {
+                  float* __restrict__ g_glob, int B, int Cd, int Cc, int Cg, int blk0) {
+  __shared__ float red[256];
+  const int b = blockIdx.x, i = blockIdx.y;
+  const float* Sb = S + ((int64_t)(blk0 + i) * B + b) * Cd;
+  // threads = (m-slice, g): blockDim.x / Cg' slices of the m range, each coalesced over g
+  const int gw = Cg < 256 ? Cg : 256;
+  const int nsl = 256 / gw, sl = threadIdx.x / gw, g0 = threadIdx.x % gw;
+  for (int g = g0; g < Cg; g += gw) {
     float acc = 0.0f;
-    for (int i = 0; i < nblk; ++i) {
+    if (sl < nsl) {
       const float* w = A.cond_w[i] + (Cc - Cg) + g;
-      const float* Sb = S + ((int64_t)(blk0 + i) * B + b) * Cd;
-      for (int m = 0; m < Cd; ++m) acc = fmaf(__ldg(w + (int64_t)m * Cc), Sb[m], acc);
+      for (int m = sl; m < Cd; m += nsl) acc = fmaf(__ldg(w + (int64_t)m * Cc), Sb[m], acc);
     }
-    g_glob[(int64_t)b * Cg + g] += acc;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (sl == 0) {
+      for (int k = 1; k < nsl; ++k) acc += red[k * gw + g0];
+      atomicAdd(g_glob + (int64_t)b * Cg + g, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -809,7 +867,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       if (int rc = mapk(&maps.m[2], ws + L.wct[0] + wo, ws + L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, TN)) return rc;
       if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cl), 1, TN)) return rc;
       for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
-      if (i > 0 || gx0 != nullptr) {
+      const bool run_gx = i > 0 || gx0 != nullptr;
+      if (run_gx) {
         GemmParams P = {};
         int n = 0;
         for (int j = 0; j < fs; ++j) P.seg[n++] = Seg{0, 1, Cd / BK, 0, j * Cd, dil * (fs - 1 - j), 0};
@@ -819,9 +878,17 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         if (i > 0) { P.p_hi = P16(L.gr_p[nxt][0]); P.p_lo = LOX(L.gr_p[nxt][1]); }
         else P.o0 = gx0;
         P.Cout = Cr;
-        if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN, B), stream)) return rc;
-      }
-      {
+        // this gx is the g_res of block i-1: its time sum is that block's res_b gradient
+        if (i > 0) P.colsum = wgrads[i - 1].res_b;
+        // the ACCUM tiles (gcond += Wp^T gh, K = Cd) ride in the same launch as extra N tiles
+        P.alt_y = Cr / TN;
+        P.alt_seg = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
+        P.alt_out = gcond;
+        P.alt_Cout = Cl;
+        if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN + ceil_div(Cl, TN), B),
+                                         stream))
+          return rc;
+      } else {
         GemmParams P = {};
         P.nseg = 1;
         P.seg[0] = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
@@ -873,7 +940,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     }
     // ---- bias gradients: gh's column sums come out of the grouped launch above (column Cl of
     // the condition job, per item) and are folded in after the loop; g_res, g_skip here ----
-    if (have_gres) {
+    if (have_gres && i == d.n_blocks - 1) {   // g_last_res: the only g_res no GX epilogue produced
       colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gr_p[cur][0]), LOX(L.gr_p[cur][1]),
                                                        gw.res_b, nullptr, Cr, NROWS, RPB, Cr, f16,
                                                        gscale);
@@ -894,11 +961,11 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       A.g_cond_b[i] = wgrads[i0 + i].cond_b;
       A.g_cond_w[i] = wgrads[i0 + i].cond_w;
     }
-    bias_tail_kernel<<<nb, 512, sizeof(float) * (size_t)(B * Cg + 1), stream>>>(A, colS, d.cond_global, B,
-                                                                              Cd, Cc, Cg, i0);
+    bias_tail_kernel<<<dim3(nb, Cd), Cg > 128 ? 256 : 128, 0, stream>>>(A, colS, d.cond_global, B, Cd, Cc,
+                                                                      Cg, i0);
     VQW_CHECK_LAUNCH("bias_tail_kernel");
     if (Cg > 0) {
-      gglob_tail_kernel<<<B, 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i0, nb);
+      gglob_tail_kernel<<<dim3(B, nb), 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i0);
       VQW_CHECK_LAUNCH("gglob_tail_kernel");
     }
   }

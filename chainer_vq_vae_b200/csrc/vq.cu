@@ -91,43 +91,34 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ W,
 
 // gW[c,:] = sum over columns n with idx[n]==c of gy[b,:,t]; one block per code, columns are
 // visited in increasing n and accumulated in float64 (the reference's eye(k)[idx].T.dot(gy)
-// is a float64 GEMM, utils.py:227-228), so the result is deterministic.
+// is a float64 GEMM, utils.py:227-228), so the result is deterministic.  The index list is
+// staged in shared memory once per chunk and scanned by the whole block: the test idx[n] == c is
+// block-uniform, so the scan is a branch per column and the gather runs only on the ~N/k hits
+// (round 1 compacted the hits with a single warp between two barriers: 0.19-0.36 ms per launch).
 __global__ void __launch_bounds__(128)
 vq_backward_w_kernel(const float* __restrict__ gy, const int32_t* __restrict__ idx,
                      float* __restrict__ gW, int B, int d, int T, int k) {
   const int c = blockIdx.x;
   const int64_t N = (int64_t)B * T;
-  extern __shared__ int hits[];   // matching columns of one chunk
-  __shared__ int nhits;
-  const int CH = 1024;
+  extern __shared__ int sidx[];   // one chunk of the index list
+  const int CH = 4096;
   // every thread owns feature rows i = threadIdx.x, +blockDim.x, ... (d <= 8 * blockDim.x)
   double acc[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) acc[r] = 0.0;
   for (int64_t n0 = 0; n0 < N; n0 += CH) {
+    const int cn = (int)((N - n0 < CH) ? (N - n0) : CH);
     __syncthreads();
-    if (threadIdx.x == 0) nhits = 0;
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) sidx[j] = idx[n0 + j];
     __syncthreads();
-    // order-preserving compaction by a single warp (N is small: B*T/64 columns)
-    if (threadIdx.x < 32) {
-      int base = 0;
-      for (int j = threadIdx.x; j < CH; j += 32) {
-        int64_t n = n0 + j;
-        bool hit = (n < N) && (idx[n] == c);
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (hit) hits[base + __popc(m & ((1u << threadIdx.x) - 1u))] = (int)j;
-        base += __popc(m);
-      }
-      if (threadIdx.x == 0) nhits = base;
-    }
-    __syncthreads();
-    for (int h = 0; h < nhits; ++h) {
-      int64_t n = n0 + hits[h];
-      int b = (int)(n / T), t = (int)(n % T);
+    for (int j = 0; j < cn; ++j) {
+      if (sidx[j] != c) continue;                     // block-uniform
+      const int64_t n = n0 + j;
+      const int b = (int)(n / T), t = (int)(n % T);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        int i = threadIdx.x + r * blockDim.x;
-        if (i < d) acc[r] += (double)gy[((int64_t)b * d + i) * T + t];
+        const int i = threadIdx.x + r * blockDim.x;
+        if (i < d) acc[r] += (double)__ldg(gy + ((int64_t)b * d + i) * T + t);
       }
     }
   }
@@ -170,7 +161,7 @@ extern "C" int vqw_vq_backward_w(const float* gy, const int32_t* idx, float* gW,
   VQW_REQUIRE(B >= 0 && T >= 0 && d > 0 && k > 0, "vqw_vq_backward_w: bad sizes");
   VQW_REQUIRE(gW && (((int64_t)B * T == 0) || (gy && idx)), "vqw_vq_backward_w: null pointer");
   VQW_REQUIRE(d <= 8 * 128, "vqw_vq_backward_w: d=%d > 1024 unsupported", d);
-  vq_backward_w_kernel<<<k, 128, 1024 * sizeof(int), (cudaStream_t)stream>>>(gy, idx, gW, B, d, T,
+  vq_backward_w_kernel<<<k, 128, 4096 * sizeof(int), (cudaStream_t)stream>>>(gy, idx, gW, B, d, T,
                                                                            k);
   VQW_CHECK_LAUNCH("vq_backward_w_kernel");
   return 0;

@@ -171,6 +171,12 @@ def vq_lookup(x: torch.Tensor, W: torch.Tensor, stats: bool = False):
     return e, idx, count, zsum, sqerr
 
 
+# Set by the VQ-VAE updaters around loss1.backward(): the reference computes d loss1 / d W of
+# the codebook and discards it at once (`model.vq.cleargrads()`, updaters.py:15-16); with the
+# flag on, the backward simply does not produce it (same state afterwards, one kernel less).
+DISCARD_CODEBOOK_GRAD = False
+
+
 class _StraightThrough(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, cached):
@@ -188,7 +194,7 @@ class _StraightThrough(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         gx = gy if ctx.needs_input_grad[0] else None          # utils.py:218-219
         gW = None
-        if ctx.needs_input_grad[1]:                            # utils.py:220-230
+        if ctx.needs_input_grad[1] and not DISCARD_CODEBOOK_GRAD:   # utils.py:220-230
             gyc = _f32c(gy)
             k, d = ctx.wshape
             B = gyc.shape[0]

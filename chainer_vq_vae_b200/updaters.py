@@ -161,7 +161,13 @@ class VQVAE_StandardUpdater:
             else self._optimizers["main"].bucket.zero()             # optimizer.target.cleargrads()
         prev, Fn.ACCUMULATE_INTO_GRAD = Fn.ACCUMULATE_INTO_GRAD, True
         try:
-            loss1.backward(retain_graph=True)                       # :15
+            # :15-16 -- the codebook gradient of loss1 is cleared right after it is computed, so
+            # it is not computed (cleargrads above already left vq.W.grad at zero)
+            Fn.DISCARD_CODEBOOK_GRAD = True
+            try:
+                loss1.backward(retain_graph=True)                   # :15
+            finally:
+                Fn.DISCARD_CODEBOOK_GRAD = False
             cleargrads(model.vq)                                    # :16
             loss2.backward(retain_graph=True)                       # :17
             loss3.backward()                                        # :18
