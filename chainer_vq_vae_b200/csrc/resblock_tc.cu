@@ -47,6 +47,7 @@ struct Params {
   int skip_accumulate;
   int write_residual;   // 0 for the last block: O_0/O_1 are skipped entirely
   int pf_dist;          // L2 prefetch distance (K slabs) of the activation operand in H_a, 0 = off
+  int stage_res;        // residual chunks go through the shared-memory tiles + TMA (needs res_hi)
   const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
   const __nv_bfloat16* xp_lo;
   const float* gbias;   // (B,512): conv_b + cond_b + W_p[:, Cl:] . global condition of the item
@@ -55,7 +56,11 @@ struct Params {
   __nv_bfloat16* res_hi;  // packed (B,T,Cr) planes for the next block (null for the last block)
   __nv_bfloat16* res_lo;
   float* skip;          // (B,Cs,T) fp32 in/out
-  float* gate_tanh;     // TIME-major (B,T,Ch) fp32 or null (thread = time row in both directions)
+  // saved for the backward, TIME-major (B,T,Ch) fp32 or null (thread = time row in both directions).
+  // bf16x3 keeps only the sigmoid: z = tanh * sigmoid is saved anyway as hi/lo planes (16
+  // significant bits), so the backward recovers tanh = z / sigmoid and the forward writes a third
+  // fewer bytes in its gate phases (which are store bound).  The single-pass modes keep both.
+  float* gate_tanh;
   float* gate_sig;
   __nv_bfloat16* zp_hi; // packed (B,T,Ch) planes of z = tanh*sigmoid, saved for the backward (or null)
   __nv_bfloat16* zp_lo;
@@ -80,7 +85,16 @@ constexpr int OB_PLANE = ON * BK * 2;                     // 8 KB per weight pla
 constexpr int OACC0 = 128, OACC1 = 384;                   // ping-pong output accumulators
 constexpr uint32_t IDESC_ON = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) |
                               ((uint32_t)(TM >> 4) << 24);
-constexpr int NBAR = 2 * STAGES + 8;                      // ring + hfull[2] zready[2] ofull[2] oempty[2]
+constexpr int NBAR = 2 * STAGES + 10;                     // ring + hfull[2] zready[2] ofull[2] oempty[2] afull[2]
+// Residual epilogue staging.  In the output phase a ring stage only holds two 8 KB weight planes
+// ([16 K, 32 K) of its 48 KB), so its activation area [0, 16 K) and its tail [32 K, 48 K) are free:
+// eight 16 KB regions = two buffers of four [128 rows x 64 channels] bf16 tiles (128-byte swizzle).
+// The addend x of a residual chunk is TMA-loaded into a buffer, every thread updates ITS row in
+// place (x + Wr z + br, re-split into hi / lo), and one thread TMA-stores the tiles to the next
+// block's input planes.  Round 2 measured why: a thread owns one time row, so every per-thread
+// 32-byte global access is its own LSU wavefront (4096 per chunk, ~8 k cycles); through TMA the
+// epilogue issues none.
+constexpr int REGION_BYTES = 128 * 128;
 
 // X3: three MMAs per product over hi/lo planes; F16: the planes hold IEEE fp16 (single pass)
 template <int X3, int F16>
@@ -92,7 +106,11 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                    const __grid_constant__ CUtensorMap map_w1_hi,
                    const __grid_constant__ CUtensorMap map_w1_lo,
                    const __grid_constant__ CUtensorMap map_w2_hi,
-                   const __grid_constant__ CUtensorMap map_w2_lo, const Params P) {
+                   const __grid_constant__ CUtensorMap map_w2_lo,
+                   const __grid_constant__ CUtensorMap map_xa_hi,   // addend tiles of x (staged epilogue)
+                   const __grid_constant__ CUtensorMap map_xa_lo,
+                   const __grid_constant__ CUtensorMap map_r_hi,    // residual output planes
+                   const __grid_constant__ CUtensorMap map_r_lo, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the dynamic window is only guaranteed 16-byte aligned: round up to the swizzle period
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -103,7 +121,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
   const uint32_t hfull0 = smem_u32(bars + 2 * STAGES), zready0 = hfull0 + 16;
-  const uint32_t ofull0 = hfull0 + 32, oempty0 = hfull0 + 48;
+  const uint32_t ofull0 = hfull0 + 32, oempty0 = hfull0 + 48, afull0 = hfull0 + 64;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,6 +153,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_init(zready0 + 8 * g, FWD_EPI_WARPS * 32);
       mbar_init(ofull0 + 8 * g, 1);
       mbar_init(oempty0 + 8 * g, FWD_EPI_WARPS * 32);
+      mbar_init(afull0 + 8 * g, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -211,7 +230,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           const uint32_t sa = base + stage * STAGE_BYTES;
           mbar_expect_tx(fb, nplanes * OB_PLANE);
           tma_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, oc * ON);
-          if (X3) tma_load_2d(sa + 2 * A_PLANE + B_PLANE, &map_w2_lo, fb, i * BK, oc * ON);
+          if (X3) tma_load_2d(sa + 2 * A_PLANE + OB_PLANE, &map_w2_lo, fb, i * BK, oc * ON);
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
       }
@@ -274,7 +293,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
             mma_ts(acc, z_hi, b_hi, idesc_o, (i | ks) ? 1u : 0u);
             if (X3) {
-              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
+              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + OB_PLANE + ks * UK * 2);
               mma_ts(acc, z_lo, b_hi, idesc_o, 1u);
               mma_ts(acc, z_hi, b_lo, idesc_o, 1u);
             }
@@ -298,12 +317,32 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     const bool t_ok = t < P.T;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool rec = rec_cta && threadIdx.x == 0;
-    const bool save_gates = P.gate_tanh != nullptr && t_ok;
+    const bool save_gates = P.gate_sig != nullptr && t_ok;
+    const bool leader = threadIdx.x == 0;
+    // tile h (0 = channels [0,64), 1 = [64,128)) of plane pl (0 = hi, 1 = lo) of staging buffer bf
+    auto tile_addr = [&](int bf, int pl, int h) -> uint32_t {
+      return base + (uint32_t)(2 * bf + pl) * STAGE_BYTES + (h ? (uint32_t)(2 * A_PLANE + 2 * OB_PLANE) : 0u);
+    };
+    // TMA-load the addend x[t0 .. t0+127][128 oc .. +127] (hi, lo) of residual chunk oc
+    auto issue_addend = [&](int bf, int oc) {
+      const uint32_t bar = afull0 + 8 * bf;
+      mbar_expect_tx(bar, (XLO ? 4 : 2) * REGION_BYTES);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(tile_addr(bf, 0, h), &map_xa_hi, bar, oc * ON + 64 * h, t0, b);
+        if (XLO) tma_load_3d(tile_addr(bf, 1, h), &map_xa_lo, bar, oc * ON + 64 * h, t0, b);
+      }
+    };
     // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), written over the tanh columns ----
     for (int gp = 0; gp < 2; ++gp) {
       mbar_wait(hfull0 + 8 * gp, 0);
       tc_fence_after();
       if (rec) P.dbg[16 + 2 * gp] = clock64();
+      if (gp == 1 && leader && P.stage_res) {
+        // every MMA of the first contraction is done: the activation areas and tails of the ring
+        // are free from here on.  The addends of the first two residual chunks land during E_b.
+        for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
+      }
       const uint32_t accb = lane_base + 256 * gp;
 #pragma unroll 1
       for (int q = grp; q < HALF / 16; q += NG) {
@@ -336,8 +375,10 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         }
         if (save_gates) {   // time-major (B,T,Ch) fp32: 64 contiguous bytes per thread and array
           const int64_t goff = ((int64_t)b * P.T + t) * CH + ch0;
-          st256(P.gate_tanh + goff, ar);
-          st256(P.gate_tanh + goff + 8, ar + 8);
+          if (!X3) {
+            st256(P.gate_tanh + goff, ar);
+            st256(P.gate_tanh + goff + 8, ar + 8);
+          }
           st256(P.gate_sig + goff, gr);
           st256(P.gate_sig + goff + 8, gr + 8);
         }
@@ -365,6 +406,82 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       const bool is_res = oc < n_res;
       const int cbase = (is_res ? oc : oc - n_res) * ON;
       const uint32_t accb = lane_base + (buf ? OACC1 : OACC0);
+      if (is_res && P.stage_res) {
+        // ---------- staged residual chunk: addend and result live in shared-memory tiles ----------
+        if (leader && j >= 1 && oc + 1 < n_res) {
+          // buffer (j+1)&1 was the source of chunk j-1's stores: wait until they have read it,
+          // then fetch the addend of chunk j+1 into it
+          tma_store_wait_read();
+          issue_addend((j + 1) & 1, oc + 1);
+        }
+        mbar_wait(afull0 + 8 * buf, use & 1);
+        mbar_wait(ofull0 + 8 * buf, use & 1);
+        tc_fence_after();
+        if (rec && j < 6) P.dbg[20 + 2 * j] = clock64();
+        const uint32_t rsw = (uint32_t)(row & 7);
+#pragma unroll 1
+        for (int q = grp; q < ON / 16; q += NG) {
+          float o[16];
+          tmem_ld16(accb + 16 * q, o);
+          const int ch0 = cbase + 16 * q;
+          // 16 channels of this thread's row: two 16-byte chunks (k0, k0+1) of a 128-byte tile row,
+          // XOR-swizzled with the row index (CU_TENSOR_MAP_SWIZZLE_128B) -> conflict-free
+          const int h = (16 * q) >> 6, k0 = ((16 * q) & 63) >> 3;
+          const uint32_t rowb = (uint32_t)row * 128u;
+          const uint32_t a0 = tile_addr(buf, 0, h) + rowb + (((uint32_t)k0 ^ rsw) << 4);
+          const uint32_t a1 = tile_addr(buf, 0, h) + rowb + (((uint32_t)(k0 + 1) ^ rsw) << 4);
+          const uint32_t l0 = a0 + (uint32_t)STAGE_BYTES, l1 = a1 + (uint32_t)STAGE_BYTES;   // lo tile: next stage
+          const uint4 h0 = lds128(a0), h1 = lds128(a1);
+          uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+          if (XLO) { w0 = lds128(l0); w1 = lds128(l1); }
+          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t lw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float bb[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(brs + ch0 + 4 * i);
+          uint32_t rh[8], rl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0, v1;
+            unpack_pair_f(hw[i], F16, v0, v1);
+            if (XLO) {
+              float e0, e1;
+              unpack_pair_f(lw[i], F16, e0, e1);
+              v0 += e0;
+              v1 += e1;
+            }
+            v0 += o[2 * i] + bb[2 * i];
+            v1 += o[2 * i + 1] + bb[2 * i + 1];
+            if (P.res_f32 != nullptr && t_ok) {
+              __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i) * P.T + t, v0);
+              __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i + 1) * P.T + t, v1);
+            }
+            if (XLO) split_pair_f(v0, v1, rh[i], rl[i], F16);
+            else rh[i] = pack_pair_f(v0, v1, F16);
+          }
+          sts128(a0, rh[0], rh[1], rh[2], rh[3]);
+          sts128(a1, rh[4], rh[5], rh[6], rh[7]);
+          if (XLO) {
+            sts128(l0, rl[0], rl[1], rl[2], rl[3]);
+            sts128(l1, rl[4], rl[5], rl[6], rl[7]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(oempty0 + 8 * buf);          // the accumulator is drained
+        fence_async_smem();                      // my tile writes -> visible to the TMA store
+        asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
+        if (leader) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_store_3d(&map_r_hi, tile_addr(buf, 0, h), oc * ON + 64 * h, t0, b);
+            if (XLO) tma_store_3d(&map_r_lo, tile_addr(buf, 1, h), oc * ON + 64 * h, t0, b);
+          }
+          tma_store_commit();
+        }
+        if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
+        continue;
+      }
       float addf[16];
       uint32_t hw[8], lw[8];
       auto fetch = [&](int q) {
@@ -381,10 +498,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
         }
       };
-      const bool fine = rec && j == 0;       // per-piece probes of the first chunk (warp 0)
-      if (fine) P.dbg[48] = clock64();
       fetch(grp);
-      if (fine) P.dbg[49] = clock64();
       mbar_wait(ofull0 + 8 * buf, use & 1);
       tc_fence_after();
       if (rec && j < 6) P.dbg[20 + 2 * j] = clock64();
@@ -392,12 +506,6 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       for (int q = grp; q < ON / 16; q += NG) {
         float o[16], add[16];
         tmem_ld16(accb + 16 * q, o);
-        if (fine && q == grp) {
-          P.dbg[50] = clock64();
-          uint32_t dep;
-          asm volatile("mov.u32 %0, %1;" : "=r"(dep) : "r"(is_res ? hw[0] : __float_as_uint(addf[0])));
-          P.dbg[51] = clock64() + (dep & 0u);
-        }
         if (is_res) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -446,12 +554,12 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
           }
         }
-        if (fine) P.dbg[q == grp ? 52 : 53] = clock64();
       }
       tc_fence_before();
       mbar_arrive(oempty0 + 8 * buf);
       if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
     }
+    if (leader && P.stage_res) tma_store_wait_all();   // the tiles must outlive their stores
   }
 
   tc_fence_before();
@@ -613,6 +721,20 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t
   return 0;
 }
 
+int make_map_tile(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B) {
+  EncodeTiledFn enc = get_encode();
+  VQW_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[3] = {C, T, B};
+  cuuint64_t strides[2] = {C * 2, C * T * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VQW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tile) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
                 uint64_t B) {
   EncodeTiledFn enc = get_encode();
@@ -769,7 +891,16 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     if (int rc = make_map(&m_w1_lo, x3 ? w1l : w1h, 2, K1, CD, 1, wrows)) return rc;
     if (int rc = make_map(&m_w2_hi, w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
     if (int rc = make_map(&m_w2_lo, x3 ? w2l : w2h, 2, CH, d.Cr + d.Cs, 1, wrows2)) return rc;
+    // staged residual epilogue: addend tiles of this block's input, output tiles of the next one's
+    const bool stage_res = write_res && !last;
+    CUtensorMap m_xa_hi, m_xa_lo, m_r_hi, m_r_lo;
+    if (int rc = make_map_tile(&m_xa_hi, x_hi[cur], d.Cr, d.T, d.B)) return rc;
+    if (int rc = make_map_tile(&m_xa_lo, xlo ? x_lo[cur] : x_hi[cur], d.Cr, d.T, d.B)) return rc;
+    if (int rc = make_map_tile(&m_r_hi, stage_res ? x_hi[nxt] : x_hi[cur], d.Cr, d.T, d.B)) return rc;
+    if (int rc = make_map_tile(&m_r_lo, stage_res ? (xlo ? x_lo[nxt] : x_hi[nxt]) : x_hi[cur], d.Cr, d.T, d.B))
+      return rc;
     Params P;
+    P.stage_res = stage_res ? 1 : 0;
     P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = Cl; P.fs = d.fs;   // Cc: contracted channels
     P.dilation = d.dilations[i];
     P.x3 = x3 ? 1 : 0;
@@ -786,12 +917,14 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     P.res_hi = last ? nullptr : x_hi[nxt];
     P.res_lo = last ? nullptr : x_lo[nxt];
     P.skip = skip;
-    P.gate_tanh = gate_tanh ? gate_tanh[i] : nullptr;
+    P.gate_tanh = (gate_tanh && !x3) ? gate_tanh[i] : nullptr;
     P.gate_sig = gate_sig ? gate_sig[i] : nullptr;
     P.zp_hi = sv ? splane(S.z0 + i * S.z_stride) : nullptr;
     P.zp_lo = sv ? splane(S.z0 + i * S.z_stride + S.z_plane) : nullptr;
-    VQW_REQUIRE((P.gate_tanh == nullptr) == (P.gate_sig == nullptr),
+    VQW_REQUIRE(x3 || (P.gate_tanh == nullptr) == (P.gate_sig == nullptr),
                 "vqw_resnet_forward: gate_tanh/gate_sig of block %d must be given together", i);
+    VQW_REQUIRE(P.gate_sig == nullptr || sv != nullptr,
+                "vqw_resnet_forward: saving the gates needs the `saved` buffer (z planes)");
     static long long* dbg_buf = nullptr;
     const bool timeline = getenv("VQW_TC_TIMELINE") && getenv("VQW_TC_TIMELINE")[0] == '1';
     P.dbg = nullptr; P.dbg_x = P.dbg_y = 0;
@@ -804,7 +937,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     }
     dim3 grid(ceil_div(d.T, TM), d.B);
     kern<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
-                                             m_w2_hi, m_w2_lo, P);
+                                             m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, P);
     VQW_CHECK_LAUNCH("resblock_tc_kernel");
     if (timeline) {
       long long h[64];
@@ -820,9 +953,6 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
         for (int n = 0; n < 6; ++n)
           fprintf(stderr, "  O_%d : mma [%lld, %lld]  epilogue [%lld, %lld]\n", n, h[4 + 2 * n] - h[0],
                   h[5 + 2 * n] - h[0], h[20 + 2 * n] - h[0], h[21 + 2 * n] - h[0]);
-        fprintf(stderr, "  O_0 warp 0: fetch issue [%lld, %lld]  tmem_ld done %lld  addend arrived %lld  "
-                        "piece 0 done %lld  piece 1 done %lld\n", h[48] - h[0], h[49] - h[0],
-                h[50] - h[0], h[51] - h[0], h[52] - h[0], h[53] - h[0]);
       }
     }
   }

@@ -68,6 +68,30 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, 
                "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// shared -> global tensor store of one box (bulk async-group completion), and its group fences
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed stores have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes become visible to the async proxy (TMA store source)
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -307,6 +331,9 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t
 // gradient GEMMs)
 int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
                 uint64_t B);
+// time-major plane (B,T,C): box = {64 channels, 128 rows, 1}, 128-byte swizzle -- the staging tiles of
+// the forward's residual epilogue (TMA load of the addend, TMA store of the result)
+int make_map_tile(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B);
 
 }  // namespace tc
 

@@ -73,7 +73,9 @@ struct GemmParams {
   int b_exact;                 // wgrad: B has no lo plane (exact bf16 values, e.g. a one-hot)
   int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
   int chunks_per_b;            // wgrad: work items per batch item
-  const float* f0;             // GATE_BWD: tanh, time-major (B,T,256) fp32
+  const float* f0;             // GATE_BWD: tanh, time-major (B,T,256) fp32, or null: tanh = z / sigmoid
+  const __nv_bfloat16* z_hi;   // GATE_BWD with f0 == null: the saved z planes (B,T,256)
+  const __nv_bfloat16* z_lo;
   const float* f1;             // GATE_BWD: sigmoid
   const __nv_bfloat16* a_hi;   // GX: addend planes (B,T,Cout) (g_res) or null
   const __nv_bfloat16* a_lo;
@@ -286,13 +288,21 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         // gz -> gh_t = gz*sig*(1-tanh^2), gh_s = gz*tanh*sig*(1-sig)   (modules.py:47-48 differentiated)
         const int CHh = TN;   // 256 gate pairs
         // saved tanh / sigmoid: time-major (B,T,256) fp32, written by the forward gate epilogue
+        const bool from_z = P.f0 == nullptr;
         const float* tp = P.f0 + ((int64_t)b * P.T + t) * CHh;
         const float* sp = P.f1 + ((int64_t)b * P.T + t) * CHh;
-        uint32_t pt[16], ps[16];
+        const __nv_bfloat16* zh = P.z_hi + ((int64_t)b * P.T + t) * CHh;
+        const __nv_bfloat16* zl = P.z_lo + ((int64_t)b * P.T + t) * CHh;
+        uint32_t pt[16], ps[16];       // tanh (or the z hi / lo pair words) and sigmoid of 16 channels
         auto fetch = [&](int q) {
           if (t_ok) {
-            ld256(tp + 16 * q, pt);
-            ld256(tp + 16 * q + 8, pt + 8);
+            if (from_z) {
+              ld256(zh + 16 * q, pt);
+              ld256(zl + 16 * q, pt + 8);
+            } else {
+              ld256(tp + 16 * q, pt);
+              ld256(tp + 16 * q + 8, pt + 8);
+            }
             ld256(sp + 16 * q, ps);
             ld256(sp + 16 * q + 8, ps + 8);
           }
@@ -305,9 +315,22 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           float gz[16], th[16], sg[16];
           tmem_ld16(lane_base + 16 * q, gz);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            th[i] = t_ok ? __uint_as_float(pt[i]) : 0.0f;
-            sg[i] = t_ok ? __uint_as_float(ps[i]) : 0.0f;
+          for (int i = 0; i < 16; ++i) sg[i] = t_ok ? __uint_as_float(ps[i]) : 0.0f;
+          if (from_z) {
+            // tanh = z / sigmoid with z = hi + lo (2^-17); sigmoid == 0 (pre-activation < -87)
+            // makes both gate derivatives vanish, whatever tanh is
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float z0, z1, e0, e1;
+              unpack_pair_f(pt[i], P.f16, z0, z1);
+              unpack_pair_f(pt[8 + i], P.f16, e0, e1);
+              const float s0 = sg[2 * i], s1 = sg[2 * i + 1];
+              th[2 * i] = (t_ok && s0 > 0.0f) ? __fdividef(z0 + e0, s0) : 0.0f;
+              th[2 * i + 1] = (t_ok && s1 > 0.0f) ? __fdividef(z1 + e1, s1) : 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) th[i] = t_ok ? __uint_as_float(pt[i]) : 0.0f;
           }
           if (q + NG < TN / 16) fetch(q + NG);
           if (!t_ok) continue;
@@ -834,7 +857,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   for (int i = d.n_blocks - 1; i >= 0; --i) {
     const vqw_resblock_wgrads& gw = wgrads[i];
     const int64_t wo = i * L.wstride;
-    VQW_REQUIRE(gate_tanh[i] && gate_sig[i], "vqw_resnet_backward: block %d saved gates", i);
+    VQW_REQUIRE((x3 || gate_tanh[i]) && gate_sig[i], "vqw_resnet_backward: block %d saved gates", i);
     const int nxt = cur ^ 1;
     const int dil = d.dilations[i];
     const uint8_t* xp_hi = sv + S.x0 + i * S.x_stride;
@@ -855,7 +878,9 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       P.seg[n++] = Seg{1, 2, Cs / BK, 0, Cr, 0, 0};
       P.nseg = n;
       P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
-      P.f0 = gate_tanh[i]; P.f1 = gate_sig[i];
+      P.f0 = x3 ? nullptr : gate_tanh[i]; P.f1 = gate_sig[i];
+      P.z_hi = reinterpret_cast<const __nv_bfloat16*>(zp_hi);
+      P.z_lo = reinterpret_cast<const __nv_bfloat16*>(zp_lo);
       P.p_hi = P16(L.gh_p[0]); P.p_lo = LO(L.gh_p[1]);
       P.Cout = Cd;
       if (int rc = launch_gemm<EPI_GATE_BWD>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;

@@ -281,8 +281,10 @@ class _ResidualStack(torch.autograd.Function):
             res = [None] * (n - 1) + [new(Cr) if keep_last_residual else None]
         gates: List[torch.Tensor] = []
         if need_grad:
+            # bf16x3 keeps only the sigmoid (tanh = z / sigmoid from the saved z planes)
+            only_sig = mode == L.MODE_BF16X3
             for _ in range(n):
-                gates += [new(Cd // 2), new(Cd // 2)]
+                gates += [x.new_empty(0) if only_sig else new(Cd // 2), new(Cd // 2)]
 
         d = L.ResnetDesc()
         d.B, d.T, d.Cr, d.Cd, d.Cs, d.Cc, d.fs = B, T, Cr, Cd, Cs, Cc, fs
@@ -301,7 +303,8 @@ class _ResidualStack(torch.autograd.Function):
         rarr = (C.c_void_p * n)(*[L.ptr(r) for r in res])
         garr_t = garr_s = None
         if gates:
-            garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
+            garr_t = (C.c_void_p * n)(*[(L.ptr(gates[2 * i]) if gates[2 * i].numel() else None)
+                                        for i in range(n)])
             garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_forward_workspace(C.byref(d))
         workspace = torch.empty(max(int(ws_bytes), 1), device=x.device, dtype=torch.uint8)
@@ -365,7 +368,8 @@ class _ResidualStack(torch.autograd.Function):
                                    for i in range(n - 1)] + [None]))
         garr_t = garr_s = None
         if gates:
-            garr_t = (C.c_void_p * n)(*[L.ptr(gates[2 * i]) for i in range(n)])
+            garr_t = (C.c_void_p * n)(*[(L.ptr(gates[2 * i]) if gates[2 * i].numel() else None)
+                                        for i in range(n)])
             garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_backward_workspace(C.byref(d))
         workspace = torch.empty(int(ws_bytes), device=dev, dtype=torch.uint8)

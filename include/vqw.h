@@ -174,6 +174,8 @@ int vqw_resblock_backward(const vqw_resblock_desc* desc, const float* g_res, con
  * B*(Cd/2)*T fp32 saved gate factors (arrays may be NULL for inference): opaque to the caller --
  * fp32 mode lays them out (B,Cd/2,T), the tensor-core modes time-major (B,T,Cd/2), because there
  * one thread owns one time row in the forward gate epilogue and in the backward that reads them.
+ * VQW_MODE_BF16X3 only writes gate_sig[i] (gate_tanh[i] may be NULL): the backward recovers
+ * tanh = z / sigmoid from the z planes in `saved`.
  *
  * Hoisted global condition (modules.py:17-18,44 with net.py:59-63): the
  * last Cg of the Cc condition channels may be CONSTANT over time -- the speaker embedding that
