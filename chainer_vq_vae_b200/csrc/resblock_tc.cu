@@ -573,6 +573,560 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   }
 }
 
+// ------------------------------------------------------------------ the kernel on a CTA pair
+// Same schedule on a cluster of two CTAs = two consecutive time tiles of one item.  Every MMA is a
+// cta_group::2 instruction with M = 256 (128 rows per SM); each SM stages only HALF of every
+// weight slab (the tensor core reads the other half from the peer's shared memory), so a K slab
+// costs an SM 32 KB of L2 -> SM traffic instead of 48 KB.  Why: round 2 measured the H phases
+// fill bound -- 48 KB per 768 MMA cycles = 62.5 B/clk per SM is asked for, ~52 B/clk is what the
+// L2 delivers when all 148 SMs stream at once (H phase 50-52 k cycles against 41.5 k of MMA).
+// Protocol (validated by round 1's experimental kernel): the TMA copies of both CTAs complete on
+// the LEADER's "full" barrier; one thread of the leader issues the MMAs; "empty", "H full" and
+// "O full" are tcgen05.commit multicasts to both CTAs; one elected lane per epilogue warp of both
+// CTAs arrives on the leader's "z ready" / "O empty" barriers.
+constexpr int PST = 4;                                    // ring stages
+constexpr int PB_PLANE = (TN / 2) * BK * 2;               // 8 KB: this CTA's 128 rows of a W1 slab
+constexpr int POB_PLANE = (ON / 2) * BK * 2;              // 4 KB: this CTA's 64 rows of a W2 slab
+constexpr int PSTAGE = 2 * A_PLANE + 2 * PB_PLANE;        // 32 KB
+constexpr uint32_t IDESC_P = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                             ((uint32_t)((2 * TM) >> 4) << 24);
+constexpr uint32_t IDESC_PON = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ON >> 3) << 17) |
+                               ((uint32_t)((2 * TM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                             int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar),
+      "h"((unsigned short)3)
+      : "memory");
+}
+
+template <int X3, int F16>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
+                   const __grid_constant__ CUtensorMap map_x_lo,
+                   const __grid_constant__ CUtensorMap map_c_hi,
+                   const __grid_constant__ CUtensorMap map_c_lo,
+                   const __grid_constant__ CUtensorMap map_w1_hi,
+                   const __grid_constant__ CUtensorMap map_w1_lo,
+                   const __grid_constant__ CUtensorMap map_w2_hi,
+                   const __grid_constant__ CUtensorMap map_w2_lo,
+                   const __grid_constant__ CUtensorMap map_xa_hi,   // addend tiles of x (staged epilogue)
+                   const __grid_constant__ CUtensorMap map_xa_lo,
+                   const __grid_constant__ CUtensorMap map_r_hi,    // residual output planes
+                   const __grid_constant__ CUtensorMap map_r_lo, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the dynamic window is only guaranteed 16-byte aligned: round up to the swizzle period
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  float* b1s = reinterpret_cast<float*>(smem + PST * PSTAGE + 4 * REGION_BYTES);   // [512] gate bias
+  float* brs = b1s + CD;                                                // [Cr]
+  float* bss = brs + P.Cr;                                              // [Cs]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bss + P.Cs);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + PST);
+  const uint32_t hfull0 = smem_u32(bars + 2 * PST), zready0 = hfull0 + 16;
+  const uint32_t ofull0 = hfull0 + 32, oempty0 = hfull0 + 48, afull0 = hfull0 + 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PST + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader of the pair (blockIdx.x even)
+  const int b = blockIdx.y, t0 = blockIdx.x * TM;
+  constexpr int XLO = X3 | F16;   // the residual stream keeps its lo plane (residual-add operand)
+  const int nplanes = X3 ? 2 : 1;
+  const bool rec_cta = P.dbg != nullptr && blockIdx.x == P.dbg_x && blockIdx.y == P.dbg_y;
+  if (rec_cta && threadIdx.x == 0) P.dbg[40] = clock64();
+  const int chunks_per_tap = P.Cr / BK;
+  const int nk1 = P.fs * chunks_per_tap + P.Cc / BK;     // K slabs of the first contraction
+  const int nk2 = CH / BK;                               // K slabs of the second contraction
+  const int n_res = P.Cr / ON;                           // output chunks: residual rows, then skip rows
+  const int o_begin = P.write_residual ? 0 : n_res;
+  const int o_end = n_res + P.Cs / ON;
+
+  if (warp == W_TMA && lane == 0) {
+    prefetch_tmap(&map_x_hi); prefetch_tmap(&map_c_hi); prefetch_tmap(&map_w1_hi);
+    prefetch_tmap(&map_w2_hi);
+    if (X3) {
+      prefetch_tmap(&map_x_lo); prefetch_tmap(&map_c_lo); prefetch_tmap(&map_w1_lo);
+      prefetch_tmap(&map_w2_lo);
+    }
+    for (int s = 0; s < PST; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(hfull0 + 8 * g, 1);
+      mbar_init(zready0 + 8 * g, 2 * FWD_EPI_WARPS);   // one elected lane per epilogue warp, both CTAs
+      mbar_init(ofull0 + 8 * g, 1);
+      mbar_init(oempty0 + 8 * g, 2 * FWD_EPI_WARPS);
+      mbar_init(afull0 + 8 * g, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp < FWD_EPI_WARPS) {
+    for (int i = threadIdx.x; i < CD; i += FWD_EPI_WARPS * 32) b1s[i] = P.gbias[(int64_t)b * CD + i];
+    for (int i = threadIdx.x; i < P.Cr; i += FWD_EPI_WARPS * 32) brs[i] = P.res_b[i];
+    for (int i = threadIdx.x; i < P.Cs; i += FWD_EPI_WARPS * 32) bss[i] = P.skip_b[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // the peer's barriers are initialised before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (rec_cta && threadIdx.x == 0) P.dbg[41] = clock64();
+
+  if (warp == W_TMA) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      // activation slab i of the first contraction: tap slabs of x (row shift = causal delay,
+      // negative rows are zero-filled by TMA), then the condition slabs
+      auto a_src = [&](int i, const CUtensorMap*& mh, const CUtensorMap*& ml, int& c0, int& tt) {
+        const int tap = i / chunks_per_tap;
+        if (tap < P.fs) {
+          mh = &map_x_hi; ml = &map_x_lo;
+          c0 = (i - tap * chunks_per_tap) * BK;
+          tt = t0 - P.dilation * (P.fs - 1 - tap);
+        } else {
+          mh = &map_c_hi; ml = &map_c_lo;
+          c0 = (i - P.fs * chunks_per_tap) * BK;
+          tt = t0;
+        }
+      };
+      for (int gp = 0; gp < 2; ++gp) {
+        for (int i = 0; i < nk1; ++i) {
+          mbar_wait(empty0 + 8 * stage, ph ^ 1);
+          // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
+          const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+          const uint32_t sa = base + stage * PSTAGE;
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + PB_PLANE));
+          const CUtensorMap *mh, *ml;
+          int c0, tt;
+          a_src(i, mh, ml, c0, tt);
+          tma2_load_3d(sa, mh, fb, c0, tt, b);
+          if (X3) tma2_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
+          // this CTA stages ITS half (128 rows) of the phase's 256 weight rows
+          const int wr = gp * TN + (int)rank * (TN / 2);
+          tma2_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, wr);
+          if (X3) tma2_load_2d(sa + 2 * A_PLANE + PB_PLANE, &map_w1_lo, fb, i * BK, wr);
+          if (++stage == PST) { stage = 0; ph ^= 1; }
+        }
+      }
+      for (int oc = o_begin; oc < o_end; ++oc) {
+        for (int i = 0; i < nk2; ++i) {
+          mbar_wait(empty0 + 8 * stage, ph ^ 1);
+          const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+          const uint32_t sa = base + stage * PSTAGE;
+          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * POB_PLANE);
+          const int wr = oc * ON + (int)rank * (ON / 2);
+          tma2_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, wr);
+          if (X3) tma2_load_2d(sa + 2 * A_PLANE + POB_PLANE, &map_w2_lo, fb, i * BK, wr);
+          if (++stage == PST) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // =============================== MMA issuer =================================
+    if (lane == 0 && rank == 0) {   // ONE thread of the pair issues the M = 256 MMAs of both SMs
+      int stage = 0;
+      uint32_t ph = 0;
+      const bool rec = rec_cta;
+      const uint32_t idesc = idesc_for(IDESC_P, F16);
+      const uint32_t idesc_o = idesc_for(IDESC_PON, F16);
+      for (int gp = 0; gp < 2; ++gp) {
+        const uint32_t acc = tmem_base + 256 * gp;
+        if (rec) P.dbg[2 * gp] = clock64();
+        for (int i = 0; i < nk1; ++i) {
+          mbar_wait(full0 + 8 * stage, ph);
+          tc_fence_after();
+          const uint32_t sa = base + stage * PSTAGE;
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
+            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            mma2_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
+            if (X3) {
+              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + PB_PLANE + ks * UK * 2);
+              mma2_ss(acc, a_lo, b_hi, idesc, 1u);
+              mma2_ss(acc, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          tc_commit2(empty0 + 8 * stage);
+          if (++stage == PST) { stage = 0; ph ^= 1; }
+        }
+        tc_commit2(hfull0 + 8 * gp);
+        if (rec) P.dbg[2 * gp + 1] = clock64();
+      }
+      // both halves of z are in TMEM (and both sigmoid halves are drained) from here on
+      mbar_wait(zready0, 0);
+      mbar_wait(zready0 + 8, 0);
+      tc_fence_after();
+      for (int oc = o_begin, j = 0; oc < o_end; ++oc, ++j) {
+        const int buf = j & 1, use = j >> 1;
+        if (use > 0) {
+          mbar_wait(oempty0 + 8 * buf, (use - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (buf ? OACC1 : OACC0);
+        if (rec && j < 6) P.dbg[4 + 2 * j] = clock64();
+        for (int i = 0; i < nk2; ++i) {
+          mbar_wait(full0 + 8 * stage, ph);
+          tc_fence_after();
+          const uint32_t sa = base + stage * PSTAGE;
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            // z channels [32 i + 16 ks, +16): hi pairs in 8 columns, lo pairs in the next 8
+            const int kstep = 2 * i + ks;
+            const uint32_t z_hi = tmem_base + (kstep < 8 ? 0 : 256) + 16 * (kstep & 7);
+            const uint32_t z_lo = z_hi + 8;
+            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            mma2_ts(acc, z_hi, b_hi, idesc_o, (i | ks) ? 1u : 0u);
+            if (X3) {
+              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + POB_PLANE + ks * UK * 2);
+              mma2_ts(acc, z_lo, b_hi, idesc_o, 1u);
+              mma2_ts(acc, z_hi, b_lo, idesc_o, 1u);
+            }
+          }
+          tc_commit2(empty0 + 8 * stage);
+          if (++stage == PST) { stage = 0; ph ^= 1; }
+        }
+        tc_commit2(ofull0 + 8 * buf);
+        if (rec && j < 6) P.dbg[4 + 2 * j + 1] = clock64();
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-15) ======================
+    // warp e: TMEM lane quadrant e%4 (hardware rule: a warp reaches lanes 32*(warp%4)..+31),
+    // column group e/4 -- the 16-column chunks of a phase are dealt round-robin to the 4 groups,
+    // so every SM sub-partition has 4 resident epilogue warps to hide latencies with.
+    const int quad = warp & 3, grp = warp >> 2;
+    constexpr int NG = FWD_EPI_WARPS / 4;
+    const int row = quad * 32 + lane;
+    const int t = t0 + row;
+    const bool t_ok = t < P.T;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool rec = rec_cta && threadIdx.x == 0;
+    const bool save_gates = P.gate_sig != nullptr && t_ok;
+    const bool leader = threadIdx.x == 0;
+    // tile h (0 = channels [0,64), 1 = [64,128)) of plane pl (0 = hi, 1 = lo) of staging buffer bf
+    // buffer 0 = the activation areas of the four ring stages (free in the output phase),
+    // buffer 1 = the dedicated 64 KB behind the ring
+    auto tile_addr = [&](int bf, int pl, int h) -> uint32_t {
+      return bf ? base + (uint32_t)(PST * PSTAGE) + (uint32_t)(2 * pl + h) * REGION_BYTES
+                : base + (uint32_t)(2 * pl + h) * PSTAGE;
+    };
+    const uint32_t zready_l = mapa_u32(zready0, 0), oempty_l = mapa_u32(oempty0, 0);   // the leader's
+    // TMA-load the addend x[t0 .. t0+127][128 oc .. +127] (hi, lo) of residual chunk oc
+    auto issue_addend = [&](int bf, int oc) {
+      const uint32_t bar = afull0 + 8 * bf;
+      mbar_expect_tx(bar, (XLO ? 4 : 2) * REGION_BYTES);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(tile_addr(bf, 0, h), &map_xa_hi, bar, oc * ON + 64 * h, t0, b);
+        if (XLO) tma_load_3d(tile_addr(bf, 1, h), &map_xa_lo, bar, oc * ON + 64 * h, t0, b);
+      }
+    };
+    // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), written over the tanh columns ----
+    for (int gp = 0; gp < 2; ++gp) {
+      mbar_wait(hfull0 + 8 * gp, 0);
+      tc_fence_after();
+      if (rec) P.dbg[16 + 2 * gp] = clock64();
+      if (gp == 1 && leader && P.stage_res) {
+        // every MMA of the first contraction is done: the activation areas and tails of the ring
+        // are free from here on.  The addends of the first two residual chunks land during E_b.
+        for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
+      }
+      const uint32_t accb = lane_base + 256 * gp;
+#pragma unroll 1
+      for (int q = grp; q < HALF / 16; q += NG) {
+        uint32_t ar[16], gr[16];
+        tmem_ld16_issue(accb + 16 * q, ar);
+        tmem_ld16_issue(accb + HALF + 16 * q, gr);
+        tmem_ld_wait(ar, gr);
+        uint32_t zh[8], zl[8];
+        const int ch0 = gp * HALF + 16 * q;
+        float bt[16], bs[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(bt + 4 * i) = *reinterpret_cast<const float4*>(b1s + ch0 + 4 * i);
+          *reinterpret_cast<float4*>(bs + 4 * i) = *reinterpret_cast<const float4*>(b1s + CH + ch0 + 4 * i);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float z2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float th, sg;
+            gate_pair(__uint_as_float(ar[i + u]) + bt[i + u], __uint_as_float(gr[i + u]) + bs[i + u],
+                      th, sg);
+            z2[u] = th * sg;
+            ar[i + u] = __float_as_uint(th);     // kept for the backward (gate derivative)
+            gr[i + u] = __float_as_uint(sg);
+          }
+          if (X3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], F16);
+          else zh[i >> 1] = pack_pair_f(z2[0], z2[1], F16);
+        }
+        if (save_gates) {   // time-major (B,T,Ch) fp32: 64 contiguous bytes per thread and array
+          const int64_t goff = ((int64_t)b * P.T + t) * CH + ch0;
+          if (!X3) {
+            st256(P.gate_tanh + goff, ar);
+            st256(P.gate_tanh + goff + 8, ar + 8);
+          }
+          st256(P.gate_sig + goff, gr);
+          st256(P.gate_sig + goff + 8, gr + 8);
+        }
+        tmem_st8(accb + 16 * q, zh);
+        if (X3) tmem_st8(accb + 16 * q + 8, zl);
+        if (P.zp_hi != nullptr && t_ok) {
+          const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
+          st256(P.zp_hi + zoff, zh);
+          if (X3) st256(P.zp_lo + zoff, zl);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(zready_l + 8 * gp);
+      if (rec) P.dbg[16 + 2 * gp + 1] = clock64();
+    }
+    // ---- output chunks: residual rows then skip rows, 128 per chunk ----
+    // residual = Wr z + br + x with x read back from the packed hi/lo planes (x = hi + lo to
+    // 2^-17: two 32-byte loads per 16 channels instead of 16 strided fp32 loads); the running
+    // skip sum is fp32 (B,Cs,T): lanes are consecutive t, so every access is a coalesced 128-byte
+    // row segment.  Operands of the NEXT 16-column piece are fetched before the current one is
+    // processed.
+    for (int oc = o_begin, j = 0; oc < o_end; ++oc, ++j) {
+      const int buf = j & 1, use = j >> 1;
+      const bool is_res = oc < n_res;
+      const int cbase = (is_res ? oc : oc - n_res) * ON;
+      const uint32_t accb = lane_base + (buf ? OACC1 : OACC0);
+      if (is_res && P.stage_res) {
+        // ---------- staged residual chunk: addend and result live in shared-memory tiles ----------
+        if (leader && j >= 1 && oc + 1 < n_res) {
+          // buffer (j+1)&1 was the source of chunk j-1's stores: wait until they have read it,
+          // then fetch the addend of chunk j+1 into it
+          tma_store_wait_read();
+          issue_addend((j + 1) & 1, oc + 1);
+        }
+        mbar_wait(afull0 + 8 * buf, use & 1);
+        mbar_wait(ofull0 + 8 * buf, use & 1);
+        tc_fence_after();
+        if (rec && j < 6) P.dbg[20 + 2 * j] = clock64();
+        const uint32_t rsw = (uint32_t)(row & 7);
+#pragma unroll 1
+        for (int q = grp; q < ON / 16; q += NG) {
+          float o[16];
+          tmem_ld16(accb + 16 * q, o);
+          const int ch0 = cbase + 16 * q;
+          // 16 channels of this thread's row: two 16-byte chunks (k0, k0+1) of a 128-byte tile row,
+          // XOR-swizzled with the row index (CU_TENSOR_MAP_SWIZZLE_128B) -> conflict-free
+          const int h = (16 * q) >> 6, k0 = ((16 * q) & 63) >> 3;
+          const uint32_t rowb = (uint32_t)row * 128u;
+          const uint32_t a0 = tile_addr(buf, 0, h) + rowb + (((uint32_t)k0 ^ rsw) << 4);
+          const uint32_t a1 = tile_addr(buf, 0, h) + rowb + (((uint32_t)(k0 + 1) ^ rsw) << 4);
+          const uint32_t lob = tile_addr(buf, 1, h) - tile_addr(buf, 0, h);
+          const uint32_t l0 = a0 + lob, l1 = a1 + lob;
+          const uint4 h0 = lds128(a0), h1 = lds128(a1);
+          uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+          if (XLO) { w0 = lds128(l0); w1 = lds128(l1); }
+          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t lw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float bb[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(bb + 4 * i) = *reinterpret_cast<const float4*>(brs + ch0 + 4 * i);
+          uint32_t rh[8], rl[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0, v1;
+            unpack_pair_f(hw[i], F16, v0, v1);
+            if (XLO) {
+              float e0, e1;
+              unpack_pair_f(lw[i], F16, e0, e1);
+              v0 += e0;
+              v1 += e1;
+            }
+            v0 += o[2 * i] + bb[2 * i];
+            v1 += o[2 * i + 1] + bb[2 * i + 1];
+            if (P.res_f32 != nullptr && t_ok) {
+              __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i) * P.T + t, v0);
+              __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i + 1) * P.T + t, v1);
+            }
+            if (XLO) split_pair_f(v0, v1, rh[i], rl[i], F16);
+            else rh[i] = pack_pair_f(v0, v1, F16);
+          }
+          sts128(a0, rh[0], rh[1], rh[2], rh[3]);
+          sts128(a1, rh[4], rh[5], rh[6], rh[7]);
+          if (XLO) {
+            sts128(l0, rl[0], rl[1], rl[2], rl[3]);
+            sts128(l1, rl[4], rl[5], rl[6], rl[7]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(oempty_l + 8 * buf);   // the accumulator is drained
+        fence_async_smem();                      // my tile writes -> visible to the TMA store
+        asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
+        if (leader) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_store_3d(&map_r_hi, tile_addr(buf, 0, h), oc * ON + 64 * h, t0, b);
+            if (XLO) tma_store_3d(&map_r_lo, tile_addr(buf, 1, h), oc * ON + 64 * h, t0, b);
+          }
+          tma_store_commit();
+        }
+        if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
+        continue;
+      }
+      float addf[16];
+      uint32_t hw[8], lw[8];
+      auto fetch = [&](int q) {
+        const int ch0 = cbase + 16 * q;
+        if (is_res) {
+          const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
+          if (t_ok) {
+            ld256(P.xp_hi + poff, hw);
+            if (XLO) ld256(P.xp_lo + poff, lw);
+          }
+        } else if (P.skip_accumulate && t_ok) {
+          const float* sp = P.skip + ((int64_t)b * P.Cs + ch0) * P.T + t;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) addf[i] = __ldcs(sp + (int64_t)i * P.T);
+        }
+      };
+      fetch(grp);
+      mbar_wait(ofull0 + 8 * buf, use & 1);
+      tc_fence_after();
+      if (rec && j < 6) P.dbg[20 + 2 * j] = clock64();
+#pragma unroll 1
+      for (int q = grp; q < ON / 16; q += NG) {
+        float o[16], add[16];
+        tmem_ld16(accb + 16 * q, o);
+        if (is_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0, v1;
+            unpack_pair_f(hw[i], F16, v0, v1);
+            if (XLO) {
+              float l0, l1;
+              unpack_pair_f(lw[i], F16, l0, l1);
+              v0 += l0;
+              v1 += l1;
+            }
+            add[2 * i] = t_ok ? v0 : 0.0f;
+            add[2 * i + 1] = t_ok ? v1 : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) add[i] = (P.skip_accumulate && t_ok) ? addf[i] : 0.0f;
+        }
+        if (q + NG < ON / 16) fetch(q + NG);
+        const int ch0 = cbase + 16 * q;
+        if (is_res) {
+          uint32_t rh[8], rl[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float v2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int ch = ch0 + i + u;
+              const float v = o[i + u] + brs[ch] + add[i + u];
+              if (t_ok && P.res_f32 != nullptr)
+                __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
+              v2[u] = v;
+            }
+            if (XLO) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
+            else rh[i >> 1] = pack_pair_f(v2[0], v2[1], F16);
+          }
+          if (t_ok && P.res_hi != nullptr) {
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cr + ch0;
+            st256(P.res_hi + poff, rh);
+            if (XLO) st256(P.res_lo + poff, rl);
+          }
+        } else if (t_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ch = ch0 + i;
+            P.skip[((int64_t)b * P.Cs + ch) * P.T + t] = o[i] + bss[ch] + add[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(oempty_l + 8 * buf);
+      if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
+    }
+    if (leader && P.stage_res) tma_store_wait_all();   // the tiles must outlive their stores
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the pair's MMAs can still touch it
+  if (warp == W_MMA) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+    if (rec_cta && lane == 0) P.dbg[42] = clock64();
+  }
+}
+
 // ------------------------------------------------------------------ packing kernels --------
 // (B,C,T) fp32 -> (B,T,C) bf16 hi/lo planes: 32x32 transpose through shared memory
 __global__ void __launch_bounds__(256)
@@ -750,6 +1304,10 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
   return 0;
 }
 
+size_t smem_bytes_pair(int Cr, int Cs) {
+  return 1024 + (size_t)PST * PSTAGE + 4 * REGION_BYTES + sizeof(float) * (CD + Cr + Cs) +
+         8 * (2 * PST + 10) + 16;
+}
 size_t smem_bytes(int Cr, int Cs) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * NBAR + 16;
 }
@@ -804,8 +1362,12 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   const bool x3 = d.mode == VQW_MODE_BF16X3;
   const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const bool xlo = x3 || f16;   // residual stream hi + lo (only the hi plane feeds the MMAs in fp16)
-  // weight rows per TMA box = UMMA N of the phase that consumes them
-  const int wrows = TN, wrows2 = ON;
+  // The CTA-pair kernel (cta_group::2, each SM stages half of every weight slab) is the default;
+  // VQW_TC_FWD_PAIR=0 selects the single-CTA kernel.
+  const char* penv = getenv("VQW_TC_FWD_PAIR");
+  const bool pair = !(penv && penv[0] == '0');
+  // weight rows per TMA box = the rows of a slab one CTA stages
+  const int wrows = pair ? TN / 2 : TN, wrows2 = pair ? ON / 2 : ON;
   const TcWorkspace L = tc_layout(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up((int64_t)(uintptr_t)workspace, 1024));
   auto plane = [&](int64_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
@@ -865,8 +1427,11 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
     }
   }
 
-  const size_t smem = smem_bytes(d.Cr, d.Cs);
-  auto kern = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
+  const size_t smem = pair ? smem_bytes_pair(d.Cr, d.Cs) : smem_bytes(d.Cr, d.Cs);
+  auto kern1 = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
+  auto kern2 = x3 ? resblock_tc_pair_kernel<1, 0>
+                  : (f16 ? resblock_tc_pair_kernel<0, 1> : resblock_tc_pair_kernel<0, 0>);
+  auto kern = pair ? kern2 : kern1;
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUtensorMap m_c_hi, m_c_lo;
   if (int rc = make_map(&m_c_hi, c_hi, 3, CP, d.T, d.B, TM)) return rc;
@@ -935,9 +1500,27 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       P.dbg_x = getenv("VQW_TC_TIMELINE_X") ? atoi(getenv("VQW_TC_TIMELINE_X")) : 1;
       P.dbg_y = getenv("VQW_TC_TIMELINE_Y") ? atoi(getenv("VQW_TC_TIMELINE_Y")) : 0;
     }
-    dim3 grid(ceil_div(d.T, TM), d.B);
-    kern<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
-                                             m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, P);
+    if (pair) {
+      // clusters of two CTAs = two consecutive time tiles (an odd tile count gets one all-padding tile)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * ceil_div(ceil_div(d.T, TM), 2), d.B);
+      cfg.blockDim = dim3(FWD_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern2, m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
+                                        m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, P));
+    } else {
+      dim3 grid(ceil_div(d.T, TM), d.B);
+      kern1<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
+                                                m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, P);
+    }
     VQW_CHECK_LAUNCH("resblock_tc_kernel");
     if (timeline) {
       long long h[64];

@@ -80,6 +80,20 @@ def test_tc_fp16_matches_oracle(dilations, B, T):
     assert e_skip < TOL and e_res < TOL
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
+def test_tc_single_cta_kernel_matches_the_pair_kernel(mode, monkeypatch):
+    """The shipped forward runs on CTA pairs (cta_group::2 MMAs with M = 256 over two SMs, each
+    staging half of every weight slab); VQW_TC_FWD_PAIR=0 selects the same schedule on single
+    CTAs.  Same arithmetic in the same order per output element: bit-identical results, including a
+    ragged last pair (T = 640 = 5 tiles: the sixth CTA is all padding)."""
+    (skip_p, res_p), skip_o, coll = _run(mode, [1, 2, 4], 3, 640, keep_last=True)
+    monkeypatch.setenv("VQW_TC_FWD_PAIR", "0")
+    (skip_1, res_1), _, _ = _run(mode, [1, 2, 4], 3, 640, keep_last=True)
+    tol = 1e-4 if mode == "bf16x3" else TOL
+    assert rel_err(skip_1, skip_o) < tol and rel_err(res_1, coll[-1]) < tol
+    assert torch.equal(skip_1, skip_p) and torch.equal(res_1, res_p)
+
+
 def test_tc_bf16_throughput_mode_is_close():
     skip, skip_o, coll = _run("bf16", [1, 2, 4], 2, 256)
     e = rel_err(skip, skip_o)
