@@ -104,17 +104,27 @@ struct Maps {
   CUtensorMap m[NMAPS];
 };
 
-template <int EPI>
+// PAIR = 1: the same GEMM on a cluster of two CTAs (two consecutive time tiles, or the two
+// 128-row halves of a 256-row weight-gradient tile): cta_group::2 MMAs with M = 256, each CTA
+// stages its own A rows and HALF of the B tile -- 32 KB instead of 48 KB of L2 -> SM traffic per K
+// slab (the fill, not the tensor pipe, bounded these kernels: see resblock_tc.cu), in a 3-stage
+// ring of the same shared-memory footprint.  Protocol as in resblock_tc_pair_kernel.
+template <int EPI, int PAIR>
 __global__ void __launch_bounds__(G_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_STAGES * STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + G_STAGES);
-  const uint32_t acc_full = smem_u32(bars + 2 * G_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 1);
-  float* csum = reinterpret_cast<float*>(bars + 2 * G_STAGES + 2);   // [TN] column sums (GX)
+  constexpr int NST = PAIR ? 3 : G_STAGES;              // ring stages
+  constexpr int BPL = PAIR ? B_PLANE / 2 : B_PLANE;     // bytes of one B plane this CTA stages per slab
+  constexpr int STG = 2 * A_PLANE + 2 * BPL;            // 32 KB / 48 KB
+  constexpr int BROWS = PAIR ? TN / 2 : TN;             // B rows (time flavour) this CTA stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * STG);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NST);
+  const uint32_t acc_full = smem_u32(bars + 2 * NST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
+  float* csum = reinterpret_cast<float*>(bars + 2 * NST + 2);   // [TN] column sums (GX)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool WG = (EPI == EPI_WGRAD);
@@ -137,7 +147,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   }
 
   if (warp == GW_TMA && lane == 0) {
-    for (int s = 0; s < G_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -145,16 +155,30 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == GW_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(256)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "r"(256)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "r"(256)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMA copy into this CTA's stage; in a pair every copy completes on the LEADER's barrier
+  auto ld3 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    if (PAIR) tma2_load_3d(dst, m, bar, c0, c1, c2);
+    else tma_load_3d(dst, m, bar, c0, c1, c2);
+  };
 
   if (warp == GW_TMA) {
     // =============================== TMA producer ===============================
@@ -173,23 +197,25 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           const int tk = (c % P.chunks_per_b) * P.slabs_per_item * BK;
           for (int i = 0; i < P.slabs_per_item; ++i) {
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            const uint32_t fb = full0 + 8 * stage;
-            const uint32_t sa = base + stage * STAGE_BYTES;
+            const uint32_t fb = PAIR ? mapa_u32(full0 + 8 * stage, 0) : full0 + 8 * stage;
+            const uint32_t sa = base + stage * STG;
             const bool blo = P.x3 && !P.b_exact;
-            mbar_expect_tx(fb, nplanes * A_PLANE + (blo ? 2 : 1) * B_PLANE);
+            if (rank == 0)
+              mbar_expect_tx(full0 + 8 * stage, (PAIR ? 2 : 1) * (nplanes * A_PLANE + (blo ? 2 : 1) * BPL));
             const int ta = tk + i * BK, tb = ta + jb.shift;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              tma_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
-              if (P.x3) tma_load_3d(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
+              ld3(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
+              if (P.x3) ld3(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
             }
+            // the B tile is 256 input channels; a CTA of a pair stages its 128-channel half
+            const int nb0 = jb.n0 + (PAIR ? (int)rank * (TN / 2) : 0);
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              tma_load_3d(sa + 2 * A_PLANE + h * 4096, mb, fb, jb.n0 + 64 * h, tb, bb);
-              if (blo)
-                tma_load_3d(sa + 2 * A_PLANE + B_PLANE + h * 4096, mb + 1, fb, jb.n0 + 64 * h, tb, bb);
+            for (int h = 0; h < BROWS / 64; ++h) {
+              ld3(sa + 2 * A_PLANE + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
+              if (blo) ld3(sa + 2 * A_PLANE + BPL + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
             }
-            if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
+            if (++stage == NST) { stage = 0; ph ^= 1; }
           }
         }
       } else {
@@ -202,31 +228,38 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           if (s == 0) { prefetch_tmap(ma); prefetch_tmap(mb); }
           for (int i = 0; i < sg.nslabs; ++i) {
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
-            const uint32_t fb = full0 + 8 * stage;
-            const uint32_t sa = base + stage * STAGE_BYTES;
-            mbar_expect_tx(fb, nplanes * (A_PLANE + B_PLANE));
-            tma_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-            tma_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, sg.b_row0 + TN * by, 0);
+            const uint32_t fb = PAIR ? mapa_u32(full0 + 8 * stage, 0) : full0 + 8 * stage;
+            const uint32_t sa = base + stage * STG;
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, (PAIR ? 2 : 1) * nplanes * (A_PLANE + BPL));
+            // this CTA's half (pair) of the 256 weight rows of the N tile
+            const int brow = sg.b_row0 + TN * by + (PAIR ? (int)rank * (TN / 2) : 0);
+            ld3(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+            ld3(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
             if (P.x3) {
-              tma_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-              tma_load_3d(sa + 2 * A_PLANE + B_PLANE, mb + 1, fb, sg.b_c0 + i * BK,
-                          sg.b_row0 + TN * by, 0);
+              ld3(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+              ld3(sa + 2 * A_PLANE + BPL, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
             }
-            if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
+            if (++stage == NST) { stage = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == GW_MMA) {
     // =============================== MMA issuer =================================
-    if (lane == 0 && total_slabs > 0) {
+    if (lane == 0 && total_slabs > 0 && rank == 0) {   // in a pair: ONE thread issues for both SMs
       int stage = 0;
       uint32_t ph = 0;
-      const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16);
+      // M = 256 over the pair: the M field of the instruction descriptor (bits [24,29)) is M >> 4
+      const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16) +
+                          (PAIR ? ((uint32_t)(TM >> 4) << 24) : 0u);
+      auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+        if (PAIR) mma2_ss(tmem_base, a, b, ID, acc);
+        else mma_ss(tmem_base, a, b, ID, acc);
+      };
       for (int i = 0; i < total_slabs; ++i) {
         mbar_wait(full0 + 8 * stage, ph);
         tc_fence_after();
-        const uint32_t sa = base + stage * STAGE_BYTES;
+        const uint32_t sa = base + stage * STG;
 #pragma unroll
         for (int ks = 0; ks < BK / UK; ++ks) {
           uint64_t a_hi, b_hi, a_lo, b_lo;
@@ -234,23 +267,25 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             a_hi = smem_desc_sw128_mn(sa + ks * 2048);
             b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
             a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
-            b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE + ks * 2048);
+            b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + BPL + ks * 2048);
           } else {
             a_hi = smem_desc_sw64(sa + ks * UK * 2);
             b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
             a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-            b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE + ks * UK * 2);
+            b_lo = smem_desc_sw64(sa + 2 * A_PLANE + BPL + ks * UK * 2);
           }
-          mma_ss(tmem_base, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
+          mma(a_hi, b_hi, (i | ks) ? 1u : 0u);
           if (P.x3) {
-            mma_ss(tmem_base, a_lo, b_hi, ID, 1u);
-            if (!(WG && P.b_exact)) mma_ss(tmem_base, a_hi, b_lo, ID, 1u);
+            mma(a_lo, b_hi, 1u);
+            if (!(WG && P.b_exact)) mma(a_hi, b_lo, 1u);
           }
         }
-        tc_commit(empty0 + 8 * stage);
-        if (++stage == G_STAGES) { stage = 0; ph ^= 1; }
+        if (PAIR) tc_commit2(empty0 + 8 * stage);
+        else tc_commit(empty0 + 8 * stage);
+        if (++stage == NST) { stage = 0; ph ^= 1; }
       }
-      tc_commit(acc_full);
+      if (PAIR) tc_commit2(acc_full);
+      else tc_commit(acc_full);
     }
   } else if (total_slabs > 0) {
     // =============================== epilogue (warps 0-7) =======================
@@ -513,22 +548,58 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves while the pair's MMAs can still touch it
   if (warp == GW_MMA) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256)
+                   : "memory");
   }
 }
 
-static size_t gemm_smem() {
-  return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * G_STAGES + 2) + sizeof(float) * TN + 16;
+static size_t gemm_smem() {   // 2 x 48 KB (single CTAs) = 3 x 32 KB (pairs)
+  return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * 3 + 2) + sizeof(float) * TN + 16;
+}
+// VQW_TC_GEMM_PAIR=0 keeps every backward / head GEMM on single CTAs
+static bool gemm_pair_enabled() {
+  const char* e = getenv("VQW_TC_GEMM_PAIR");
+  return !(e && e[0] == '0');
 }
 
+// weight rows per TMA box of a time-flavour GEMM = the rows one CTA stages per slab
+static uint32_t WROWS() { return gemm_pair_enabled() ? tc::TN / 2 : tc::TN; }
+
+// `pair_ok`: consecutive blockIdx.x values form valid pairs (same B tile, adjacent A row blocks);
+// the grid's x extent is rounded up to even -- the extra CTA of a time-flavour launch is all
+// padding (its loads are out of bounds = zero, its stores are masked)
 template <int EPI>
-static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream) {
-  auto kern = tc_gemm_kernel<EPI>;
+static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream,
+                       bool pair_ok = true) {
   const size_t smem = gemm_smem();
+  if (pair_ok && gemm_pair_enabled() && (EPI != EPI_WGRAD || grid.x % 2 == 0)) {
+    auto kern = tc_gemm_kernel<EPI, 1>;
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid.x + 1) / 2 * 2, grid.y, grid.z);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, P));
+    VQW_CHECK_LAUNCH("tc_gemm_kernel(pair)");
+    return 0;
+  }
+  auto kern = tc_gemm_kernel<EPI, 0>;
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
   static const char* names[5] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
@@ -871,7 +942,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       GemmParams P = {};
       if (int rc = mapk(&maps.m[0], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr, T, B, TM)) return rc;
       if (int rc = mapk(&maps.m[2], ws + L.gs_p[0], ws + L.gs_p[1], Cs, T, B, TM)) return rc;
-      if (int rc = mapk(&maps.m[4], ws + L.w2t[0] + wo, ws + L.w2t[1] + wo, Cr + Cs, Ch, 1, TN)) return rc;
+      if (int rc = mapk(&maps.m[4], ws + L.w2t[0] + wo, ws + L.w2t[1] + wo, Cr + Cs, Ch, 1, WROWS())) return rc;
       for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
       int n = 0;
       if (have_gres) P.seg[n++] = Seg{0, 2, Cr / BK, 0, 0, 0, 0};
@@ -889,8 +960,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     {
       Maps maps;
       if (int rc = mapk(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd, T, B, TM)) return rc;
-      if (int rc = mapk(&maps.m[2], ws + L.wct[0] + wo, ws + L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, TN)) return rc;
-      if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cl), 1, TN)) return rc;
+      if (int rc = mapk(&maps.m[2], ws + L.wct[0] + wo, ws + L.wct[1] + wo, (uint64_t)fs * Cd, Cr, 1, WROWS())) return rc;
+      if (int rc = mapk(&maps.m[4], ws + L.wpt[0] + wo, ws + L.wpt[1] + wo, Cd, pad256(Cl), 1, WROWS())) return rc;
       for (int k = 6; k < NMAPS; ++k) maps.m[k] = maps.m[k % 6];
       const bool run_gx = i > 0 || gx0 != nullptr;
       if (run_gx) {
@@ -939,13 +1010,16 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       P.slabs_per_item = ceil_div(T, BK);
       P.chunks_per_b = 1;
       int nj = 0;
+      bool wg_pair = true;
       // `ncols` >= N columns of the product are computed; column `col_n` (if col_out) is the
       // per-item column sum that the constant-one channel of the condition planes produces
       auto add_jobs = [&](int a_map, int M, int b_map, int N, int shift, float* out, long long gm,
                           long long gk, int ncols = 0, float* col_out = nullptr, int col_n = -1) -> int {
         if (ncols < N) ncols = N;
-        for (int m0 = 0; m0 < M; m0 += TM)
-          for (int n0 = 0; n0 < ncols; n0 += TN) {
+        // m0 runs fastest: consecutive jobs are the two 128-row halves of a 256-row tile (a CTA pair)
+        if ((ceil_div(M, TM) & 1) != 0) wg_pair = false;
+        for (int n0 = 0; n0 < ncols; n0 += TN)
+          for (int m0 = 0; m0 < M; m0 += TM) {
             VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 backward: too many weight-gradient tiles");
             P.jobs[nj++] = Job{a_map, b_map, m0, n0, shift, M, N, out, gm, gk, col_out, col_n,
                                (long long)Cd};
@@ -961,7 +1035,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         if (int rc = add_jobs(4, Cr, 3, Ch, 0, gw.res_w, Ch, 1)) return rc;
       if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
       P.njobs = nj;
-      if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+      if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
     }
     // ---- bias gradients: gh's column sums come out of the grouped launch above (column Cl of
     // the condition job, per item) and are folded in after the loop; g_res, g_skip here ----
@@ -1072,7 +1146,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
   {   // h1 = relu(W1 s + b1) -> planes
     Maps maps;
     if (int rc = mapk(&maps.m[0], s_hi, s_lo, Cs, T, B, TM)) return rc;
-    if (int rc = mapk(&maps.m[2], ws + L.w1[0], ws + L.w1[1], Cs, Cs, 1, TN)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w1[0], ws + L.w1[1], Cs, Cs, 1, WROWS())) return rc;
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
@@ -1083,7 +1157,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
   {   // y = W2 h1 + b2 -> fp32 (B,Q,T)
     Maps maps;
     if (int rc = mapk(&maps.m[0], h_hi, h_lo, Cs, T, B, TM)) return rc;
-    if (int rc = mapk(&maps.m[2], ws + L.w2[0], ws + L.w2[1], Cs, pad256(Q), 1, TN)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w2[0], ws + L.w2[1], Cs, pad256(Q), 1, WROWS())) return rc;
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
@@ -1135,7 +1209,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   {   // g_h1 = (W2^T g_y) * (h1 > 0) -> planes
     Maps maps;
     if (int rc = mapk(&maps.m[0], ws + L.gy[0], ws + L.gy[1], Qp, T, B, TM)) return rc;
-    if (int rc = mapk(&maps.m[2], ws + L.w2t[0], ws + L.w2t[1], Qp, Cs, 1, TN)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w2t[0], ws + L.w2t[1], Qp, Cs, 1, WROWS())) return rc;
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Qp / BK, 0, 0, 0, 0};
@@ -1147,7 +1221,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   {   // g_skip = (W1^T g_h1) * (skip > 0) -> fp32 (B,Cs,T)
     Maps maps;
     if (int rc = mapk(&maps.m[0], ws + L.gh1[0], ws + L.gh1[1], Cs, T, B, TM)) return rc;
-    if (int rc = mapk(&maps.m[2], ws + L.w1t[0], ws + L.w1t[1], Cs, Cs, 1, TN)) return rc;
+    if (int rc = mapk(&maps.m[2], ws + L.w1t[0], ws + L.w1t[1], Cs, Cs, 1, WROWS())) return rc;
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
@@ -1168,18 +1242,20 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     P.slabs_per_item = ceil_div(T, BK);
     P.chunks_per_b = 1;
     int nj = 0;
-    for (int m0 = 0; m0 < Q; m0 += TM)
-      for (int n0 = 0; n0 < Cs; n0 += TN) {
+    // m0 fastest: consecutive jobs = the halves of a 256-row tile (CTA pair); Q < 256 has an odd tile
+    const bool wg_pair = (ceil_div(Q, TM) & 1) == 0 && (ceil_div(Cs, TM) & 1) == 0;
+    for (int n0 = 0; n0 < Cs; n0 += TN)
+      for (int m0 = 0; m0 < Q; m0 += TM) {
         VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 head: too many weight-gradient tiles");
         P.jobs[nj++] = Job{0, 1, m0, n0, 0, Q, Cs, gW2, Cs, 1};
       }
-    for (int m0 = 0; m0 < Cs; m0 += TM)
-      for (int n0 = 0; n0 < Cs; n0 += TN) {
+    for (int n0 = 0; n0 < Cs; n0 += TN)
+      for (int m0 = 0; m0 < Cs; m0 += TM) {
         VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 head: too many weight-gradient tiles");
         P.jobs[nj++] = Job{2, 3, m0, n0, 0, Cs, Cs, gW1, Cs, 1};
       }
     P.njobs = nj;
-    if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+    if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
   }
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gy[0]), LOW(W16(L.gy[1])), gb2, nullptr, Qp,
                                                    NROWS, RPB, Q, f16, gscale);
@@ -1250,15 +1326,16 @@ int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, in
   P.slabs_per_item = ceil_div(T, BK);
   P.chunks_per_b = 1;
   int nj = 0;
+  const bool wg_pair = (ceil_div(Cr, TM) & 1) == 0;
   for (int j = 0; j < 2; ++j)
-    for (int m0 = 0; m0 < Cr; m0 += TM)
-      for (int n0 = 0; n0 < Q; n0 += TN) {
+    for (int n0 = 0; n0 < Q; n0 += TN)
+      for (int m0 = 0; m0 < Cr; m0 += TM) {
         VQW_REQUIRE(nj < MAX_JOBS, "tcgen05 embed backward: too many tiles");
         // tap j reads the index at t - 1 + j  (j = 0: previous sample, j = 1: current sample)
         P.jobs[nj++] = Job{0, 1, m0, n0, j - 1, Cr, Q, gW + j, (long long)Q * 2, 2};
       }
   P.njobs = nj;
-  if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+  if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
   if (gb) {
     const int RPB = 256;
     colsum_planes_kernel<<<(int)((N + RPB - 1) / RPB), 256, 0, stream>>>(g_hi, x3 ? g_lo : nullptr, gb,
