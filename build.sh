@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJS=""
 for f in *.cu; do
   o="${f%.cu}.o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tc_common.cuh -nt "$o" ] || [ ../../include/vqw.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ mol.cuh -nt "$o" ] || [ tc_common.cuh -nt "$o" ] || [ ../../include/vqw.h -nt "$o" ]; then
     echo "nvcc $f"
     $NVCC $FLAGS ${EXTRA_NVCC_FLAGS} -c "$f" -o "$o" &
   fi

@@ -107,6 +107,9 @@ _SIGNATURES = {
     "vqw_head_saved_bytes": (C.c_int64, [C.POINTER(HeadDesc)]),
     "vqw_head_forward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 9),
     "vqw_head_backward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 11),
+    "vqw_head_loss_forward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 7 + [c_int, C.c_float] +
+                              [C.c_void_p] * 5),
+    "vqw_head_loss_backward": (c_int, [C.POINTER(HeadDesc)] + [C.c_void_p] * 11),
     "vqw_softmax_ce": (c_int, [C.c_void_p] * 4 + [c_int] * 3 + [C.c_void_p]),
     "vqw_mol_loss": (c_int, [C.c_void_p] * 4 + [c_int] * 4 + [C.c_float, C.c_void_p]),
     "vqw_upsample_concat_forward": (c_int, [C.c_void_p] * 3 + [c_int] * 5 + [C.c_void_p]),

@@ -77,9 +77,13 @@ int64_t head_tc_saved_bytes(const vqw_head_desc& d);
 int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
                     const float* W2, const float* b2, float* y, void* workspace, void* saved,
                     cudaStream_t stream);
-int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, const float* W2,
-                     float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
-                     const void* saved, cudaStream_t stream);
+int head_loss_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                         const float* W2, const float* b2, const int32_t* tgt_i, const float* tgt_f,
+                         int quantize, float log_scale_min, double* loss, float* y, void* workspace,
+                         void* saved, cudaStream_t stream);
+int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* g_loss, const float* W1,
+                     const float* W2, float* gskip, float* gW1, float* gb1, float* gW2, float* gb2,
+                     void* workspace, const void* saved, cudaStream_t stream);
 
 bool embed_bwd_tc_supported(int B, int T, int Cr, int Q);
 int64_t embed_bwd_tc_workspace(int B, int T, int Cr, int Q);

@@ -9,48 +9,11 @@
 //                    embedding to 64x its length (1-D align-corners linear interpolation, exact
 //                    integer coordinates), the speaker embedding broadcast over time (a resize
 //                    from length 1), and the channel concat (local first); and its backward.
-#include "common.cuh"
+#include "mol.cuh"
 
 namespace vqw {
 
-__device__ __forceinline__ float sigmoid_chainer(float v) { return tanhf(v * 0.5f) * 0.5f + 0.5f; }
-__device__ __forceinline__ float softplus_chainer(float v) {
-  return fmaxf(v, 0.0f) + log1pf(expf(-fabsf(v)));
-}
-
-// log-probability of component k before the mixture weight (modules.py:181-226) and, optionally,
-// its derivatives with respect to the mean and the (floored) log scale
-__device__ __forceinline__ float mol_component(float x, float mean, float ls, float half, float lo,
-                                               float hi, float* d_mean, float* d_ls) {
-  const float c = x - mean;
-  const float inv = expf(-ls);
-  const float pin = inv * (c + half), min_ = inv * (c - half);
-  const float cp = sigmoid_chainer(pin), cm = sigmoid_chainer(min_);
-  float f;
-  if (x < lo) {
-    f = pin - softplus_chainer(pin);                      // log cdf_plus
-    if (d_mean) { *d_mean = -inv * (1.0f - cp); *d_ls = -pin * (1.0f - cp); }
-  } else if (x > hi) {
-    f = -softplus_chainer(min_);                          // log (1 - cdf_min)
-    if (d_mean) { *d_mean = inv * cm; *d_ls = min_ * cm; }
-  } else {
-    const float delta = cp - cm;
-    f = logf(fmaxf(delta, 1e-12f));
-    if (d_mean) {
-      if (delta >= 1e-12f) {   // F.maximum routes the gradient to its first argument on >=
-        const float sp = cp * (1.0f - cp), sm = cm * (1.0f - cm);
-        *d_mean = -inv * (sp - sm) / delta;
-        *d_ls = -(pin * sp - min_ * sm) / delta;
-      } else {
-        *d_mean = 0.0f;
-        *d_ls = 0.0f;
-      }
-    }
-  }
-  return f;
-}
-
-// thread = one (b, t) position (coalesced along T); two sweeps over the nr mixture components
+// thread = one (b, t) position (coalesced along T); sweeps over the nr mixture components
 __global__ void __launch_bounds__(256)
 mol_loss_kernel(const float* __restrict__ y, const float* __restrict__ tgt, float* __restrict__ gy,
                 double* __restrict__ loss, int B, int nr, int T, float half, float log_scale_min,
@@ -59,48 +22,9 @@ mol_loss_kernel(const float* __restrict__ y, const float* __restrict__ tgt, floa
   const int b = blockIdx.y;
   double local = 0.0;
   if (t < T) {
-    const float* yc = y + (int64_t)b * 3 * nr * T + t;
-    const float x = 127.5f * tgt[(int64_t)b * T + t];
-    const float lo = 127.5f * -0.999f, hi = 127.5f * 0.999f;
-    // log_softmax(logit_probs)
-    float mx = -INFINITY;
-    for (int k = 0; k < nr; ++k) mx = fmaxf(mx, __ldg(yc + (int64_t)k * T));
-    float s = 0.0f;
-    for (int k = 0; k < nr; ++k) s += expf(__ldg(yc + (int64_t)k * T) - mx);
-    const float lse_l = mx + logf(s);
-    // logsumexp_k(log_probs_k)
-    float m2 = -INFINITY;
-    for (int k = 0; k < nr; ++k) {
-      const float ls = fmaxf(__ldg(yc + (int64_t)(2 * nr + k) * T), log_scale_min);
-      const float lp = mol_component(x, __ldg(yc + (int64_t)(nr + k) * T), ls, half, lo, hi, nullptr,
-                                     nullptr) + (__ldg(yc + (int64_t)k * T) - lse_l);
-      m2 = fmaxf(m2, lp);
-    }
-    float s2 = 0.0f;
-    for (int k = 0; k < nr; ++k) {
-      const float ls = fmaxf(__ldg(yc + (int64_t)(2 * nr + k) * T), log_scale_min);
-      const float lp = mol_component(x, __ldg(yc + (int64_t)(nr + k) * T), ls, half, lo, hi, nullptr,
-                                     nullptr) + (__ldg(yc + (int64_t)k * T) - lse_l);
-      s2 += expf(lp - m2);
-    }
-    const float lse = m2 + logf(s2);
-    local = -(double)lse;
-    if (gy) {
-      float* gc = gy + (int64_t)b * 3 * nr * T + t;
-      for (int k = 0; k < nr; ++k) {
-        const float raw = __ldg(yc + (int64_t)(2 * nr + k) * T);
-        const float ls = fmaxf(raw, log_scale_min);
-        const float lk = __ldg(yc + (int64_t)k * T);
-        float dm, dl;
-        const float lp = mol_component(x, __ldg(yc + (int64_t)(nr + k) * T), ls, half, lo, hi, &dm, &dl) +
-                         (lk - lse_l);
-        const float w = expf(lp - lse);            // posterior responsibility of component k
-        const float pi = expf(lk - lse_l);         // prior mixture weight
-        gc[(int64_t)k * T] = -(w - pi) * inv_n;
-        gc[(int64_t)(nr + k) * T] = -w * dm * inv_n;
-        gc[(int64_t)(2 * nr + k) * T] = (raw >= log_scale_min) ? -w * dl * inv_n : 0.0f;
-      }
-    }
+    const int64_t off = (int64_t)b * 3 * nr * T + t;
+    local = (double)mol_position(y + off, T, tgt[(int64_t)b * T + t], nr, half, log_scale_min, inv_n,
+                                 gy ? gy + off : nullptr, T);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);

@@ -472,6 +472,26 @@ extern "C" int vqw_head_backward(const vqw_head_desc* desc, const float* gy, con
                                  float* gb2, void* workspace, const void* saved,
                                  vqw_stream_t stream) {
   if (int rc = head_check(desc, "vqw_head_backward")) return rc;
-  return vqw::head_backward_tc(*desc, gy, W1, W2, gskip, gW1, gb1, gW2, gb2, workspace, saved,
+  VQW_REQUIRE(gy != nullptr, "vqw_head_backward: null argument");
+  return vqw::head_backward_tc(*desc, gy, nullptr, W1, W2, gskip, gW1, gb1, gW2, gb2, workspace, saved,
                                (cudaStream_t)stream);
+}
+extern "C" int vqw_head_loss_forward(const vqw_head_desc* desc, const float* skip, const float* W1,
+                                     const float* b1, const float* W2, const float* b2,
+                                     const int32_t* t_labels, const float* t_values, int quantize,
+                                     float log_scale_min, double* loss, float* y_opt, void* workspace,
+                                     void* saved, vqw_stream_t stream) {
+  if (int rc = head_check(desc, "vqw_head_loss_forward")) return rc;
+  return vqw::head_loss_forward_tc(*desc, skip, W1, b1, W2, b2, t_labels, t_values, quantize,
+                                   log_scale_min, loss, y_opt, workspace, saved, (cudaStream_t)stream);
+}
+extern "C" int vqw_head_loss_backward(const vqw_head_desc* desc, const float* g_loss, const float* W1,
+                                      const float* W2, float* gskip, float* gW1, float* gb1,
+                                      float* gW2, float* gb2, void* workspace, const void* saved,
+                                      vqw_stream_t stream) {
+  using namespace vqw;
+  if (int rc = head_check(desc, "vqw_head_loss_backward")) return rc;
+  VQW_REQUIRE(g_loss != nullptr, "vqw_head_loss_backward: null upstream gradient");
+  return head_backward_tc(*desc, nullptr, g_loss, W1, W2, gskip, gW1, gb1, gW2, gb2, workspace, saved,
+                          (cudaStream_t)stream);
 }

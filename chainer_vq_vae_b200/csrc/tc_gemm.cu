@@ -25,6 +25,7 @@
 // epilogue, two per TMEM lane quadrant) with a 2-stage ring and a 256-column accumulator so
 // that TWO CTAs are resident per SM: one CTA's epilogue overlaps the other's MMAs.
 #include "tc_common.cuh"
+#include "mol.cuh"
 #include <stdlib.h>
 
 namespace vqw {
@@ -37,7 +38,7 @@ constexpr int GW_TMA = G_EPI_WARPS, GW_MMA = G_EPI_WARPS + 1;
 constexpr int MAX_SEG = 4;
 constexpr int MAX_JOBS = 48;
 constexpr int NMAPS = 12;
-enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3, EPI_HEAD = 4 };
+enum { EPI_GATE_BWD = 0, EPI_GX = 1, EPI_ACCUM = 2, EPI_WGRAD = 3, EPI_HEAD = 4, EPI_HEAD_LOSS = 5 };
 
 struct Seg {
   int a_map, b_map;   // tensor-map pair index: hi plane = maps[2*i], lo plane = maps[2*i+1]
@@ -90,6 +91,13 @@ struct GemmParams {
   // (>= alt_y): those CTAs stream gh once more (from L2: the GX tiles of the same rows read the
   // same slabs) and are bound by that stream, so they overlap the MMA-bound GX tiles instead of
   // running as a separate launch
+  // HEAD_LOSS: the loss and d loss / d y in the epilogue of the proj2 GEMM (Cout = Q <= 256: the
+  // whole row of logits is one accumulator tile) -- the logits never go to HBM unless o0 is set
+  const int32_t* tgt_i;        // (B,T) class labels (softmax cross entropy), or null
+  const float* tgt_f;          // (B,T) waveform values (mixture of logistics), or null
+  double* loss;                // {loss (accumulated), number of valid labels (set before the launch)}
+  int Qv;                      // real number of output channels (<= Cout = padded plane pitch)
+  float mol_half, mol_lsmin;   // 127.5 / (quantize - 1), log_scale_min
   float* colsum;               // GX: column sums of the result (+= , the bias gradient
                                // sum_t g_res of the NEXT block to run) or null
   int alt_y;                   // 0 = no ACCUM tiles in this launch
@@ -469,6 +477,114 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           for (int i = threadIdx.x; i < TN; i += G_EPI_WARPS * 32)
             atomicAdd(P.colsum + cbase + i, csum[i] * inv);
         }
+      } else if (EPI == EPI_HEAD_LOSS) {
+        // ---- y = acc + bias (one N tile = the whole row), loss and gy = d loss / d y -> planes ----
+        float* red = csum;                                  // [2][128] floats of row exchange
+        const int Q = P.Qv;
+        const float inv_n = (float)(P.loss[1] > 0.0 ? 1.0 / P.loss[1] : 0.0);
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        double nll = 0.0;
+        if (P.tgt_i != nullptr) {
+          // softmax cross entropy (train.py:95): two warps share a row (column chunks dealt
+          // round-robin), so max and sum are combined through shared memory
+          const int k = t_ok ? P.tgt_i[(int64_t)b * P.T + t] : -1;
+          const bool valid = k >= 0 && k < Q;               // ignore_label = -1
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int q = grp; 16 * q < Q; q += NG) {
+            float o[16];
+            tmem_ld16(lane_base + 16 * q, o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (16 * q + i < Q) mx = fmaxf(mx, o[i] + __ldg(P.bias + 16 * q + i));
+          }
+          red[grp * TM + row] = mx;
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          mx = fmaxf(red[row], red[TM + row]);
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          float sum = 0.0f, vt = 0.0f;
+#pragma unroll 1
+          for (int q = grp; 16 * q < Q; q += NG) {
+            float o[16];
+            tmem_ld16(lane_base + 16 * q, o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (16 * q + i < Q) {
+                const float v = o[i] + __ldg(P.bias + 16 * q + i);
+                sum += expf(v - mx);
+                if (16 * q + i == k) vt = v;
+              }
+            }
+          }
+          red[grp * TM + row] = sum;
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          const float lse = mx + logf(red[row] + red[TM + row]);
+          if (valid && (k >> 4) % NG == grp) nll = (double)(lse - vt);   // the warp that owns column k
+#pragma unroll 1
+          for (int q = grp; 16 * q < P.Cout; q += NG) {
+            float o[16];
+            tmem_ld16(lane_base + 16 * q, o);
+            if (!t_ok) continue;
+            float g[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = 16 * q + i;
+              const float v = (c < Q) ? o[i] + __ldg(P.bias + c) : 0.0f;
+              o[i] = v;
+              g[i] = (c < Q && valid) ? (expf(v - lse) - (c == k ? 1.0f : 0.0f)) * inv_n : 0.0f;
+            }
+            if (P.o0 != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (16 * q + i < Q) P.o0[((int64_t)b * Q + 16 * q + i) * P.T + t] = o[i];
+            }
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (P.x3) split_pair_f(g[2 * i], g[2 * i + 1], vh[i], vl[i], P.f16);
+              else vh[i] = pack_pair_f(g[2 * i], g[2 * i + 1], P.f16);
+            }
+            const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + 16 * q;
+            st256(P.p_hi + poff, vh);
+            if (P.x3) st256(P.p_lo + poff, vl);
+          }
+        } else {
+          // mixture of logistics (modules.py:169-230): 3 * nr <= 32 outputs, one thread per row
+          const int nr = Q / 3;
+          if (grp == 0) {
+            float yv[32], gv[32];
+            tmem_ld16(lane_base, yv);
+            tmem_ld16(lane_base + 16, yv + 16);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              yv[i] = (i < Q) ? yv[i] + __ldg(P.bias + i) : 0.0f;
+              gv[i] = 0.0f;
+            }
+            if (t_ok) {
+              nll = (double)mol_position(yv, 1, P.tgt_f[(int64_t)b * P.T + t], nr, P.mol_half,
+                                         P.mol_lsmin, inv_n, gv, 1);
+              if (P.o0 != nullptr)
+                for (int i = 0; i < Q; ++i) P.o0[((int64_t)b * Q + i) * P.T + t] = yv[i];
+              for (int q = 0; 16 * q < P.Cout; ++q) {
+                uint32_t vh[8], vl[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float g0 = (q < 2) ? gv[16 * q + 2 * i] : 0.0f;
+                  const float g1 = (q < 2) ? gv[16 * q + 2 * i + 1] : 0.0f;
+                  if (P.x3) split_pair_f(g0, g1, vh[i], vl[i], P.f16);
+                  else vh[i] = pack_pair_f(g0, g1, P.f16);
+                }
+                const int64_t poff = ((int64_t)b * P.T + t) * P.Cout + 16 * q;
+                st256(P.p_hi + poff, vh);
+                if (P.x3) st256(P.p_lo + poff, vl);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) nll += __shfl_xor_sync(0xffffffffu, nll, off);
+        if (lane == 0 && nll != 0.0) atomicAdd(P.loss, nll * (double)inv_n);
       } else if (EPI == EPI_HEAD) {
         const int cbase = TN * blockIdx.y;
         mbar_wait(acc_full, 0);
@@ -602,9 +718,9 @@ static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStr
   auto kern = tc_gemm_kernel<EPI, 0>;
   VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, G_THREADS, smem, stream>>>(maps, P);
-  static const char* names[5] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
+  static const char* names[6] = {"tc_gemm_kernel<GATE_BWD>", "tc_gemm_kernel<GX>",
                                  "tc_gemm_kernel<ACCUM>", "tc_gemm_kernel<WGRAD>",
-                                 "tc_gemm_kernel<HEAD>"};
+                                 "tc_gemm_kernel<HEAD>", "tc_gemm_kernel<HEAD_LOSS>"};
   VQW_CHECK_LAUNCH(names[EPI]);
   return 0;
 }
@@ -1098,24 +1214,58 @@ static HeadLayout head_layout(const vqw_head_desc& d) {
   L.total = off + 1024;
   return L;
 }
-struct HeadSaved { int64_t s[2], h1[2], total; };
+struct HeadSaved { int64_t s[2], h1[2], gy[2], scale, total; };
 static HeadSaved head_saved(const vqw_head_desc& d) {
   HeadSaved S;
   const int64_t plane = al((int64_t)d.B * d.T * d.Cs * 2);
+  const int64_t gplane = al((int64_t)d.B * d.T * qpad(d.Q) * 2);
   S.s[0] = 0; S.s[1] = plane; S.h1[0] = 2 * plane; S.h1[1] = 3 * plane;
-  S.total = 4 * plane + 1024;
+  S.gy[0] = 4 * plane; S.gy[1] = 4 * plane + gplane;     // d loss / d y planes (fused loss)
+  S.scale = 4 * plane + 2 * gplane;                      // {1/g, g}: upstream gradient of the loss
+  S.total = S.scale + 1024 + 1024;
   return S;
 }
 
 int64_t head_tc_workspace(const vqw_head_desc& d) { return head_layout(d).total; }
 int64_t head_tc_saved_bytes(const vqw_head_desc& d) { return head_saved(d).total; }
 
-int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
-                    const float* W2, const float* b2, float* y, void* workspace, void* saved,
-                    cudaStream_t stream) {
+namespace tc {
+__global__ void set_double_kernel(double* p, double v) { *p = v; }
+__global__ void __launch_bounds__(256)
+count_labels_kernel(const int32_t* __restrict__ tgt, int64_t n, int Q, double* __restrict__ count) {
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = tgt[i];
+    c += (k >= 0 && k < Q) ? 1 : 0;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (double)c);
+}
+}  // namespace tc
+
+// Loss description of the fused head: exactly one of tgt_i (softmax cross entropy, train.py:95) and
+// tgt_f (mixture of logistics, modules.py:169-230) is set; loss = {loss, valid count} (zeroed by
+// the caller); the logits go to `y` only if it is non-null.
+struct HeadLoss {
+  const int32_t* tgt_i;
+  const float* tgt_f;
+  double* loss;
+  int quantize;
+  float log_scale_min;
+};
+
+static int head_forward_impl(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                             const float* W2, const float* b2, float* y, void* workspace, void* saved,
+                             const HeadLoss* hl, cudaStream_t stream) {
   using namespace tc;
   VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: needs skip_channels %% 256 == 0, T >= 128, T %% 8 == 0");
-  VQW_REQUIRE(skip && W1 && b1 && W2 && b2 && y && workspace, "vqw_head_forward: null argument");
+  VQW_REQUIRE(skip && W1 && b1 && W2 && b2 && (y || hl) && workspace, "vqw_head_forward: null argument");
+  VQW_REQUIRE(!hl || (saved && d.Q <= TN && (hl->tgt_i != nullptr) != (hl->tgt_f != nullptr) && hl->loss),
+              "vqw_head_loss_forward: needs `saved`, Q <= 256 and exactly one target");
+  VQW_REQUIRE(!hl || !hl->tgt_f || (d.Q % 3 == 0 && d.Q <= 32),
+              "vqw_head_loss_forward: the mixture-of-logistics head has 3 * n_mix <= 32 outputs");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
   const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const HeadLayout L = head_layout(d);
@@ -1154,7 +1304,7 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
     P.p_hi = h_hi; P.p_lo = LOW(h_lo);
     if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), Cs / TN, B), stream)) return rc;
   }
-  {   // y = W2 h1 + b2 -> fp32 (B,Q,T)
+  {   // y = W2 h1 + b2 -> fp32 (B,Q,T), or straight into the loss
     Maps maps;
     if (int rc = mapk(&maps.m[0], h_hi, h_lo, Cs, T, B, TM)) return rc;
     if (int rc = mapk(&maps.m[2], ws + L.w2[0], ws + L.w2[1], Cs, pad256(Q), 1, WROWS())) return rc;
@@ -1162,18 +1312,64 @@ int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, 
     GemmParams P = {};
     P.nseg = 1; P.seg[0] = Seg{0, 1, Cs / BK, 0, 0, 0, 0};
     P.x3 = x3; P.f16 = f16; P.B = B; P.T = T; P.Cout = Q; P.bias = b2; P.o0 = y;
-    if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), ceil_div(Q, TN), B), stream)) return rc;
+    if (hl == nullptr) {
+      if (int rc = launch_gemm<EPI_HEAD>(maps, P, dim3(ceil_div(T, TM), ceil_div(Q, TN), B), stream)) return rc;
+    } else {
+      // number of labels the mean runs over (normalize=True, ignore_label=-1), then the GEMM whose
+      // epilogue turns each row of logits into its loss term and its gradient planes
+      if (hl->tgt_i) {
+        count_labels_kernel<<<148, 256, 0, stream>>>(hl->tgt_i, (int64_t)B * T, Q, hl->loss + 1);
+        VQW_CHECK_LAUNCH("count_labels_kernel");
+      } else {
+        set_double_kernel<<<1, 1, 0, stream>>>(hl->loss + 1, (double)B * (double)T);
+        VQW_CHECK_LAUNCH("set_double_kernel");
+      }
+      P.Cout = qpad(Q); P.Qv = Q;
+      P.tgt_i = hl->tgt_i; P.tgt_f = hl->tgt_f; P.loss = hl->loss;
+      P.mol_half = (float)(127.5 / (hl->quantize - 1)); P.mol_lsmin = hl->log_scale_min;
+      P.p_hi = reinterpret_cast<__nv_bfloat16*>(sv + S.gy[0]);
+      P.p_lo = LOW(reinterpret_cast<__nv_bfloat16*>(sv + S.gy[1]));
+      if (int rc = launch_gemm<EPI_HEAD_LOSS>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;
+    }
   }
   return 0;
 }
 
-int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, const float* W2,
-                     float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
-                     const void* saved, cudaStream_t stream) {
+int head_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                    const float* W2, const float* b2, float* y, void* workspace, void* saved,
+                    cudaStream_t stream) {
+  VQW_REQUIRE(y != nullptr, "vqw_head_forward: null argument");
+  return head_forward_impl(d, skip, W1, b1, W2, b2, y, workspace, saved, nullptr, stream);
+}
+
+int head_loss_forward_tc(const vqw_head_desc& d, const float* skip, const float* W1, const float* b1,
+                         const float* W2, const float* b2, const int32_t* tgt_i, const float* tgt_f,
+                         int quantize, float log_scale_min, double* loss, float* y, void* workspace,
+                         void* saved, cudaStream_t stream) {
+  HeadLoss hl = {tgt_i, tgt_f, loss, quantize, log_scale_min};
+  return head_forward_impl(d, skip, W1, b1, W2, b2, y, workspace, saved, &hl, stream);
+}
+
+namespace tc {
+// {1/g, g} from the upstream gradient g of the scalar loss (device memory, no host sync)
+__global__ void loss_scale_kernel(const float* __restrict__ g, float* __restrict__ scale) {
+  const float v = *g;
+  scale[0] = v != 0.0f ? 1.0f / v : 0.0f;
+  scale[1] = v;
+}
+}  // namespace tc
+
+// gy == nullptr: the gradient planes were written by head_loss_forward_tc (in `saved`); g_loss is
+// the upstream gradient of the scalar loss (device pointer), applied to every fp32 result
+int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* g_loss, const float* W1,
+                     const float* W2, float* gskip, float* gW1, float* gb1, float* gW2, float* gb2,
+                     void* workspace, const void* saved, cudaStream_t stream) {
   using namespace tc;
   VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: unsupported shape");
-  VQW_REQUIRE(gy && W1 && W2 && gskip && gW1 && gb1 && gW2 && gb2 && workspace && saved,
+  VQW_REQUIRE((gy || g_loss) && W1 && W2 && gskip && gW1 && gb1 && gW2 && gb2 && workspace && saved,
               "vqw_head_backward: null argument");
+  VQW_REQUIRE(gy || d.mode != VQW_MODE_FP16,
+              "vqw_head_loss_backward: the fused loss needs a bf16 mode (fp16 planes carry a scale)");
   const bool x3 = d.mode == VQW_MODE_BF16X3;
   const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
   const HeadLayout L = head_layout(d);
@@ -1191,8 +1387,18 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
                                  reinterpret_cast<float*>(ws + L.scale), stream, &gscale))
       return rc;
   }
-  if (int rc = pack_act_launch_ex(gy, W16(L.gy[0]), LOW(W16(L.gy[1])), B, Q, T, Qp, 0, f16, gscale, stream))
-    return rc;
+  const uint8_t* gyp[2] = {ws + L.gy[0], ws + L.gy[1]};
+  if (gy != nullptr) {
+    if (int rc = pack_act_launch_ex(gy, W16(L.gy[0]), LOW(W16(L.gy[1])), B, Q, T, Qp, 0, f16, gscale, stream))
+      return rc;
+  } else {
+    gyp[0] = sv + S.gy[0];
+    gyp[1] = sv + S.gy[1];
+    float* sc = reinterpret_cast<float*>(const_cast<uint8_t*>(sv) + S.scale);
+    loss_scale_kernel<<<1, 1, 0, stream>>>(g_loss, sc);
+    VQW_CHECK_LAUNCH("loss_scale_kernel");
+    gscale = sc;
+  }
   pack_mat_kernel<<<148, 256, 0, stream>>>(W2, Q, Cs, 1, W16(L.w2t[0]), LOW(W16(L.w2t[1])), Cs, Qp, f16);
   VQW_CHECK_LAUNCH("pack_mat_kernel(W2T)");
   pack_mat_kernel<<<148, 256, 0, stream>>>(W1, Cs, Cs, 1, W16(L.w1t[0]), LOW(W16(L.w1t[1])), Cs, Cs, f16);
@@ -1208,7 +1414,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   };
   {   // g_h1 = (W2^T g_y) * (h1 > 0) -> planes
     Maps maps;
-    if (int rc = mapk(&maps.m[0], ws + L.gy[0], ws + L.gy[1], Qp, T, B, TM)) return rc;
+    if (int rc = mapk(&maps.m[0], gyp[0], gyp[1], Qp, T, B, TM)) return rc;
     if (int rc = mapk(&maps.m[2], ws + L.w2t[0], ws + L.w2t[1], Qp, Cs, 1, WROWS())) return rc;
     for (int k = 4; k < NMAPS; ++k) maps.m[k] = maps.m[k % 4];
     GemmParams P = {};
@@ -1232,7 +1438,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
   }
   {   // gW2 = g_y (x) h1, gW1 = g_h1 (x) relu(skip): one grouped launch
     Maps maps;
-    if (int rc = mapmn(&maps.m[0], ws + L.gy[0], ws + L.gy[1], Qp)) return rc;
+    if (int rc = mapmn(&maps.m[0], gyp[0], gyp[1], Qp)) return rc;
     if (int rc = mapmn(&maps.m[2], sv + S.h1[0], sv + S.h1[1], Cs)) return rc;
     if (int rc = mapmn(&maps.m[4], ws + L.gh1[0], ws + L.gh1[1], Cs)) return rc;
     if (int rc = mapmn(&maps.m[6], sv + S.s[0], sv + S.s[1], Cs)) return rc;
@@ -1257,8 +1463,9 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* W1, c
     P.njobs = nj;
     if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
   }
-  colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gy[0]), LOW(W16(L.gy[1])), gb2, nullptr, Qp,
-                                                   NROWS, RPB, Q, f16, gscale);
+  colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gyp[0]),
+      x3 ? reinterpret_cast<const __nv_bfloat16*>(gyp[1]) : nullptr, gb2, nullptr, Qp, NROWS, RPB, Q, f16, gscale);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(gy)");
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(W16(L.gh1[0]), LOW(W16(L.gh1[1])), gb1, nullptr,
                                                    Cs, NROWS, RPB, Cs, f16, gscale);

@@ -504,6 +504,79 @@ def head(skip, W1, b1, W2, b2, mode):
     return _Head.apply(skip, W1, b1, W2, b2, mode, torch.is_grad_enabled())
 
 
+def head_loss_supported(skip: torch.Tensor, Q: int, mode: int, use_logistic: bool) -> bool:
+    """The fused head + loss (vqw_head_loss_*): bf16 modes, one accumulator tile of logits."""
+    if mode not in (L.MODE_BF16X3, L.MODE_BF16) or not head_supported(skip, mode):
+        return False
+    return (Q % 3 == 0 and Q <= 32) if use_logistic else Q <= 256
+
+
+class _HeadLoss(torch.autograd.Function):
+    """loss = L(proj2(relu(proj1(relu(skip)))), t) with the loss and d loss / d y computed in the
+    epilogue of the proj2 GEMM (modules.py:155-160 + train.py:92-95 / modules.py:169-230): the
+    logits are only materialised when `keep_logits` asks for them."""
+
+    @staticmethod
+    def forward(ctx, skip, W1, b1, W2, b2, target, mode, use_logistic, quantize, log_scale_min,
+                keep_logits, grad_enabled):
+        skip, W1, b1, W2, b2 = (_f32c(t) for t in (skip, W1, b1, W2, b2))
+        B, Cs, T = _as3(skip)
+        Q = W2.shape[0]
+        d = L.HeadDesc()
+        d.B, d.T, d.Cs, d.Q, d.mode = B, T, Cs, Q, mode
+        if target.numel() != B * T:
+            raise ValueError(f"target has {target.numel()} elements, expected B*T = {B * T}")
+        t_lab = t_val = None
+        if use_logistic:
+            t_val = target.reshape(B, T).to(torch.float32).contiguous()
+        else:
+            t_lab = target.reshape(B, T).to(torch.int32).contiguous()
+        y = torch.empty((B, Q, T, 1), device=skip.device, dtype=torch.float32) if keep_logits else None
+        loss = torch.zeros(2, device=skip.device, dtype=torch.float64)
+        ws = torch.empty(int(L.lib.vqw_head_workspace(C.byref(d))), device=skip.device, dtype=torch.uint8)
+        saved = torch.empty(int(L.lib.vqw_head_saved_bytes(C.byref(d))), device=skip.device,
+                            dtype=torch.uint8)
+        with L.timed("head_forward"):
+            L.check(L.lib.vqw_head_loss_forward(C.byref(d), L.ptr(skip), L.ptr(W1), L.ptr(b1), L.ptr(W2),
+                                                L.ptr(b2), L.ptr(t_lab), L.ptr(t_val), int(quantize),
+                                                float(log_scale_min), L.ptr(loss), L.ptr(y), L.ptr(ws),
+                                                L.ptr(saved), L.stream()), "vqw_head_loss_forward")
+        if grad_enabled and any(ctx.needs_input_grad):
+            ctx.cfg = (B, T, Cs, Q, mode)
+            ctx.tc_saved = saved
+            ctx.save_for_backward(W1, W2)
+        out_y = y if y is not None else skip.new_empty(0)
+        ctx.mark_non_differentiable(out_y)
+        return loss[0].to(torch.float32).reshape(()), out_y
+
+    @staticmethod
+    def backward(ctx, g_loss, _gy):
+        B, T, Cs, Q, mode = ctx.cfg
+        W1, W2 = ctx.saved_tensors
+        d = L.HeadDesc()
+        d.B, d.T, d.Cs, d.Q, d.mode = B, T, Cs, Q, mode
+        dev = W1.device
+        g = g_loss.reshape(1).to(torch.float32).contiguous()
+        gskip = torch.empty((B, Cs, T, 1), device=dev, dtype=torch.float32)
+        gW1, gW2 = torch.zeros_like(W1), torch.zeros_like(W2)
+        gb1 = torch.zeros(Cs, device=dev, dtype=torch.float32)
+        gb2 = torch.zeros(Q, device=dev, dtype=torch.float32)
+        ws = torch.empty(int(L.lib.vqw_head_workspace(C.byref(d))), device=dev, dtype=torch.uint8)
+        with L.timed("head_backward"):
+            L.check(L.lib.vqw_head_loss_backward(C.byref(d), L.ptr(g), L.ptr(W1), L.ptr(W2), L.ptr(gskip),
+                                                 L.ptr(gW1), L.ptr(gb1), L.ptr(gW2), L.ptr(gb2), L.ptr(ws),
+                                                 L.ptr(ctx.tc_saved), L.stream()), "vqw_head_loss_backward")
+        return gskip, gW1, gb1, gW2, gb2, None, None, None, None, None, None, None
+
+
+def head_loss(skip, W1, b1, W2, b2, target, mode, use_logistic, quantize, log_scale_min,
+              keep_logits=False):
+    """Returns (loss, logits or None)."""
+    loss, y = _HeadLoss.apply(skip, W1, b1, W2, b2, target, mode, bool(use_logistic), quantize,
+                              log_scale_min, bool(keep_logits), torch.is_grad_enabled())
+    return loss, (y if y.numel() else None)
+
+
 # ---------------------------------------------------------------------------------------
 # ConditionEmbed tail: x64 linear upsampling + speaker broadcast + concat (net.py:58-63)
 # ---------------------------------------------------------------------------------------

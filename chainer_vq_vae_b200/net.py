@@ -6,6 +6,7 @@ from torch import nn
 
 from . import functions as Fn
 from .links import Convolution2D, DilatedConvolution2D, EmbedID
+from .losses import softmax_cross_entropy
 from .utils import VQ, ExponentialMovingAverage  # noqa: F401
 
 
@@ -83,6 +84,10 @@ class VAE(nn.Module):
         self.condition_embed = condition_embed
         self.decoder = decoder
         self.observation = {}
+        # the decoder's logits are a local of the reference's __call__ (net.py:86); set
+        # keep_logits to have them in `self.y` (the fused head + loss otherwise never writes them)
+        self.keep_logits = False
+        self.y = None
 
     def forward(self, x_enc, x_dec, global_condition, t):
         z = self.encoder(x_enc)                                        # :81
@@ -93,14 +98,26 @@ class VAE(nn.Module):
         dec = getattr(self.decoder, "target", self.decoder)
         split = getattr(getattr(dec, "resnet", None), "mode", 0) != 0   # tensor-core modes hoist it
         condition = self.condition_embed(e, global_condition, split=split)   # :85
-        y = self.decoder(x_dec, condition)                             # :86
-        loss1 = self.loss_func(y, t)                                   # :89
+        wn = getattr(dec, "forward_loss", None)
+        std_loss = wn is not None and (
+            self.loss_func is softmax_cross_entropy and not dec.use_logistic or
+            getattr(self.loss_func, "__func__", None) is type(dec).calculate_logistic_loss
+            and dec.use_logistic)
+        if std_loss:
+            # :86 + :89 in one pass: loss_func is one of the reference's two losses (train.py:92-95)
+            if hasattr(self.decoder, "run"):
+                loss1, y = self.decoder.run("forward_loss", x_dec, condition, t, self.keep_logits)
+            else:
+                loss1, y = self.decoder.forward_loss(x_dec, condition, t, self.keep_logits)
+        else:
+            y = self.decoder(x_dec, condition)                         # :86
+            loss1 = self.loss_func(y, t)                               # :89
         loss2 = torch.mean((zd - e_) ** 2)                             # :90
         loss3 = self.beta * torch.mean((z - e.detach()) ** 2)          # :91
         loss = loss1 + loss2 + loss3
         self.observation = {"loss1": loss1.detach(), "loss2": loss2.detach(),
                             "loss3": loss3.detach(), "loss": loss.detach()}   # reporter, :93-95
-        self.y = y.detach()
+        self.y = y.detach() if y is not None else None
         return loss1, loss2, loss3
 
     @torch.no_grad()

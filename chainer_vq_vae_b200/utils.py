@@ -91,6 +91,16 @@ class ExponentialMovingAverage(nn.Module):
             if hasattr(m, "set_mode"):
                 m.set_mode(mode)
 
+    def run(self, method, *args, **kwargs):
+        """`forward` for another entry point of the wrapped link (e.g. WaveNet.forward_loss):
+        training calls the target and refreshes the average, evaluation calls the copy."""
+        if self.training:
+            ys = getattr(self.target, method)(*args, **kwargs)
+            self.update_average()
+        else:
+            ys = getattr(self.ema, method)(*args, **kwargs)
+        return ys
+
     def forward(self, *args, **kwargs):
         if self.training:                                    # configuration.config.train
             ys = self.target(*args, **kwargs)

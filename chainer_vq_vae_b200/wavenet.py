@@ -144,6 +144,31 @@ class WaveNet(nn.Module):
         z = self.proj1(z, relu=True, relu_in=True)                             # :155,158
         return self.proj2(z)                                                   # :159
 
+    def forward_loss(self, x, condition, t, keep_logits=False):
+        """loss_func(self(x, condition), t) for the reference's two losses -- softmax cross entropy
+        (train.py:95) or calculate_logistic_loss (train.py:93), by `use_logistic` -- returning
+        (loss, logits or None).  On the tensor-core path head and loss are ONE pass: the loss and
+        its gradient are computed in the epilogue of the proj2 GEMM and the logits are only
+        written when `keep_logits` asks for them."""
+        if x.dtype == torch.int32:
+            h = Fn.embed_gather(x, self.embed.W, self.embed.b, self.resnet.mode)
+        else:
+            h = self.embed(x, out_len=x.shape[2])
+        z = self.resnet(h, condition)
+        Q = self.proj2.W.shape[0]
+        if Fn.head_loss_supported(z, Q, self.resnet.mode, self.use_logistic):
+            return Fn.head_loss(z, self.proj1.W, self.proj1.b, self.proj2.W, self.proj2.b, t,
+                                self.resnet.mode, self.use_logistic, self.quantize,
+                                self.log_scale_min, keep_logits)
+        if Fn.head_supported(z, self.resnet.mode):
+            y = Fn.head(z, self.proj1.W, self.proj1.b, self.proj2.W, self.proj2.b, self.resnet.mode)
+        else:
+            y = self.proj2(self.proj1(z, relu=True, relu_in=True))
+        if self.use_logistic:
+            return self.calculate_logistic_loss(y, t), y
+        from .losses import softmax_cross_entropy
+        return softmax_cross_entropy(y, t), y
+
     def calculate_logistic_loss(self, y, t):
         from .losses import logistic_loss
         return logistic_loss(y, t, self.quantize, self.log_scale_min)

@@ -244,6 +244,23 @@ int vqw_head_forward(const vqw_head_desc* desc, const float* skip, const float* 
 int vqw_head_backward(const vqw_head_desc* desc, const float* gy, const float* W1, const float* W2,
                       float* gskip, float* gW1, float* gb1, float* gW2, float* gb2, void* workspace,
                       const void* saved, vqw_stream_t stream);
+/* Head and loss in one pass (modules.py:155-160 + train.py:92-95 /
+ * modules.py:169-230).  Q <= 256 output channels are ONE accumulator tile, so the epilogue of the
+ * proj2 GEMM sees a whole row of logits: it reduces the loss and writes d loss / d y straight into
+ * the bf16 hi/lo planes the backward GEMMs consume (kept in `saved`) -- the (B,Q,T) logits and
+ * their gradient never go to HBM (y_opt != NULL also stores the logits).  Exactly one target:
+ *   t_labels (B,T) i32 : softmax cross entropy, mean over the labels in [0,Q) (ignore_label -1)
+ *   t_values (B,T) f32 : discretised mixture of logistics on Q = 3*n_mix <= 32 outputs
+ * loss = 2 doubles {loss (accumulated: zero both first), number of positions averaged over}.
+ * The backward takes the upstream gradient of the scalar loss from DEVICE memory (g_loss, 1 f32).
+ * Weight / bias gradients are ACCUMULATED, gskip (B,Cs,T) is overwritten.  bf16 modes only. */
+int vqw_head_loss_forward(const vqw_head_desc* desc, const float* skip, const float* W1,
+                          const float* b1, const float* W2, const float* b2, const int32_t* t_labels,
+                          const float* t_values, int quantize, float log_scale_min, double* loss,
+                          float* y_opt, void* workspace, void* saved, vqw_stream_t stream);
+int vqw_head_loss_backward(const vqw_head_desc* desc, const float* g_loss, const float* W1,
+                           const float* W2, float* gskip, float* gW1, float* gb1, float* gW2,
+                           float* gb2, void* workspace, const void* saved, vqw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Causal embedding of mu-law indices.  Replaces WaveNet.__call__'s embed conv over a one-hot

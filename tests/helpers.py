@@ -27,6 +27,7 @@ def build_model(cfg: O.Config, params, device="cuda", ema_decay=None, mode="fp32
     decoder = V.ExponentialMovingAverage(wavenet, ema_decay) if ema_decay else wavenet
     loss = wavenet.calculate_logistic_loss if cfg.use_logistic else V.softmax_cross_entropy
     model = V.VAE(encoder, decoder, cond, cfg.d, cfg.k, cfg.beta, loss)
+    model.keep_logits = True          # the tests compare model.y with the oracle's logits
     load_params(model, params, ema=bool(ema_decay))
     decoder.set_mode(mode)      # both the training copy and the EMA (evaluation) copy
     return model.to(device)

@@ -375,3 +375,57 @@ def test_full_size_stack_is_causal_and_batch_independent():
         alone = V.residual_stack(xg[1:2].contiguous(), cg[1:2].contiguous(), dil, fs, weights,
                                  L.MODE_BF16X3)
         assert torch.equal(alone[0], base[1])
+
+
+@pytest.mark.parametrize("use_logistic", [False, True])
+@pytest.mark.parametrize("upstream", [1.0, 0.37])
+def test_tc_fused_head_loss_matches_unfused_path_and_oracle(use_logistic, upstream):
+    """relu -> proj1 -> relu -> proj2 -> loss with the loss and d loss / d y
+    in the epilogue of the proj2 GEMM (the logits never go to HBM) against (a) the same head with
+    the stand-alone loss kernels and (b) the oracle's loss on the head's own logits: softmax
+    cross entropy (train.py:95, with Chainer's ignore_label = -1 / normalize semantics) and the
+    discretised mixture of logistics (modules.py:169-230)."""
+    from chainer_vq_vae_b200 import functions as Fn
+    torch.manual_seed(1)
+    B, Cs, T = 2, 256, 384
+    Q = 30 if use_logistic else 256
+    skip = torch.randn(B, Cs, T, 1, device=DEV)
+    W1 = torch.randn(Cs, Cs, 1, 1, device=DEV) / 16
+    b1 = torch.randn(Cs, device=DEV) * 0.1
+    W2 = torch.randn(Q, Cs, 1, 1, device=DEV) / 16
+    b2 = torch.randn(Q, device=DEV) * 0.1
+    if use_logistic:
+        t = (torch.rand(B, 1, T, 1, device=DEV) * 2 - 1)
+        t[0, 0, :4, 0] = torch.tensor([-1.0, 1.0, -0.9995, 0.9995], device=DEV)   # the edge branches
+    else:
+        t = torch.randint(0, Q, (B, T, 1), device=DEV, dtype=torch.int32)
+        t[1, 5:40, 0] = -1                                                        # ignore_label
+    cfg = O.Config(use_logistic=use_logistic)
+    out = {}
+    for fused in (False, True):
+        ts = [v.clone().requires_grad_(True) for v in (skip, W1, b1, W2, b2)]
+        if fused:
+            assert Fn.head_loss_supported(ts[0], Q, L.MODE_BF16X3, use_logistic)
+            loss, y = Fn.head_loss(*ts, t, L.MODE_BF16X3, use_logistic, 256, -40.0, keep_logits=True)
+            loss2, y2 = Fn.head_loss(*[v.detach() for v in ts], t, L.MODE_BF16X3, use_logistic, 256, -40.0)
+            assert y2 is None and float(loss2) == float(loss)        # no logits unless asked for
+        else:
+            y = Fn.head(*ts, L.MODE_BF16X3)
+            loss = V.logistic_loss(y, t, 256, -40.0) if use_logistic else V.softmax_cross_entropy(y, t)
+        (loss * upstream).backward()
+        out[fused] = [loss.detach(), y.detach()] + [v.grad for v in ts]
+    names = ["loss", "y", "gskip", "gW1", "gb1", "gW2", "gb2"]
+    for n, a, b in zip(names, out[True], out[False]):
+        assert rel_err(a, b) < 2e-5, (use_logistic, n, rel_err(a, b))
+    # (b) the loss itself against the oracle evaluated on the SAME logits
+    y = out[True][1].double().cpu()
+    if use_logistic:
+        want = O.calculate_logistic_loss_numpy(cfg, y.numpy().astype(np.float32), t.cpu().numpy())
+        tol = 1e-2     # the float32 formula cancels (cdf_plus - cdf_min): DESIGN.md section 2
+    else:
+        valid = (t.cpu().long() >= 0).reshape(B, T)
+        logp = torch.log_softmax(y[..., 0], dim=1)
+        picked = torch.gather(logp, 1, t.cpu().long().clamp(min=0).reshape(B, 1, T))[:, 0]
+        want = float(-(picked * valid).sum() / valid.sum())
+        tol = 1e-5
+    assert abs(float(out[True][0]) - want) <= tol * abs(want), (float(out[True][0]), want)
