@@ -42,7 +42,8 @@ class WgradDesc(C.Structure):
                 ("a", C.c_void_p), ("a_mask", C.c_void_p), ("in_", C.c_void_p),
                 ("in_mul", C.c_void_p), ("K", c_int), ("Tin", c_int),
                 ("mul", c_int), ("shift", c_int), ("div", c_int), ("relu_in", c_int),
-                ("gm", c_int), ("gk", c_int)]
+                ("gm", c_int), ("gk", c_int),
+                ("ntaps", c_int), ("tap_dshift", c_int), ("tap_gw", c_int)]
 
 
 class ResblockDesc(C.Structure):
@@ -60,7 +61,8 @@ class ResnetDesc(C.Structure):
     _fields_ = [("B", c_int), ("T", c_int), ("Cr", c_int), ("Cd", c_int), ("Cs", c_int),
                 ("Cc", c_int), ("fs", c_int), ("n_blocks", c_int),
                 ("dilations", C.POINTER(c_int)), ("mode", c_int), ("keep_last_residual", c_int),
-                ("Cg", c_int), ("cond_global", C.c_void_p), ("g_cond_global", C.c_void_p)]
+                ("Cg", c_int), ("cond_global", C.c_void_p), ("g_cond_global", C.c_void_p),
+                ("block_events", C.POINTER(C.c_void_p))]
 
 
 class GenerateDesc(C.Structure):

@@ -13,7 +13,7 @@
 
 namespace vqw {
 
-constexpr int BM = 64, BT = 64, KC = 16, NT = 256;
+constexpr int BM = 64, BT = 64, KC = 32, NT = 256;
 constexpr int WPITCH = BM + 4;
 
 __device__ __forceinline__ float conv_fetch(const vqw_conv_src& s, int b, int k, int t) {
@@ -35,6 +35,10 @@ __device__ __forceinline__ float conv_fetch(const vqw_conv_src& s, int b, int k,
 
 __global__ void __launch_bounds__(NT)
 conv_sum_kernel(const __grid_constant__ vqw_conv_desc D, float* __restrict__ out) {
+  // K chunks of KC = 32 channels, all sources flattened into one chunk sequence; the operands of
+  // chunk c+1 are fetched into registers while chunk c is multiplied out of shared memory (round
+  // 2: the small encoder / condition layers were bound by the load -> barrier -> FMA -> barrier
+  // latency chain of 16-channel chunks: 40-110 us per launch for ~1 us of arithmetic)
   __shared__ __align__(16) float Xs[KC][BT];
   __shared__ __align__(16) float Ws[KC][WPITCH];
   const int tid = threadIdx.x;
@@ -46,40 +50,70 @@ conv_sum_kernel(const __grid_constant__ vqw_conv_desc D, float* __restrict__ out
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
+  constexpr int XR = (KC * BT) / NT, WR = (KC * BM) / NT;
+  float xr[XR], wr[WR];
+  int chunk_src[VQW_MAX_SRC + 1];
+  int nchunks = 0;
   for (int si = 0; si < D.nsrc; ++si) {
+    chunk_src[si] = nchunks;
+    nchunks += (D.src[si].K + KC - 1) / KC;
+  }
+  chunk_src[D.nsrc] = nchunks;
+  auto fetch = [&](int c) {
+    int si = 0;
+    while (c >= chunk_src[si + 1]) ++si;
     const vqw_conv_src& s = D.src[si];
+    const int k0 = (c - chunk_src[si]) * KC;
     const bool k_fast = s.wk <= s.wm;
-    for (int k0 = 0; k0 < s.K; k0 += KC) {
-      __syncthreads();
 #pragma unroll
-      for (int r = 0; r < (KC * BT) / NT; ++r) {
-        int e = tid + r * NT;
-        int kc = e / BT, tt = e % BT;
-        int t = t0 + tt;
-        Xs[kc][tt] = (t < D.T) ? conv_fetch(s, b, k0 + kc, t) : 0.0f;
-      }
+    for (int r = 0; r < XR; ++r) {
+      const int e = tid + r * NT;
+      const int kc = e / BT, tt = e % BT;
+      const int t = t0 + tt;
+      xr[r] = (t < D.T) ? conv_fetch(s, b, k0 + kc, t) : 0.0f;
+    }
 #pragma unroll
-      for (int r = 0; r < (KC * BM) / NT; ++r) {
-        int e = tid + r * NT;
-        int kc, mm;
-        if (k_fast) { kc = e % KC; mm = e / KC; } else { mm = e % BM; kc = e / BM; }
-        int m = m0 + mm, k = k0 + kc;
-        float v = 0.0f;
-        if (m < D.M && k < s.K) v = __ldg(s.w + (int64_t)m * s.wm + (int64_t)k * s.wk);
-        Ws[kc][mm] = v;
-      }
-      __syncthreads();
+    for (int r = 0; r < WR; ++r) {
+      const int e = tid + r * NT;
+      int kc, mm;
+      if (k_fast) { kc = e % KC; mm = e / KC; } else { mm = e % BM; kc = e / BM; }
+      const int m = m0 + mm, k = k0 + kc;
+      wr[r] = (m < D.M && k < s.K) ? __ldg(s.w + (int64_t)m * s.wm + (int64_t)k * s.wk) : 0.0f;
+    }
+  };
+  auto stash = [&](int c) {
+    int si = 0;
+    while (c >= chunk_src[si + 1]) ++si;
+    const bool k_fast = D.src[si].wk <= D.src[si].wm;
 #pragma unroll
-      for (int kc = 0; kc < KC; ++kc) {
-        float4 xv = *reinterpret_cast<const float4*>(&Xs[kc][tx * 4]);
-        float4 wv = *reinterpret_cast<const float4*>(&Ws[kc][ty * 4]);
-        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+    for (int r = 0; r < XR; ++r) {
+      const int e = tid + r * NT;
+      Xs[e / BT][e % BT] = xr[r];
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int r = 0; r < WR; ++r) {
+      const int e = tid + r * NT;
+      int kc, mm;
+      if (k_fast) { kc = e % KC; mm = e / KC; } else { mm = e % BM; kc = e / BM; }
+      Ws[kc][mm] = wr[r];
+    }
+  };
+  if (nchunks > 0) fetch(0);
+  for (int c = 0; c < nchunks; ++c) {
+    __syncthreads();                 // the previous chunk has been multiplied out
+    stash(c);
+    __syncthreads();
+    if (c + 1 < nchunks) fetch(c + 1);   // in flight during the FMAs below
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], xa[j], acc[i][j]);
-      }
+    for (int kc = 0; kc < KC; ++kc) {
+      float4 xv = *reinterpret_cast<const float4*>(&Xs[kc][tx * 4]);
+      float4 wv = *reinterpret_cast<const float4*>(&Ws[kc][ty * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], xa[j], acc[i][j]);
     }
   }
 
@@ -120,12 +154,17 @@ constexpr int GPITCH = 68;
 
 __global__ void __launch_bounds__(NT)
 conv_wgrad_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ gw,
-                  float* __restrict__ gb, int chunks_per_b, int total_chunks) {
+                  float* __restrict__ gb, int chunks_per_b, int total_chunks, int ktiles) {
+  // blockIdx.y = tap * ktiles + k-tile: every tap of the filter in one launch; the next chunk's
+  // operands are fetched into registers while the current one is multiplied out of shared memory
   __shared__ __align__(16) float As[TC][GPITCH];
   __shared__ __align__(16) float Bs[TC][GPITCH];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * BM, k0 = blockIdx.y * GK;
+  const int tap = blockIdx.y / ktiles;
+  const int m0 = blockIdx.x * BM, k0 = (blockIdx.y - tap * ktiles) * GK;
+  const int shift = D.shift + tap * D.tap_dshift;
+  gw += (int64_t)tap * D.tap_gw;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -133,45 +172,61 @@ conv_wgrad_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ 
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
   float bsum = 0.0f;
   const bool do_bias = (gb != nullptr) && (blockIdx.y == 0) && (tid < BM);
-
-  for (int c = blockIdx.z; c < total_chunks; c += gridDim.z) {
+  constexpr int AR = (TC * BM) / NT, BR = (TC * GK) / NT;
+  float ar[AR], br[BR];
+  auto fetch = [&](int c) {
     const int b = c / chunks_per_b;
     const int tbase = (c % chunks_per_b) * TC;
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < (TC * BM) / NT; ++r) {
-      int e = tid + r * NT;
-      int tt = e % TC, mm = e / TC;
-      int m = m0 + mm, t = tbase + tt;
+    for (int r = 0; r < AR; ++r) {
+      const int e = tid + r * NT;
+      const int tt = e % TC, mm = e / TC;
+      const int m = m0 + mm, t = tbase + tt;
       float v = 0.0f;
       if (m < D.M && t < D.T) {
-        int64_t off = ((int64_t)b * D.M + m) * D.T + t;
+        const int64_t off = ((int64_t)b * D.M + m) * D.T + t;
         v = __ldg(D.a + off);
         if (D.a_mask) v = (__ldg(D.a_mask + off) > 0.0f) ? v : 0.0f;
       }
-      As[tt][mm] = v;
+      ar[r] = v;
     }
 #pragma unroll
-    for (int r = 0; r < (TC * GK) / NT; ++r) {
-      int e = tid + r * NT;
-      int tt = e % TC, kk = e / TC;
-      int k = k0 + kk, t = tbase + tt;
+    for (int r = 0; r < BR; ++r) {
+      const int e = tid + r * NT;
+      const int tt = e % TC, kk = e / TC;
+      const int k = k0 + kk, t = tbase + tt;
       float v = 0.0f;
       if (k < D.K && t < D.T) {
-        int num = t * D.mul + D.shift;
+        const int num = t * D.mul + shift;
         int ti = num;
         bool ok = num >= 0;
         if (ok && D.div > 1) { ti = num / D.div; ok = (ti * D.div == num); }
         if (ok && ti < D.Tin) {
-          int64_t off = ((int64_t)b * D.K + k) * D.Tin + ti;
+          const int64_t off = ((int64_t)b * D.K + k) * D.Tin + ti;
           v = __ldg(D.in + off);
           if (D.relu_in) v = fmaxf(v, 0.0f);
           if (D.in_mul) v *= __ldg(D.in_mul + off);
         }
       }
-      Bs[tt][kk] = v;
+      br[r] = v;
+    }
+  };
+  int c = blockIdx.z;
+  if (c < total_chunks) fetch(c);
+  for (; c < total_chunks; c += gridDim.z) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < AR; ++r) {
+      const int e = tid + r * NT;
+      As[e % TC][e / TC] = ar[r];
+    }
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      const int e = tid + r * NT;
+      Bs[e % TC][e / TC] = br[r];
     }
     __syncthreads();
+    if (c + (int)gridDim.z < total_chunks) fetch(c + gridDim.z);
 #pragma unroll
     for (int tt = 0; tt < TC; ++tt) {
       float4 av = *reinterpret_cast<const float4*>(&As[tt][ty * 4]);
@@ -229,15 +284,19 @@ int launch_wgrad(const vqw_wgrad_desc& d, float* gw, float* gb, cudaStream_t str
   VQW_REQUIRE(d.B >= 0 && d.M > 0 && d.T >= 0 && d.K > 0 && d.div >= 1 && d.mul >= 1,
               "vqw_conv_wgrad: bad sizes");
   if (d.B == 0 || d.T == 0) return 0;
+  const int ntaps = d.ntaps > 1 ? d.ntaps : 1;
+  VQW_REQUIRE(ntaps * ceil_div(d.K, GK) <= 65535, "vqw_conv_wgrad: too many taps / input channels");
   int chunks_per_b = ceil_div(d.T, TC);
   int total = chunks_per_b * d.B;
-  int tiles = ceil_div(d.M, BM) * ceil_div(d.K, GK);
-  int splits = ceil_div(148 * 4, tiles);
+  const int ktiles = ceil_div(d.K, GK);
+  int tiles = ceil_div(d.M, BM) * ktiles * ntaps;
+  // enough CTAs to fill the chip about twice, no more: every CTA ends with a tile of atomics
+  int splits = ceil_div(148 * 2, tiles);
   if (splits > total) splits = total;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
-  dim3 grid(ceil_div(d.M, BM), ceil_div(d.K, GK), splits);
-  conv_wgrad_kernel<<<grid, NT, 0, stream>>>(d, gw, gb, chunks_per_b, total);
+  dim3 grid(ceil_div(d.M, BM), ktiles * ntaps, splits);
+  conv_wgrad_kernel<<<grid, NT, 0, stream>>>(d, gw, gb, chunks_per_b, total, ktiles);
   VQW_CHECK_LAUNCH("conv_wgrad_kernel");
   return 0;
 }

@@ -840,9 +840,46 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
     }
     P.use_tags = ok ? 1 : 0;
   }
-  void* args[] = {(void*)&P};
-  VQW_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)generate_kernel, dim3(grid), dim3(GEN_THREADS),
-                                             args, smem, st));
+  // Queue residency.  The dilation queues of the configs[4] decoder are 16.8 MB (40 blocks x up to
+  // 1025 columns x 512 channels fp32): they cannot live in shared memory / registers (148 SMs x
+  // 227 KB = 33 MB in total, but every CTA of a phase needs the WHOLE 512-channel past column, and
+  // distributed shared memory only spans a cluster of <= 16 CTAs = 3.6 MB).  They are kept resident
+  // ON CHIP instead: an L2 access-policy window marks the queues and the re-associated matrices
+  // M_l (38 MB together, < the 126 MB L2) persisting, while the 175 MB weight stream -- which
+  // would otherwise evict them every sample -- is left evict-first.  VQW_GEN_L2PERSIST=0 disables it.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  int nattr = 1;
+  const bool persist = !(getenv("VQW_GEN_L2PERSIST") && getenv("VQW_GEN_L2PERSIST")[0] == '0');
+  if (persist) {
+    int max_win = 0, max_persist = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    size_t want = (size_t)(L.xbuf - L.queues);            // queues, z buffer, M_l: contiguous
+    if (max_win > 0 && max_persist > 0) {
+      if (want > (size_t)max_win) want = (size_t)max_win;
+      static size_t limit_set = 0;                        // device-wide set-aside, grown on demand
+      const size_t lim = want < (size_t)max_persist ? want : (size_t)max_persist;
+      if (lim > limit_set && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess)
+        limit_set = lim;
+      attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[1].val.accessPolicyWindow.base_ptr = ws + L.queues;
+      attr[1].val.accessPolicyWindow.num_bytes = want;
+      attr[1].val.accessPolicyWindow.hitRatio = limit_set >= want ? 1.0f : (float)limit_set / (float)want;
+      attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      nattr = 2;
+    }
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, generate_kernel, P));
   VQW_CHECK_LAUNCH("generate_kernel");
   if (P.dbg) {
     long long h[128];

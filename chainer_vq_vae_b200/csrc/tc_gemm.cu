@@ -1163,26 +1163,26 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     }
     add_vec_kernel<<<ceil_div(Cs, 256), 256, 0, stream>>>(gw.skip_b, gs_sum, Cs);
     VQW_CHECK_LAUNCH("add_vec_kernel(skip_b)");
+    // ---- conv_b / cond_b, the global-condition columns of cond_w, g_cond_global: per block, so
+    // that every gradient of block i is final here (block_events) ----
+    {
+      TailArgs A = {};
+      A.cond_w[0] = weights[i].cond_w;
+      A.g_conv_b[0] = gw.conv_b;
+      A.g_cond_b[0] = gw.cond_b;
+      A.g_cond_w[0] = gw.cond_w;
+      bias_tail_kernel<<<dim3(1, Cd), Cg > 128 ? 256 : 128, 0, stream>>>(A, colS, d.cond_global, B, Cd, Cc,
+                                                                       Cg, i);
+      VQW_CHECK_LAUNCH("bias_tail_kernel");
+      if (Cg > 0) {
+        gglob_tail_kernel<<<dim3(B, 1), 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i);
+        VQW_CHECK_LAUNCH("gglob_tail_kernel");
+      }
+    }
+    if (d.block_events != nullptr && d.block_events[i] != nullptr)
+      VQW_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d.block_events[i]), stream));
     have_gres = true;
     cur = nxt;
-  }
-  // ---- conv_b / cond_b, the global-condition columns of cond_w, and g_cond_global ----
-  for (int i0 = 0; i0 < d.n_blocks; i0 += TAIL_MAX) {
-    TailArgs A = {};
-    const int nb = d.n_blocks - i0 < TAIL_MAX ? d.n_blocks - i0 : TAIL_MAX;
-    for (int i = 0; i < nb; ++i) {
-      A.cond_w[i] = weights[i0 + i].cond_w;
-      A.g_conv_b[i] = wgrads[i0 + i].conv_b;
-      A.g_cond_b[i] = wgrads[i0 + i].cond_b;
-      A.g_cond_w[i] = wgrads[i0 + i].cond_w;
-    }
-    bias_tail_kernel<<<dim3(nb, Cd), Cg > 128 ? 256 : 128, 0, stream>>>(A, colS, d.cond_global, B, Cd, Cc,
-                                                                      Cg, i0);
-    VQW_CHECK_LAUNCH("bias_tail_kernel");
-    if (Cg > 0) {
-      gglob_tail_kernel<<<dim3(B, nb), 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i0);
-      VQW_CHECK_LAUNCH("gglob_tail_kernel");
-    }
   }
   return 0;
 }

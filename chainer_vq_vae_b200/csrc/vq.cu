@@ -89,43 +89,81 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ W,
   }
 }
 
-// gW[c,:] = sum over columns n with idx[n]==c of gy[b,:,t]; one block per code, columns are
-// visited in increasing n and accumulated in float64 (the reference's eye(k)[idx].T.dot(gy)
-// is a float64 GEMM, utils.py:227-228), so the result is deterministic.  The index list is
-// staged in shared memory once per chunk and scanned by the whole block: the test idx[n] == c is
-// block-uniform, so the scan is a branch per column and the gather runs only on the ~N/k hits
-// (round 1 compacted the hits with a single warp between two barriers: 0.19-0.36 ms per launch).
-__global__ void __launch_bounds__(128)
+// gW[c,:] = sum over columns n with idx[n]==c of gy[b,:,t] in float64 (the reference's
+// eye(k)[idx].T.dot(gy) is a float64 GEMM, utils.py:227-228).  One block per code:
+//   1. the whole block compacts the matching columns into shared memory (order preserving:
+//      ballot + prefix per warp, warps in column order);
+//   2. warp w sums the hits h = w, w + 8, ... (features strided over the lanes, four independent
+//      loads in flight), 3. the eight partial sums are added in warp order.
+// Deterministic: the partition and the order of every addition are fixed.  (A random-init
+// codebook sends most columns to a handful of codes -- hundreds of hits in one block; round 2's
+// first version walked them one dependent load at a time: 0.32 ms.)
+constexpr int VQB_WARPS = 8, VQB_CH = 2048;
+__global__ void __launch_bounds__(VQB_WARPS * 32)
 vq_backward_w_kernel(const float* __restrict__ gy, const int32_t* __restrict__ idx,
                      float* __restrict__ gW, int B, int d, int T, int k) {
   const int c = blockIdx.x;
   const int64_t N = (int64_t)B * T;
-  extern __shared__ int sidx[];   // one chunk of the index list
-  const int CH = 4096;
-  // every thread owns feature rows i = threadIdx.x, +blockDim.x, ... (d <= 8 * blockDim.x)
-  double acc[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-  for (int64_t n0 = 0; n0 < N; n0 += CH) {
-    const int cn = (int)((N - n0 < CH) ? (N - n0) : CH);
+  __shared__ int hits[VQB_CH];
+  __shared__ int wcount[VQB_WARPS];
+  extern __shared__ double part[];          // [VQB_WARPS][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < VQB_WARPS * d; i += blockDim.x) part[i] = 0.0;
+  for (int64_t n0 = 0; n0 < N; n0 += VQB_CH) {
+    const int cn = (int)((N - n0 < VQB_CH) ? (N - n0) : VQB_CH);
     __syncthreads();
-    for (int j = threadIdx.x; j < cn; j += blockDim.x) sidx[j] = idx[n0 + j];
+    // ---- compaction: warp w scans columns [w*seg, (w+1)*seg) of the chunk ----
+    const int seg = (cn + VQB_WARPS - 1) / VQB_WARPS;
+    const int s0 = warp * seg, s1 = min(cn, s0 + seg);
+    int cnt = 0;
+    for (int j0 = s0; j0 < s1; j0 += 32) {
+      const int j = j0 + lane;
+      const bool hit = j < s1 && idx[n0 + j] == c;
+      cnt += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == 0) wcount[warp] = cnt;
     __syncthreads();
-    for (int j = 0; j < cn; ++j) {
-      if (sidx[j] != c) continue;                     // block-uniform
-      const int64_t n = n0 + j;
-      const int b = (int)(n / T), t = (int)(n % T);
+    int base = 0, total = 0;
+    for (int w = 0; w < VQB_WARPS; ++w) {
+      if (w < warp) base += wcount[w];
+      total += wcount[w];
+    }
+    for (int j0 = s0; j0 < s1; j0 += 32) {
+      const int j = j0 + lane;
+      const bool hit = j < s1 && idx[n0 + j] == c;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) hits[base + __popc(m & ((1u << lane) - 1u))] = j;
+      base += __popc(m);
+    }
+    __syncthreads();
+    // ---- warp w: hits w, w + 8, ...; lane: features lane, lane + 32, ... ----
+    for (int i0 = lane; i0 < d; i0 += 32) {
+      double acc = part[warp * d + i0];
+      int h = warp;
+      for (; h + 3 * VQB_WARPS < total; h += 4 * VQB_WARPS) {
+        float v[4];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int i = threadIdx.x + r * blockDim.x;
-        if (i < d) acc[r] += (double)__ldg(gy + ((int64_t)b * d + i) * T + t);
+        for (int u = 0; u < 4; ++u) {
+          const int64_t n = n0 + hits[h + u * VQB_WARPS];
+          const int bb = (int)(n / T), t = (int)(n % T);
+          v[u] = __ldg(gy + ((int64_t)bb * d + i0) * T + t);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += (double)v[u];
       }
+      for (; h < total; h += VQB_WARPS) {
+        const int64_t n = n0 + hits[h];
+        const int bb = (int)(n / T), t = (int)(n % T);
+        acc += (double)__ldg(gy + ((int64_t)bb * d + i0) * T + t);
+      }
+      part[warp * d + i0] = acc;
     }
   }
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    int i = threadIdx.x + r * blockDim.x;
-    if (i < d) gW[(int64_t)c * d + i] = (float)acc[r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    double acc = 0.0;
+    for (int w = 0; w < VQB_WARPS; ++w) acc += part[w * d + i];
+    gW[(int64_t)c * d + i] = (float)acc;
   }
 }
 
@@ -160,9 +198,12 @@ extern "C" int vqw_vq_backward_w(const float* gy, const int32_t* idx, float* gW,
   using namespace vqw;
   VQW_REQUIRE(B >= 0 && T >= 0 && d > 0 && k > 0, "vqw_vq_backward_w: bad sizes");
   VQW_REQUIRE(gW && (((int64_t)B * T == 0) || (gy && idx)), "vqw_vq_backward_w: null pointer");
-  VQW_REQUIRE(d <= 8 * 128, "vqw_vq_backward_w: d=%d > 1024 unsupported", d);
-  vq_backward_w_kernel<<<k, 128, 4096 * sizeof(int), (cudaStream_t)stream>>>(gy, idx, gW, B, d, T,
-                                                                           k);
+  VQW_REQUIRE(d <= 2048, "vqw_vq_backward_w: d=%d > 2048 unsupported", d);
+  const size_t smem = sizeof(double) * VQB_WARPS * d;
+  if (smem > 40 * 1024)
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(vq_backward_w_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vq_backward_w_kernel<<<k, VQB_WARPS * 32, smem, (cudaStream_t)stream>>>(gy, idx, gW, B, d, T, k);
   VQW_CHECK_LAUNCH("vq_backward_w_kernel");
   return 0;
 }

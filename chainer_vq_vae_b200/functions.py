@@ -112,17 +112,16 @@ class _Conv(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
             gW = torch.zeros_like(W)
             gb = torch.zeros(Cout, device=x.device, dtype=torch.float32) if has_b else None
-            for j in range(kh):
-                g = L.WgradDesc()
-                g.B, g.M, g.T = B, Cout, Tout
-                g.a, g.a_mask = L.ptr(gy), (L.ptr(y) if relu_out else None)
-                g.in_, g.in_mul = L.ptr(x), None
-                g.K, g.Tin = Cin, Tin
-                g.mul, g.shift, g.div, g.relu_in = stride, j * dilate - pad, 1, int(relu_in)
-                g.gm, g.gk = Cin * kh, kh
-                L.check(L.lib.vqw_conv_wgrad(C.byref(g), L.ptr(gW) + 4 * j,
-                                             L.ptr(gb) if (j == 0 and has_b) else None,
-                                             L.stream()), "vqw_conv_wgrad")
+            g = L.WgradDesc()                      # all kh taps in one launch
+            g.B, g.M, g.T = B, Cout, Tout
+            g.a, g.a_mask = L.ptr(gy), (L.ptr(y) if relu_out else None)
+            g.in_, g.in_mul = L.ptr(x), None
+            g.K, g.Tin = Cin, Tin
+            g.mul, g.shift, g.div, g.relu_in = stride, -pad, 1, int(relu_in)
+            g.gm, g.gk = Cin * kh, kh
+            g.ntaps, g.tap_dshift, g.tap_gw = kh, dilate, 1
+            L.check(L.lib.vqw_conv_wgrad(C.byref(g), L.ptr(gW), L.ptr(gb) if has_b else None,
+                                         L.stream()), "vqw_conv_wgrad")
         return gx, gW, gb, None, None, None, None, None, None
 
 
@@ -236,6 +235,14 @@ def _rb_weights(ws: Sequence[Optional[torch.Tensor]]) -> L.ResblockWeights:
 # (the views of the flat gradient bucket) instead of materialising 8*n_blocks zero-filled
 # tensors that autograd then adds -- same result, ~300 fewer tiny kernels per step.
 ACCUMULATE_INTO_GRAD = False
+
+# Data-parallel overlap (set by VQVAE_ParallelUpdater around loss1.backward()): an object with
+#   .events(n_blocks) -> list of torch.cuda.Event (or None) to be recorded by the library when the
+#                        gradients of block i are final, and
+#   .launched(weights) called right after the backward kernels of the stack have been ENQUEUED,
+# so that the gradient all-reduce of the blocks already finished runs on a side stream under the
+# rest of the backward (vqw_resnet_desc.block_events).
+STACK_BACKWARD_OBSERVER = None
 
 
 class _ResidualStack(torch.autograd.Function):
@@ -373,6 +380,11 @@ class _ResidualStack(torch.autograd.Function):
             garr_s = (C.c_void_p * n)(*[L.ptr(gates[2 * i + 1]) for i in range(n)])
         ws_bytes = L.lib.vqw_resnet_backward_workspace(C.byref(d))
         workspace = torch.empty(int(ws_bytes), device=dev, dtype=torch.uint8)
+        obs = STACK_BACKWARD_OBSERVER if (direct and tc_saved is not None) else None
+        evs = obs.events(n) if obs is not None else None
+        if evs is not None:
+            ev_arr = (C.c_void_p * n)(*[e.cuda_event for e in evs])
+            d.block_events = C.cast(ev_arr, C.POINTER(C.c_void_p))
         g_last = _f32c(g_last_res) if (keep_last and g_last_res is not None) else None
         g_res = torch.empty((B, Cr, T, 1), device=dev, dtype=torch.float32) \
             if ctx.needs_input_grad[0] else None
@@ -381,6 +393,8 @@ class _ResidualStack(torch.autograd.Function):
                 C.byref(d), L.ptr(g_skip), L.ptr(g_last), L.ptr(xs[0]), L.ptr(cond), rarr, garr_t,
                 garr_s, warr, L.ptr(g_res), L.ptr(gcond), gwarr, L.ptr(workspace),
                 L.ptr(tc_saved), L.stream()), "vqw_resnet_backward")
+        if evs is not None:
+            obs.launched(targets, evs)
         if direct:
             gws = [None] * len(gws)
         return (g_res, gcond, g_glob, None, None, None, None, None, None, *gws)

@@ -43,6 +43,69 @@ class GradBucket:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
+    def offset_of(self, grad: torch.Tensor) -> int:
+        """Element offset of a gradient view inside the flat bucket."""
+        return (grad.data_ptr() - self.flat.data_ptr()) // self.flat.element_size()
+
+
+def block_segments(n_blocks: int, n_segments: int):
+    """Split blocks 0..n-1 into <= n_segments contiguous groups, returned in the order the
+    backward finishes them (highest blocks first): [(first_block, last_block_exclusive), ...]."""
+    n_segments = max(1, min(n_segments, n_blocks))
+    bounds = [round(i * n_blocks / n_segments) for i in range(n_segments + 1)]
+    segs = [(bounds[i], bounds[i + 1]) for i in range(n_segments) if bounds[i + 1] > bounds[i]]
+    return segs[::-1]
+
+
+class _OverlappedReduce:
+    """Gradient all-reduce of the residual stack overlapped with its own backward.  The stack
+    backward walks the blocks from the last to the first and records an event per block
+    (vqw_resnet_desc.block_events); the bucket range of every finished group of blocks is
+    all-reduced on a side stream while the remaining blocks still compute.  What is left of the
+    bucket (encoder, codebook, ConditionEmbed, embed and head parameters) is reduced after the
+    last backward pass.  Same sum, same result as one all-reduce over the whole bucket."""
+
+    def __init__(self, bucket: GradBucket, group, n_segments: int = 4):
+        self.bucket, self.group, self.n_segments = bucket, group, n_segments
+        self.side = torch.cuda.Stream()
+        self.pending = []
+        self.done_ranges = []
+        self._events = None
+
+    def events(self, n_blocks):
+        if self._events is None or len(self._events) != n_blocks:
+            self._events = [torch.cuda.Event() for _ in range(n_blocks)]
+            for e in self._events:
+                e.record()          # materialises the CUDA event handle
+        return self._events
+
+    def launched(self, params, events):
+        n = len(events)
+        per = len(params) // n
+        flat = self.bucket.flat
+        for a, b in block_segments(n, self.n_segments):
+            lo = self.bucket.offset_of(params[a * per].grad)
+            last = params[b * per - 1].grad
+            hi = self.bucket.offset_of(last) + last.numel()
+            self.side.wait_event(events[a])          # block a is the last of the group to finish
+            with torch.cuda.stream(self.side):
+                self.pending.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM,
+                                                    group=self.group, async_op=True))
+            self.done_ranges.append((lo, hi))
+
+    def finish(self):
+        """Reduce whatever `launched` did not cover and join the side stream."""
+        flat = self.bucket.flat
+        ranges = sorted(self.done_ranges)
+        pos = 0
+        for lo, hi in ranges + [(flat.numel(), flat.numel())]:
+            if lo > pos:
+                dist.all_reduce(flat[pos:lo], op=dist.ReduceOp.SUM, group=self.group)
+            pos = max(pos, hi)
+        for w in self.pending:
+            w.wait()
+        self.pending, self.done_ranges = [], []
+
 
 class Adam:
     """chainer.optimizers.Adam (train.py:101) [dep]:
@@ -164,10 +227,12 @@ class VQVAE_StandardUpdater:
             # :15-16 -- the codebook gradient of loss1 is cleared right after it is computed, so
             # it is not computed (cleargrads above already left vq.W.grad at zero)
             Fn.DISCARD_CODEBOOK_GRAD = True
+            Fn.STACK_BACKWARD_OBSERVER = self._overlap()     # decoder grads come from loss1 only
             try:
                 loss1.backward(retain_graph=True)                   # :15
             finally:
                 Fn.DISCARD_CODEBOOK_GRAD = False
+                Fn.STACK_BACKWARD_OBSERVER = None
             cleargrads(model.vq)                                    # :16
             loss2.backward(retain_graph=True)                       # :17
             loss3.backward()                                        # :18
@@ -176,6 +241,10 @@ class VQVAE_StandardUpdater:
 
     def _reduce(self, optimizer) -> None:
         """gradient exchange between replicas (none for the single-device updater)"""
+
+    def _overlap(self):
+        """observer of the stack backward (see functions.STACK_BACKWARD_OBSERVER) or None"""
+        return None
 
     def _step(self, in_arrays, captured_lr=None):
         optimizer = self._optimizers["main"]
@@ -260,6 +329,11 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
                          graph_warmup)
         self.group = group
         self._synced = False
+        # all-reduce of the stack's gradients under the stack's own backward (tensor-core modes)
+        import os
+        self.overlap_allreduce = os.environ.get("VQW_OVERLAP_ALLREDUCE", "1") != "0"
+        self.n_reduce_segments = 4
+        self._ovl = None
 
     def sync_replicas(self) -> None:
         """The reference re-broadcasts the main model's parameters after every step
@@ -303,5 +377,22 @@ class VQVAE_ParallelUpdater(VQVAE_StandardUpdater):
             self.sync_replicas()
         return super().update_from_arrays(in_arrays)
 
+    def _overlap(self):
+        """Overlap the all-reduce of the residual stack's gradients with the stack's own backward
+        (NCCL, more than one rank, not while a CUDA graph is being captured or replayed)."""
+        if not self.overlap_allreduce or self.use_cuda_graph:
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) < 2:
+            return None
+        opt = self._optimizers["main"]
+        if not opt.bucket.flat.is_cuda:
+            return None
+        if self._ovl is None:
+            self._ovl = _OverlappedReduce(opt.bucket, self.group, self.n_reduce_segments)
+        return self._ovl
+
     def _reduce(self, optimizer) -> None:
-        optimizer.bucket.allreduce(self.group)                      # addgrads, :71-72
+        if self._ovl is not None and (self._ovl.pending or self._ovl.done_ranges):
+            self._ovl.finish()                                      # addgrads, :71-72, in pieces
+        else:
+            optimizer.bucket.allreduce(self.group)                  # addgrads, :71-72

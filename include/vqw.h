@@ -107,6 +107,9 @@ typedef struct {
   int mul, shift, div;
   int relu_in;
   int gm, gk;           /* gw strides */
+  /* all taps of a (k,1) filter in ONE launch: tap j reads the input at shift + j*tap_dshift and
+   * accumulates into gw + j*tap_gw (ntaps <= 1: a single tap, the fields above as given) */
+  int ntaps, tap_dshift, tap_gw;
 } vqw_wgrad_desc;
 
 int vqw_conv_wgrad(const vqw_wgrad_desc* desc, float* gw, float* gb /* or NULL */,
@@ -194,6 +197,11 @@ typedef struct {
   int Cg;                       /* trailing time-constant condition channels, 0 = none */
   const float* cond_global;     /* (B,Cg) f32 or NULL */
   float* g_cond_global;         /* backward: (B,Cg) f32, accumulated, or NULL */
+  /* backward, tensor-core modes: n_blocks cudaEvent_t handles or NULL.  block_events[i] is recorded
+   * on the stream once EVERY weight / bias gradient of block i is final (blocks complete from
+   * n_blocks-1 down to 0), so that a data-parallel caller can start reducing the gradients of
+   * the blocks already done on another stream while the rest of the backward is still running */
+  void* const* block_events;
 } vqw_resnet_desc;
 
 int64_t vqw_resnet_forward_workspace(const vqw_resnet_desc* desc);

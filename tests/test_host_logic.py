@@ -166,3 +166,17 @@ def test_snapshot_keeps_optimizer_state_and_extensionless_names(tmp_path):
     assert V.load_optimizer_state(str(path), model2, opt2) == 12
     assert opt2.t == 12 and torch.equal(opt2.flat_m, opt.flat_m) and torch.equal(opt2.flat_v, opt.flat_v)
     assert torch.equal(opt2.flat_p, opt.flat_p)
+
+
+def test_overlapped_allreduce_segments_cover_the_stack_in_completion_order():
+    """The stack backward finishes blocks from the last to the first; the overlapped all-reduce
+    (updaters._OverlappedReduce) reduces contiguous groups of blocks as they complete."""
+    from chainer_vq_vae_b200.updaters import block_segments
+    assert block_segments(20, 4) == [(15, 20), (10, 15), (5, 10), (0, 5)]
+    assert block_segments(3, 8) == [(2, 3), (1, 2), (0, 1)]
+    assert block_segments(30, 1) == [(0, 30)]
+    for n, s in ((20, 4), (30, 4), (7, 3), (40, 6)):
+        segs = block_segments(n, s)
+        covered = sorted(b for a, e in segs for b in range(a, e))
+        assert covered == list(range(n))                       # every block exactly once
+        assert all(x[0] >= y[1] for x, y in zip(segs, segs[1:]))   # highest blocks first
