@@ -104,6 +104,7 @@ struct GemmParams {
   Seg alt_seg;
   float* alt_out;              // gcond (B, alt_Cout, T)
   int alt_Cout;
+  long long* dbg;              // optional per-CTA timestamps (VQW_GEMM_TIMELINE=<epilogue id>)
   int njobs;
   Job jobs[MAX_JOBS];
 };
@@ -117,6 +118,12 @@ struct Maps {
 // stages its own A rows and HALF of the B tile -- 32 KB instead of 48 KB of L2 -> SM traffic per K
 // slab (the fill, not the tensor pipe, bounded these kernels: see resblock_tc.cu), in a 3-stage
 // ring of the same shared-memory footprint.  Protocol as in resblock_tc_pair_kernel.
+__device__ __forceinline__ long long gtime_ns() {   // chip-wide clock (ns): comparable across SMs
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int EPI, int PAIR>
 __global__ void __launch_bounds__(G_THREADS, 2)
 tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmParams P) {
@@ -136,6 +143,17 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool WG = (EPI == EPI_WGRAD);
+  // timeline of 64 CTAs: blockIdx.x in [0,32) of (y,z) = (0,0) and (0,1): {entry, setup, first slab
+  // full, MMAs issued, accumulator full seen by warp 0, epilogue done, smid}
+  long long* dbg = nullptr;
+  if (P.dbg != nullptr && blockIdx.x < 32 && blockIdx.y == 0 && blockIdx.z < 2)
+    dbg = P.dbg + (blockIdx.z * 32 + blockIdx.x) * 8;
+  if (dbg && threadIdx.x == 0) {
+    dbg[0] = gtime_ns();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[6] = smid;
+  }
   if (EPI == EPI_GX && P.colsum != nullptr)
     for (int i = threadIdx.x; i < TN; i += G_THREADS) csum[i] = 0.0f;
   const int nplanes = P.x3 ? 2 : 1;
@@ -182,6 +200,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime_ns();
   // TMA copy into this CTA's stage; in a pair every copy completes on the LEADER's barrier
   auto ld3 = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
     if (PAIR) tma2_load_3d(dst, m, bar, c0, c1, c2);
@@ -267,6 +286,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       for (int i = 0; i < total_slabs; ++i) {
         mbar_wait(full0 + 8 * stage, ph);
         tc_fence_after();
+        if (dbg && i == 0) dbg[2] = gtime_ns();
         const uint32_t sa = base + stage * STG;
 #pragma unroll
         for (int ks = 0; ks < BK / UK; ++ks) {
@@ -294,6 +314,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       }
       if (PAIR) tc_commit2(acc_full);
       else tc_commit(acc_full);
+      if (dbg) dbg[3] = gtime_ns();
     }
   } else if (total_slabs > 0) {
     // =============================== epilogue (warps 0-7) =======================
@@ -660,6 +681,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       }
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 0) dbg[5] = gtime_ns();
   }
 
   tc_fence_before();
@@ -693,9 +715,36 @@ static uint32_t WROWS() { return gemm_pair_enabled() ? tc::TN / 2 : tc::TN; }
 // the grid's x extent is rounded up to even -- the extra CTA of a time-flavour launch is all
 // padding (its loads are out of bounds = zero, its stores are masked)
 template <int EPI>
-static int launch_gemm(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream,
+static int launch_gemm(const Maps& maps, const GemmParams& P_in, dim3 grid, cudaStream_t stream,
                        bool pair_ok = true) {
   const size_t smem = gemm_smem();
+  GemmParams P = P_in;
+  static long long* dbg_buf = nullptr;
+  const char* tl = getenv("VQW_GEMM_TIMELINE");
+  const bool timeline = tl && atoi(tl) == EPI && tl[0] >= '0' && tl[0] <= '9';
+  if (timeline) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 64 * 8 * sizeof(long long), stream);
+    P.dbg = dbg_buf;
+  }
+  struct Dump {
+    bool on; cudaStream_t st; long long* buf; int epi;
+    ~Dump() {
+      if (!on) return;
+      long long h[64 * 8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      long long t0 = 0;
+      for (int c = 0; c < 64; ++c) if (h[8 * c] && (!t0 || h[8 * c] < t0)) t0 = h[8 * c];
+      fprintf(stderr, "[vqw gemm timeline] epilogue %d: CTA(x,z) sm | entry setup first-slab mma-issued epi-done"
+                      " (ns rel. to the earliest entry)\n", epi);
+      for (int c = 0; c < 64; ++c)
+        if (h[8 * c])
+          fprintf(stderr, "  (%2d,%d) sm %3lld | %7lld %7lld %7lld %7lld %7lld\n", c % 32, c / 32, h[8 * c + 6],
+                  h[8 * c] - t0, h[8 * c + 1] - t0, h[8 * c + 2] ? h[8 * c + 2] - t0 : -1,
+                  h[8 * c + 3] ? h[8 * c + 3] - t0 : -1, h[8 * c + 5] - t0);
+    }
+  } dump{timeline, stream, dbg_buf, EPI};
   if (pair_ok && gemm_pair_enabled() && (EPI != EPI_WGRAD || grid.x % 2 == 0)) {
     auto kern = tc_gemm_kernel<EPI, 1>;
     VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
