@@ -104,6 +104,7 @@ struct GemmParams {
   Seg alt_seg;
   float* alt_out;              // gcond (B, alt_Cout, T)
   int alt_Cout;
+  int stage_epi;               // GX / GATE_BWD: epilogue through shared-memory tiles + TMA (see below)
   long long* dbg;              // optional per-CTA timestamps (VQW_GEMM_TIMELINE=<epilogue id>)
   int njobs;
   Job jobs[MAX_JOBS];
@@ -139,6 +140,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
   const uint32_t acc_full = smem_u32(bars + 2 * NST);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 1);
   float* csum = reinterpret_cast<float*>(bars + 2 * NST + 2);   // [TN] column sums (GX)
+  const uint32_t afull0 = smem_u32(csum + TN);                   // [2] staged-epilogue tiles landed
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader of the pair
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,6 +180,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(afull0, 1);
+    mbar_init(afull0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == GW_MMA) {
@@ -420,6 +424,115 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             st256(P.p_lo + poff, th_lo);
             st256(P.p_lo + poff + CHh, sg_lo);
           }
+        }
+      } else if (EPI == EPI_GX && !alt && P.stage_epi) {
+        // ---- staged: gx = acc + g_res through shared-memory tiles and TMA.  Round 2 measured the
+        // direct version LSU bound: a thread owns one time row, so each of its 32-byte plane
+        // accesses is its own wavefront (8192 per tile, 17 us of a 63 us CTA with the tensor pipe
+        // idle).  Here the addend quarter (128 rows x 64 channels, hi / lo) is TMA-loaded into the
+        // ring (idle once the accumulator is full), every thread updates ITS row in place, and
+        // one thread TMA-stores the quarter to the next block's g_res planes; two buffers. ----
+        const int cbase = TN * blockIdx.y, t0 = blockIdx.x * TM;
+        const bool has_add = P.a_hi != nullptr, lo2 = P.add_lo != 0;
+        const bool leader = threadIdx.x == 0;
+        auto tile = [&](int bf, int pl) -> uint32_t { return base + (uint32_t)(2 * bf + pl) * 16384u; };
+        auto issue = [&](int bf, int c) {
+          const uint32_t bar = afull0 + 8 * bf;
+          mbar_expect_tx(bar, (lo2 ? 2 : 1) * 16384);
+          tma_load_3d(tile(bf, 0), &maps.m[6], bar, cbase + 64 * c, t0, b);
+          if (lo2) tma_load_3d(tile(bf, 1), &maps.m[7], bar, cbase + 64 * c, t0, b);
+        };
+        mbar_wait(acc_full, 0);      // every MMA of the pair is done: the ring is free
+        tc_fence_after();
+        if (leader && has_add) { issue(0, 0); issue(1, 1); }
+        const uint32_t rsw = (uint32_t)(row & 7), rowb = (uint32_t)row * 128u;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int bf = c & 1;
+          if (has_add) {
+            if (leader && c >= 1 && c + 1 < 4) {   // buffer (c+1)&1 was the source of quarter c-1's store
+              tma_store_wait_read();
+              issue((c + 1) & 1, c + 1);
+            }
+            mbar_wait(afull0 + 8 * bf, (c >> 1) & 1);
+          } else if (c >= 2) {
+            if (leader) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          }
+#pragma unroll 1
+          for (int u = 0; u < 2; ++u) {
+            const int cq = 2 * grp + u;            // 16-column chunk of this quarter
+            const int q = 4 * c + cq;              // ... and of the accumulator
+            float o[16];
+            tmem_ld16(lane_base + 16 * q, o);
+            const uint32_t a0 = tile(bf, 0) + rowb + (((uint32_t)(2 * cq) ^ rsw) << 4);
+            const uint32_t a1 = tile(bf, 0) + rowb + (((uint32_t)(2 * cq + 1) ^ rsw) << 4);
+            const uint32_t l0 = a0 + 16384u, l1 = a1 + 16384u;
+            if (has_add) {
+              const uint4 h0 = lds128(a0), h1 = lds128(a1);
+              const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v0, v1;
+                unpack_pair_f(hw[i], P.f16, v0, v1);
+                o[2 * i] += v0;
+                o[2 * i + 1] += v1;
+              }
+              if (lo2) {
+                const uint4 w0 = lds128(l0), w1 = lds128(l1);
+                const uint32_t lw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float v0, v1;
+                  unpack_pair_f(lw[i], P.f16, v0, v1);
+                  o[2 * i] += v0;
+                  o[2 * i + 1] += v1;
+                }
+              }
+            }
+            if (P.colsum != nullptr) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = t_ok ? o[i] : 0.0f;
+#pragma unroll
+              for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+                const bool up = lane & bit;
+#pragma unroll
+                for (int i = 0; i < w; ++i) {
+                  const float send = up ? v[i] : v[i + w];
+                  const float keep = up ? v[i + w] : v[i];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+              }
+              v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+              if ((lane & 1) == 0) atomicAdd(csum + 16 * q + (lane >> 1), v[0]);
+            }
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (lo2) split_pair_f(o[2 * i], o[2 * i + 1], vh[i], vl[i], P.f16);
+              else vh[i] = pack_pair_f(o[2 * i], o[2 * i + 1], P.f16);
+            }
+            sts128(a0, vh[0], vh[1], vh[2], vh[3]);
+            sts128(a1, vh[4], vh[5], vh[6], vh[7]);
+            if (lo2) {
+              sts128(l0, vl[0], vl[1], vl[2], vl[3]);
+              sts128(l1, vl[4], vl[5], vl[6], vl[7]);
+            }
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          if (leader) {
+            tma_store_3d(&maps.m[8], tile(bf, 0), cbase + 64 * c, t0, b);
+            if (lo2) tma_store_3d(&maps.m[9], tile(bf, 1), cbase + 64 * c, t0, b);
+            tma_store_commit();
+          }
+        }
+        if (leader) tma_store_wait_all();
+        if (P.colsum != nullptr) {
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          for (int i = threadIdx.x; i < TN; i += G_EPI_WARPS * 32)
+            atomicAdd(P.colsum + cbase + i, csum[i] * inv);
         }
       } else if (EPI == EPI_GX && !alt) {
         // gx = acc + g_res: the addend and the result are time-major planes (16-byte accesses);
@@ -700,7 +813,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 }
 
 static size_t gemm_smem() {   // 2 x 48 KB (single CTAs) = 3 x 32 KB (pairs)
-  return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * 3 + 2) + sizeof(float) * TN + 16;
+  return 1024 + (size_t)G_STAGES * STAGE_BYTES + 8 * (2 * 3 + 2) + sizeof(float) * TN + 16 + 16;
 }
 // VQW_TC_GEMM_PAIR=0 keeps every backward / head GEMM on single CTAs
 static bool gemm_pair_enabled() {
@@ -1141,6 +1254,17 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         P.Cout = Cr;
         // this gx is the g_res of block i-1: its time sum is that block's res_b gradient
         if (i > 0) P.colsum = wgrads[i - 1].res_b;
+        // staged epilogue (shared-memory tiles + TMA) whenever the result goes to planes
+        if (i > 0 && !(getenv("VQW_GEMM_STAGE") && getenv("VQW_GEMM_STAGE")[0] == '0')) {
+          P.stage_epi = 1;
+          const void* ah = have_gres ? (const void*)(ws + L.gr_p[cur][0]) : (const void*)(ws + L.gr_p[nxt][0]);
+          const void* al_ = (have_gres && xlo) ? (const void*)(ws + L.gr_p[cur][1]) : ah;
+          if (int rc = make_map_tile(&maps.m[6], ah, Cr, T, B)) return rc;
+          if (int rc = make_map_tile(&maps.m[7], al_, Cr, T, B)) return rc;
+          if (int rc = make_map_tile(&maps.m[8], ws + L.gr_p[nxt][0], Cr, T, B)) return rc;
+          if (int rc = make_map_tile(&maps.m[9], xlo ? ws + L.gr_p[nxt][1] : ws + L.gr_p[nxt][0], Cr, T, B))
+            return rc;
+        }
         // the ACCUM tiles (gcond += Wp^T gh, K = Cd) ride in the same launch as extra N tiles
         P.alt_y = Cr / TN;
         P.alt_seg = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
