@@ -887,6 +887,463 @@ static int launch_gemm(const Maps& maps, const GemmParams& P_in, dim3 grid, cuda
   return 0;
 }
 
+// ------------------------------------------------------------------ persistent time-flavour kernel
+// GX (+ the ACCUM tiles of the same block) and GATE_BWD as ONE persistent launch: a cluster of two
+// CTAs per SM pair walks the tile list, the accumulator is double buffered in TMEM (2 x 256
+// columns) and every epilogue goes through shared-memory tiles + TMA, so the epilogue of tile i
+// runs under the MMAs of tile i + 1.  Why (round 2 timelines, profiles/r2_gemm_timeline_*.log):
+// with one tile per CTA and two CTAs per SM both CTAs of an SM run in lockstep -- they share the
+// tensor pipe during their MMA phases and then both sit in their epilogues with the pipe idle
+// (GX: 43 us of MMA + 12-23 us of epilogue; GATE_BWD: 9 us + 43 us), and the direct epilogues were
+// LSU bound (one 32-byte access per thread and row = one wavefront each).
+constexpr int P_NST = 4;                         // ring stages of 32 KB (A 16 KB + this CTA's half of B)
+constexpr int P_STG = 2 * A_PLANE + B_PLANE;     // 32 KB
+constexpr int P_STAGING = 64 * 1024;             // epilogue tiles (two buffers of 32 KB)
+constexpr int P_NBAR = 2 * P_NST + 6;            // ring + acc_full[2] + acc_empty[2] + afull[2]
+
+static size_t persist_smem() {
+  return 1024 + (size_t)P_NST * P_STG + P_STAGING + 8 * P_NBAR + 16 + sizeof(float) * TN + 16;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1)
+tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmParams P,
+                          int n_x, int n_y, int n_z) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stg0 = base + P_NST * P_STG;                       // staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_NST * P_STG + P_STAGING);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_NST);
+  const uint32_t acc_full0 = smem_u32(bars + 2 * P_NST), acc_empty0 = acc_full0 + 16, afull0 = acc_full0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NBAR);
+  float* csum = reinterpret_cast<float*>(bars + P_NBAR + 2);       // [TN] column sums (GX)
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nplanes = P.x3 ? 2 : 1;
+  const int n_tiles = n_x * n_y * n_z;                             // pair tiles
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == GW_TMA && lane == 0) {
+    for (int s = 0; s < P_NST; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full0 + 8 * s, 1);
+      mbar_init(acc_empty0 + 8 * s, 2 * G_EPI_WARPS);   // one elected lane per epilogue warp, both CTAs
+      mbar_init(afull0 + 8 * s, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == GW_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> (time-tile pair, N tile, batch item); x runs fastest, so the clusters working at
+  // the same time share their weight tile and neighbouring activation rows in L2
+  auto decode = [&](int tile, int& bx, int& y, int& z) {
+    const int xp = tile % n_x;
+    y = (tile / n_x) % n_y;
+    z = tile / (n_x * n_y);
+    bx = 2 * xp + (int)rank;
+  };
+
+  if (warp == GW_TMA) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int tile = cid; tile < n_tiles; tile += ncl) {
+        int bx, y, bb;
+        decode(tile, bx, y, bb);
+        const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && y >= P.alt_y;
+        const int by = alt ? y - P.alt_y : y;
+        const int t0 = bx * TM;
+        const int nseg = alt ? 1 : P.nseg;
+        for (int s = 0; s < nseg; ++s) {
+          const Seg& sg = alt ? P.alt_seg : P.seg[s];
+          const CUtensorMap* ma = &maps.m[2 * sg.a_map];
+          const CUtensorMap* mb = &maps.m[2 * sg.b_map];
+          for (int i = 0; i < sg.nslabs; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+            const uint32_t sa = base + stage * P_STG;
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + B_PLANE / 2));
+            const int brow = sg.b_row0 + TN * by + (int)rank * (TN / 2);
+            tma2_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+            tma2_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
+            if (P.x3) {
+              tma2_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+              tma2_load_3d(sa + 2 * A_PLANE + B_PLANE / 2, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
+            }
+            if (++stage == P_NST) { stage = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == GW_MMA) {
+    // =============================== MMA issuer (leader CTA) ====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      const uint32_t ID = idesc_for(IDESC, P.f16) + ((uint32_t)(TM >> 4) << 24);   // M = 256
+      int it = 0;
+      for (int tile = cid; tile < n_tiles; tile += ncl, ++it) {
+        int bx, y, bb;
+        decode(tile, bx, y, bb);
+        const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && y >= P.alt_y;
+        int total_slabs = 0;
+        if (alt) total_slabs = P.alt_seg.nslabs;
+        else for (int s = 0; s < P.nseg; ++s) total_slabs += P.seg[s].nslabs;
+        const int buf = it & 1;
+        if (it >= 2) {                       // the epilogue of tile it-2 has drained this accumulator
+          mbar_wait(acc_empty0 + 8 * buf, ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + 256 * buf;
+        if (P.dbg && cid == 0 && it < 8) P.dbg[4 * it] = gtime_ns();
+        for (int i = 0; i < total_slabs; ++i) {
+          mbar_wait(full0 + 8 * stage, ph);
+          tc_fence_after();
+          const uint32_t sa = base + stage * P_STG;
+#pragma unroll
+          for (int ks = 0; ks < BK / UK; ++ks) {
+            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
+            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            mma2_ss(acc, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
+            if (P.x3) {
+              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE / 2 + ks * UK * 2);
+              mma2_ss(acc, a_lo, b_hi, ID, 1u);
+              mma2_ss(acc, a_hi, b_lo, ID, 1u);
+            }
+          }
+          tc_commit2(empty0 + 8 * stage);
+          if (++stage == P_NST) { stage = 0; ph ^= 1; }
+        }
+        tc_commit2(acc_full0 + 8 * buf);
+        if (P.dbg && cid == 0 && it < 8) P.dbg[4 * it + 1] = gtime_ns();
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-7) =======================
+    const int quad = warp & 3, grp = warp >> 2;
+    const int row = quad * 32 + lane;
+    const float inv = P.scale ? P.scale[1] : 1.0f;
+    const bool leader = threadIdx.x == 0;
+    const bool rec = P.dbg != nullptr && cid == 0 && rank == 0 && threadIdx.x == 0;
+    const uint32_t acc_empty_l = mapa_u32(acc_empty0, 0);
+    uint32_t nld[2] = {0, 0};                 // loads issued so far into each staging buffer
+    int it = 0;
+    for (int tile = cid; tile < n_tiles; tile += ncl, ++it) {
+      int bx, y, b;
+      decode(tile, bx, y, b);
+      const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && y >= P.alt_y;
+      const int by = alt ? y - P.alt_y : y;
+      const int buf = it & 1;
+      const int t0 = bx * TM, t = t0 + row;
+      const bool t_ok = t < P.T;
+      const uint32_t lane_base = tmem_base + 256 * buf + ((uint32_t)(quad * 32) << 16);
+      mbar_wait(acc_full0 + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      if (rec && it < 8) P.dbg[4 * it + 2] = gtime_ns();
+      if (EPI == EPI_GX && !alt) {
+        // ---- gx = acc + g_res, quarter by quarter through [128 rows x 64 ch] hi / lo tiles ----
+        const int cbase = TN * y;
+        const bool has_add = P.a_hi != nullptr, lo2 = P.add_lo != 0;
+        auto tl = [&](int bf, int pl) -> uint32_t { return stg0 + (uint32_t)(2 * bf + pl) * 16384u; };
+        auto issue = [&](int bf, int c) {
+          const uint32_t bar = afull0 + 8 * bf;
+          mbar_expect_tx(bar, (lo2 ? 2 : 1) * 16384);
+          tma_load_3d(tl(bf, 0), &maps.m[6], bar, cbase + 64 * c, t0, b);
+          if (lo2) tma_load_3d(tl(bf, 1), &maps.m[7], bar, cbase + 64 * c, t0, b);
+        };
+        if (P.colsum != nullptr) {
+          for (int i = threadIdx.x; i < TN; i += G_EPI_WARPS * 32) csum[i] = 0.0f;
+        }
+        if (leader) {
+          tma_store_wait_read();             // the previous tile's stores have left the buffers
+          if (has_add) { issue(0, 0); issue(1, 1); }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+        const uint32_t rsw = (uint32_t)(row & 7), rowb = (uint32_t)row * 128u;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int bf = c & 1;
+          if (has_add) {
+            if (leader && c >= 1 && c + 1 < 4) {
+              tma_store_wait_read();
+              issue((c + 1) & 1, c + 1);
+            }
+            mbar_wait(afull0 + 8 * bf, nld[bf] & 1);
+            ++nld[bf];
+          } else if (c >= 2) {
+            if (leader) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          }
+#pragma unroll 1
+          for (int u = 0; u < 2; ++u) {
+            const int cq = 2 * grp + u, q = 4 * c + cq;
+            float o[16];
+            tmem_ld16(lane_base + 16 * q, o);
+            const uint32_t a0 = tl(bf, 0) + rowb + (((uint32_t)(2 * cq) ^ rsw) << 4);
+            const uint32_t a1 = tl(bf, 0) + rowb + (((uint32_t)(2 * cq + 1) ^ rsw) << 4);
+            const uint32_t l0 = a0 + 16384u, l1 = a1 + 16384u;
+            if (has_add) {
+              const uint4 h0 = lds128(a0), h1 = lds128(a1);
+              const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float v0, v1;
+                unpack_pair_f(hw[i], P.f16, v0, v1);
+                o[2 * i] += v0;
+                o[2 * i + 1] += v1;
+              }
+              if (lo2) {
+                const uint4 w0 = lds128(l0), w1 = lds128(l1);
+                const uint32_t lw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float v0, v1;
+                  unpack_pair_f(lw[i], P.f16, v0, v1);
+                  o[2 * i] += v0;
+                  o[2 * i + 1] += v1;
+                }
+              }
+            }
+            if (P.colsum != nullptr) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = t_ok ? o[i] : 0.0f;
+#pragma unroll
+              for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+                const bool up = lane & bit;
+#pragma unroll
+                for (int i = 0; i < w; ++i) {
+                  const float send = up ? v[i] : v[i + w];
+                  const float keep = up ? v[i + w] : v[i];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+              }
+              v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+              if ((lane & 1) == 0) atomicAdd(csum + 16 * q + (lane >> 1), v[0]);
+            }
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (lo2) split_pair_f(o[2 * i], o[2 * i + 1], vh[i], vl[i], P.f16);
+              else vh[i] = pack_pair_f(o[2 * i], o[2 * i + 1], P.f16);
+            }
+            sts128(a0, vh[0], vh[1], vh[2], vh[3]);
+            sts128(a1, vh[4], vh[5], vh[6], vh[7]);
+            if (lo2) {
+              sts128(l0, vl[0], vl[1], vl[2], vl[3]);
+              sts128(l1, vl[4], vl[5], vl[6], vl[7]);
+            }
+          }
+          if (c == 3) {                      // every TMEM read of this tile is done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_l + 8 * buf);
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          if (leader) {
+            tma_store_3d(&maps.m[8], tl(bf, 0), cbase + 64 * c, t0, b);
+            if (lo2) tma_store_3d(&maps.m[9], tl(bf, 1), cbase + 64 * c, t0, b);
+            tma_store_commit();
+          }
+        }
+        if (P.colsum != nullptr) {           // csum is complete after the last quarter's barrier
+          for (int i = threadIdx.x; i < TN; i += G_EPI_WARPS * 32)
+            atomicAdd(P.colsum + cbase + i, csum[i] * inv);
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");   // before the next tile zeroes it
+        }
+      } else if (EPI == EPI_GX) {
+        // ---- ACCUM tile: gcond[b, ch, t] += acc (fp32 (B,Cout,T): lanes = consecutive t) ----
+        constexpr int NG = G_EPI_WARPS / 4;
+        const int cbase = TN * by, Cout = P.alt_Cout;
+        float* op = P.alt_out + ((int64_t)b * Cout + cbase) * P.T + t;
+        const int nq = (Cout - cbase + 15) / 16 < TN / 16 ? (Cout - cbase + 15) / 16 : TN / 16;
+#pragma unroll 1
+        for (int q = grp; q < nq; q += NG) {
+          float o[16], pre[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)        // 16 independent loads in flight, then the accumulator
+            pre[i] = (t_ok && cbase + 16 * q + i < Cout) ? __ldcs(op + (int64_t)(16 * q + i) * P.T) : 0.0f;
+          tmem_ld16(lane_base + 16 * q, o);
+          if (!t_ok) continue;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cbase + 16 * q + i < Cout) op[(int64_t)(16 * q + i) * P.T] = fmaf(o[i], inv, pre[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_l + 8 * buf);
+      } else {
+        // ---- GATE_BWD: gz -> gh_t = gz sig (1 - tanh^2), gh_s = gz tanh sig (1 - sig) with
+        // tanh = z / sig (bf16x3: the forward saves sig and the z planes), eighth by eighth:
+        // 32 pairs = [128 rows x 32 ch] tiles (64-byte rows, 64-byte swizzle); z hi / lo arrive by
+        // TMA and are overwritten in place by gh_t hi / lo, gh_s hi / lo go to two more tiles, all
+        // four leave by TMA; sig is read directly (fp32, 64 contiguous bytes per thread) ----
+        constexpr int CHh = TN;
+        auto tl = [&](int bf, int k) -> uint32_t { return stg0 + (uint32_t)bf * 32768u + (uint32_t)k * 8192u; };
+        auto issue = [&](int bf, int e) {
+          const uint32_t bar = afull0 + 8 * bf;
+          mbar_expect_tx(bar, 2 * 8192);
+          tma_load_3d(tl(bf, 0), &maps.m[6], bar, 32 * e, t0, b);
+          tma_load_3d(tl(bf, 1), &maps.m[7], bar, 32 * e, t0, b);
+        };
+        const float* sp = P.f1 + ((int64_t)b * P.T + t) * CHh + 16 * grp;
+        uint32_t ps[16];
+        auto fetch_sig = [&](int e) {
+          if (t_ok) {
+            ld256(sp + 32 * e, ps);
+            ld256(sp + 32 * e + 8, ps + 8);
+          }
+        };
+        if (leader) {
+          tma_store_wait_read();
+          issue(0, 0);
+          issue(1, 1);
+        }
+        fetch_sig(0);
+        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+        // this thread's 16 pairs of an eighth: 32 bytes = 16-byte chunks 2 grp, 2 grp + 1 of its 64-byte row
+        const uint32_t sw = (uint32_t)((row >> 1) & 3), rowb = (uint32_t)row * 64u;
+        const uint32_t o0 = rowb + (((uint32_t)(2 * grp) ^ sw) << 4), o1 = rowb + (((uint32_t)(2 * grp + 1) ^ sw) << 4);
+#pragma unroll 1
+        for (int e = 0; e < 8; ++e) {
+          const int bf = e & 1;
+          if (leader && e >= 1 && e + 1 < 8) {
+            tma_store_wait_read();
+            issue((e + 1) & 1, e + 1);
+          }
+          mbar_wait(afull0 + 8 * bf, nld[bf] & 1);
+          ++nld[bf];
+          float gz[16], sg[16];
+          tmem_ld16(lane_base + 32 * e + 16 * grp, gz);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sg[i] = t_ok ? __uint_as_float(ps[i]) : 0.0f;
+          if (e + 1 < 8) fetch_sig(e + 1);
+          const uint4 zh0 = lds128(tl(bf, 0) + o0), zh1 = lds128(tl(bf, 0) + o1);
+          const uint4 zl0 = lds128(tl(bf, 1) + o0), zl1 = lds128(tl(bf, 1) + o1);
+          const uint32_t zh[8] = {zh0.x, zh0.y, zh0.z, zh0.w, zh1.x, zh1.y, zh1.z, zh1.w};
+          const uint32_t zl[8] = {zl0.x, zl0.y, zl0.z, zl0.w, zl1.x, zl1.y, zl1.z, zl1.w};
+          uint32_t th_hi[8], th_lo[8], sg_hi[8], sg_lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float z0, z1, e0, e1;
+            unpack_pair_f(zh[i], P.f16, z0, z1);
+            unpack_pair_f(zl[i], P.f16, e0, e1);
+            const float s0 = sg[2 * i], s1 = sg[2 * i + 1];
+            const float a0 = (t_ok && s0 > 0.0f) ? __fdividef(z0 + e0, s0) : 0.0f;
+            const float a1 = (t_ok && s1 > 0.0f) ? __fdividef(z1 + e1, s1) : 0.0f;
+            const float g0 = gz[2 * i], g1 = gz[2 * i + 1];
+            const float ht0 = g0 * s0 * (1.0f - a0 * a0), ht1 = g1 * s1 * (1.0f - a1 * a1);
+            const float hs0 = g0 * a0 * s0 * (1.0f - s0), hs1 = g1 * a1 * s1 * (1.0f - s1);
+            split_pair_f(ht0, ht1, th_hi[i], th_lo[i], P.f16);
+            split_pair_f(hs0, hs1, sg_hi[i], sg_lo[i], P.f16);
+          }
+          sts128(tl(bf, 0) + o0, th_hi[0], th_hi[1], th_hi[2], th_hi[3]);
+          sts128(tl(bf, 0) + o1, th_hi[4], th_hi[5], th_hi[6], th_hi[7]);
+          sts128(tl(bf, 1) + o0, th_lo[0], th_lo[1], th_lo[2], th_lo[3]);
+          sts128(tl(bf, 1) + o1, th_lo[4], th_lo[5], th_lo[6], th_lo[7]);
+          sts128(tl(bf, 2) + o0, sg_hi[0], sg_hi[1], sg_hi[2], sg_hi[3]);
+          sts128(tl(bf, 2) + o1, sg_hi[4], sg_hi[5], sg_hi[6], sg_hi[7]);
+          sts128(tl(bf, 3) + o0, sg_lo[0], sg_lo[1], sg_lo[2], sg_lo[3]);
+          sts128(tl(bf, 3) + o1, sg_lo[4], sg_lo[5], sg_lo[6], sg_lo[7]);
+          if (e == 7) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_l + 8 * buf);
+          }
+          fence_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+          if (leader) {
+            tma_store_3d(&maps.m[8], tl(bf, 0), 32 * e, t0, b);            // gh_t hi
+            tma_store_3d(&maps.m[9], tl(bf, 1), 32 * e, t0, b);            // gh_t lo
+            tma_store_3d(&maps.m[8], tl(bf, 2), CHh + 32 * e, t0, b);      // gh_s hi
+            tma_store_3d(&maps.m[9], tl(bf, 3), CHh + 32 * e, t0, b);      // gh_s lo
+            tma_store_commit();
+          }
+        }
+      }
+      if (rec && it < 8) P.dbg[4 * it + 3] = gtime_ns();
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == GW_MMA) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512)
+                 : "memory");
+  }
+}
+
+// time-flavour launch on the persistent kernel: grid (x, y, z) as for launch_gemm
+template <int EPI>
+static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream) {
+  auto kern = tc_time_persistent_kernel<EPI>;
+  const size_t smem = persist_smem();
+  VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  VQW_CHECK_CUDA(cudaGetDevice(&dev));
+  VQW_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_x = (int)(grid.x + 1) / 2, n_y = (int)grid.y, n_z = (int)grid.z;
+  const long long n_tiles = (long long)n_x * n_y * n_z;
+  int ncl = sms / 2;
+  if (n_tiles < ncl) ncl = (int)n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * ncl);
+  cfg.blockDim = dim3(G_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GemmParams Pd = P;
+  static long long* dbg_buf = nullptr;
+  const char* tl = getenv("VQW_GEMM_TIMELINE");
+  const bool timeline = tl && atoi(tl) == 10 + EPI;
+  if (timeline) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+    Pd.dbg = dbg_buf;
+  }
+  VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, Pd, n_x, n_y, n_z));
+  VQW_CHECK_LAUNCH(EPI == EPI_GX ? "tc_time_persistent_kernel<GX>" : "tc_time_persistent_kernel<GATE_BWD>");
+  if (timeline) {
+    long long h[64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[vqw persistent timeline] epilogue %d, cluster 0: tile | mma [start, issued] epilogue [start, done] (ns)\n", EPI);
+    for (int i = 0; i < 8; ++i)
+      if (h[4 * i])
+        fprintf(stderr, "  %d | %7lld %7lld | %7lld %7lld\n", i, h[4 * i] - h[0], h[4 * i + 1] - h[0],
+                h[4 * i + 2] - h[0], h[4 * i + 3] - h[0]);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ operand preparation ----
 // out[r][k] (rows x K, K contiguous) = src(r, k) for the three transposed weight operands
 //   kind 0: W2T [Ch rows][Cr + Cs]   = [Wr ; Ws]^T
@@ -1150,6 +1607,9 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   VQW_REQUIRE(Cg == 0 || (d.cond_global && d.g_cond_global),
               "vqw_resnet_backward: Cg > 0 needs cond_global and g_cond_global");
   float* colS = reinterpret_cast<float*>(ws + L.colS);
+  // persistent double-buffered GX / GATE_BWD (needs the CTA-pair weight boxes); VQW_GEMM_PERSIST=0: off
+  const bool persist = gemm_pair_enabled() &&
+                       !(getenv("VQW_GEMM_PERSIST") && getenv("VQW_GEMM_PERSIST")[0] == '0');
   const int64_t NROWS = (int64_t)B * T;
   const int RPB = 256;   // rows per block of the bias column sums
   const int CS_GRID = (int)((NROWS + RPB - 1) / RPB);
@@ -1232,7 +1692,16 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       P.z_lo = reinterpret_cast<const __nv_bfloat16*>(zp_lo);
       P.p_hi = P16(L.gh_p[0]); P.p_lo = LO(L.gh_p[1]);
       P.Cout = Cd;
-      if (int rc = launch_gemm<EPI_GATE_BWD>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;
+      if (x3 && persist) {
+        // persistent, double-buffered, TMA-staged epilogue (tc_time_persistent_kernel)
+        if (int rc = make_map(&maps.m[6], zp_hi, 3, Ch, T, B, TM)) return rc;
+        if (int rc = make_map(&maps.m[7], zp_lo, 3, Ch, T, B, TM)) return rc;
+        if (int rc = make_map(&maps.m[8], ws + L.gh_p[0], 3, Cd, T, B, TM)) return rc;
+        if (int rc = make_map(&maps.m[9], ws + L.gh_p[1], 3, Cd, T, B, TM)) return rc;
+        if (int rc = launch_persistent<EPI_GATE_BWD>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;
+      } else {
+        if (int rc = launch_gemm<EPI_GATE_BWD>(maps, P, dim3(ceil_div(T, TM), 1, B), stream)) return rc;
+      }
     }
     // ---- A2: gx = g_res + sum_j Wc_j^T gh[t + s_j] ; gcond += Wp^T gh ----
     {
@@ -1270,9 +1739,12 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         P.alt_seg = Seg{0, 2, Cd / BK, 0, 0, 0, 0};
         P.alt_out = gcond;
         P.alt_Cout = Cl;
-        if (int rc = launch_gemm<EPI_GX>(maps, P, dim3(ceil_div(T, TM), Cr / TN + ceil_div(Cl, TN), B),
-                                         stream))
-          return rc;
+        const dim3 gxgrid(ceil_div(T, TM), Cr / TN + ceil_div(Cl, TN), B);
+        if (P.stage_epi && persist) {
+          if (int rc = launch_persistent<EPI_GX>(maps, P, gxgrid, stream)) return rc;
+        } else {
+          if (int rc = launch_gemm<EPI_GX>(maps, P, gxgrid, stream)) return rc;
+        }
       } else {
         GemmParams P = {};
         P.nseg = 1;
