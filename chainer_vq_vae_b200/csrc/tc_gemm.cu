@@ -921,6 +921,7 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nplanes = P.x3 ? 2 : 1;
+  constexpr bool WG = (EPI == EPI_WGRAD);   // weight gradients: tile = (256-row job pair, batch item), K = time
   const int n_tiles = n_x * n_y * n_z;                             // pair tiles
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -966,6 +967,31 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
       for (int tile = cid; tile < n_tiles; tile += ncl) {
         int bx, y, bb;
         decode(tile, bx, y, bb);
+        if (WG) {
+          // a stage = 2 (A) + 2 (this CTA's half of B) boxes of {64 channels, 32 time steps} per plane
+          const Job& jb = P.jobs[bx];
+          const CUtensorMap* ma = &maps.m[2 * jb.a_map];
+          const CUtensorMap* mb = &maps.m[2 * jb.b_map];
+          const bool blo = P.x3 && !P.b_exact;
+          const int nb0 = jb.n0 + (int)rank * (TN / 2);
+          for (int i = 0; i < P.slabs_per_item; ++i) {
+            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
+            const uint32_t sa = base + stage * P_STG;
+            if (rank == 0)
+              mbar_expect_tx(full0 + 8 * stage, 2 * (nplanes * A_PLANE + (blo ? 2 : 1) * (B_PLANE / 2)));
+            const int ta = i * BK, tb = ta + jb.shift;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma2_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
+              if (P.x3) tma2_load_3d(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
+              tma2_load_3d(sa + 2 * A_PLANE + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
+              if (blo) tma2_load_3d(sa + 2 * A_PLANE + B_PLANE / 2 + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
+            }
+            if (++stage == P_NST) { stage = 0; ph ^= 1; }
+          }
+          continue;
+        }
         const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && y >= P.alt_y;
         const int by = alt ? y - P.alt_y : y;
         const int t0 = bx * TM;
@@ -996,14 +1022,15 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
     if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t ph = 0;
-      const uint32_t ID = idesc_for(IDESC, P.f16) + ((uint32_t)(TM >> 4) << 24);   // M = 256
+      const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16) + ((uint32_t)(TM >> 4) << 24);   // M = 256
       int it = 0;
       for (int tile = cid; tile < n_tiles; tile += ncl, ++it) {
         int bx, y, bb;
         decode(tile, bx, y, bb);
         const bool alt = (EPI == EPI_GX) && P.alt_y > 0 && y >= P.alt_y;
         int total_slabs = 0;
-        if (alt) total_slabs = P.alt_seg.nslabs;
+        if (WG) total_slabs = P.slabs_per_item;
+        else if (alt) total_slabs = P.alt_seg.nslabs;
         else for (int s = 0; s < P.nseg; ++s) total_slabs += P.seg[s].nslabs;
         const int buf = it & 1;
         if (it >= 2) {                       // the epilogue of tile it-2 has drained this accumulator
@@ -1018,14 +1045,22 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
           const uint32_t sa = base + stage * P_STG;
 #pragma unroll
           for (int ks = 0; ks < BK / UK; ++ks) {
-            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            uint64_t a_hi, b_hi, a_lo, b_lo;
+            if (WG) {   // MN-major tiles: 16 K-rows = two 1024-byte swizzle atoms per step
+              a_hi = smem_desc_sw128_mn(sa + ks * 2048);
+              b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
+              a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
+              b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE / 2 + ks * 2048);
+            } else {
+              a_hi = smem_desc_sw64(sa + ks * UK * 2);
+              b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+              a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
+              b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE / 2 + ks * UK * 2);
+            }
             mma2_ss(acc, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
             if (P.x3) {
-              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE / 2 + ks * UK * 2);
               mma2_ss(acc, a_lo, b_hi, ID, 1u);
-              mma2_ss(acc, a_hi, b_lo, ID, 1u);
+              if (!(WG && P.b_exact)) mma2_ss(acc, a_hi, b_lo, ID, 1u);
             }
           }
           tc_commit2(empty0 + 8 * stage);
@@ -1057,7 +1092,29 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
       mbar_wait(acc_full0 + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       if (rec && it < 8) P.dbg[4 * it + 2] = gtime_ns();
-      if (EPI == EPI_GX && !alt) {
+      if (WG) {
+        // ---- weight-gradient tile: fp32 atomics into gW (K is split over the batch items) ----
+        constexpr int NG = G_EPI_WARPS / 4;
+        const Job& jb = P.jobs[bx];
+        const int m = jb.m0 + row;
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
+          float o[16];
+          tmem_ld16(lane_base + 16 * q, o);
+          if (m < jb.M) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = jb.n0 + 16 * q + i;
+              if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i] * inv);
+              else if (jb.col_out != nullptr && n == jb.col_n)
+                jb.col_out[(long long)b * jb.col_stride + m] = o[i] * inv;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_l + 8 * buf);
+      } else if (EPI == EPI_GX && !alt) {
         // ---- gx = acc + g_res, quarter by quarter through [128 rows x 64 ch] hi / lo tiles ----
         const int cbase = TN * y;
         const bool has_add = P.a_hi != nullptr, lo2 = P.add_lo != 0;
@@ -1330,7 +1387,9 @@ static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, c
     Pd.dbg = dbg_buf;
   }
   VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, Pd, n_x, n_y, n_z));
-  VQW_CHECK_LAUNCH(EPI == EPI_GX ? "tc_time_persistent_kernel<GX>" : "tc_time_persistent_kernel<GATE_BWD>");
+  VQW_CHECK_LAUNCH(EPI == EPI_GX ? "tc_time_persistent_kernel<GX>"
+                                 : (EPI == EPI_WGRAD ? "tc_time_persistent_kernel<WGRAD>"
+                                                     : "tc_time_persistent_kernel<GATE_BWD>"));
   if (timeline) {
     long long h[64];
     cudaStreamSynchronize(stream);
@@ -1796,7 +1855,11 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         if (int rc = add_jobs(4, Cr, 3, Ch, 0, gw.res_w, Ch, 1)) return rc;
       if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
       P.njobs = nj;
-      if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
+      if (wg_pair && persist) {
+        if (int rc = launch_persistent<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+      } else {
+        if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
+      }
     }
     // ---- bias gradients: gh's column sums come out of the grouped launch above (column Cl of
     // the condition job, per item) and are folded in after the loop; g_res, g_skip here ----
