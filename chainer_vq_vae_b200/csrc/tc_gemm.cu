@@ -56,7 +56,8 @@ struct Job {          // one 128 x 256 tile of one weight-gradient GEMM
   float* out;         // gW base (already offset to the tap)
   long long gm, gk;   // strides along m / n
   // optional column col_n of the product (a constant-one channel of B, see cond_pitch): the sum
-  // over time of A's rows for THIS batch item, stored (not accumulated) at col_out[b*col_stride + m]
+  // over time of A's rows for THIS batch item, accumulated into col_out[b*col_stride + m] (zeroed
+  // by the caller: the time axis may be split over several tiles)
   float* col_out;
   int col_n;
   long long col_stride;
@@ -344,7 +345,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             const int n = jb.n0 + 16 * q + i;
             if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i] * inv);
             else if (jb.col_out != nullptr && n == jb.col_n)
-              jb.col_out[(long long)blockIdx.z * jb.col_stride + m] = o[i] * inv;
+              atomicAdd(jb.col_out + (long long)blockIdx.z * jb.col_stride + m, o[i] * inv);
           }
         }
       }
@@ -980,7 +981,7 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
             const uint32_t sa = base + stage * P_STG;
             if (rank == 0)
               mbar_expect_tx(full0 + 8 * stage, 2 * (nplanes * A_PLANE + (blo ? 2 : 1) * (B_PLANE / 2)));
-            const int ta = i * BK, tb = ta + jb.shift;
+            const int ta = (y * P.slabs_per_item + i) * BK, tb = ta + jb.shift;   // y = time chunk
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               tma2_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
@@ -1107,7 +1108,7 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
               const int n = jb.n0 + 16 * q + i;
               if (n < jb.N) atomicAdd(jb.out + (long long)m * jb.gm + (long long)n * jb.gk, o[i] * inv);
               else if (jb.col_out != nullptr && n == jb.col_n)
-                jb.col_out[(long long)b * jb.col_stride + m] = o[i] * inv;
+                atomicAdd(jb.col_out + (long long)b * jb.col_stride + m, o[i] * inv);   // over time chunks
             }
           }
         }
@@ -1666,6 +1667,7 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   VQW_REQUIRE(Cg == 0 || (d.cond_global && d.g_cond_global),
               "vqw_resnet_backward: Cg > 0 needs cond_global and g_cond_global");
   float* colS = reinterpret_cast<float*>(ws + L.colS);
+  VQW_CHECK_CUDA(cudaMemsetAsync(colS, 0, sizeof(float) * (size_t)d.n_blocks * B * Cd, stream));
   // persistent double-buffered GX / GATE_BWD (needs the CTA-pair weight boxes); VQW_GEMM_PERSIST=0: off
   const bool persist = gemm_pair_enabled() &&
                        !(getenv("VQW_GEMM_PERSIST") && getenv("VQW_GEMM_PERSIST")[0] == '0');
@@ -1856,7 +1858,15 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
       if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
       P.njobs = nj;
       if (wg_pair && persist) {
-        if (int rc = launch_persistent<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream)) return rc;
+        // split the time axis in two: 544 tiles instead of 272 for the 74 clusters (measured on the
+        // B200 shape: 1 chunk 0.586 ms, 2 chunks 0.569 ms, 4 chunks 0.595 ms, 8 chunks 0.898 ms --
+        // every extra chunk is another tile of atomics)
+        int chunks = getenv("VQW_WGRAD_CHUNKS") ? atoi(getenv("VQW_WGRAD_CHUNKS")) : 2;
+        if (chunks < 1) chunks = 1;
+        while (chunks > 1 && ceil_div(T, BK) / chunks < 16) chunks /= 2;
+        P.chunks_per_b = chunks;
+        P.slabs_per_item = ceil_div(ceil_div(T, BK), chunks);
+        if (int rc = launch_persistent<EPI_WGRAD>(maps, P, dim3(nj, chunks, B), stream)) return rc;
       } else {
         if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
       }
