@@ -1505,29 +1505,28 @@ bias_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S
     gw[g] += acc;
   }
 }
-// grid (B, blocks): g_glob[b][g] += sum_m cond_w_i[m][Cl + g] * S[i][b][m]  (coalesced over g)
+// grid (Cd / 32, blocks), 256 threads: CTA (mc, i) owns the 32 dilated channels m0 = 32 mc .. of
+// block i; thread -> (item b, global channel g) pairs; g_glob[b][g] += sum_m cond_w_i[m][Cl + g] *
+// S[i][b][m] over its 32 channels (weights coalesced over g, S broadcast from shared memory), one
+// atomic per output and CTA.  (A first version looped one thread over all 512 channels: 97 us.)
 __global__ void __launch_bounds__(256)
 gglob_tail_kernel(const __grid_constant__ TailArgs A, const float* __restrict__ S,
                   float* __restrict__ g_glob, int B, int Cd, int Cc, int Cg, int blk0) {
-  __shared__ float red[256];
-  const int b = blockIdx.x, i = blockIdx.y;
-  const float* Sb = S + ((int64_t)(blk0 + i) * B + b) * Cd;
-  // threads = (m-slice, g): blockDim.x / Cg' slices of the m range, each coalesced over g
-  const int gw = Cg < 256 ? Cg : 256;
-  const int nsl = 256 / gw, sl = threadIdx.x / gw, g0 = threadIdx.x % gw;
-  for (int g = g0; g < Cg; g += gw) {
+  extern __shared__ float Ss[];                          // [B][32]
+  const int m0 = blockIdx.x * 32, i = blockIdx.y;
+  for (int e = threadIdx.x; e < B * 32; e += blockDim.x) {
+    const int b = e >> 5, mm = e & 31;
+    Ss[e] = (m0 + mm < Cd) ? S[((int64_t)(blk0 + i) * B + b) * Cd + m0 + mm] : 0.0f;
+  }
+  __syncthreads();
+  const float* w = A.cond_w[i] + (int64_t)m0 * Cc + (Cc - Cg);
+  for (int e = threadIdx.x; e < B * Cg; e += blockDim.x) {
+    const int b = e / Cg, g = e - b * Cg;
     float acc = 0.0f;
-    if (sl < nsl) {
-      const float* w = A.cond_w[i] + (Cc - Cg) + g;
-      for (int m = sl; m < Cd; m += nsl) acc = fmaf(__ldg(w + (int64_t)m * Cc), Sb[m], acc);
-    }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    if (sl == 0) {
-      for (int k = 1; k < nsl; ++k) acc += red[k * gw + g0];
-      atomicAdd(g_glob + (int64_t)b * Cg + g, acc);
-    }
-    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < 32; ++mm)
+      if (m0 + mm < Cd) acc = fmaf(__ldg(w + (int64_t)mm * Cc + g), Ss[b * 32 + mm], acc);
+    atomicAdd(g_glob + (int64_t)b * Cg + g, acc);
   }
 }
 
@@ -1893,7 +1892,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
                                                                        Cg, i);
       VQW_CHECK_LAUNCH("bias_tail_kernel");
       if (Cg > 0) {
-        gglob_tail_kernel<<<dim3(B, 1), 256, 0, stream>>>(A, colS, d.g_cond_global, B, Cd, Cc, Cg, i);
+        gglob_tail_kernel<<<dim3(ceil_div(Cd, 32), 1), 256, sizeof(float) * B * 32, stream>>>(
+            A, colS, d.g_cond_global, B, Cd, Cc, Cg, i);
         VQW_CHECK_LAUNCH("gglob_tail_kernel");
       }
     }
