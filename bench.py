@@ -302,10 +302,12 @@ def train_workload(args, mol, steps, warmup, world, rank, local, dev, with_cpu_b
     # ---- roofline of the fused residual-block forward kernel ----
     pk, pk_src = peaks()
     n_samples = B * T
-    # one vqw_resnet_forward call = n_blocks fused block kernels (+ operand packing in the
-    # tensor-core modes); the per-launch figure is its duration / n_blocks (conservative).
+    # one vqw_resnet_forward call = operand packing + n_blocks fused block kernels; the library
+    # brackets the n_blocks kernel launches alone with CUDA events on their stream
+    # (vqw_probe_forward_kernels): per-launch duration = (end - start) / n_blocks, launch gaps
+    # included.  fp32 mode has no packing: the whole call / n_blocks.
     n_blocks = cfg["n_loop"] * cfg["n_layer"]
-    ncalls, call_ms = timers.get("resnet_forward", (0, float("nan")))
+    ncalls, call_ms = timers.get("resblock_forward_kernels", timers.get("resnet_forward", (0, float("nan"))))
     nfw, fw_ms = ncalls * n_blocks, call_ms / n_blocks
     flops = block_flops(cfg, n_samples, True)
     bytes_ = block_bytes(cfg, n_samples)

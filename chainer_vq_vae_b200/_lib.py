@@ -81,6 +81,7 @@ _SIGNATURES = {
     "vqw_version": (c_int, []),
     "vqw_last_error": (C.c_char_p, []),
     "vqw_launch_count": (C.c_longlong, []),
+    "vqw_probe_forward_kernels": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vqw_vq_forward": (c_int, [C.c_void_p] * 7 + [c_int] * 4 + [C.c_void_p]),
     "vqw_vq_backward_w": (c_int, [C.c_void_p] * 3 + [c_int] * 4 + [C.c_void_p]),
     "vqw_conv_forward": (c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p]),
@@ -198,6 +199,21 @@ class timed:
             self.b.record()
             TIMERS.setdefault(self.name, []).append((self.a, self.b))
         return False
+
+
+def probe_forward_kernels(name="resblock_forward_kernels") -> None:
+    """When timers are on: have the next tensor-core vqw_resnet_forward bracket its block kernels
+    (only them, not the operand packing) with two timing events filed under `name`."""
+    if TIMERS is None:
+        return
+    import torch
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    b.record()          # materialise the CUDA event handles; the library records them again
+    check(lib.vqw_probe_forward_kernels(C.c_void_p(a.cuda_event), C.c_void_p(b.cuda_event)),
+          "vqw_probe_forward_kernels")
+    TIMERS.setdefault(name, []).append((a, b))
 
 
 def timer_summary():

@@ -48,6 +48,7 @@ struct Params {
   int write_residual;   // 0 for the last block: O_0/O_1 are skipped entirely
   int pf_dist;          // L2 prefetch distance (K slabs) of the activation operand in H_a, 0 = off
   int stage_res;        // residual chunks go through the shared-memory tiles + TMA (needs res_hi)
+  int stage_gate;       // pair kernel: sigmoid / z of the second gate phase leave as TMA stores
   const __nv_bfloat16* xp_hi;   // packed (B,T,Cr) planes of the block input (residual-add operand)
   const __nv_bfloat16* xp_lo;
   const float* gbias;   // (B,512): conv_b + cond_b + W_p[:, Cl:] . global condition of the item
@@ -606,7 +607,10 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                    const __grid_constant__ CUtensorMap map_xa_hi,   // addend tiles of x (staged epilogue)
                    const __grid_constant__ CUtensorMap map_xa_lo,
                    const __grid_constant__ CUtensorMap map_r_hi,    // residual output planes
-                   const __grid_constant__ CUtensorMap map_r_lo, const Params P) {
+                   const __grid_constant__ CUtensorMap map_r_lo,
+                   const __grid_constant__ CUtensorMap map_z_hi,    // saved z planes / sigmoid (staged
+                   const __grid_constant__ CUtensorMap map_z_lo,    // gate of H_b, P.stage_gate)
+                   const __grid_constant__ CUtensorMap map_sig, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the dynamic window is only guaranteed 16-byte aligned: round up to the swizzle period
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -757,12 +761,19 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         tc_commit2(hfull0 + 8 * gp);
         if (rec) P.dbg[2 * gp + 1] = clock64();
       }
-      // both halves of z are in TMEM (and both sigmoid halves are drained) from here on
+      // z_a is in TMEM and the sigmoid half of H_a (= the first output accumulator) is drained:
+      // the K steps of output chunk 0 that contract z_a run under the gate of H_b; everything
+      // else needs z_b in TMEM and the sigmoid half of H_b drained
       mbar_wait(zready0, 0);
-      mbar_wait(zready0 + 8, 0);
       tc_fence_after();
+      bool zb_ready = false;
       for (int oc = o_begin, j = 0; oc < o_end; ++oc, ++j) {
         const int buf = j & 1, use = j >> 1;
+        if (j > 0 && !zb_ready) {
+          mbar_wait(zready0 + 8, 0);
+          tc_fence_after();
+          zb_ready = true;
+        }
         if (use > 0) {
           mbar_wait(oempty0 + 8 * buf, (use - 1) & 1);
           tc_fence_after();
@@ -770,6 +781,11 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         const uint32_t acc = tmem_base + (buf ? OACC1 : OACC0);
         if (rec && j < 6) P.dbg[4 + 2 * j] = clock64();
         for (int i = 0; i < nk2; ++i) {
+          if (2 * i >= 8 && !zb_ready) {      // first K slab of z_b
+            mbar_wait(zready0 + 8, 0);
+            tc_fence_after();
+            zb_ready = true;
+          }
           mbar_wait(full0 + 8 * stage, ph);
           tc_fence_after();
           const uint32_t sa = base + stage * PSTAGE;
@@ -831,11 +847,17 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_wait(hfull0 + 8 * gp, 0);
       tc_fence_after();
       if (rec) P.dbg[16 + 2 * gp] = clock64();
-      if (gp == 1 && leader && P.stage_res) {
+      // staged gate of H_b: sigmoid and the z planes of this phase go through the two staging
+      // buffers (sigma: four [128 x 32] fp32 tiles in buffer 0, z hi/lo: four [128 x 64] bf16 tiles in
+      // buffer 1) and leave as TMA stores -- 128 KB of per-thread 32-byte stores were the whole
+      // exposed cost of this phase
+      const bool stage_gate = gp == 1 && P.stage_gate;
+      if (gp == 1 && leader && P.stage_res && !stage_gate) {
         // every MMA of the first contraction is done: the activation areas and tails of the ring
         // are free from here on.  The addends of the first two residual chunks land during E_b.
         for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
       }
+      const uint32_t rswg = (uint32_t)(row & 7);
       const uint32_t accb = lane_base + 256 * gp;
 #pragma unroll 1
       for (int q = grp; q < HALF / 16; q += NG) {
@@ -866,7 +888,26 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           if (X3) split_pair_f(z2[0], z2[1], zh[i >> 1], zl[i >> 1], F16);
           else zh[i >> 1] = pack_pair_f(z2[0], z2[1], F16);
         }
-        if (save_gates) {   // time-major (B,T,Ch) fp32: 64 contiguous bytes per thread and array
+        if (stage_gate) {
+          // 16-byte chunks of a 128-byte tile row, XOR-swizzled with the row (SWIZZLE_128B)
+          const uint32_t rowb = (uint32_t)row * 128u;
+          const int st = (16 * q) >> 5, c0 = ((16 * q) & 31) >> 2;
+          const uint32_t sb = tile_addr(0, st >> 1, st & 1) + rowb;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            sts128(sb + (((uint32_t)(c0 + c) ^ rswg) << 4), gr[4 * c], gr[4 * c + 1], gr[4 * c + 2],
+                   gr[4 * c + 3]);
+          const int h = (16 * q) >> 6, k0 = ((16 * q) & 63) >> 3;
+          const uint32_t zb = tile_addr(1, 0, h) + rowb;
+          const uint32_t o0 = ((uint32_t)k0 ^ rswg) << 4, o1 = ((uint32_t)(k0 + 1) ^ rswg) << 4;
+          sts128(zb + o0, zh[0], zh[1], zh[2], zh[3]);
+          sts128(zb + o1, zh[4], zh[5], zh[6], zh[7]);
+          if (X3) {
+            const uint32_t lb = tile_addr(1, 1, h) + rowb;
+            sts128(lb + o0, zl[0], zl[1], zl[2], zl[3]);
+            sts128(lb + o1, zl[4], zl[5], zl[6], zl[7]);
+          }
+        } else if (save_gates) {   // time-major (B,T,Ch) fp32: 64 contiguous bytes per thread and array
           const int64_t goff = ((int64_t)b * P.T + t) * CH + ch0;
           if (!X3) {
             st256(P.gate_tanh + goff, ar);
@@ -877,7 +918,7 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         }
         tmem_st8(accb + 16 * q, zh);
         if (X3) tmem_st8(accb + 16 * q + 8, zl);
-        if (P.zp_hi != nullptr && t_ok) {
+        if (!stage_gate && P.zp_hi != nullptr && t_ok) {
           const int64_t zoff = ((int64_t)b * P.T + t) * CH + ch0;
           st256(P.zp_hi + zoff, zh);
           if (X3) st256(P.zp_lo + zoff, zl);
@@ -887,6 +928,27 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(zready_l + 8 * gp);
+      if (stage_gate) {
+        fence_async_smem();                      // tile writes -> visible to the TMA stores
+        asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
+        if (leader) {
+#pragma unroll
+          for (int st = 0; st < 4; ++st)
+            tma_store_3d(&map_sig, tile_addr(0, st >> 1, st & 1), HALF + 32 * st, t0, b);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_store_3d(&map_z_hi, tile_addr(1, 0, h), HALF + 64 * h, t0, b);
+            if (X3) tma_store_3d(&map_z_lo, tile_addr(1, 1, h), HALF + 64 * h, t0, b);
+          }
+          tma_store_commit();
+          if (P.stage_res) {
+            // the addends of the first two residual chunks take the buffers over once the stores
+            // have read them; they land under the MMAs of chunk 0
+            tma_store_wait_read();
+            for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
+          }
+        }
+      }
       if (rec) P.dbg[16 + 2 * gp + 1] = clock64();
     }
     // ---- output chunks: residual rows then skip rows, 128 per chunk ----
@@ -1056,7 +1118,7 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       if (lane == 0) mbar_arrive_cluster(oempty_l + 8 * buf);
       if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
     }
-    if (leader && P.stage_res) tma_store_wait_all();   // the tiles must outlive their stores
+    if (leader && (P.stage_res || P.stage_gate)) tma_store_wait_all();   // the tiles must outlive their stores
   }
 
   tc_fence_before();
@@ -1117,10 +1179,10 @@ int pack_act_launch(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int B
 // per accumulator chunk (v1: 128, v2: 64):
 //   half = 128: [0,128) tanh 0..127 | [128,256) sigmoid 0..127 | [256,384) tanh 128..255 | ...
 //   half = 64 : [0,64) tanh 0..63 | [64,128) sigmoid 0..63 | [128,192) tanh 64..127 | ...
-__global__ void __launch_bounds__(256)
-pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_w,
-               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cc,
-               int Cl, int fs, int f16, int half) {
+__device__ __forceinline__ void
+pack_w1(const float* __restrict__ conv_w, const float* __restrict__ cond_w,
+        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cc,
+        int Cl, int fs, int f16, int half) {
   const int K1 = fs * Cr + Cl;         // only the Cl time-varying condition columns are contracted
   const int64_t n = (int64_t)CD * K1;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
@@ -1143,10 +1205,10 @@ pack_w1_kernel(const float* __restrict__ conv_w, const float* __restrict__ cond_
 }
 
 // W2 packed [(Cr + Cs) rows][Ch]: residual rows then skip rows
-__global__ void __launch_bounds__(256)
-pack_w2_kernel(const float* __restrict__ res_w, const float* __restrict__ skip_w,
-               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cs,
-               int f16) {
+__device__ __forceinline__ void
+pack_w2(const float* __restrict__ res_w, const float* __restrict__ skip_w,
+        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int Cr, int Cs,
+        int f16) {
   const int64_t n = (int64_t)(Cr + Cs) * CH;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -1157,6 +1219,25 @@ pack_w2_kernel(const float* __restrict__ res_w, const float* __restrict__ skip_w
     hi[e] = h;
     if (lo) lo[e] = l;
   }
+}
+
+// both weight operands of up to GB_MAX blocks in one launch: grid (x, blocks); block i's planes
+// sit at i * stride elements behind the given ones (w1 hi, w1 lo, w2 hi, w2 lo: see the layout)
+struct PackWArgs {
+  const float* conv_w[32];
+  const float* cond_w[32];
+  const float* res_w[32];
+  const float* skip_w[32];
+};
+__global__ void __launch_bounds__(256)
+pack_w_kernel(const __grid_constant__ PackWArgs A, __nv_bfloat16* __restrict__ w1h,
+              __nv_bfloat16* __restrict__ w1l, __nv_bfloat16* __restrict__ w2h,
+              __nv_bfloat16* __restrict__ w2l, int64_t stride, int Cr, int Cs, int Cc, int Cl, int fs,
+              int f16, int half) {
+  const int i = blockIdx.y;
+  const int64_t o = (int64_t)i * stride;
+  pack_w1(A.conv_w[i], A.cond_w[i], w1h + o, w1l ? w1l + o : nullptr, Cr, Cc, Cl, fs, f16, half);
+  pack_w2(A.res_w[i], A.skip_w[i], w2h + o, w2l ? w2l + o : nullptr, Cr, Cs, f16);
 }
 
 // Per-(block, item) gate bias: conv_b + cond_b + W_p[:, Cl:] . g_b -- the condition projection of
@@ -1233,6 +1314,21 @@ int make_map_tile(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint6
   return 0;
 }
 
+// [128 rows x 32 channels] fp32 tiles of a time-major (B,T,C) fp32 tensor, 128-byte rows
+int make_map_tile_f32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B) {
+  EncodeTiledFn enc = get_encode();
+  VQW_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[3] = {C, T, B};
+  cuuint64_t strides[2] = {C * 4, C * T * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VQW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tile f32) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
                 uint64_t B) {
   EncodeTiledFn enc = get_encode();
@@ -1290,6 +1386,9 @@ static TcWorkspace tc_layout(const vqw_resnet_desc& d) {
 
 int64_t resnet_tc_workspace(const vqw_resnet_desc& d) { return tc_layout(d).total + 1024; }
 int64_t resnet_tc_saved_bytes(const vqw_resnet_desc& d) { return tc_saved_layout(d).total; }
+
+// vqw_probe_forward_kernels: events recorded around the block kernels of the NEXT forward call
+static void* g_probe_events[2] = {nullptr, nullptr};
 
 int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* cond,
                       const vqw_resblock_weights* weights, float* const* residuals, float* skip,
@@ -1358,16 +1457,20 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       const vqw_resblock_weights& w = weights[i];
       VQW_REQUIRE(w.conv_w && w.conv_b && w.cond_w && w.cond_b && w.res_w && w.res_b && w.skip_w &&
                       w.skip_b, "vqw_resnet_forward: block %d has a null weight", i);
-      __nv_bfloat16* w1h = plane(L.off_w + i * L.block_stride);
-      __nv_bfloat16* w1l = plane(L.off_w + i * L.block_stride + L.w1_plane);
-      __nv_bfloat16* w2h = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane);
-      __nv_bfloat16* w2l = plane(L.off_w + i * L.block_stride + 2 * L.w1_plane + L.w2_plane);
-      pack_w1_kernel<<<296, 256, 0, stream>>>(w.conv_w, w.cond_w, w1h, x3 ? w1l : nullptr, d.Cr,
-                                               d.Cc, Cl, d.fs, f16, HALF);
-      VQW_CHECK_LAUNCH("pack_w1_kernel");
-      pack_w2_kernel<<<148, 256, 0, stream>>>(w.res_w, w.skip_w, w2h, x3 ? w2l : nullptr, d.Cr, d.Cs,
-                                               f16);
-      VQW_CHECK_LAUNCH("pack_w2_kernel");
+    }
+    for (int i0 = 0; i0 < d.n_blocks; i0 += 32) {
+      PackWArgs A = {};
+      const int nb = d.n_blocks - i0 < 32 ? d.n_blocks - i0 : 32;
+      for (int i = 0; i < nb; ++i) {
+        const vqw_resblock_weights& w = weights[i0 + i];
+        A.conv_w[i] = w.conv_w; A.cond_w[i] = w.cond_w; A.res_w[i] = w.res_w; A.skip_w[i] = w.skip_w;
+      }
+      const int64_t o = L.off_w + i0 * L.block_stride;
+      pack_w_kernel<<<dim3(74, nb), 256, 0, stream>>>(
+          A, plane(o), x3 ? plane(o + L.w1_plane) : nullptr, plane(o + 2 * L.w1_plane),
+          x3 ? plane(o + 2 * L.w1_plane + L.w2_plane) : nullptr, L.block_stride / 2, d.Cr, d.Cs, d.Cc,
+          Cl, d.fs, f16, HALF);
+      VQW_CHECK_LAUNCH("pack_w_kernel");
     }
   }
 
@@ -1375,12 +1478,18 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   auto kern1 = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
   auto kern2 = x3 ? resblock_tc_pair_kernel<1, 0>
                   : (f16 ? resblock_tc_pair_kernel<0, 1> : resblock_tc_pair_kernel<0, 0>);
-  auto kern = pair ? kern2 : kern1;
-  VQW_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (pair) {
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    VQW_CHECK_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   CUtensorMap m_c_hi, m_c_lo;
   if (int rc = make_map(&m_c_hi, c_hi, 3, CP, d.T, d.B, TM)) return rc;
   if (int rc = make_map(&m_c_lo, x3 ? c_lo : c_hi, 3, CP, d.T, d.B, TM)) return rc;
 
+  void* probe[2] = {g_probe_events[0], g_probe_events[1]};
+  g_probe_events[0] = g_probe_events[1] = nullptr;
+  if (probe[0]) VQW_CHECK_CUDA(cudaEventRecord((cudaEvent_t)probe[0], stream));
   for (int i = 0; i < d.n_blocks; ++i) {
     const bool last = (i == d.n_blocks - 1);
     const bool write_res = !last || d.keep_last_residual;
@@ -1410,6 +1519,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       return rc;
     Params P;
     P.stage_res = stage_res ? 1 : 0;
+    P.stage_gate = 0;
     P.B = d.B; P.T = d.T; P.Cr = d.Cr; P.Cs = d.Cs; P.Cc = Cl; P.fs = d.fs;   // Cc: contracted channels
     P.dilation = d.dilations[i];
     P.x3 = x3 ? 1 : 0;
@@ -1444,6 +1554,14 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       P.dbg_x = getenv("VQW_TC_TIMELINE_X") ? atoi(getenv("VQW_TC_TIMELINE_X")) : 1;
       P.dbg_y = getenv("VQW_TC_TIMELINE_Y") ? atoi(getenv("VQW_TC_TIMELINE_Y")) : 0;
     }
+    CUtensorMap m_z_hi = m_xa_hi, m_z_lo = m_xa_hi, m_sig = m_xa_hi;
+    static const bool stage_gate_on = !(getenv("VQW_TC_STAGE_GATE") && getenv("VQW_TC_STAGE_GATE")[0] == '0');
+    if (pair && x3 && stage_gate_on && P.gate_sig != nullptr && P.zp_hi != nullptr) {
+      if (int rc = make_map_tile(&m_z_hi, P.zp_hi, CH, d.T, d.B)) return rc;
+      if (int rc = make_map_tile(&m_z_lo, P.zp_lo, CH, d.T, d.B)) return rc;
+      if (int rc = make_map_tile_f32(&m_sig, P.gate_sig, CH, d.T, d.B)) return rc;
+      P.stage_gate = 1;
+    }
     if (pair) {
       // clusters of two CTAs = two consecutive time tiles (an odd tile count gets one all-padding tile)
       cudaLaunchConfig_t cfg = {};
@@ -1459,7 +1577,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       VQW_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern2, m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
-                                        m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, P));
+                                        m_w2_hi, m_w2_lo, m_xa_hi, m_xa_lo, m_r_hi, m_r_lo, m_z_hi,
+                                        m_z_lo, m_sig, P));
     } else {
       dim3 grid(ceil_div(d.T, TM), d.B);
       kern1<<<grid, FWD_THREADS, smem, stream>>>(m_x_hi, m_x_lo, m_c_hi, m_c_lo, m_w1_hi, m_w1_lo,
@@ -1483,7 +1602,14 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       }
     }
   }
+  if (probe[1]) VQW_CHECK_CUDA(cudaEventRecord((cudaEvent_t)probe[1], stream));
   return 0;
 }
 
 }  // namespace vqw
+
+extern "C" int vqw_probe_forward_kernels(void* start_event, void* end_event) {
+  vqw::g_probe_events[0] = start_event;
+  vqw::g_probe_events[1] = end_event;
+  return 0;
+}

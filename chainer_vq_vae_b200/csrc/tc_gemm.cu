@@ -1410,10 +1410,10 @@ static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, c
 //   kind 1: WcT [Cr rows][fs * Cd]   : WcT[cr][j*Cd + cd] = conv_w[cd][cr][j]
 //   kind 2: WpT [rows >= Cl][Cd]     : WpT[cc][cd] = cond_w[cd][cc] for the Cl time-varying
 //           condition channels, zero rows beyond
-__global__ void __launch_bounds__(256)
-pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__ w1,
-               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int K,
-               int Cr, int Cs, int Cd, int Cc, int Cl, int fs, int f16) {
+__device__ __forceinline__ void
+pack_wt(int kind, const float* __restrict__ w0, const float* __restrict__ w1,
+        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows, int K,
+        int Cr, int Cs, int Cd, int Cc, int Cl, int fs, int f16) {
   const int Ch = Cd / 2;
   const int64_t n = (int64_t)rows * K;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
@@ -1433,6 +1433,30 @@ pack_wt_kernel(int kind, const float* __restrict__ w0, const float* __restrict__
     hi[e] = h;
     if (lo) lo[e] = l;
   }
+}
+
+// the three transposed operands of up to PW_MAX blocks in one launch: grid (x, blocks)
+constexpr int PW_MAX = 32;
+struct PackWtArgs {
+  const float* conv_w[PW_MAX];
+  const float* cond_w[PW_MAX];
+  const float* res_w[PW_MAX];
+  const float* skip_w[PW_MAX];
+};
+__global__ void __launch_bounds__(256)
+pack_wt_kernel(const __grid_constant__ PackWtArgs A, __nv_bfloat16* __restrict__ w2t_hi,
+               __nv_bfloat16* __restrict__ w2t_lo, __nv_bfloat16* __restrict__ wct_hi,
+               __nv_bfloat16* __restrict__ wct_lo, __nv_bfloat16* __restrict__ wpt_hi,
+               __nv_bfloat16* __restrict__ wpt_lo, int64_t stride, int wp_rows, int Cr, int Cs,
+               int Cd, int Cc, int Cl, int fs, int f16) {
+  const int i = blockIdx.y;
+  const int64_t o = (int64_t)i * stride;   // elements
+  pack_wt(0, A.res_w[i], A.skip_w[i], w2t_hi + o, w2t_lo ? w2t_lo + o : nullptr, Cd / 2, Cr + Cs, Cr,
+          Cs, Cd, Cc, Cl, fs, f16);
+  pack_wt(1, A.conv_w[i], nullptr, wct_hi + o, wct_lo ? wct_lo + o : nullptr, Cr, fs * Cd, Cr, Cs, Cd,
+          Cc, Cl, fs, f16);
+  pack_wt(2, A.cond_w[i], nullptr, wpt_hi + o, wpt_lo ? wpt_lo + o : nullptr, wp_rows, Cd, Cr, Cs, Cd,
+          Cc, Cl, fs, f16);
 }
 
 // bias gradients: g0[c] (and g1[c]) += sum over all (b,t) rows of a time-major plane pair
@@ -1688,18 +1712,18 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   colsum_planes_kernel<<<CS_GRID, 256, 0, stream>>>(P16(L.gs_p[0]), LO(L.gs_p[1]), gs_sum, nullptr, Cs,
                                                    NROWS, RPB, Cs, f16, gscale);
   VQW_CHECK_LAUNCH("colsum_planes_kernel(g_skip)");
-  for (int i = 0; i < d.n_blocks; ++i) {
-    const vqw_resblock_weights& w = weights[i];
-    const int64_t wo = i * L.wstride;
-    pack_wt_kernel<<<148, 256, 0, stream>>>(0, w.res_w, w.skip_w, P16(L.w2t[0] + wo),
-                                            LO(L.w2t[1] + wo), Ch, Cr + Cs, Cr, Cs, Cd, Cc, Cl, fs, f16);
-    VQW_CHECK_LAUNCH("pack_wt_kernel(0)");
-    pack_wt_kernel<<<296, 256, 0, stream>>>(1, w.conv_w, nullptr, P16(L.wct[0] + wo),
-                                            LO(L.wct[1] + wo), Cr, fs * Cd, Cr, Cs, Cd, Cc, Cl, fs, f16);
-    VQW_CHECK_LAUNCH("pack_wt_kernel(1)");
-    pack_wt_kernel<<<148, 256, 0, stream>>>(2, w.cond_w, nullptr, P16(L.wpt[0] + wo),
-                                            LO(L.wpt[1] + wo), pad256(Cl), Cd, Cr, Cs, Cd, Cc, Cl, fs, f16);
-    VQW_CHECK_LAUNCH("pack_wt_kernel(2)");
+  for (int i0 = 0; i0 < d.n_blocks; i0 += PW_MAX) {
+    PackWtArgs A = {};
+    const int nb = d.n_blocks - i0 < PW_MAX ? d.n_blocks - i0 : PW_MAX;
+    for (int i = 0; i < nb; ++i) {
+      const vqw_resblock_weights& w = weights[i0 + i];
+      A.conv_w[i] = w.conv_w; A.cond_w[i] = w.cond_w; A.res_w[i] = w.res_w; A.skip_w[i] = w.skip_w;
+    }
+    const int64_t wo = i0 * L.wstride;
+    pack_wt_kernel<<<dim3(74, nb), 256, 0, stream>>>(
+        A, P16(L.w2t[0] + wo), LO(L.w2t[1] + wo), P16(L.wct[0] + wo), LO(L.wct[1] + wo),
+        P16(L.wpt[0] + wo), LO(L.wpt[1] + wo), L.wstride / 2, pad256(Cl), Cr, Cs, Cd, Cc, Cl, fs, f16);
+    VQW_CHECK_LAUNCH("pack_wt_kernel");
   }
 
   // K-major (64-byte swizzle) map pair of a time-major plane / weight plane

@@ -321,6 +321,8 @@ class _ResidualStack(torch.autograd.Function):
         if need_grad and tc_mode:
             saved = torch.empty(int(L.lib.vqw_resnet_saved_bytes(C.byref(d))), device=x.device,
                                 dtype=torch.uint8)
+        if tc_mode:
+            L.probe_forward_kernels()
         with L.timed("resnet_forward"):
             L.check(L.lib.vqw_resnet_forward(C.byref(d), L.ptr(x), L.ptr(cond), warr, rarr,
                                              L.ptr(skip), garr_t, garr_s, L.ptr(workspace),

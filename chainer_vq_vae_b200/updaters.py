@@ -218,6 +218,8 @@ class VQVAE_StandardUpdater:
         self._graph = None
         self._eager_steps = 0
 
+    MERGE_ENCODER_BACKWARD = True
+
     def backward_three(self, model, loss1, loss2, loss3) -> None:
         from . import functions as Fn
         model.zero_grad(set_to_none=False) if not hasattr(self._optimizers["main"], "bucket") \
@@ -225,17 +227,28 @@ class VQVAE_StandardUpdater:
         prev, Fn.ACCUMULATE_INTO_GRAD = Fn.ACCUMULATE_INTO_GRAD, True
         try:
             # :15-16 -- the codebook gradient of loss1 is cleared right after it is computed, so
-            # it is not computed (cleargrads above already left vq.W.grad at zero)
+            # it is not computed (cleargrads above already left vq.W.grad at zero).
+            # :15 + :18 in one pass: loss1 and loss3 meet at the encoder output z, gradients
+            # accumulate (no cleargrads between :15 and :18 touches the encoder), and backward is
+            # linear -- so the encoder's backward runs ONCE on d(loss1)/dz + d(loss3)/dz instead of
+            # twice.  loss3 reaches nothing but the encoder (e is detached, net.py:91), so the
+            # codebook still only sees loss2 (:16-17).  MERGE_ENCODER_BACKWARD = False restores
+            # the literal three calls.
             Fn.DISCARD_CODEBOOK_GRAD = True
             Fn.STACK_BACKWARD_OBSERVER = self._overlap()     # decoder grads come from loss1 only
+            merged = self.MERGE_ENCODER_BACKWARD and loss3.requires_grad and loss1.requires_grad
             try:
-                loss1.backward(retain_graph=True)                   # :15
+                if merged:
+                    torch.autograd.backward((loss1, loss3), retain_graph=True)   # :15, :18
+                else:
+                    loss1.backward(retain_graph=True)               # :15
             finally:
                 Fn.DISCARD_CODEBOOK_GRAD = False
                 Fn.STACK_BACKWARD_OBSERVER = None
             cleargrads(model.vq)                                    # :16
-            loss2.backward(retain_graph=True)                       # :17
-            loss3.backward()                                        # :18
+            loss2.backward(retain_graph=not merged)                 # :17
+            if not merged:
+                loss3.backward()                                    # :18
         finally:
             Fn.ACCUMULATE_INTO_GRAD = prev
 

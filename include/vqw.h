@@ -32,6 +32,12 @@ int vqw_version(void);
 const char* vqw_last_error(void);
 /* number of CUDA kernels this process has launched through the library (diagnostic) */
 long long vqw_launch_count(void);
+/* measurement hook (bench.py's roofline leg): the next vqw_resnet_forward call in a tensor-core
+ * mode records `start_event` on its stream right before the first fused block kernel and
+ * `end_event` right after the last one (cudaEvent_t handles created with timing enabled), so
+ * that (end - start) / n_blocks is the block kernel's launch duration inside the running step,
+ * without the operand packing that precedes it.  One-shot; NULL handles clear it. */
+int vqw_probe_forward_kernels(void* start_event, void* end_event);
 
 /* ------------------------------------------------------------------------------------
  * VQ nearest-codebook lookup.  Replaces StraightThrough.forward, utils.py:176-211
