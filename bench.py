@@ -344,7 +344,9 @@ def train_workload(args, mol, steps, warmup, world, rank, local, dev, with_cpu_b
             "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16, fp32 accumulate)",
-                      "bf16": "bf16", "fp16": "fp16 (IEEE half operands, fp32 accumulate)"}[args.mode],
+                      "bf16": "bf16", "fp16": "fp16 (IEEE half operands, fp32 accumulate)",
+                      "fp16x3": "fp16x3 (split-fp16 hi/lo operands = 22 significant bits, fp32 accumulate; "
+                                "weight-gradient GEMMs on the hi planes)"}[args.mode],
             "data": "synthetic (sinusoid mixtures, mu-law 256, random-init weights)",
             "config": workload_config(mol, world, args.mode, graphed),
             "e2e": {"value": e2e_value, "unit": "audio-samples/s", "h2d_bytes_per_step": h2d,
@@ -554,7 +556,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("VQW_BENCH_MODE", "bf16x3"),
-                    choices=["fp32", "bf16x3", "bf16", "fp16"])
+                    choices=["fp32", "bf16x3", "bf16", "fp16", "fp16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
                     help="replay the training step from a CUDA graph (updater use_cuda_graph=True)")

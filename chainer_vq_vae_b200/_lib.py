@@ -16,8 +16,10 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 VQW_MAX_SRC = 4
-MODE_FP32, MODE_BF16X3, MODE_BF16, MODE_FP16 = 0, 1, 2, 3
-MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "fp16": MODE_FP16}
+MODE_FP32, MODE_BF16X3, MODE_BF16, MODE_FP16, MODE_FP16X3 = 0, 1, 2, 3, 4
+MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16, "fp16": MODE_FP16,
+         "fp16x3": MODE_FP16X3}
+X3_MODES = (MODE_BF16X3, MODE_FP16X3)      # split hi/lo operand planes, sigma-only gate save
 
 c_float_p = C.c_void_p   # device pointers are passed as integers
 c_int = C.c_int

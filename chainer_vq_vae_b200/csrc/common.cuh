@@ -6,6 +6,13 @@
 #include <stdarg.h>
 #include "../../include/vqw.h"
 
+// arithmetic modes (include/vqw.h): split hi/lo operands with 3 MMAs per product / IEEE-fp16 planes
+static inline bool vqw_mode_x3(int m) { return m == VQW_MODE_BF16X3 || m == VQW_MODE_FP16X3; }
+static inline bool vqw_mode_f16(int m) { return m == VQW_MODE_FP16 || m == VQW_MODE_FP16X3; }
+static inline bool vqw_mode_tc(int m) {
+  return m == VQW_MODE_BF16X3 || m == VQW_MODE_BF16 || m == VQW_MODE_FP16 || m == VQW_MODE_FP16X3;
+}
+
 namespace vqw {
 
 // thread-local error text returned by vqw_last_error()

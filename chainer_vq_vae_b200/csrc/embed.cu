@@ -109,7 +109,7 @@ extern "C" int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout,
                                             int B, int T, int Cr, int Q, int mode, void* workspace,
                                             vqw_stream_t stream) {
   using namespace vqw;
-  VQW_REQUIRE(mode == VQW_MODE_BF16X3 || mode == VQW_MODE_BF16 || mode == VQW_MODE_FP16,
+  VQW_REQUIRE(vqw_mode_tc(mode),
               "vqw_embed_gather_backward_tc: tensor-core modes only");
   return embed_backward_tc(q, gout, gW, gb, B, T, Cr, Q, mode, workspace, (cudaStream_t)stream);
 }

@@ -347,7 +347,7 @@ extern "C" int vqw_resnet_forward(const vqw_resnet_desc* desc, const float* x, c
   VQW_REQUIRE((gate_tanh == nullptr) == (gate_sig == nullptr),
               "vqw_resnet_forward: gate_tanh and gate_sig must be given together");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16 || d.mode == VQW_MODE_FP16)
+  if (vqw_mode_tc(d.mode))
     return resnet_forward_tc(d, x, cond, weights, residuals, skip, gate_tanh, gate_sig, workspace,
                              saved, st);
   VQW_REQUIRE(d.mode == VQW_MODE_FP32, "vqw_resnet_forward: unknown mode %d", d.mode);
@@ -411,7 +411,7 @@ extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_s
   if (d.B == 0 || d.T == 0) return 0;
   VQW_REQUIRE(g_skip && gate_tanh && gate_sig && workspace && gcond,
               "vqw_resnet_backward: null tensor");
-  if (d.mode == VQW_MODE_BF16X3 || d.mode == VQW_MODE_BF16 || d.mode == VQW_MODE_FP16) {
+  if (vqw_mode_tc(d.mode)) {
     VQW_REQUIRE(saved, "vqw_resnet_backward: the tensor-core modes need the `saved` buffer that "
                        "vqw_resnet_forward filled");
     return resnet_backward_tc(d, g_skip, g_last_res, gate_tanh, gate_sig, weights, gx, gcond,
@@ -448,7 +448,7 @@ extern "C" int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_s
 static int head_check(const vqw_head_desc* desc, const char* who) {
   using namespace vqw;
   VQW_REQUIRE(desc != nullptr, "%s: null descriptor", who);
-  VQW_REQUIRE(desc->mode == VQW_MODE_BF16X3 || desc->mode == VQW_MODE_BF16 || desc->mode == VQW_MODE_FP16,
+  VQW_REQUIRE(vqw_mode_tc(desc->mode),
               "%s: tensor-core modes only (fp32 runs through vqw_conv_forward)", who);
   VQW_REQUIRE(head_tc_supported(*desc),
               "%s: needs skip_channels %% 256 == 0, T >= 128 and T %% 8 == 0 (Cs=%d T=%d)", who,

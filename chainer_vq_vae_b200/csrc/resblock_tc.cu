@@ -679,7 +679,11 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
 
   if (warp == W_TMA) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // the whole warp walks the loop in uniform control flow and one elected lane issues (inside an
+    // `if (lane == 0)` region every UTMALDG / UTCHMMA operand came out of per-thread registers
+    // through an ELECT / R2UR waterfall: ~100+ cycles of issue per instruction)
+    {
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
       // activation slab i of the first contraction: tap slabs of x (row shift = causal delay,
@@ -702,16 +706,16 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
           const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
           const uint32_t sa = base + stage * PSTAGE;
-          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + PB_PLANE));
+          if (rank == 0 && el) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + PB_PLANE));
           const CUtensorMap *mh, *ml;
           int c0, tt;
           a_src(i, mh, ml, c0, tt);
-          tma2_load_3d(sa, mh, fb, c0, tt, b);
-          if (X3) tma2_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
+          if (el) tma2_load_3d(sa, mh, fb, c0, tt, b);
+          if (X3 && el) tma2_load_3d(sa + A_PLANE, ml, fb, c0, tt, b);
           // this CTA stages ITS half (128 rows) of the phase's 256 weight rows
           const int wr = gp * TN + (int)rank * (TN / 2);
-          tma2_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, wr);
-          if (X3) tma2_load_2d(sa + 2 * A_PLANE + PB_PLANE, &map_w1_lo, fb, i * BK, wr);
+          if (el) tma2_load_2d(sa + 2 * A_PLANE, &map_w1_hi, fb, i * BK, wr);
+          if (X3 && el) tma2_load_2d(sa + 2 * A_PLANE + PB_PLANE, &map_w1_lo, fb, i * BK, wr);
           if (++stage == PST) { stage = 0; ph ^= 1; }
         }
       }
@@ -720,20 +724,21 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           mbar_wait(empty0 + 8 * stage, ph ^ 1);
           const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
           const uint32_t sa = base + stage * PSTAGE;
-          if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * POB_PLANE);
+          if (rank == 0 && el) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * POB_PLANE);
           const int wr = oc * ON + (int)rank * (ON / 2);
-          tma2_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, wr);
-          if (X3) tma2_load_2d(sa + 2 * A_PLANE + POB_PLANE, &map_w2_lo, fb, i * BK, wr);
+          if (el) tma2_load_2d(sa + 2 * A_PLANE, &map_w2_hi, fb, i * BK, wr);
+          if (X3 && el) tma2_load_2d(sa + 2 * A_PLANE + POB_PLANE, &map_w2_lo, fb, i * BK, wr);
           if (++stage == PST) { stage = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == W_MMA) {
     // =============================== MMA issuer =================================
-    if (lane == 0 && rank == 0) {   // ONE thread of the pair issues the M = 256 MMAs of both SMs
+    if (rank == 0) {   // ONE (elected) thread of the pair issues the M = 256 MMAs of both SMs
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
-      const bool rec = rec_cta;
+      const bool rec = rec_cta && el;
       const uint32_t idesc = idesc_for(IDESC_P, F16);
       const uint32_t idesc_o = idesc_for(IDESC_PON, F16);
       for (int gp = 0; gp < 2; ++gp) {
@@ -745,20 +750,19 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
           const uint32_t sa = base + stage * PSTAGE;
 #pragma unroll
           for (int ks = 0; ks < BK / UK; ++ks) {
-            const uint64_t a_hi = smem_desc_sw64(sa + ks * UK * 2);
-            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma2_ss(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
-            if (X3) {
-              const uint64_t a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + PB_PLANE + ks * UK * 2);
-              mma2_ss(acc, a_lo, b_hi, idesc, 1u);
-              mma2_ss(acc, a_hi, b_lo, idesc, 1u);
+            const uint32_t a_hi = desc_lo_sw64(sa + ks * UK * 2);
+            const uint32_t b_hi = desc_lo_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            if (el) mma2_ss_w<DESC_HI_SW64>(acc, a_hi, b_hi, idesc, (i | ks) ? 1u : 0u);
+            if (X3 && el) {
+              mma2_ss_w<DESC_HI_SW64>(acc, desc_lo_sw64(sa + A_PLANE + ks * UK * 2), b_hi, idesc, 1u);
+              mma2_ss_w<DESC_HI_SW64>(acc, a_hi, desc_lo_sw64(sa + 2 * A_PLANE + PB_PLANE + ks * UK * 2),
+                                      idesc, 1u);
             }
           }
-          tc_commit2(empty0 + 8 * stage);
+          if (el) tc_commit2(empty0 + 8 * stage);
           if (++stage == PST) { stage = 0; ph ^= 1; }
         }
-        tc_commit2(hfull0 + 8 * gp);
+        if (el) tc_commit2(hfull0 + 8 * gp);
         if (rec) P.dbg[2 * gp + 1] = clock64();
       }
       // z_a is in TMEM and the sigmoid half of H_a (= the first output accumulator) is drained:
@@ -795,18 +799,18 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
             const int kstep = 2 * i + ks;
             const uint32_t z_hi = tmem_base + (kstep < 8 ? 0 : 256) + 16 * (kstep & 7);
             const uint32_t z_lo = z_hi + 8;
-            const uint64_t b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-            mma2_ts(acc, z_hi, b_hi, idesc_o, (i | ks) ? 1u : 0u);
-            if (X3) {
-              const uint64_t b_lo = smem_desc_sw64(sa + 2 * A_PLANE + POB_PLANE + ks * UK * 2);
-              mma2_ts(acc, z_lo, b_hi, idesc_o, 1u);
-              mma2_ts(acc, z_hi, b_lo, idesc_o, 1u);
+            const uint32_t b_hi = desc_lo_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+            if (el) mma2_ts_w<DESC_HI_SW64>(acc, z_hi, b_hi, idesc_o, (i | ks) ? 1u : 0u);
+            if (X3 && el) {
+              mma2_ts_w<DESC_HI_SW64>(acc, z_lo, b_hi, idesc_o, 1u);
+              mma2_ts_w<DESC_HI_SW64>(acc, z_hi, desc_lo_sw64(sa + 2 * A_PLANE + POB_PLANE + ks * UK * 2),
+                                      idesc_o, 1u);
             }
           }
-          tc_commit2(empty0 + 8 * stage);
+          if (el) tc_commit2(empty0 + 8 * stage);
           if (++stage == PST) { stage = 0; ph ^= 1; }
         }
-        tc_commit2(ofull0 + 8 * buf);
+        if (el) tc_commit2(ofull0 + 8 * buf);
         if (rec && j < 6) P.dbg[4 + 2 * j + 1] = clock64();
       }
     }
@@ -1314,6 +1318,24 @@ int make_map_tile(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint6
   return 0;
 }
 
+// MN-major operand, two 64-channel groups per copy: the plane as {64 ch, T, C/64 groups, B}, box
+// {64, 32, 2, 1} = two consecutive [32 steps x 128 B] swizzle tiles (8 KB) from ONE TMA instruction
+// (the weight-gradient producer is bound by its TMA issue rate, ~130-180 cycles per copy)
+int make_map_mn4(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B) {
+  EncodeTiledFn enc = get_encode();
+  VQW_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  VQW_REQUIRE(C % 128 == 0, "make_map_mn4: channel count must be a multiple of 128");
+  cuuint64_t dims[4] = {64, T, C / 64, B};
+  cuuint64_t strides[3] = {C * 2, 128, C * T * 2};
+  cuuint32_t box[4] = {64, 32, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VQW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(mn4) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // [128 rows x 32 channels] fp32 tiles of a time-major (B,T,C) fp32 tensor, 128-byte rows
 int make_map_tile_f32(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B) {
   EncodeTiledFn enc = get_encode();
@@ -1402,8 +1424,8 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   VQW_REQUIRE(d.Cg == 0 || d.cond_global != nullptr, "vqw_resnet_forward: Cg > 0 needs cond_global");
   VQW_REQUIRE(workspace != nullptr, "vqw_resnet_forward: workspace is null");
   VQW_REQUIRE(d.B <= 65535, "vqw_resnet_forward: B > 65535");
-  const bool x3 = d.mode == VQW_MODE_BF16X3;
-  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool x3 = vqw_mode_x3(d.mode);
+  const int f16 = vqw_mode_f16(d.mode) ? 1 : 0;
   const bool xlo = x3 || f16;   // residual stream hi + lo (only the hi plane feeds the MMAs in fp16)
   // The CTA-pair kernel (cta_group::2, each SM stages half of every weight slab) is the default;
   // VQW_TC_FWD_PAIR=0 selects the single-CTA kernel.
@@ -1475,8 +1497,9 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
   }
 
   const size_t smem = pair ? smem_bytes_pair(d.Cr, d.Cs) : smem_bytes(d.Cr, d.Cs);
-  auto kern1 = x3 ? resblock_tc_kernel<1, 0> : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
-  auto kern2 = x3 ? resblock_tc_pair_kernel<1, 0>
+  auto kern1 = x3 ? (f16 ? resblock_tc_kernel<1, 1> : resblock_tc_kernel<1, 0>)
+                  : (f16 ? resblock_tc_kernel<0, 1> : resblock_tc_kernel<0, 0>);
+  auto kern2 = x3 ? (f16 ? resblock_tc_pair_kernel<1, 1> : resblock_tc_pair_kernel<1, 0>)
                   : (f16 ? resblock_tc_pair_kernel<0, 1> : resblock_tc_pair_kernel<0, 0>);
   if (pair) {
     VQW_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

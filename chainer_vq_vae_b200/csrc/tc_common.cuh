@@ -33,6 +33,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded spin: a protocol bug must surface as a launch error, never as a hung GPU.
+// one non-blocking probe of a barrier phase: issued early, its result is consumed after the work
+// that does not depend on it (the instruction itself has ~150 cycles of latency)
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
@@ -203,6 +216,24 @@ __device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* ma
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// one lane of a converged warp (elect.sync): the issuing lane of the TMA / MMA roles
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                             int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void mma2_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {
   asm volatile(
@@ -217,6 +248,38 @@ __device__ __forceinline__ void mma2_ts(uint32_t d, uint32_t a_tmem, uint64_t bd
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same MMAs with the shared-memory descriptors passed as their LOW words only: the high word
+// (SBO, version, swizzle mode) is a compile-time constant that ptxas materialises in a uniform
+// register for free, which halves the R2UR traffic in front of every UTCHMMA (the issue loop of
+// one elected thread is what bounds the K = 16 steps of the thin GEMMs).
+constexpr uint32_t DESC_HI_SW64 = 0x80004020u;      // smem_desc_sw64() >> 32
+constexpr uint32_t DESC_HI_SW128_MN = 0x40004040u;  // smem_desc_sw128_mn() >> 32
+__device__ __forceinline__ uint32_t desc_lo_sw64(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t desc_lo_sw128_mn(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((4096u >> 4) << 16);
+}
+template <uint32_t HI>
+__device__ __forceinline__ void mma2_ss_w(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI)
+      : "memory");
+}
+template <uint32_t HI>
+__device__ __forceinline__ void mma2_ts_w(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}" ::"r"(d),
+      "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI)
       : "memory");
 }
 // arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far are done
@@ -390,6 +453,7 @@ int make_map(CUtensorMap* m, const void* ptr, int rank, uint64_t inner, uint64_t
 // gradient GEMMs)
 int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uint64_t T,
                 uint64_t B);
+int make_map_mn4(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B);
 // time-major plane (B,T,C): box = {64 channels, 128 rows, 1}, 128-byte swizzle -- the staging tiles of
 // the forward's residual epilogue (TMA load of the addend, TMA store of the result)
 int make_map_tile(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t B);

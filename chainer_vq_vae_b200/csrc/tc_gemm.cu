@@ -73,6 +73,18 @@ struct GemmParams {
                                // operand planes carry; fp32 outputs are multiplied by 1/s (or null)
   int B, T;
   int b_exact;                 // wgrad: B has no lo plane (exact bf16 values, e.g. a one-hot)
+  int a_exact;                 // wgrad: A's lo plane is not contracted (hi-plane passes, see wgrad_passes)
+  int wg_sub;                  // persistent wgrad: slabs of 32 time steps per ring stage (1 or 2);
+                               // slabs_per_item counts stages
+  int dbg_mode;                // persistent wgrad, timing experiments only (VQW_WGRAD_DEBUG): 1 = no
+                               // operand loads, 2 = no MMAs, 3 = MMAs without barriers -- garbage results
+  unsigned wide_maps;          // persistent wgrad: bit i = plane pair i has 4-D maps (make_map_mn4):
+                               // one copy brings both 64-channel groups of a 128-channel operand half
+  float* wg_partial;           // persistent wgrad: every (item, time chunk, job pair) tile is stored
+                               // here as [256 rows][256 cols] fp32 instead of fp32 atomics into gW;
+                               // wgrad_reduce_kernel sums them in a fixed order afterwards
+  const float* plane_s;        // head + loss: device scalar the gradient planes are multiplied by
+                               // (fp16 planes: a power of two near the label count), or null
   int slabs_per_item;          // wgrad: K slabs per (batch item, time chunk) work item
   int chunks_per_b;            // wgrad: work items per batch item
   const float* f0;             // GATE_BWD: tanh, time-major (B,T,256) fp32, or null: tanh = z / sigmoid
@@ -231,14 +243,15 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
             const uint32_t fb = PAIR ? mapa_u32(full0 + 8 * stage, 0) : full0 + 8 * stage;
             const uint32_t sa = base + stage * STG;
-            const bool blo = P.x3 && !P.b_exact;
+            const bool blo = P.x3 && !P.b_exact, alo = P.x3 && !P.a_exact;
             if (rank == 0)
-              mbar_expect_tx(full0 + 8 * stage, (PAIR ? 2 : 1) * (nplanes * A_PLANE + (blo ? 2 : 1) * BPL));
+              mbar_expect_tx(full0 + 8 * stage,
+                             (PAIR ? 2 : 1) * ((alo ? 2 : 1) * A_PLANE + (blo ? 2 : 1) * BPL));
             const int ta = tk + i * BK, tb = ta + jb.shift;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               ld3(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
-              if (P.x3) ld3(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
+              if (alo) ld3(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
             }
             // the B tile is 256 input channels; a CTA of a pair stages its 128-channel half
             const int nb0 = jb.n0 + (PAIR ? (int)rank * (TN / 2) : 0);
@@ -309,7 +322,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
           }
           mma(a_hi, b_hi, (i | ks) ? 1u : 0u);
           if (P.x3) {
-            mma(a_lo, b_hi, 1u);
+            if (!(WG && P.a_exact)) mma(a_lo, b_hi, 1u);
             if (!(WG && P.b_exact)) mma(a_hi, b_lo, 1u);
           }
         }
@@ -617,6 +630,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
         float* red = csum;                                  // [2][128] floats of row exchange
         const int Q = P.Qv;
         const float inv_n = (float)(P.loss[1] > 0.0 ? 1.0 / P.loss[1] : 0.0);
+        const float gmul = inv_n * (P.plane_s ? *P.plane_s : 1.0f);   // what the gradient planes hold
         mbar_wait(acc_full, 0);
         tc_fence_after();
         double nll = 0.0;
@@ -667,7 +681,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
               const int c = 16 * q + i;
               const float v = (c < Q) ? o[i] + __ldg(P.bias + c) : 0.0f;
               o[i] = v;
-              g[i] = (c < Q && valid) ? (expf(v - lse) - (c == k ? 1.0f : 0.0f)) * inv_n : 0.0f;
+              g[i] = (c < Q && valid) ? (expf(v - lse) - (c == k ? 1.0f : 0.0f)) * gmul : 0.0f;
             }
             if (P.o0 != nullptr) {
 #pragma unroll
@@ -698,7 +712,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             }
             if (t_ok) {
               nll = (double)mol_position(yv, 1, P.tgt_f[(int64_t)b * P.T + t], nr, P.mol_half,
-                                         P.mol_lsmin, inv_n, gv, 1);
+                                         P.mol_lsmin, gmul, gv, 1);
               if (P.o0 != nullptr)
                 for (int i = 0; i < Q; ++i) P.o0[((int64_t)b * Q + i) * P.T + t] = yv[i];
               for (int q = 0; 16 * q < P.Cout; ++q) {
@@ -900,7 +914,13 @@ static int launch_gemm(const Maps& maps, const GemmParams& P_in, dim3 grid, cuda
 constexpr int P_NST = 4;                         // ring stages of 32 KB (A 16 KB + this CTA's half of B)
 constexpr int P_STG = 2 * A_PLANE + B_PLANE;     // 32 KB
 constexpr int P_STAGING = 64 * 1024;             // epilogue tiles (two buffers of 32 KB)
-constexpr int P_NBAR = 2 * P_NST + 6;            // ring + acc_full[2] + acc_empty[2] + afull[2]
+// weight-gradient tiles do not use the staging tiles: their ring spans ring + staging (192 KB) in
+// stages of 8 KB per operand plane actually loaded -- 6 stages of 32 KB with all four planes, 12
+// of 16 KB with the hi planes only (a 4-stage ring of 16 KB loads was bound by the TMA latency:
+// ~700 cycles per 256-cycle slab)
+constexpr int P_MAXST = 12;
+constexpr int P_WG_RING = P_NST * P_STG + P_STAGING;
+constexpr int P_NBAR = 2 * P_MAXST + 6;          // ring + acc_full[2] + acc_empty[2] + afull[2]
 
 static size_t persist_smem() {
   return 1024 + (size_t)P_NST * P_STG + P_STAGING + 8 * P_NBAR + 16 + sizeof(float) * TN + 16;
@@ -915,19 +935,28 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stg0 = base + P_NST * P_STG;                       // staging tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_NST * P_STG + P_STAGING);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_NST);
-  const uint32_t acc_full0 = smem_u32(bars + 2 * P_NST), acc_empty0 = acc_full0 + 16, afull0 = acc_full0 + 32;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_MAXST);
+  const uint32_t acc_full0 = smem_u32(bars + 2 * P_MAXST), acc_empty0 = acc_full0 + 16, afull0 = acc_full0 + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + P_NBAR);
   float* csum = reinterpret_cast<float*>(bars + P_NBAR + 2);       // [TN] column sums (GX)
   const uint32_t rank = cluster_ctarank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nplanes = P.x3 ? 2 : 1;
   constexpr bool WG = (EPI == EPI_WGRAD);   // weight gradients: tile = (256-row job pair, batch item), K = time
+  // ring geometry: stage size / count and the plane offsets inside a stage
+  const bool wg_alo = P.x3 && !P.a_exact, wg_blo = P.x3 && !P.b_exact;
+  // a weight-gradient stage holds wg_sub slabs of 32 time steps (2 with the hi planes only: the
+  // ~300 cycles of barrier wait + fence + commit per stage are then spread over 4 MMAs instead of 2)
+  const uint32_t stg1 = (uint32_t)(((wg_alo ? 2 : 1) + (wg_blo ? 2 : 1)) * A_PLANE);
+  const int wg_sub = (WG && P.wg_sub > 1) ? P.wg_sub : 1;
+  const uint32_t stg = WG ? stg1 * (uint32_t)wg_sub : (uint32_t)P_STG;
+  const int nst = WG ? min(P_MAXST, (int)(P_WG_RING / stg)) : P_NST;
+  const uint32_t wg_boff = (uint32_t)((wg_alo ? 2 : 1) * A_PLANE);
   const int n_tiles = n_x * n_y * n_z;                             // pair tiles
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   if (warp == GW_TMA && lane == 0) {
-    for (int s = 0; s < P_NST; ++s) {
+    for (int s = 0; s < P_MAXST; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -962,9 +991,15 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
 
   if (warp == GW_TMA) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // the WHOLE warp walks the loop (uniform control flow: counters, addresses and coordinates live
+    // in uniform registers) and one elected lane issues; inside `if (lane == 0) { loop }` every
+    // operand of a UTMALDG / UTCHMMA came from a per-thread register through an ELECT / R2UR
+    // waterfall: ~350 cycles of issue per K = 16 step, measured (profiles/r2_summary.md)
+    {
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
+      bool free_seen = false;   // (weight-gradient path) the empty barrier of `stage` has been seen complete
       for (int tile = cid; tile < n_tiles; tile += ncl) {
         int bx, y, bb;
         decode(tile, bx, y, bb);
@@ -973,23 +1008,51 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
           const Job& jb = P.jobs[bx];
           const CUtensorMap* ma = &maps.m[2 * jb.a_map];
           const CUtensorMap* mb = &maps.m[2 * jb.b_map];
-          const bool blo = P.x3 && !P.b_exact;
+          const bool blo = wg_blo, alo = wg_alo;
           const int nb0 = jb.n0 + (int)rank * (TN / 2);
           for (int i = 0; i < P.slabs_per_item; ++i) {
-            mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            if (P.dbg_mode >= 3) continue;
+            if (!free_seen) mbar_wait(empty0 + 8 * stage, ph ^ 1);
+            // probe the next stage's empty barrier; the answer arrives while this stage is issued
+            const int nstage = (stage + 1 == nst) ? 0 : stage + 1;
+            const uint32_t nph = (stage + 1 == nst) ? ph ^ 1 : ph;
+            const bool nfree = mbar_try(empty0 + 8 * nstage, nph ^ 1);
             const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
-            const uint32_t sa = base + stage * P_STG;
-            if (rank == 0)
-              mbar_expect_tx(full0 + 8 * stage, 2 * (nplanes * A_PLANE + (blo ? 2 : 1) * (B_PLANE / 2)));
-            const int ta = (y * P.slabs_per_item + i) * BK, tb = ta + jb.shift;   // y = time chunk
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              tma2_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
-              if (P.x3) tma2_load_3d(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
-              tma2_load_3d(sa + 2 * A_PLANE + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
-              if (blo) tma2_load_3d(sa + 2 * A_PLANE + B_PLANE / 2 + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
+            const uint32_t sa0 = base + stage * stg;
+            if (rank == 0 && el)
+              mbar_expect_tx(full0 + 8 * stage, P.dbg_mode == 1 ? 0 :
+                             2 * wg_sub * ((alo ? 2 : 1) * A_PLANE + (blo ? 2 : 1) * (B_PLANE / 2)));
+            if (P.dbg_mode == 1) {
+              stage = nstage; ph = nph; free_seen = nfree;
+              continue;
             }
-            if (++stage == P_NST) { stage = 0; ph ^= 1; }
+            for (int u = 0; u < wg_sub; ++u) {
+              const uint32_t sa = sa0 + u * stg1;
+              // y = time chunk; steps past T are zero-filled by TMA
+              const int ta = ((y * P.slabs_per_item + i) * wg_sub + u) * BK, tb = ta + jb.shift;
+              if ((P.wide_maps >> jb.a_map) & 1u) {
+                if (el) tma2_load_4d(sa, ma, fb, 0, ta, jb.m0 >> 6, bb);
+                if (alo && el) tma2_load_4d(sa + A_PLANE, ma + 1, fb, 0, ta, jb.m0 >> 6, bb);
+              } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (el) tma2_load_3d(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
+                  if (alo && el) tma2_load_3d(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
+                }
+              }
+              if ((P.wide_maps >> jb.b_map) & 1u) {
+                if (el) tma2_load_4d(sa + wg_boff, mb, fb, 0, tb, nb0 >> 6, bb);
+                if (blo && el) tma2_load_4d(sa + wg_boff + B_PLANE / 2, mb + 1, fb, 0, tb, nb0 >> 6, bb);
+              } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (el) tma2_load_3d(sa + wg_boff + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
+                  if (blo && el)
+                    tma2_load_3d(sa + wg_boff + B_PLANE / 2 + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
+                }
+              }
+            }
+            stage = nstage; ph = nph; free_seen = nfree;
           }
           continue;
         }
@@ -1005,25 +1068,27 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
             const uint32_t fb = mapa_u32(full0 + 8 * stage, 0);
             const uint32_t sa = base + stage * P_STG;
-            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + B_PLANE / 2));
+            if (rank == 0 && el) mbar_expect_tx(full0 + 8 * stage, 2 * nplanes * (A_PLANE + B_PLANE / 2));
             const int brow = sg.b_row0 + TN * by + (int)rank * (TN / 2);
-            tma2_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-            tma2_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
+            if (el) tma2_load_3d(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+            if (el) tma2_load_3d(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
             if (P.x3) {
-              tma2_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-              tma2_load_3d(sa + 2 * A_PLANE + B_PLANE / 2, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
+              if (el) tma2_load_3d(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+              if (el) tma2_load_3d(sa + 2 * A_PLANE + B_PLANE / 2, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
             }
-            if (++stage == P_NST) { stage = 0; ph ^= 1; }
+            if (++stage == nst) { stage = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == GW_MMA) {
     // =============================== MMA issuer (leader CTA) ====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
       const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16) + ((uint32_t)(TM >> 4) << 24);   // M = 256
+      bool ready = false;      // the full barrier of `stage` has already been seen complete
       int it = 0;
       for (int tile = cid; tile < n_tiles; tile += ncl, ++it) {
         int bx, y, bb;
@@ -1039,36 +1104,54 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
           tc_fence_after();
         }
         const uint32_t acc = tmem_base + 256 * buf;
-        if (P.dbg && cid == 0 && it < 8) P.dbg[4 * it] = gtime_ns();
+        if (el && P.dbg && cid == 0 && it < 8) P.dbg[4 * it] = gtime_ns();
         for (int i = 0; i < total_slabs; ++i) {
-          mbar_wait(full0 + 8 * stage, ph);
-          tc_fence_after();
-          const uint32_t sa = base + stage * P_STG;
-#pragma unroll
-          for (int ks = 0; ks < BK / UK; ++ks) {
-            uint64_t a_hi, b_hi, a_lo, b_lo;
+          const bool probe = el && P.dbg && cid == 0 && it == 1 && (i == 100 || i == 101);
+          long long* pd = P.dbg + 32 + 5 * (i - 100);
+          if (probe) pd[0] = clock64();
+          if (!(WG && P.dbg_mode >= 3) && !ready) mbar_wait(full0 + 8 * stage, ph);
+          if (probe) pd[1] = clock64();
+          if (!(WG && P.dbg_mode >= 3)) tc_fence_after();
+          if (probe) pd[2] = clock64();
+          // probe the NEXT stage now: the answer arrives while this stage's MMAs are being issued
+          const int nstage = (stage + 1 == nst) ? 0 : stage + 1;
+          const uint32_t nph = (stage + 1 == nst) ? ph ^ 1 : ph;
+          const bool nready = mbar_try(full0 + 8 * nstage, nph);
+          const uint32_t sa0 = base + stage * stg;
+          const int nks = (BK / UK) * wg_sub;
+#pragma unroll 4
+          for (int kq = 0; kq < nks; ++kq) {
+            const int ks = kq & (BK / UK - 1);
+            const uint32_t sa = sa0 + (uint32_t)(kq / (BK / UK)) * stg1;   // sub-slab of this K step
+            if (WG && P.dbg_mode == 2) continue;
             if (WG) {   // MN-major tiles: 16 K-rows = two 1024-byte swizzle atoms per step
-              a_hi = smem_desc_sw128_mn(sa + ks * 2048);
-              b_hi = smem_desc_sw128_mn(sa + 2 * A_PLANE + ks * 2048);
-              a_lo = smem_desc_sw128_mn(sa + A_PLANE + ks * 2048);
-              b_lo = smem_desc_sw128_mn(sa + 2 * A_PLANE + B_PLANE / 2 + ks * 2048);
+              const uint32_t a_hi = desc_lo_sw128_mn(sa + ks * 2048);
+              const uint32_t b_hi = desc_lo_sw128_mn(sa + wg_boff + ks * 2048);
+              if (el) mma2_ss_w<DESC_HI_SW128_MN>(acc, a_hi, b_hi, ID, (i | kq) ? 1u : 0u);
+              if (probe && i == 100 && kq < 2) P.dbg[44 + kq] = clock64();
+              if (wg_alo && el)
+                mma2_ss_w<DESC_HI_SW128_MN>(acc, desc_lo_sw128_mn(sa + A_PLANE + ks * 2048), b_hi, ID, 1u);
+              if (wg_blo && el)
+                mma2_ss_w<DESC_HI_SW128_MN>(acc, a_hi, desc_lo_sw128_mn(sa + wg_boff + B_PLANE / 2 + ks * 2048),
+                                            ID, 1u);
             } else {
-              a_hi = smem_desc_sw64(sa + ks * UK * 2);
-              b_hi = smem_desc_sw64(sa + 2 * A_PLANE + ks * UK * 2);
-              a_lo = smem_desc_sw64(sa + A_PLANE + ks * UK * 2);
-              b_lo = smem_desc_sw64(sa + 2 * A_PLANE + B_PLANE / 2 + ks * UK * 2);
-            }
-            mma2_ss(acc, a_hi, b_hi, ID, (i | ks) ? 1u : 0u);
-            if (P.x3) {
-              mma2_ss(acc, a_lo, b_hi, ID, 1u);
-              if (!(WG && P.b_exact)) mma2_ss(acc, a_hi, b_lo, ID, 1u);
+              const uint32_t a_hi = desc_lo_sw64(sa + ks * UK * 2);
+              const uint32_t b_hi = desc_lo_sw64(sa + 2 * A_PLANE + ks * UK * 2);
+              if (el) mma2_ss_w<DESC_HI_SW64>(acc, a_hi, b_hi, ID, (i | kq) ? 1u : 0u);
+              if (P.x3 && el) {
+                mma2_ss_w<DESC_HI_SW64>(acc, desc_lo_sw64(sa + A_PLANE + ks * UK * 2), b_hi, ID, 1u);
+                mma2_ss_w<DESC_HI_SW64>(acc, a_hi, desc_lo_sw64(sa + 2 * A_PLANE + B_PLANE / 2 + ks * UK * 2),
+                                        ID, 1u);
+              }
             }
           }
-          tc_commit2(empty0 + 8 * stage);
-          if (++stage == P_NST) { stage = 0; ph ^= 1; }
+          if (probe) pd[3] = clock64();
+          if (!(WG && P.dbg_mode >= 3) && el) tc_commit2(empty0 + 8 * stage);
+          if (probe) pd[4] = clock64();
+          stage = nstage; ph = nph; ready = nready;
         }
-        tc_commit2(acc_full0 + 8 * buf);
-        if (P.dbg && cid == 0 && it < 8) P.dbg[4 * it + 1] = gtime_ns();
+        if (el) tc_commit2(acc_full0 + 8 * buf);
+        if (el && P.dbg && cid == 0 && it < 8) P.dbg[4 * it + 1] = gtime_ns();
       }
     }
   } else {
@@ -1093,7 +1176,23 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
       mbar_wait(acc_full0 + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       if (rec && it < 8) P.dbg[4 * it + 2] = gtime_ns();
-      if (WG) {
+      if (WG && P.wg_partial != nullptr) {
+        // ---- weight-gradient tile -> its own [256 x 256] fp32 slot (plain 64-byte stores per
+        // thread; 18-36 M scattered fp32 atomics per launch were what bounded this kernel) ----
+        constexpr int NG = G_EPI_WARPS / 4;
+        float* pt = P.wg_partial + ((size_t)(b * n_y + y) * n_x + (bx >> 1)) * 65536 +
+                    (size_t)((int)rank * TM + row) * TN;
+#pragma unroll 1
+        for (int q = grp; q < TN / 16; q += NG) {
+          uint32_t o[16];
+          tmem_ld16(lane_base + 16 * q, reinterpret_cast<float*>(o));
+          st256(pt + 16 * q, o);
+          st256(pt + 16 * q + 8, o + 8);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_l + 8 * buf);
+      } else if (WG) {
         // ---- weight-gradient tile: fp32 atomics into gW (K is split over the batch items) ----
         constexpr int NG = G_EPI_WARPS / 4;
         const Job& jb = P.jobs[bx];
@@ -1354,6 +1453,50 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
 }
 
 // time-flavour launch on the persistent kernel: grid (x, y, z) as for launch_gemm
+// Fixed-order sum of the weight-gradient tiles the persistent kernel stored (wg_partial): pair
+// tile `blockIdx.x`, 8 of its 256 rows per CTA, thread = column.  gW += inv * sum over (item, time
+// chunk); the constant-one column of the condition job goes to col_out per item.  Every output
+// element has exactly one owner, so the result is deterministic (no atomics).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const __grid_constant__ GemmParams P, const float* __restrict__ partial,
+                    int n_pairs, int n_chunks, int B) {
+  // CTA = 4 rows of pair tile blockIdx.x, thread = 4 consecutive columns of one row
+  const float inv = P.scale ? P.scale[1] : 1.0f;
+  const int pair = blockIdx.x;
+  const int r = blockIdx.y * 4 + (threadIdx.x >> 6), n4 = (threadIdx.x & 63) * 4;
+  const size_t ustride = (size_t)n_pairs * 65536;
+  const Job& jb = P.jobs[2 * pair + (r >> 7)];
+  const int m = jb.m0 + (r & 127);
+  if (m >= jb.M) return;
+  const int na = jb.n0 + n4;
+  const bool has_col = jb.col_out != nullptr && jb.col_n >= na && jb.col_n < na + 4;
+  if (na >= jb.N && !has_col) return;
+  const float* p = partial + (size_t)pair * 65536 + (size_t)r * TN + n4;
+  const int units = B * n_chunks;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u0 = 0; u0 < units; u0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (u0 + k < units) ? __ldcs(reinterpret_cast<const float4*>(p + (size_t)(u0 + k) * ustride))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+  }
+  const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (na + i < jb.N) jb.out[(long long)m * jb.gm + (long long)(na + i) * jb.gk] += sv[i] * inv;
+  if (has_col) {   // the constant-one column: per item, summed over its time chunks
+    const float* pc = p + (jb.col_n - na);
+    for (int b = 0; b < B; ++b) {
+      float c = 0.0f;
+      for (int k = 0; k < n_chunks; ++k) c += pc[(size_t)(b * n_chunks + k) * ustride];
+      jb.col_out[(long long)b * jb.col_stride + m] += c * inv;
+    }
+  }
+}
+
 template <int EPI>
 static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, cudaStream_t stream) {
   auto kern = tc_time_persistent_kernel<EPI>;
@@ -1400,6 +1543,15 @@ static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, c
       if (h[4 * i])
         fprintf(stderr, "  %d | %7lld %7lld | %7lld %7lld\n", i, h[4 * i] - h[0], h[4 * i + 1] - h[0],
                 h[4 * i + 2] - h[0], h[4 * i + 3] - h[0]);
+    for (int k = 0; k < 2; ++k)
+      if (h[32 + 5 * k])
+        fprintf(stderr, "  slab %d of tile 1 (cycles): wait %lld, fence %lld, mma issue %lld, commit %lld; "
+                        "to next slab %lld\n", 100 + k, h[33 + 5 * k] - h[32 + 5 * k],
+                h[34 + 5 * k] - h[33 + 5 * k], h[35 + 5 * k] - h[34 + 5 * k], h[36 + 5 * k] - h[35 + 5 * k],
+                k == 0 ? h[37] - h[32] : 0LL);
+    if (h[44])
+      fprintf(stderr, "  slab 100: first MMA issued after %lld cycles, second after %lld more\n",
+              h[44] - h[34], h[45] - h[44]);
   }
   return 0;
 }
@@ -1637,9 +1789,19 @@ struct BwdLayout {
   int64_t gs_sum;   // column sum of g_skip (the same bias gradient for every block)
   int64_t colS;     // S[i][b][m]: per-item column sums of gh (n_blocks * B * Cd floats)
   int64_t scale;    // 4 floats: gradient-scale scratch of the fp16 mode
+  int64_t wg_partial;   // [B * chunks][job pairs][256][256] fp32 weight-gradient tiles of one block
   int64_t w2t[2], wct[2], wpt[2];
   int64_t wstride;
 };
+
+// time chunks of the persistent weight-gradient GEMM (work units = job pairs x items x chunks)
+static int wgrad_chunks(int T) {
+  int chunks = getenv("VQW_WGRAD_CHUNKS") ? atoi(getenv("VQW_WGRAD_CHUNKS")) : 1;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 8) chunks = 8;
+  while (chunks > 1 && ceil_div(T, tc::BK) / chunks < 16) chunks /= 2;
+  return chunks;
+}
 
 static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   BwdLayout L;
@@ -1659,6 +1821,7 @@ static BwdLayout bwd_layout(const vqw_resnet_desc& d) {
   for (int p = 0; p < 2; ++p) L.wpt[p] = take((int64_t)pad256(cond_local(d)) * d.Cd * 2);
   L.wstride = off - wbase;
   off = wbase + L.wstride * d.n_blocks;
+  L.wg_partial = take((int64_t)d.B * wgrad_chunks(d.T) * (tc::MAX_JOBS / 2) * 65536 * 4);
   L.total = off + 1024;
   return L;
 }
@@ -1675,8 +1838,8 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
   VQW_REQUIRE(workspace && saved && g_skip && gate_tanh && gate_sig && weights && wgrads && gcond,
               "vqw_resnet_backward: null argument");
   VQW_REQUIRE(d.fs <= MAX_SEG, "tcgen05 backward: filter_size > %d unsupported", MAX_SEG);
-  const bool x3 = d.mode == VQW_MODE_BF16X3;
-  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool x3 = vqw_mode_x3(d.mode);
+  const int f16 = vqw_mode_f16(d.mode) ? 1 : 0;
   const bool xlo = x3 || f16;   // the g_res stream keeps hi + lo (addend of GX), like x in the forward
   const BwdLayout L = bwd_layout(d);
   const TcSaved S = tc_saved_layout(d);
@@ -1843,15 +2006,40 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
     // ---- all weight gradients of the block: one grouped launch ----
     {
       Maps maps;
-      // pairs: 0 gh, 1 x_i, 2 cond, 3 z_i, 4 g_res, 5 g_skip
-      if (int rc = mapmn(&maps.m[0], ws + L.gh_p[0], ws + L.gh_p[1], Cd)) return rc;
-      if (int rc = mapmn(&maps.m[2], xp_hi, xp_lo, Cr)) return rc;
-      if (int rc = mapmn(&maps.m[4], sv + S.cond[0], sv + S.cond[1], CP)) return rc;
-      if (int rc = mapmn(&maps.m[6], zp_hi, zp_lo, Ch)) return rc;
-      if (int rc = mapmn(&maps.m[8], ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr)) return rc;
-      if (int rc = mapmn(&maps.m[10], ws + L.gs_p[0], ws + L.gs_p[1], Cs)) return rc;
       GemmParams P = {};
+      // the persistent kernel runs when every job has an even number of 128-row tiles (CTA pairs);
+      // its producer then takes 4-D maps: one copy per 128-channel operand half instead of two
+      const bool even_tiles = (ceil_div(Cd, TM) & 1) == 0 && (ceil_div(Cs, TM) & 1) == 0 &&
+                              (!have_gres || (ceil_div(Cr, TM) & 1) == 0);
+      static const bool wide_on = !(getenv("VQW_WGRAD_WIDE") && getenv("VQW_WGRAD_WIDE")[0] == '0');
+      const bool wide = persist && even_tiles && wide_on;
+      auto mapmn_w = [&](int pair, const void* hi, const void* lo, uint64_t C) -> int {
+        if (wide && C % 128 == 0) {
+          P.wide_maps |= 1u << pair;
+          if (int rc = make_map_mn4(&maps.m[2 * pair], hi, C, T, B)) return rc;
+          return make_map_mn4(&maps.m[2 * pair + 1], x3 ? lo : hi, C, T, B);
+        }
+        return mapmn(&maps.m[2 * pair], hi, lo, C);
+      };
+      // pairs: 0 gh, 1 x_i, 2 cond, 3 z_i, 4 g_res, 5 g_skip
+      if (int rc = mapmn_w(0, ws + L.gh_p[0], ws + L.gh_p[1], Cd)) return rc;
+      if (int rc = mapmn_w(1, xp_hi, xp_lo, Cr)) return rc;
+      if (int rc = mapmn(&maps.m[4], sv + S.cond[0], sv + S.cond[1], CP)) return rc;
+      if (int rc = mapmn_w(3, zp_hi, zp_lo, Ch)) return rc;
+      if (int rc = mapmn_w(4, ws + L.gr_p[cur][0], ws + L.gr_p[cur][1], Cr)) return rc;
+      if (int rc = mapmn_w(5, ws + L.gs_p[0], ws + L.gs_p[1], Cs)) return rc;
       P.x3 = x3; P.f16 = f16; P.scale = gscale; P.B = B; P.T = T;
+      // MMA passes per product of the weight-gradient GEMMs (split modes): 3 = hi*hi + lo*hi + hi*lo,
+      // 2 = the activations' lo plane is left out, 1 = hi planes only.  One contraction over time
+      // per weight, so the rounding of a hi plane (2^-12 per operand in fp16) enters each gradient
+      // once and does not accumulate over the depth of the stack.  Default: 3 for bf16 planes
+      // (2^-9 per operand is outside the parity bar), 1 for fp16 planes.
+      {
+        static const int env_passes = getenv("VQW_WGRAD_PASSES") ? atoi(getenv("VQW_WGRAD_PASSES")) : 0;
+        const int passes = env_passes >= 1 && env_passes <= 3 ? env_passes : ((x3 && f16) ? 1 : 3);
+        P.b_exact = (x3 && passes <= 2) ? 1 : 0;
+        P.a_exact = (x3 && passes <= 1) ? 1 : 0;
+      }
       P.slabs_per_item = ceil_div(T, BK);
       P.chunks_per_b = 1;
       int nj = 0;
@@ -1880,16 +2068,25 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         if (int rc = add_jobs(4, Cr, 3, Ch, 0, gw.res_w, Ch, 1)) return rc;
       if (int rc = add_jobs(5, Cs, 3, Ch, 0, gw.skip_w, Ch, 1)) return rc;
       P.njobs = nj;
+      VQW_REQUIRE(!wide || wg_pair, "tcgen05 backward: weight-gradient tiles are not pairable");
       if (wg_pair && persist) {
-        // split the time axis in two: 544 tiles instead of 272 for the 74 clusters (measured on the
-        // B200 shape: 1 chunk 0.586 ms, 2 chunks 0.569 ms, 4 chunks 0.595 ms, 8 chunks 0.898 ms --
-        // every extra chunk is another tile of atomics)
-        int chunks = getenv("VQW_WGRAD_CHUNKS") ? atoi(getenv("VQW_WGRAD_CHUNKS")) : 2;
-        if (chunks < 1) chunks = 1;
-        while (chunks > 1 && ceil_div(T, BK) / chunks < 16) chunks /= 2;
+        // every (job pair, item, time chunk) tile goes to its own slot of wg_partial and a second
+        // kernel sums the slots in a fixed order (round 2: with fp32 atomics straight into gW this
+        // launch was bound by 18 M scattered atomics, not by its MMAs; VQW_WGRAD_ATOMICS=1 restores it)
+        static const bool use_atomics = getenv("VQW_WGRAD_ATOMICS") && getenv("VQW_WGRAD_ATOMICS")[0] == '1';
+        const int chunks = wgrad_chunks(T);
+        static const bool sub_on = !(getenv("VQW_WGRAD_SUB") && getenv("VQW_WGRAD_SUB")[0] == '1');
+        P.wg_sub = (x3 && P.a_exact && P.b_exact && sub_on) ? 2 : 1;   // hi planes only: 2 slabs per stage
         P.chunks_per_b = chunks;
-        P.slabs_per_item = ceil_div(ceil_div(T, BK), chunks);
+        P.slabs_per_item = ceil_div(ceil_div(ceil_div(T, BK), chunks), P.wg_sub);
+        float* partial = reinterpret_cast<float*>(ws + L.wg_partial);
+        P.wg_partial = use_atomics ? nullptr : partial;
+        P.dbg_mode = getenv("VQW_WGRAD_DEBUG") ? atoi(getenv("VQW_WGRAD_DEBUG")) : 0;
         if (int rc = launch_persistent<EPI_WGRAD>(maps, P, dim3(nj, chunks, B), stream)) return rc;
+        if (!use_atomics) {
+          wgrad_reduce_kernel<<<dim3(nj / 2, 256 / 4), 256, 0, stream>>>(P, partial, nj / 2, chunks, B);
+          VQW_CHECK_LAUNCH("wgrad_reduce_kernel");
+        }
       } else {
         if (int rc = launch_gemm<EPI_WGRAD>(maps, P, dim3(nj, 1, B), stream, wg_pair)) return rc;
       }
@@ -1973,6 +2170,15 @@ int64_t head_tc_saved_bytes(const vqw_head_desc& d) { return head_saved(d).total
 
 namespace tc {
 __global__ void set_double_kernel(double* p, double v) { *p = v; }
+// scale[2] = 1 (bf16 planes) or, for fp16 planes, a power of two near n * 2^up for the n labels the
+// loss is averaged over: d loss / d y = (p - onehot) / n would be subnormal in fp16; with up = 7 the
+// softmax gradient planes hold values up to 256 (hi AND lo plane in the normal range), up = 0 leaves
+// the mixture-of-logistics gradient (|g| up to ~1e3 per position) four decades of headroom
+__global__ void plane_scale_kernel(const double* __restrict__ count, float* __restrict__ scale, int f16,
+                                   int up) {
+  const double n = *count;
+  scale[2] = (f16 && n >= 1.0) ? exp2f(floorf(log2f((float)n)) + (float)up) : 1.0f;
+}
 __global__ void __launch_bounds__(256)
 count_labels_kernel(const int32_t* __restrict__ tgt, int64_t n, int Q, double* __restrict__ count) {
   int c = 0;
@@ -2008,8 +2214,8 @@ static int head_forward_impl(const vqw_head_desc& d, const float* skip, const fl
               "vqw_head_loss_forward: needs `saved`, Q <= 256 and exactly one target");
   VQW_REQUIRE(!hl || !hl->tgt_f || (d.Q % 3 == 0 && d.Q <= 32),
               "vqw_head_loss_forward: the mixture-of-logistics head has 3 * n_mix <= 32 outputs");
-  const bool x3 = d.mode == VQW_MODE_BF16X3;
-  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool x3 = vqw_mode_x3(d.mode);
+  const int f16 = vqw_mode_f16(d.mode) ? 1 : 0;
   const HeadLayout L = head_layout(d);
   const HeadSaved S = head_saved(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
@@ -2066,6 +2272,10 @@ static int head_forward_impl(const vqw_head_desc& d, const float* skip, const fl
         set_double_kernel<<<1, 1, 0, stream>>>(hl->loss + 1, (double)B * (double)T);
         VQW_CHECK_LAUNCH("set_double_kernel");
       }
+      float* sc = reinterpret_cast<float*>(sv + S.scale);
+      plane_scale_kernel<<<1, 1, 0, stream>>>(hl->loss + 1, sc, f16, hl->tgt_i ? 7 : 0);
+      VQW_CHECK_LAUNCH("plane_scale_kernel");
+      P.plane_s = sc + 2;
       P.Cout = qpad(Q); P.Qv = Q;
       P.tgt_i = hl->tgt_i; P.tgt_f = hl->tgt_f; P.loss = hl->loss;
       P.mol_half = (float)(127.5 / (hl->quantize - 1)); P.mol_lsmin = hl->log_scale_min;
@@ -2093,12 +2303,14 @@ int head_loss_forward_tc(const vqw_head_desc& d, const float* skip, const float*
 }
 
 namespace tc {
-// {1/g, g} from the upstream gradient g of the scalar loss (device memory, no host sync)
+// {s/g, g/s} from the upstream gradient g of the scalar loss (device memory, no host sync) and the
+// factor s = scale[2] the fused loss multiplied its gradient planes by
 __global__ void loss_scale_kernel(const float* __restrict__ g, float* __restrict__ scale) {
-  const float v = *g;
-  scale[0] = v != 0.0f ? 1.0f / v : 0.0f;
-  scale[1] = v;
+  const float v = *g, s = scale[2];
+  scale[0] = v != 0.0f ? s / v : 0.0f;
+  scale[1] = v / s;
 }
+
 }  // namespace tc
 
 // gy == nullptr: the gradient planes were written by head_loss_forward_tc (in `saved`); g_loss is
@@ -2110,10 +2322,8 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* g_los
   VQW_REQUIRE(head_tc_supported(d), "tcgen05 head: unsupported shape");
   VQW_REQUIRE((gy || g_loss) && W1 && W2 && gskip && gW1 && gb1 && gW2 && gb2 && workspace && saved,
               "vqw_head_backward: null argument");
-  VQW_REQUIRE(gy || d.mode != VQW_MODE_FP16,
-              "vqw_head_loss_backward: the fused loss needs a bf16 mode (fp16 planes carry a scale)");
-  const bool x3 = d.mode == VQW_MODE_BF16X3;
-  const int f16 = d.mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool x3 = vqw_mode_x3(d.mode);
+  const int f16 = vqw_mode_f16(d.mode) ? 1 : 0;
   const HeadLayout L = head_layout(d);
   const HeadSaved S = head_saved(d);
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));
@@ -2124,7 +2334,7 @@ int head_backward_tc(const vqw_head_desc& d, const float* gy, const float* g_los
   const int64_t NROWS = (int64_t)B * T;
   const int RPB = 256, CS_GRID = (int)((NROWS + RPB - 1) / RPB);
   const float* gscale = nullptr;
-  if (f16) {
+  if (f16 && gy != nullptr) {
     if (int rc = make_grad_scale(gy, (int64_t)B * Q * T, nullptr, 0,
                                  reinterpret_cast<float*>(ws + L.scale), stream, &gscale))
       return rc;
@@ -2246,8 +2456,8 @@ int embed_backward_tc(const int32_t* q, const float* g, float* gW, float* gb, in
   using namespace tc;
   VQW_REQUIRE(embed_bwd_tc_supported(B, T, Cr, Q), "tcgen05 embed backward: unsupported shape");
   VQW_REQUIRE(q && g && gW && workspace, "vqw_embed_gather_backward_tc: null pointer");
-  const bool x3 = mode == VQW_MODE_BF16X3;
-  const int f16 = mode == VQW_MODE_FP16 ? 1 : 0;
+  const bool x3 = vqw_mode_x3(mode);
+  const int f16 = vqw_mode_f16(mode) ? 1 : 0;
   const int Qp = pad256(Q);
   const int64_t N = (int64_t)B * T;
   uint8_t* ws = reinterpret_cast<uint8_t*>(al((int64_t)(uintptr_t)workspace));

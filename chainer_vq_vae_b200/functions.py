@@ -289,7 +289,7 @@ class _ResidualStack(torch.autograd.Function):
         gates: List[torch.Tensor] = []
         if need_grad:
             # bf16x3 keeps only the sigmoid (tanh = z / sigmoid from the saved z planes)
-            only_sig = mode == L.MODE_BF16X3
+            only_sig = mode in L.X3_MODES
             for _ in range(n):
                 gates += [x.new_empty(0) if only_sig else new(Cd // 2), new(Cd // 2)]
 
@@ -521,8 +521,8 @@ def head(skip, W1, b1, W2, b2, mode):
 
 
 def head_loss_supported(skip: torch.Tensor, Q: int, mode: int, use_logistic: bool) -> bool:
-    """The fused head + loss (vqw_head_loss_*): bf16 modes, one accumulator tile of logits."""
-    if mode not in (L.MODE_BF16X3, L.MODE_BF16) or not head_supported(skip, mode):
+    """The fused head + loss (vqw_head_loss_*): tensor-core modes, one accumulator tile of logits."""
+    if mode == L.MODE_FP32 or not head_supported(skip, mode):
         return False
     return (Q % 3 == 0 and Q <= 32) if use_logistic else Q <= 256
 

@@ -136,6 +136,12 @@ int vqw_conv_wgrad(const vqw_wgrad_desc* desc, float* gw, float* gb /* or NULL *
 #define VQW_MODE_FP16 3      /* tcgen05, single IEEE-fp16 pass (11 significant bits: ~2e-4 relative per
                               * product, inside the 1e-3 parity bar), fp32 accumulation; the backward
                               * carries its gradients with a power-of-two scale chosen on the device */
+#define VQW_MODE_FP16X3 4    /* tcgen05, IEEE-fp16 hi/lo split operands (22 significant bits), 3 MMAs per
+                              * product like VQW_MODE_BF16X3, gradients carried with the power-of-two
+                              * scale of VQW_MODE_FP16.  Because an fp16 hi plane alone already holds
+                              * 11 bits, the weight-gradient GEMMs -- one contraction over time each,
+                              * no accumulation of rounding over the depth of the stack -- may run on
+                              * the hi planes only (VQW_WGRAD_PASSES=1|2|3) */
 
 typedef struct {
   int B, T;
@@ -242,7 +248,7 @@ int vqw_resnet_backward(const vqw_resnet_desc* desc, const float* g_skip, const 
  * WaveNet output head on the tensor cores.  Replaces relu -> proj1 -> relu -> proj2 of
  * WaveNet.__call__, modules.py:155-159 (two 1x1 convolutions) and their backward.
  *   skip (B,Cs,T) f32, W1 (Cs,Cs), b1 (Cs), W2 (Q,Cs), b2 (Q)  ->  y (B,Q,T) f32.
- * mode = VQW_MODE_BF16X3 / VQW_MODE_BF16 / VQW_MODE_FP16; needs Cs % 256 == 0, T >= 128, T % 8 == 0 (other
+ * mode = VQW_MODE_BF16X3 / VQW_MODE_BF16 / VQW_MODE_FP16 / VQW_MODE_FP16X3; needs Cs % 256 == 0, T >= 128, T % 8 == 0 (other
  * shapes and fp32 go through vqw_conv_forward).  `saved` (vqw_head_saved_bytes) keeps the
  * bf16 planes of relu(skip) and of the hidden activation for the backward; NULL = inference.
  * Backward: gy (B,Q,T) -> gskip (B,Cs,T) overwritten; gW1, gb1, gW2, gb2 ACCUMULATED. */
@@ -286,7 +292,7 @@ int vqw_embed_gather_forward(const int32_t* q, const float* W, const float* bias
 int vqw_embed_gather_backward(const int32_t* q, const float* gout, float* gW, float* gb, int B,
                               int T, int Cr, int Q, vqw_stream_t stream);
 /* Same gradient as two K=time tcgen05 GEMMs of the gradient planes against a one-hot plane
- * (mode = VQW_MODE_BF16X3 / VQW_MODE_BF16 / VQW_MODE_FP16; needs Cr % 64 == 0, T >= 128, T % 8 == 0; the
+ * (mode = VQW_MODE_BF16X3 / VQW_MODE_BF16 / VQW_MODE_FP16 / VQW_MODE_FP16X3; needs Cr % 64 == 0, T >= 128, T % 8 == 0; the
  * workspace query returns -1 for unsupported shapes).  gW, gb accumulated. */
 int64_t vqw_embed_gather_backward_tc_workspace(int B, int T, int Cr, int Q);
 int vqw_embed_gather_backward_tc(const int32_t* q, const float* gout, float* gW, float* gb, int B,

@@ -256,7 +256,7 @@ def test_tc_wavenet_with_head_matches_fp32_path_and_oracle():
 
 
 @pytest.mark.parametrize("B,T,Cr,Q", [(2, 256, 512, 256), (1, 136, 128, 100), (3, 384, 64, 300)])
-@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_BF16, L.MODE_FP16])
+@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_BF16, L.MODE_FP16, L.MODE_FP16X3])
 def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
     """Embed backward (modules.py:151-152 differentiated) as one-hot tcgen05 GEMMs against the
     CUDA-core histogram kernel and a float64 restatement."""
@@ -276,7 +276,7 @@ def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
     oh = torch.nn.functional.one_hot(q.long().cpu(), Q).double()          # (B,T,Q)
     ref1 = torch.einsum("bct,btk->ck", g64, oh)
     ref0 = torch.einsum("bct,btk->ck", g64[:, :, 1:], oh[:, :-1])
-    tol = {L.MODE_BF16X3: 1e-5, L.MODE_BF16: 5e-3, L.MODE_FP16: 5e-4}[mode]
+    tol = {L.MODE_BF16X3: 1e-5, L.MODE_BF16: 5e-3, L.MODE_FP16: 5e-4, L.MODE_FP16X3: 1e-5}[mode]
     assert rel_err(out[mode][0][:, :, 1, 0], ref1) < tol
     assert rel_err(out[mode][0][:, :, 0, 0], ref0) < tol
     assert rel_err(out[L.MODE_FP32][0][:, :, 1, 0], ref1) < 1e-5
@@ -284,7 +284,7 @@ def test_tc_embed_weight_gradient_matches_histogram_kernel(B, T, Cr, Q, mode):
     assert rel_err(out[mode][0], out[L.MODE_FP32][0]) < tol
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("mode", ["bf16x3", "fp16x3", "fp16"])
 def test_full_depth_step_matches_oracle(mode):
     """The bench configuration at full depth and length (BASELINE.json configs[1]: 20 blocks,
     512/512/256, T=7680; two items instead of 16) against the oracle's forward + three-loss
@@ -314,7 +314,7 @@ def test_full_depth_step_matches_oracle(mode):
 
     e_y, e_y2 = rel_err(model.y, inter["y"]), l2_err(model.y, inter["y"])
     print(f"{mode} full depth: logits max-norm rel err {e_y:.2e}, L2 rel err {e_y2:.2e}")
-    assert e_y < (1e-4 if mode == "bf16x3" else 3e-3)
+    assert e_y < (1e-4 if mode in ("bf16x3", "fp16x3") else 3e-3)
     for got, want in zip((l1, l2, l3), losses):
         assert abs(float(got.detach()) - float(want)) <= TOL * abs(float(want))
     got = grads_by_name(model)
@@ -335,7 +335,7 @@ def test_full_depth_step_matches_oracle(mode):
         worst_cos = min(worst_cos, cos)
     print(f"{mode} full depth: gradients worst cosine {worst_cos:.6f}, worst L2 rel err {worst2:.2e} "
           f"({worst_name})")
-    if mode == "bf16x3":
+    if mode in ("bf16x3", "fp16x3"):
         assert worst_cos > 0.9999 and worst2 < 1e-2, (worst_name, worst_cos, worst2)
     else:
         assert worst_cos > 0.999 and worst2 < 5e-2, (worst_name, worst_cos, worst2)
@@ -377,9 +377,10 @@ def test_full_size_stack_is_causal_and_batch_independent():
         assert torch.equal(alone[0], base[1])
 
 
+@pytest.mark.parametrize("mode", [L.MODE_BF16X3, L.MODE_FP16X3])
 @pytest.mark.parametrize("use_logistic", [False, True])
 @pytest.mark.parametrize("upstream", [1.0, 0.37])
-def test_tc_fused_head_loss_matches_unfused_path_and_oracle(use_logistic, upstream):
+def test_tc_fused_head_loss_matches_unfused_path_and_oracle(use_logistic, upstream, mode):
     """relu -> proj1 -> relu -> proj2 -> loss with the loss and d loss / d y
     in the epilogue of the proj2 GEMM (the logits never go to HBM) against (a) the same head with
     the stand-alone loss kernels and (b) the oracle's loss on the head's own logits: softmax
@@ -405,12 +406,12 @@ def test_tc_fused_head_loss_matches_unfused_path_and_oracle(use_logistic, upstre
     for fused in (False, True):
         ts = [v.clone().requires_grad_(True) for v in (skip, W1, b1, W2, b2)]
         if fused:
-            assert Fn.head_loss_supported(ts[0], Q, L.MODE_BF16X3, use_logistic)
-            loss, y = Fn.head_loss(*ts, t, L.MODE_BF16X3, use_logistic, 256, -40.0, keep_logits=True)
-            loss2, y2 = Fn.head_loss(*[v.detach() for v in ts], t, L.MODE_BF16X3, use_logistic, 256, -40.0)
+            assert Fn.head_loss_supported(ts[0], Q, mode, use_logistic)
+            loss, y = Fn.head_loss(*ts, t, mode, use_logistic, 256, -40.0, keep_logits=True)
+            loss2, y2 = Fn.head_loss(*[v.detach() for v in ts], t, mode, use_logistic, 256, -40.0)
             assert y2 is None and float(loss2) == float(loss)        # no logits unless asked for
         else:
-            y = Fn.head(*ts, L.MODE_BF16X3)
+            y = Fn.head(*ts, mode)
             loss = V.logistic_loss(y, t, 256, -40.0) if use_logistic else V.softmax_cross_entropy(y, t)
         (loss * upstream).backward()
         out[fused] = [loss.detach(), y.detach()] + [v.grad for v in ts]
