@@ -257,6 +257,63 @@ conv_wgrad_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ 
   if (do_bias && (m0 + tid) < D.M) atomicAdd(gb + m0 + tid, bsum);
 }
 
+// Weight gradient of a convolution with ONE input channel (the embed layer of the mixture-of-
+// logistics decoder reads the raw waveform, modules.py:127-128 with input_dim = 1): gw[m, j] =
+// sum_{b,t} a[b,m,t] * x[b, ti_j(t)] is a reduction, not a GEMM -- CTA = (output channel, slice of
+// the (b,t) axis), coalesced rows of a, the taps from L1/L2, one atomic per tap and CTA.
+constexpr int K1_MAXTAPS = 8;
+__global__ void __launch_bounds__(256)
+conv_wgrad_k1_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ gw,
+                     float* __restrict__ gb) {
+  const int m = blockIdx.x;
+  const int ntaps = D.ntaps > 1 ? D.ntaps : 1;
+  const int64_t n = (int64_t)D.B * D.T;
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t i0 = per * blockIdx.y, i1 = (i0 + per < n) ? i0 + per : n;
+  float acc[K1_MAXTAPS], bsum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < K1_MAXTAPS; ++j) acc[j] = 0.0f;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const int b = (int)(i / D.T), t = (int)(i - (int64_t)b * D.T);
+    const int64_t off = ((int64_t)b * D.M + m) * D.T + t;
+    float a = __ldg(D.a + off);
+    if (D.a_mask) a = (__ldg(D.a_mask + off) > 0.0f) ? a : 0.0f;
+    bsum += a;
+#pragma unroll
+    for (int j = 0; j < K1_MAXTAPS; ++j) {
+      if (j >= ntaps) break;
+      const int num = t * D.mul + D.shift + j * D.tap_dshift;
+      int ti = num;
+      bool ok = num >= 0;
+      if (ok && D.div > 1) { ti = num / D.div; ok = (ti * D.div == num); }
+      if (ok && ti < D.Tin) {
+        const int64_t io = (int64_t)b * D.Tin + ti;
+        float v = __ldg(D.in + io);
+        if (D.relu_in) v = fmaxf(v, 0.0f);
+        if (D.in_mul) v *= __ldg(D.in_mul + io);
+        acc[j] = fmaf(a, v, acc[j]);
+      }
+    }
+  }
+  __shared__ float red[8][K1_MAXTAPS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j <= K1_MAXTAPS; ++j) {
+    float v = (j < K1_MAXTAPS) ? acc[j] : bsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= K1_MAXTAPS) {
+    const int j = threadIdx.x;
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += red[w][j];
+    if (j < ntaps) atomicAdd(gw + (int64_t)j * D.tap_gw + (int64_t)m * D.gm, v);
+    else if (j == K1_MAXTAPS && gb != nullptr) atomicAdd(gb + m, v);
+  }
+}
+
 int launch_conv(const vqw_conv_desc& d, float* out, cudaStream_t stream) {
   VQW_REQUIRE(out != nullptr, "vqw_conv_forward: out is null");
   VQW_REQUIRE(d.B >= 0 && d.M > 0 && d.T >= 0, "vqw_conv_forward: bad sizes B=%d M=%d T=%d", d.B,
@@ -285,6 +342,15 @@ int launch_wgrad(const vqw_wgrad_desc& d, float* gw, float* gb, cudaStream_t str
               "vqw_conv_wgrad: bad sizes");
   if (d.B == 0 || d.T == 0) return 0;
   const int ntaps = d.ntaps > 1 ? d.ntaps : 1;
+  if (d.K == 1 && ntaps <= K1_MAXTAPS && d.M <= 65535) {
+    int parts = ceil_div(148 * 8, d.M);
+    const int64_t n = (int64_t)d.B * d.T;
+    if ((int64_t)parts * 256 > n) parts = (int)((n + 255) / 256);
+    if (parts < 1) parts = 1;
+    conv_wgrad_k1_kernel<<<dim3(d.M, parts), 256, 0, stream>>>(d, gw, gb);
+    VQW_CHECK_LAUNCH("conv_wgrad_k1_kernel");
+    return 0;
+  }
   VQW_REQUIRE(ntaps * ceil_div(d.K, GK) <= 65535, "vqw_conv_wgrad: too many taps / input channels");
   int chunks_per_b = ceil_div(d.T, TC);
   int total = chunks_per_b * d.B;
