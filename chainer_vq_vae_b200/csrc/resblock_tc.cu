@@ -7,9 +7,10 @@
 //
 // Precision.  The reference computes in fp32.  tcgen05 has no fp32 operand type and
 // kind::tf32 truncates fp32 operands (a -1e-3 systematic bias), so operands are SPLIT into two
-// bf16 planes (hi = bf16(v), lo = bf16(v - hi), 16 significant bits) and every product is
-// issued as three MMAs  hi*hi + lo*hi + hi*lo  accumulated in fp32 in TMEM ("bf16x3", error
-// ~2^-16: parity mode).  VQW_MODE_BF16 issues only hi*hi (throughput mode, not parity).
+// 16-bit planes (hi = r(v), lo = r(v - hi): bf16 pairs = 16 significant bits, "bf16x3"; IEEE fp16
+// pairs = 22 bits, "fp16x3") and every product is issued as three MMAs  hi*hi + lo*hi + hi*lo
+// accumulated in fp32 in TMEM (parity modes).  VQW_MODE_BF16 / VQW_MODE_FP16 issue only hi*hi
+// (throughput modes, not parity).
 //
 // Data layout.  Between blocks activations live in a packed (B, T, C) layout, channel
 // contiguous, one bf16 plane for hi and one for lo: the K axis (channels) of both MMA operands

@@ -123,7 +123,7 @@ class WaveNet(nn.Module):
         self.condition_dim = condition_dim
 
     def set_mode(self, mode) -> None:
-        """Arithmetic of the residual stack: 'fp32' | 'bf16x3' | 'bf16' (include/vqw.h)."""
+        """Arithmetic of the residual stack: 'fp32' | 'fp16x3' | 'bf16x3' | 'bf16' | 'fp16' (include/vqw.h)."""
         m = L.MODES[mode] if isinstance(mode, str) else mode
         self.resnet.mode = m
         for blk in self.resnet:
