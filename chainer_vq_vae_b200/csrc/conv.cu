@@ -264,34 +264,48 @@ conv_wgrad_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ 
 constexpr int K1_MAXTAPS = 8;
 __global__ void __launch_bounds__(256)
 conv_wgrad_k1_kernel(const __grid_constant__ vqw_wgrad_desc D, float* __restrict__ gw,
-                     float* __restrict__ gb) {
+                     float* __restrict__ gb, int tparts) {
+  // blockIdx.y = item * tparts + slice of the time axis: no division in the loop, 4 rows of loads
+  // in flight per thread
   const int m = blockIdx.x;
   const int ntaps = D.ntaps > 1 ? D.ntaps : 1;
-  const int64_t n = (int64_t)D.B * D.T;
-  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
-  const int64_t i0 = per * blockIdx.y, i1 = (i0 + per < n) ? i0 + per : n;
+  const int b = blockIdx.y / tparts, tp = blockIdx.y - b * tparts;
+  const int per = (D.T + tparts - 1) / tparts;
+  const int t0 = tp * per, t1 = (t0 + per < D.T) ? t0 + per : D.T;
+  const float* __restrict__ arow = D.a + ((int64_t)b * D.M + m) * D.T;
+  const float* __restrict__ mrow = D.a_mask ? D.a_mask + ((int64_t)b * D.M + m) * D.T : nullptr;
+  const float* __restrict__ xrow = D.in + (int64_t)b * D.Tin;
+  const float* __restrict__ xmul = D.in_mul ? D.in_mul + (int64_t)b * D.Tin : nullptr;
   float acc[K1_MAXTAPS], bsum = 0.0f;
 #pragma unroll
   for (int j = 0; j < K1_MAXTAPS; ++j) acc[j] = 0.0f;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const int b = (int)(i / D.T), t = (int)(i - (int64_t)b * D.T);
-    const int64_t off = ((int64_t)b * D.M + m) * D.T + t;
-    float a = __ldg(D.a + off);
-    if (D.a_mask) a = (__ldg(D.a_mask + off) > 0.0f) ? a : 0.0f;
-    bsum += a;
+  for (int tb = t0 + threadIdx.x; tb < t1; tb += 4 * blockDim.x) {
+    float av[4];
 #pragma unroll
-    for (int j = 0; j < K1_MAXTAPS; ++j) {
-      if (j >= ntaps) break;
-      const int num = t * D.mul + D.shift + j * D.tap_dshift;
-      int ti = num;
-      bool ok = num >= 0;
-      if (ok && D.div > 1) { ti = num / D.div; ok = (ti * D.div == num); }
-      if (ok && ti < D.Tin) {
-        const int64_t io = (int64_t)b * D.Tin + ti;
-        float v = __ldg(D.in + io);
-        if (D.relu_in) v = fmaxf(v, 0.0f);
-        if (D.in_mul) v *= __ldg(D.in_mul + io);
-        acc[j] = fmaf(a, v, acc[j]);
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + u * blockDim.x;
+      av[u] = (t < t1) ? __ldg(arow + t) : 0.0f;
+      if (mrow && t < t1) av[u] = (__ldg(mrow + t) > 0.0f) ? av[u] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + u * blockDim.x;
+      if (t >= t1) break;
+      const float a = av[u];
+      bsum += a;
+#pragma unroll
+      for (int j = 0; j < K1_MAXTAPS; ++j) {
+        if (j >= ntaps) break;
+        const int num = t * D.mul + D.shift + j * D.tap_dshift;
+        int ti = num;
+        bool ok = num >= 0;
+        if (ok && D.div > 1) { ti = num / D.div; ok = (ti * D.div == num); }
+        if (ok && ti < D.Tin) {
+          float v = __ldg(xrow + ti);
+          if (D.relu_in) v = fmaxf(v, 0.0f);
+          if (xmul) v *= __ldg(xmul + ti);
+          acc[j] = fmaf(a, v, acc[j]);
+        }
       }
     }
   }
@@ -343,11 +357,13 @@ int launch_wgrad(const vqw_wgrad_desc& d, float* gw, float* gb, cudaStream_t str
   if (d.B == 0 || d.T == 0) return 0;
   const int ntaps = d.ntaps > 1 ? d.ntaps : 1;
   if (d.K == 1 && ntaps <= K1_MAXTAPS && d.M <= 65535) {
-    int parts = ceil_div(148 * 8, d.M);
-    const int64_t n = (int64_t)d.B * d.T;
-    if ((int64_t)parts * 256 > n) parts = (int)((n + 255) / 256);
-    if (parts < 1) parts = 1;
-    conv_wgrad_k1_kernel<<<dim3(d.M, parts), 256, 0, stream>>>(d, gw, gb);
+    // about eight CTAs per SM; a slice is at least 1024 time steps (4 per thread)
+    int tparts = ceil_div(148 * 8, d.M * d.B);
+    if (tparts > ceil_div(d.T, 1024)) tparts = ceil_div(d.T, 1024);
+    if (tparts < 1) tparts = 1;
+    if ((int64_t)d.B * tparts > 65535) tparts = 65535 / d.B > 0 ? 65535 / d.B : 1;
+    VQW_REQUIRE((int64_t)d.B * tparts <= 65535, "vqw_conv_wgrad: batch too large for the one-channel kernel");
+    conv_wgrad_k1_kernel<<<dim3(d.M, d.B * tparts), 256, 0, stream>>>(d, gw, gb, tparts);
     VQW_CHECK_LAUNCH("conv_wgrad_k1_kernel");
     return 0;
   }
