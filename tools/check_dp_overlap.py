@@ -22,7 +22,7 @@ cfg = dict(bench.CFG)
 cfg["batch"] = 4
 out = {}
 for overlap in (False, True):
-    model = bench.build_model(cfg, dev, "bf16x3")
+    model = bench.build_model(cfg, dev, os.environ.get("VQW_BENCH_MODE", "fp16x3"))
     model.train()
     opt = V.Adam(cfg["lr"] / world).setup(model)
     batch = bench.synthetic_examples(cfg["batch"], cfg["length"], 71 + rank)
