@@ -459,7 +459,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i) * P.T + t, v0);
               __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i + 1) * P.T + t, v1);
             }
-            if (XLO) split_pair_f(v0, v1, rh[i], rl[i], F16);
+            if (XLO) split_pair_sat_f(v0, v1, rh[i], rl[i], F16);
             else rh[i] = pack_pair_f(v0, v1, F16);
           }
           sts128(a0, rh[0], rh[1], rh[2], rh[3]);
@@ -541,7 +541,7 @@ resblock_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                 __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
-            if (XLO) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
+            if (XLO) split_pair_sat_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
             else rh[i >> 1] = pack_pair_f(v2[0], v2[1], F16);
           }
           if (t_ok && P.res_hi != nullptr) {
@@ -1019,7 +1019,7 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
               __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i) * P.T + t, v0);
               __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch0 + 2 * i + 1) * P.T + t, v1);
             }
-            if (XLO) split_pair_f(v0, v1, rh[i], rl[i], F16);
+            if (XLO) split_pair_sat_f(v0, v1, rh[i], rl[i], F16);
             else rh[i] = pack_pair_f(v0, v1, F16);
           }
           sts128(a0, rh[0], rh[1], rh[2], rh[3]);
@@ -1102,7 +1102,7 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                 __stcs(P.res_f32 + ((int64_t)b * P.Cr + ch) * P.T + t, v);
               v2[u] = v;
             }
-            if (XLO) split_pair_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
+            if (XLO) split_pair_sat_f(v2[0], v2[1], rh[i >> 1], rl[i >> 1], F16);
             else rh[i >> 1] = pack_pair_f(v2[0], v2[1], F16);
           }
           if (t_ok && P.res_hi != nullptr) {

@@ -428,9 +428,19 @@ __device__ __forceinline__ void split_pair_f(float v0, float v1, uint32_t& hi, u
   unpack_pair_f(hi, f16, b0, b1);
   lo = pack_pair_f(v0 - b0, v1 - b1, f16);
 }
+// the same for values that are not bounded by construction (the residual stream, packed inputs):
+// fp16 planes saturate at +-65504 instead of producing hi = inf, lo = -inf (a NaN on recombination)
+__device__ __forceinline__ void split_pair_sat_f(float v0, float v1, uint32_t& hi, uint32_t& lo, int f16) {
+  if (f16) {
+    v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
+    v1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
+  }
+  split_pair_f(v0, v1, hi, lo, f16);
+}
 // one value -> raw 16-bit patterns of its hi and lo parts
 __device__ __forceinline__ void split_16(float v, int f16, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   if (f16) {
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);          // saturate instead of inf / NaN
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     hi = __ushort_as_bfloat16(__half_as_ushort(h));

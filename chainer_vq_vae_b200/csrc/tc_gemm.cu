@@ -226,7 +226,9 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
 
   if (warp == GW_TMA) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && total_slabs > 0) {
+    // whole warp in uniform control flow, one elected lane issues (see tc_time_persistent_kernel)
+    if (total_slabs > 0) {
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
       if (WG) {
@@ -244,21 +246,21 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             const uint32_t fb = PAIR ? mapa_u32(full0 + 8 * stage, 0) : full0 + 8 * stage;
             const uint32_t sa = base + stage * STG;
             const bool blo = P.x3 && !P.b_exact, alo = P.x3 && !P.a_exact;
-            if (rank == 0)
+            if (rank == 0 && el)
               mbar_expect_tx(full0 + 8 * stage,
                              (PAIR ? 2 : 1) * ((alo ? 2 : 1) * A_PLANE + (blo ? 2 : 1) * BPL));
             const int ta = tk + i * BK, tb = ta + jb.shift;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              ld3(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
-              if (alo) ld3(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
+              if (el) ld3(sa + h * 4096, ma, fb, jb.m0 + 64 * h, ta, bb);
+              if (alo && el) ld3(sa + A_PLANE + h * 4096, ma + 1, fb, jb.m0 + 64 * h, ta, bb);
             }
             // the B tile is 256 input channels; a CTA of a pair stages its 128-channel half
             const int nb0 = jb.n0 + (PAIR ? (int)rank * (TN / 2) : 0);
 #pragma unroll
             for (int h = 0; h < BROWS / 64; ++h) {
-              ld3(sa + 2 * A_PLANE + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
-              if (blo) ld3(sa + 2 * A_PLANE + BPL + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
+              if (el) ld3(sa + 2 * A_PLANE + h * 4096, mb, fb, nb0 + 64 * h, tb, bb);
+              if (blo && el) ld3(sa + 2 * A_PLANE + BPL + h * 4096, mb + 1, fb, nb0 + 64 * h, tb, bb);
             }
             if (++stage == NST) { stage = 0; ph ^= 1; }
           }
@@ -275,14 +277,14 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             mbar_wait(empty0 + 8 * stage, ph ^ 1);
             const uint32_t fb = PAIR ? mapa_u32(full0 + 8 * stage, 0) : full0 + 8 * stage;
             const uint32_t sa = base + stage * STG;
-            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, (PAIR ? 2 : 1) * nplanes * (A_PLANE + BPL));
+            if (rank == 0 && el) mbar_expect_tx(full0 + 8 * stage, (PAIR ? 2 : 1) * nplanes * (A_PLANE + BPL));
             // this CTA's half (pair) of the 256 weight rows of the N tile
             const int brow = sg.b_row0 + TN * by + (PAIR ? (int)rank * (TN / 2) : 0);
-            ld3(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-            ld3(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
+            if (el) ld3(sa, ma, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+            if (el) ld3(sa + 2 * A_PLANE, mb, fb, sg.b_c0 + i * BK, brow, 0);
             if (P.x3) {
-              ld3(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
-              ld3(sa + 2 * A_PLANE + BPL, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
+              if (el) ld3(sa + A_PLANE, ma + 1, fb, sg.a_c0 + i * BK, t0 + sg.a_shift, bb);
+              if (el) ld3(sa + 2 * A_PLANE + BPL, mb + 1, fb, sg.b_c0 + i * BK, brow, 0);
             }
             if (++stage == NST) { stage = 0; ph ^= 1; }
           }
@@ -291,20 +293,22 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
     }
   } else if (warp == GW_MMA) {
     // =============================== MMA issuer =================================
-    if (lane == 0 && total_slabs > 0 && rank == 0) {   // in a pair: ONE thread issues for both SMs
+    if (total_slabs > 0 && rank == 0) {   // in a pair: ONE (elected) thread issues for both SMs
+      const bool el = elect_one_sync();
       int stage = 0;
       uint32_t ph = 0;
       // M = 256 over the pair: the M field of the instruction descriptor (bits [24,29)) is M >> 4
       const uint32_t ID = idesc_for(WG ? IDESC_MN : IDESC, P.f16) +
                           (PAIR ? ((uint32_t)(TM >> 4) << 24) : 0u);
       auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+        if (!el) return;
         if (PAIR) mma2_ss(tmem_base, a, b, ID, acc);
         else mma_ss(tmem_base, a, b, ID, acc);
       };
       for (int i = 0; i < total_slabs; ++i) {
         mbar_wait(full0 + 8 * stage, ph);
         tc_fence_after();
-        if (dbg && i == 0) dbg[2] = gtime_ns();
+        if (el && dbg && i == 0) dbg[2] = gtime_ns();
         const uint32_t sa = base + stage * STG;
 #pragma unroll
         for (int ks = 0; ks < BK / UK; ++ks) {
@@ -326,13 +330,17 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, const __grid_constant__ GemmPa
             if (!(WG && P.b_exact)) mma(a_hi, b_lo, 1u);
           }
         }
-        if (PAIR) tc_commit2(empty0 + 8 * stage);
-        else tc_commit(empty0 + 8 * stage);
+        if (el) {
+          if (PAIR) tc_commit2(empty0 + 8 * stage);
+          else tc_commit(empty0 + 8 * stage);
+        }
         if (++stage == NST) { stage = 0; ph ^= 1; }
       }
-      if (PAIR) tc_commit2(acc_full);
-      else tc_commit(acc_full);
-      if (dbg) dbg[3] = gtime_ns();
+      if (el) {
+        if (PAIR) tc_commit2(acc_full);
+        else tc_commit(acc_full);
+        if (dbg) dbg[3] = gtime_ns();
+      }
     }
   } else if (total_slabs > 0) {
     // =============================== epilogue (warps 0-7) =======================

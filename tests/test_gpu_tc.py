@@ -430,3 +430,24 @@ def test_tc_fused_head_loss_matches_unfused_path_and_oracle(use_logistic, upstre
         want = float(-(picked * valid).sum() / valid.sum())
         tol = 1e-5
     assert abs(float(out[True][0]) - want) <= tol * abs(want), (float(out[True][0]), want)
+
+
+def test_fp16x3_planes_saturate_instead_of_nan():
+    """fp16 planes have a narrow range: a residual stream beyond +-65504 must saturate (finite,
+    wrong) rather than turn into hi = inf, lo = -inf = NaN on recombination.  bf16x3 has fp32's
+    range and stays exact to its usual tolerance on the same input."""
+    dil = [1, 2, 4]
+    cfg, p, x, c = _stack_case(dil, 1, 256)
+    w = [p[f"resnet/{i}/{k}"].to(DEV) for i in range(len(dil)) for k in ORDER]
+    big = (x * 3.0e5).to(DEV)                       # |x| up to ~1.2e6
+    with torch.no_grad():
+        s16, r16 = V.residual_stack(big, c.to(DEV), dil, cfg.filter_size, w, L.MODE_FP16X3,
+                                    keep_last_residual=True)
+        sb, rb = V.residual_stack(big, c.to(DEV), dil, cfg.filter_size, w, L.MODE_BF16X3,
+                                  keep_last_residual=True)
+    assert bool(torch.isfinite(s16).all()) and bool(torch.isfinite(r16).all())
+    assert float(r16.abs().max()) <= 65504.0 * 1.01 + 64.0
+    # bf16 planes have fp32's range: the residual stream passes through at its magnitude
+    assert bool(torch.isfinite(sb).all()) and bool(torch.isfinite(rb).all())
+    _, coll = _oracle_stack(cfg, p, x * 3.0e5, c, dil)
+    assert rel_err(rb, coll[-1]) < 1e-4
