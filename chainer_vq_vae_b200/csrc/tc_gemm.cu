@@ -1114,13 +1114,8 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
         const uint32_t acc = tmem_base + 256 * buf;
         if (el && P.dbg && cid == 0 && it < 8) P.dbg[4 * it] = gtime_ns();
         for (int i = 0; i < total_slabs; ++i) {
-          const bool probe = el && P.dbg && cid == 0 && it == 1 && (i == 100 || i == 101);
-          long long* pd = P.dbg + 32 + 5 * (i - 100);
-          if (probe) pd[0] = clock64();
           if (!(WG && P.dbg_mode >= 3) && !ready) mbar_wait(full0 + 8 * stage, ph);
-          if (probe) pd[1] = clock64();
           if (!(WG && P.dbg_mode >= 3)) tc_fence_after();
-          if (probe) pd[2] = clock64();
           // probe the NEXT stage now: the answer arrives while this stage's MMAs are being issued
           const int nstage = (stage + 1 == nst) ? 0 : stage + 1;
           const uint32_t nph = (stage + 1 == nst) ? ph ^ 1 : ph;
@@ -1136,7 +1131,6 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
               const uint32_t a_hi = desc_lo_sw128_mn(sa + ks * 2048);
               const uint32_t b_hi = desc_lo_sw128_mn(sa + wg_boff + ks * 2048);
               if (el) mma2_ss_w<DESC_HI_SW128_MN>(acc, a_hi, b_hi, ID, (i | kq) ? 1u : 0u);
-              if (probe && i == 100 && kq < 2) P.dbg[44 + kq] = clock64();
               if (wg_alo && el)
                 mma2_ss_w<DESC_HI_SW128_MN>(acc, desc_lo_sw128_mn(sa + A_PLANE + ks * 2048), b_hi, ID, 1u);
               if (wg_blo && el)
@@ -1153,9 +1147,7 @@ tc_time_persistent_kernel(const __grid_constant__ Maps maps, const __grid_consta
               }
             }
           }
-          if (probe) pd[3] = clock64();
           if (!(WG && P.dbg_mode >= 3) && el) tc_commit2(empty0 + 8 * stage);
-          if (probe) pd[4] = clock64();
           stage = nstage; ph = nph; ready = nready;
         }
         if (el) tc_commit2(acc_full0 + 8 * buf);
@@ -1551,15 +1543,6 @@ static int launch_persistent(const Maps& maps, const GemmParams& P, dim3 grid, c
       if (h[4 * i])
         fprintf(stderr, "  %d | %7lld %7lld | %7lld %7lld\n", i, h[4 * i] - h[0], h[4 * i + 1] - h[0],
                 h[4 * i + 2] - h[0], h[4 * i + 3] - h[0]);
-    for (int k = 0; k < 2; ++k)
-      if (h[32 + 5 * k])
-        fprintf(stderr, "  slab %d of tile 1 (cycles): wait %lld, fence %lld, mma issue %lld, commit %lld; "
-                        "to next slab %lld\n", 100 + k, h[33 + 5 * k] - h[32 + 5 * k],
-                h[34 + 5 * k] - h[33 + 5 * k], h[35 + 5 * k] - h[34 + 5 * k], h[36 + 5 * k] - h[35 + 5 * k],
-                k == 0 ? h[37] - h[32] : 0LL);
-    if (h[44])
-      fprintf(stderr, "  slab 100: first MMA issued after %lld cycles, second after %lld more\n",
-              h[44] - h[34], h[45] - h[44]);
   }
   return 0;
 }

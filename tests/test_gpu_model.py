@@ -166,7 +166,13 @@ def test_cuda_graph_updater_matches_eager_updater():
     for graph in (False, True):
         model = build_model(cfg, params, ema_decay=0.9999)
         model.train()
-        opt = V.Adam(1e-3).setup(model)
+        # eps = 1e-4 instead of 1e-8: Adam normalises every element's step to ~lr whatever the size
+        # of its gradient, so with the default eps the last-bit run-to-run differences of the
+        # atomically accumulated weight gradients (conv_wgrad_kernel's split-K) flip the direction
+        # of elements whose gradient is at noise level -- in eager-vs-eager just as in graph-vs-
+        # eager.  The larger eps makes the comparison well conditioned; the code path (device-side
+        # learning rate, captured Adam / EMA kernels) is the same.
+        opt = V.Adam(1e-3, eps=1e-4).setup(model)
         upd = V.VQVAE_StandardUpdater(It(), opt, device="cuda", use_cuda_graph=graph, graph_warmup=3)
         losses = [[float(v) for v in upd.update()] for _ in range(len(batches))]
         assert (upd._graph is not None) == graph
@@ -174,14 +180,9 @@ def test_cuda_graph_updater_matches_eager_updater():
         out[graph] = (losses, {n: p.detach().clone() for n, p in model.named_parameters()})
     for a, b in zip(out[True][0], out[False][0]):
         assert np.allclose(a, b, rtol=2e-4, atol=1e-7), (a, b)
-    # Parameters after 7 Adam steps.  Adam normalises every element's step to ~lr whatever the size
-    # of its gradient, so the last-bit run-to-run differences of the atomically accumulated weight
-    # gradients (conv_wgrad_kernel's split-K) can flip the direction of the few elements whose
-    # gradient is at noise level: all but a vanishing fraction of elements must agree to 2e-4, and
-    # no element may differ by more than the 7 * 2 * lr such a flip can cause.
+    # parameters after 7 Adam steps
     for n, p in out[False][1].items():
         a, b = out[True][1][n].double(), p.double()
         scale = float(b.abs().max()) or 1.0
         diff = (a - b).abs()
-        assert float((diff > 2e-4 * scale).double().mean()) < 2e-3, n
-        assert float(diff.max()) <= 7 * 2 * 1e-3 + 2e-4 * scale, n
+        assert float(diff.max()) <= 2e-4 * scale + 2e-5, (n, float(diff.max()), scale)

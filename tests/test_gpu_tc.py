@@ -341,7 +341,8 @@ def test_full_depth_step_matches_oracle(mode):
         assert worst_cos > 0.999 and worst2 < 5e-2, (worst_name, worst_cos, worst2)
 
 
-def test_full_size_stack_is_causal_and_batch_independent():
+@pytest.mark.parametrize("mode", [L.MODE_FP16X3, L.MODE_BF16X3])
+def test_full_size_stack_is_causal_and_batch_independent(mode):
     """Size-independent properties at the BASELINE configs[1] size (20 blocks, dilations 1..512
     twice, 512/512/256, T = 7680): (a) causality -- perturbing x and the condition from t0 on
     leaves every output before t0 BIT-identical (modules.py:16,41: the pad/slice makes the conv
@@ -354,12 +355,12 @@ def test_full_size_stack_is_causal_and_batch_independent():
     weights = [p[f"resnet/{i}/{n}"].to(DEV) for i in range(len(dil)) for n in ORDER]
     xg, cg = x.to(DEV), c.to(DEV)
     with torch.no_grad():
-        base = V.residual_stack(xg, cg, dil, fs, weights, L.MODE_BF16X3)
+        base = V.residual_stack(xg, cg, dil, fs, weights, mode)
         t0 = 5000
         x2, c2 = xg.clone(), cg.clone()
         x2[:, :, t0:] += 1.0
         c2[:, :, t0:] -= 0.5
-        pert = V.residual_stack(x2, c2, dil, fs, weights, L.MODE_BF16X3)
+        pert = V.residual_stack(x2, c2, dil, fs, weights, mode)
         assert torch.equal(base[:, :, :t0], pert[:, :, :t0])
         assert not torch.equal(base[:, :, t0:], pert[:, :, t0:])
         # receptive field: an impulse at t1 reaches exactly rf - 1 later steps
@@ -367,13 +368,13 @@ def test_full_size_stack_is_causal_and_batch_independent():
         t1 = 100
         x3 = xg.clone()
         x3[0, :, t1] += 1.0
-        imp = V.residual_stack(x3, cg, dil, fs, weights, L.MODE_BF16X3)
+        imp = V.residual_stack(x3, cg, dil, fs, weights, mode)
         changed = ((imp[0] - base[0]).abs().amax(dim=(0, 2)) > 0).nonzero().flatten()
         assert int(changed.min()) == t1 and int(changed.max()) == t1 + rf - 1
         assert torch.equal(imp[1], base[1])                       # the other item is untouched
         # batch independence: item 1 alone gives the same bits as item 1 inside the batch
         alone = V.residual_stack(xg[1:2].contiguous(), cg[1:2].contiguous(), dil, fs, weights,
-                                 L.MODE_BF16X3)
+                                 mode)
         assert torch.equal(alone[0], base[1])
 
 
