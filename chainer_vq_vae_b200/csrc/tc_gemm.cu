@@ -2066,8 +2066,10 @@ int resnet_backward_tc(const vqw_resnet_desc& d, const float* g_skip, const floa
         // launch was bound by 18 M scattered atomics, not by its MMAs; VQW_WGRAD_ATOMICS=1 restores it)
         static const bool use_atomics = getenv("VQW_WGRAD_ATOMICS") && getenv("VQW_WGRAD_ATOMICS")[0] == '1';
         const int chunks = wgrad_chunks(T);
-        static const bool sub_on = !(getenv("VQW_WGRAD_SUB") && getenv("VQW_WGRAD_SUB")[0] == '1');
-        P.wg_sub = (x3 && P.a_exact && P.b_exact && sub_on) ? 2 : 1;   // hi planes only: 2 slabs per stage
+        // hi planes only: several 32-step slabs per ring stage (VQW_WGRAD_SUB = 1..4, default 2)
+        static const int sub_env = getenv("VQW_WGRAD_SUB") ? atoi(getenv("VQW_WGRAD_SUB")) : 0;
+        const int sub = (sub_env >= 1 && sub_env <= 4) ? sub_env : 2;
+        P.wg_sub = (x3 && P.a_exact && P.b_exact) ? sub : 1;
         P.chunks_per_b = chunks;
         P.slabs_per_item = ceil_div(ceil_div(ceil_div(T, BK), chunks), P.wg_sub);
         float* partial = reinterpret_cast<float*>(ws + L.wg_partial);
