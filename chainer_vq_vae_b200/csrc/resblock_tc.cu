@@ -38,6 +38,8 @@ constexpr int STAGES = 4;
 constexpr int FWD_EPI_WARPS = 16;                       // 4 warps per TMEM lane quadrant
 constexpr int FWD_THREADS = (FWD_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
 constexpr int W_TMA = FWD_EPI_WARPS, W_MMA = FWD_EPI_WARPS + 1;
+constexpr int W_ST = FWD_EPI_WARPS + 2;                 // pair kernel: staging-tile store / addend warp
+constexpr int PAIR_THREADS = FWD_THREADS + 32;
 constexpr int CD = 512, CH = 256, HALF = 128;             // dilated channels handled by this kernel
 
 struct Params {
@@ -596,7 +598,7 @@ constexpr uint32_t IDESC_PON = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(
                                ((uint32_t)((2 * TM) >> 4) << 24);
 
 template <int X3, int F16>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
                    const __grid_constant__ CUtensorMap map_x_lo,
                    const __grid_constant__ CUtensorMap map_c_hi,
@@ -623,7 +625,8 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + PST);
   const uint32_t hfull0 = smem_u32(bars + 2 * PST), zready0 = hfull0 + 16;
   const uint32_t ofull0 = hfull0 + 32, oempty0 = hfull0 + 48, afull0 = hfull0 + 64;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PST + 10);
+  const uint32_t sready0 = hfull0 + 80, gready0 = hfull0 + 96;   // staging tiles written (-> store warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PST + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();   // 0 = leader of the pair (blockIdx.x even)
@@ -656,7 +659,9 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       mbar_init(ofull0 + 8 * g, 1);
       mbar_init(oempty0 + 8 * g, 2 * FWD_EPI_WARPS);
       mbar_init(afull0 + 8 * g, 1);
+      mbar_init(sready0 + 8 * g, FWD_EPI_WARPS);       // one elected lane per epilogue warp (this CTA)
     }
+    mbar_init(gready0, FWD_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
@@ -677,6 +682,23 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (rec_cta && threadIdx.x == 0) P.dbg[41] = clock64();
+  // tile h (0 = channels [0,64), 1 = [64,128)) of plane pl (0 = hi, 1 = lo) of staging buffer bf
+  // buffer 0 = the activation areas of the four ring stages (free in the output phase),
+  // buffer 1 = the dedicated 64 KB behind the ring
+  auto tile_addr = [&](int bf, int pl, int h) -> uint32_t {
+    return bf ? base + (uint32_t)(PST * PSTAGE) + (uint32_t)(2 * pl + h) * REGION_BYTES
+              : base + (uint32_t)(2 * pl + h) * PSTAGE;
+  };
+  // TMA-load the addend x[t0 .. t0+127][128 oc .. +127] (hi, lo) of residual chunk oc
+  auto issue_addend = [&](int bf, int oc) {
+    const uint32_t bar = afull0 + 8 * bf;
+    mbar_expect_tx(bar, ((X3 | F16) ? 4 : 2) * REGION_BYTES);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      tma_load_3d(tile_addr(bf, 0, h), &map_xa_hi, bar, oc * ON + 64 * h, t0, b);
+      if (X3 | F16) tma_load_3d(tile_addr(bf, 1, h), &map_xa_lo, bar, oc * ON + 64 * h, t0, b);
+    }
+  };
 
   if (warp == W_TMA) {
     // =============================== TMA producer ===============================
@@ -829,6 +851,57 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         if (rec && j < 6) P.dbg[4 + 2 * j + 1] = clock64();
       }
     }
+  } else if (warp == W_ST) {
+    // =============================== store warp =================================
+    // Everything that moves staging tiles: the TMA stores of finished tiles, the wait until a
+    // store has read its tile, and the TMA load of the next addend into the freed buffer.  With
+    // the epilogue's own leader thread doing this, every residual chunk waited ~3 k cycles for
+    // `cp.async.bulk.wait_group.read` before 512 threads could start (timeline: the gap between
+    // the end of a chunk's MMAs and the start of its epilogue).
+    if (P.stage_res || P.stage_gate) {
+      const bool el = elect_one_sync();
+      if (P.stage_gate) {
+        mbar_wait(gready0, 0);                 // sigma / z tiles of the second gate phase are written
+        if (el) {
+#pragma unroll
+          for (int st = 0; st < 4; ++st)
+            tma_store_3d(&map_sig, tile_addr(0, st >> 1, st & 1), HALF + 32 * st, t0, b);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_store_3d(&map_z_hi, tile_addr(1, 0, h), HALF + 64 * h, t0, b);
+            if (X3) tma_store_3d(&map_z_lo, tile_addr(1, 1, h), HALF + 64 * h, t0, b);
+          }
+          tma_store_commit();
+        }
+      } else {
+        mbar_wait(hfull0 + 8, 0);              // every MMA of the first contraction is done: the
+        tc_fence_after();                      // activation areas of the ring are free
+      }
+      if (P.stage_res) {
+        if (el) {
+          if (P.stage_gate) tma_store_wait_read();
+          // the addends of the first two residual chunks land under the MMAs of chunk 0
+          for (int j = 0; j < 2 && j < n_res; ++j) issue_addend(j, j);
+        }
+        for (int j = 0; j < n_res; ++j) {      // stage_res implies write_residual: chunk j = rows 128 j..
+          const int buf = j & 1;
+          mbar_wait(sready0 + 8 * buf, (j >> 1) & 1);
+          if (el) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_store_3d(&map_r_hi, tile_addr(buf, 0, h), j * ON + 64 * h, t0, b);
+              if (X3 | F16) tma_store_3d(&map_r_lo, tile_addr(buf, 1, h), j * ON + 64 * h, t0, b);
+            }
+            tma_store_commit();
+            if (j + 2 < n_res) {               // the buffer's next user: chunk j + 2
+              tma_store_wait_read();
+              issue_addend(buf, j + 2);
+            }
+          }
+        }
+      }
+      if (el) tma_store_wait_all();            // the tiles must outlive their stores
+    }
   } else {
     // =============================== epilogue (warps 0-15) ======================
     // warp e: TMEM lane quadrant e%4 (hardware rule: a warp reaches lanes 32*(warp%4)..+31),
@@ -842,25 +915,7 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool rec = rec_cta && threadIdx.x == 0;
     const bool save_gates = P.gate_sig != nullptr && t_ok;
-    const bool leader = threadIdx.x == 0;
-    // tile h (0 = channels [0,64), 1 = [64,128)) of plane pl (0 = hi, 1 = lo) of staging buffer bf
-    // buffer 0 = the activation areas of the four ring stages (free in the output phase),
-    // buffer 1 = the dedicated 64 KB behind the ring
-    auto tile_addr = [&](int bf, int pl, int h) -> uint32_t {
-      return bf ? base + (uint32_t)(PST * PSTAGE) + (uint32_t)(2 * pl + h) * REGION_BYTES
-                : base + (uint32_t)(2 * pl + h) * PSTAGE;
-    };
     const uint32_t zready_l = mapa_u32(zready0, 0), oempty_l = mapa_u32(oempty0, 0);   // the leader's
-    // TMA-load the addend x[t0 .. t0+127][128 oc .. +127] (hi, lo) of residual chunk oc
-    auto issue_addend = [&](int bf, int oc) {
-      const uint32_t bar = afull0 + 8 * bf;
-      mbar_expect_tx(bar, (XLO ? 4 : 2) * REGION_BYTES);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tma_load_3d(tile_addr(bf, 0, h), &map_xa_hi, bar, oc * ON + 64 * h, t0, b);
-        if (XLO) tma_load_3d(tile_addr(bf, 1, h), &map_xa_lo, bar, oc * ON + 64 * h, t0, b);
-      }
-    };
     // ---- gate phases: z = tanh(h_t) * sigmoid(h_s), written over the tanh columns ----
     for (int gp = 0; gp < 2; ++gp) {
       mbar_wait(hfull0 + 8 * gp, 0);
@@ -871,11 +926,6 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       // buffer 1) and leave as TMA stores -- 128 KB of per-thread 32-byte stores were the whole
       // exposed cost of this phase
       const bool stage_gate = gp == 1 && P.stage_gate;
-      if (gp == 1 && leader && P.stage_res && !stage_gate) {
-        // every MMA of the first contraction is done: the activation areas and tails of the ring
-        // are free from here on.  The addends of the first two residual chunks land during E_b.
-        for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
-      }
       const uint32_t rswg = (uint32_t)(row & 7);
       const uint32_t accb = lane_base + 256 * gp;
 #pragma unroll 1
@@ -949,24 +999,8 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       if (lane == 0) mbar_arrive_cluster(zready_l + 8 * gp);
       if (stage_gate) {
         fence_async_smem();                      // tile writes -> visible to the TMA stores
-        asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
-        if (leader) {
-#pragma unroll
-          for (int st = 0; st < 4; ++st)
-            tma_store_3d(&map_sig, tile_addr(0, st >> 1, st & 1), HALF + 32 * st, t0, b);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_store_3d(&map_z_hi, tile_addr(1, 0, h), HALF + 64 * h, t0, b);
-            if (X3) tma_store_3d(&map_z_lo, tile_addr(1, 1, h), HALF + 64 * h, t0, b);
-          }
-          tma_store_commit();
-          if (P.stage_res) {
-            // the addends of the first two residual chunks take the buffers over once the stores
-            // have read them; they land under the MMAs of chunk 0
-            tma_store_wait_read();
-            for (int j = 0; j < 2 && o_begin + j < n_res; ++j) issue_addend(j, o_begin + j);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gready0);     // the store warp takes it from here
       }
       if (rec) P.dbg[16 + 2 * gp + 1] = clock64();
     }
@@ -983,12 +1017,6 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       const uint32_t accb = lane_base + (buf ? OACC1 : OACC0);
       if (is_res && P.stage_res) {
         // ---------- staged residual chunk: addend and result live in shared-memory tiles ----------
-        if (leader && j >= 1 && oc + 1 < n_res) {
-          // buffer (j+1)&1 was the source of chunk j-1's stores: wait until they have read it,
-          // then fetch the addend of chunk j+1 into it
-          tma_store_wait_read();
-          issue_addend((j + 1) & 1, oc + 1);
-        }
         mbar_wait(afull0 + 8 * buf, use & 1);
         mbar_wait(ofull0 + 8 * buf, use & 1);
         tc_fence_after();
@@ -1047,15 +1075,8 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(oempty_l + 8 * buf);   // the accumulator is drained
         fence_async_smem();                      // my tile writes -> visible to the TMA store
-        asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
-        if (leader) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_store_3d(&map_r_hi, tile_addr(buf, 0, h), oc * ON + 64 * h, t0, b);
-            if (XLO) tma_store_3d(&map_r_lo, tile_addr(buf, 1, h), oc * ON + 64 * h, t0, b);
-          }
-          tma_store_commit();
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sready0 + 8 * buf);   // the store warp stores the tile
         if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
         continue;
       }
@@ -1137,7 +1158,6 @@ resblock_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi,
       if (lane == 0) mbar_arrive_cluster(oempty_l + 8 * buf);
       if (rec && j < 6) P.dbg[20 + 2 * j + 1] = clock64();
     }
-    if (leader && (P.stage_res || P.stage_gate)) tma_store_wait_all();   // the tiles must outlive their stores
   }
 
   tc_fence_before();
@@ -1383,7 +1403,7 @@ int make_map_mn(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t pitch, uin
 
 size_t smem_bytes_pair(int Cr, int Cs) {
   return 1024 + (size_t)PST * PSTAGE + 4 * REGION_BYTES + sizeof(float) * (CD + Cr + Cs) +
-         8 * (2 * PST + 10) + 16;
+         8 * (2 * PST + 13) + 16;
 }
 size_t smem_bytes(int Cr, int Cs) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(float) * (CD + Cr + Cs) + 8 * NBAR + 16;
@@ -1606,7 +1626,7 @@ int resnet_forward_tc(const vqw_resnet_desc& d, const float* x, const float* con
       // clusters of two CTAs = two consecutive time tiles (an odd tile count gets one all-padding tile)
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * ceil_div(ceil_div(d.T, TM), 2), d.B);
-      cfg.blockDim = dim3(FWD_THREADS);
+      cfg.blockDim = dim3(PAIR_THREADS);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];

@@ -406,8 +406,11 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 // exponent range is handled by power-of-two gradient scaling in the backward (tc_gemm.cu).
 __device__ __forceinline__ uint32_t pack_pair_f(float v0, float v1, int f16) {
   if (f16) {
-    const __half2 h = __floats2half2_rn(v0, v1);
-    return *reinterpret_cast<const uint32_t*>(&h);
+    // one F2FP.SATFINITE: values beyond +-65504 saturate instead of becoming inf (and then, in a
+    // hi/lo split, hi = inf, lo = -inf = NaN on recombination)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v1), "f"(v0));
+    return r;
   }
   const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -431,11 +434,7 @@ __device__ __forceinline__ void split_pair_f(float v0, float v1, uint32_t& hi, u
 // the same for values that are not bounded by construction (the residual stream, packed inputs):
 // fp16 planes saturate at +-65504 instead of producing hi = inf, lo = -inf (a NaN on recombination)
 __device__ __forceinline__ void split_pair_sat_f(float v0, float v1, uint32_t& hi, uint32_t& lo, int f16) {
-  if (f16) {
-    v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
-    v1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
-  }
-  split_pair_f(v0, v1, hi, lo, f16);
+  split_pair_f(v0, v1, hi, lo, f16);      // pack_pair_f saturates by itself
 }
 // one value -> raw 16-bit patterns of its hi and lo parts
 __device__ __forceinline__ void split_16(float v, int f16, __nv_bfloat16& hi, __nv_bfloat16& lo) {
