@@ -436,9 +436,36 @@ generate_kernel(const GenParams P) {
         const uint32_t want = phase_tag(t, l - 1);
         const uint2* xt = P.xtag + ((l - 1) & 1) * P.Cr;
         const uint2* zt = P.ztag + ((l - 1) & 1) * Ch;
+        // all of this thread's words are requested before the first one is looked at: one L2 round
+        // trip for the lot instead of one per word (only words whose tag is still old are re-polled)
+        constexpr int PQ = 6;
+        const uint2* pp[PQ];
+        float* dst[PQ];
+        int np = 0;
         if (has_t1)
-          for (int c = tid; c < P.Cr; c += GEN_THREADS) vx[c * P.fs + P.fs - 1] = ld_tagged(xt + c, want);
-        for (int i = tid; i < Ch; i += GEN_THREADS) zs[i] = ld_tagged(zt + i, want);
+          for (int c = tid; c < P.Cr && np < PQ - 2; c += GEN_THREADS) {
+            pp[np] = xt + c;
+            dst[np++] = vx + c * P.fs + P.fs - 1;
+          }
+        const int nx = np;
+        for (int i = tid; i < Ch && np < PQ; i += GEN_THREADS) {
+          pp[np] = zt + i;
+          dst[np++] = zs + i;
+        }
+        uint32_t pv[PQ], pg[PQ];
+#pragma unroll
+        for (int k = 0; k < PQ; ++k)
+          if (k < np)
+            asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(pv[k]), "=r"(pg[k]) : "l"(pp[k]) : "memory");
+#pragma unroll
+        for (int k = 0; k < PQ; ++k)
+          if (k < np) *dst[k] = (pg[k] == want) ? __uint_as_float(pv[k]) : ld_tagged(pp[k], want);
+        // vectors longer than the batch (Cr > 4 * 256 or Ch > 2 * 256): the rest one by one
+        if (has_t1)
+          for (int c = tid + nx * GEN_THREADS; c < P.Cr; c += GEN_THREADS)
+            vx[c * P.fs + P.fs - 1] = ld_tagged(xt + c, want);
+        for (int i = tid + (np - nx) * GEN_THREADS; i < Ch; i += GEN_THREADS) zs[i] = ld_tagged(zt + i, want);
       } else {
         if (has_t1) {
           // l = 0: plain x_0 (just pushed into ring_0); l >= 1: x_{l-1} + br_{l-1} (xbuf)
