@@ -378,6 +378,7 @@ generate_kernel(const GenParams P) {
 
   for (int step = 0; step < P.n_steps; ++step) {
     const int t = P.t_start + step;
+    const long long step_start = P.dbg ? clock64() : 0;
     // ---- embed: x_0 = b + W[:, s(t-2), 0] + W[:, s(t-1), 1]   (modules.py:246-247; zeros at start)
     if (tid < P.n_blocks) s_slot[tid] = t % sblk[tid].qlen;
     __syncthreads();
@@ -417,6 +418,7 @@ generate_kernel(const GenParams P) {
     // phase l = 0..n-1 computes z_l (T1) and, for l >= 1, x_l and the skip rows of block l-1
     // (T2); phase n only runs T2 for the last block's skip rows.
     const bool rec = P.dbg != nullptr && (int)blockIdx.x == P.dbg_cta && step == P.dbg_step && tid == 0;
+    if (rec) P.dbg[105] = step_start;
     for (int l = 0; l <= P.n_blocks; ++l) {
       const bool has_t1 = l < P.n_blocks, has_t2 = l >= 1;
       if (rec && l < 12) P.dbg[8 * l] = clock64();
@@ -597,6 +599,7 @@ generate_kernel(const GenParams P) {
     }
 
     // ---- head: relu -> proj1 -> relu -> proj2 (modules.py:248-254) ----
+    if (rec) P.dbg[100] = clock64();
     for (int i = tid; i < P.Cs; i += GEN_THREADS)
       xs[i] = fmaxf(__ldcg(P.skipacc + i) + (tagx ? __ldcg(P.skiplast + i) : 0.0f), 0.0f);
     __syncthreads();
@@ -605,6 +608,7 @@ generate_kernel(const GenParams P) {
       if (lane == 0) P.h1[r] = fmaxf(v + __ldg(P.proj1_b + r), 0.0f);
     }
     grid_barrier(P.barrier, epoch);
+    if (rec) P.dbg[101] = clock64();
     for (int i = tid; i < P.Cs; i += GEN_THREADS) xs[i] = __ldcg(P.h1 + i);
     __syncthreads();
     for (int r = gwarp; r < P.Q; r += nwarps) {
@@ -614,6 +618,7 @@ generate_kernel(const GenParams P) {
     grid_barrier(P.barrier, epoch);
 
     // ---- softmax + draw: every CTA does it redundantly (identical inputs -> identical result)
+    if (rec) P.dbg[102] = clock64();
     for (int i = tid; i < P.Q; i += GEN_THREADS) xs[i] = __ldcg(P.logit_buf + i);
     __syncthreads();
     if (warp == 0 && P.mol) {
@@ -632,14 +637,22 @@ generate_kernel(const GenParams P) {
       }
       s = warp_sum(s);
       __syncwarp();
-      if (lane == 0) {
-        double acc = 0.0;
-        for (int k = 0; k < nr; ++k) {
+      // the float64 logarithms of the components are evaluated by one lane each; the terms are then
+      // added in component order (the order of the reference's sum), so the result is unchanged
+      double acc = 0.0;
+      for (int k0 = 0; k0 < nr; k0 += 32) {
+        const int k = k0 + lane;
+        double term = 0.0;
+        if (k < nr) {
           const float sc = expf(fmaxf(xs[2 * nr + k], P.log_scale_min));
           const double u = P.uniforms[(long long)step * nr + k];
           const double r = (double)xs[nr + k] + (double)sc * (log(u) - log(1.0 - u));
-          acc += r * (double)(ps[k] / s);
+          term = r * (double)(ps[k] / s);
         }
+        const int nk = min(32, nr - k0);
+        for (int j = 0; j < nk; ++j) acc += __shfl_sync(0xffffffffu, term, j);
+      }
+      if (lane == 0) {
         float v = (float)acc;
         v = v / 127.5f;
         v = fminf(fmaxf(v, -1.0f), 1.0f);
@@ -658,21 +671,45 @@ generate_kernel(const GenParams P) {
       }
       s = warp_sum(s);
       __syncwarp();
-      if (lane == 0) {
-        // numpy.random.choice: cdf = cumsum(p as float64); cdf /= cdf[-1]; searchsorted(u, 'right')
-        double tot = 0.0;
-        for (int i = 0; i < P.Q; ++i) tot += (double)(ps[i] / s);
-        const double u = P.uniforms[step];
-        double run = 0.0;
-        int pick = P.Q - 1;
-        for (int i = 0; i < P.Q; ++i) {
-          run += (double)(ps[i] / s);
-          if (run / tot > u) { pick = i; break; }
+      for (int i = lane; i < P.Q; i += 32) ps[i] = ps[i] / s;     // the float32 softmax, in parallel
+      __syncwarp();
+      {
+        // numpy.random.choice: cdf = cumsum(p as float64); cdf /= cdf[-1]; searchsorted(u, 'right'),
+        // i.e. the first i with run_i / tot > u.  One lane doing it element by element cost 65 k
+        // cycles per sample (a float64 division per element, then still 42 k: a dependent float64
+        // add is ~64 cycles here), a fifth of the whole step.  Now every lane sums a contiguous run
+        // of Q/32 elements, a warp scan gives the prefixes, and each lane tests its own elements;
+        // run_i <= u * tot * (1 - 2^-40) rules an element out without dividing.  The float64 sums
+        // are associated differently from NumPy's sequential cumsum (last-ulp differences, ~1e-16):
+        // the draw can only differ when u lies within that distance of a cdf step.
+        const int per = (P.Q + 31) / 32, e0 = lane * per;
+        double loc = 0.0;
+        for (int k = 0; k < per; ++k)
+          if (e0 + k < P.Q) loc += (double)ps[e0 + k];
+        double inc = loc;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const double o = __shfl_up_sync(0xffffffffu, inc, off);
+          if (lane >= off) inc += o;
         }
-        s_sample = pick;
+        const double tot = __shfl_sync(0xffffffffu, inc, 31);
+        double run = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) run = 0.0;
+        const double u = P.uniforms[step];
+        const double lo = u * tot * (1.0 - 9.094947017729282e-13);
+        int mine = P.Q;
+        for (int k = 0; k < per; ++k) {
+          if (e0 + k >= P.Q) break;
+          run += (double)ps[e0 + k];
+          if (run > lo && run / tot > u) { mine = e0 + k; break; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, off));
+        if (lane == 0) s_sample = mine < P.Q ? mine : P.Q - 1;
       }
     }
     __syncthreads();
+    if (rec) P.dbg[103] = clock64();
     const int pick = s_sample;
     const int fed = P.forced ? P.forced[step] : pick;
     if (blockIdx.x == 0) {
@@ -686,6 +723,7 @@ generate_kernel(const GenParams P) {
       P.state[0] = fed;
     }
     grid_barrier(P.barrier, epoch);
+    if (rec) P.dbg[104] = clock64();
   }
 }
 
@@ -918,6 +956,9 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
       fprintf(stderr, "  phase %2d: start %6lld staged %6lld T1 %6lld T2 %6lld prefetch issued %6lld "
                       "barrier passed %6lld\n", l, h[8 * l] - h[0], h[8 * l + 1] - h[0],
               h[8 * l + 2] - h[0], h[8 * l + 3] - h[0], h[8 * l + 4] - h[0], h[8 * l + 5] - h[0]);
+    fprintf(stderr, "  step start %lld | phases done / head start %lld, proj1 + barrier %lld, proj2 + barrier %lld, "
+                    "softmax + draw %lld, state hand-over (2 barriers) %lld\n", h[105] - h[0], h[100] - h[0],
+            h[101] - h[100], h[102] - h[101], h[103] - h[102], h[104] - h[103]);
   }
   return 0;
 }
