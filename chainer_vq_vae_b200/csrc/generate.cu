@@ -376,6 +376,10 @@ generate_kernel(const GenParams P) {
     }
   };
 
+  // the last two inputs (modules.py:246: the embed queue).  Every CTA draws the same sample from the
+  // same logits, so each keeps its own copy instead of handing the state over through global
+  // memory behind two grid barriers per sample
+  int st1 = P.state[0], st2 = P.state[1];
   for (int step = 0; step < P.n_steps; ++step) {
     const int t = P.t_start + step;
     const long long step_start = P.dbg ? clock64() : 0;
@@ -383,7 +387,7 @@ generate_kernel(const GenParams P) {
     if (tid < P.n_blocks) s_slot[tid] = t % sblk[tid].qlen;
     __syncthreads();
     {
-      const int s1 = P.state[0], s2 = P.state[1];
+      const int s1 = st1, s2 = st2;
       float* ring0 = P.queues + sblk[0].qoff + (long long)s_slot[0] * P.Cr;
       for (int c = blockIdx.x * GEN_THREADS + tid; c < P.Cr; c += gridDim.x * GEN_THREADS) {
         float v = __ldg(P.embed_b + c);
@@ -717,13 +721,15 @@ generate_kernel(const GenParams P) {
         for (int i = tid; i < P.Q; i += GEN_THREADS) P.logits[(long long)step * P.Q + i] = xs[i];
       if (tid == 0) P.samples[step] = pick;
     }
-    grid_barrier(P.barrier, epoch);   // everyone has read state/logit_buf before they change
-    if (blockIdx.x == 0 && tid == 0) {
-      P.state[1] = P.state[0];
-      P.state[0] = fed;
-    }
-    grid_barrier(P.barrier, epoch);
+    // logit_buf, h1 and skipacc are next written behind at least two grid barriers of the next step
+    // (initial barrier, phase-n barrier), which every CTA only passes after the reads above
+    st2 = st1;
+    st1 = fed;
     if (rec) P.dbg[104] = clock64();
+  }
+  if (blockIdx.x == 0 && tid == 0) {   // for the step-wise API (WaveNetState.step)
+    P.state[0] = st1;
+    P.state[1] = st2;
   }
 }
 
@@ -957,7 +963,7 @@ extern "C" int vqw_generate(const vqw_generate_desc* desc, const vqw_resblock_we
                       "barrier passed %6lld\n", l, h[8 * l] - h[0], h[8 * l + 1] - h[0],
               h[8 * l + 2] - h[0], h[8 * l + 3] - h[0], h[8 * l + 4] - h[0], h[8 * l + 5] - h[0]);
     fprintf(stderr, "  step start %lld | phases done / head start %lld, proj1 + barrier %lld, proj2 + barrier %lld, "
-                    "softmax + draw %lld, state hand-over (2 barriers) %lld\n", h[105] - h[0], h[100] - h[0],
+                    "softmax + draw %lld, sample hand-over %lld\n", h[105] - h[0], h[100] - h[0],
             h[101] - h[100], h[102] - h[101], h[103] - h[102], h[104] - h[103]);
   }
   return 0;
