@@ -558,7 +558,7 @@ def generate_workload(args, dev, steps, length):
                      "note": "algorithmic bytes = every weight read once per sample (174.9 MB "
                              "fp32, streamed from HBM: L2 hit rate 10 %); the kernel is bound by the "
                              "dependent chain of 41 phases per sample (one tagged store->load "
-                             "exchange each, ~3.3 us per phase) plus 6 grid barriers"},
+                             "exchange each, ~3.3 us per phase) plus 4 grid barriers"},
         "cpu_baseline": cpu, "first_samples": [int(v) for v in out[:8].tolist()],
     }
 
