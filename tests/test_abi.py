@@ -53,3 +53,19 @@ def test_no_oracle_or_cpu_fallback_in_the_product():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_arithmetic_modes_agree_between_header_binding_and_bench():
+    """include/vqw.h's VQW_MODE_* constants, _lib.MODES and bench.py's --mode choices name the same
+    set of arithmetic modes with the same values."""
+    import re
+    import chainer_vq_vae_b200._lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "vqw.h")).read()
+    in_header = {m.group(1).lower(): int(m.group(2))
+                 for m in re.finditer(r"#define\s+VQW_MODE_(\w+)\s+(\d+)", hdr)}
+    assert in_header == dict(L.MODES), (in_header, L.MODES)
+    bench = open(os.path.join(root, "bench.py")).read()
+    choices = re.search(r'"--mode".*?choices=\[(.*?)\]', bench, re.S).group(1)
+    assert {c.strip().strip('"') for c in choices.split(",")} == set(L.MODES)
+    assert set(L.X3_MODES) == {L.MODES["bf16x3"], L.MODES["fp16x3"]}
